@@ -1,0 +1,163 @@
+/*
+ * fastani_b200.h -- C ABI of libfastani_b200.so, the B200 (sm_100a) implementation of
+ * pyfastani's FastANI/MashMap mapping path.
+ *
+ * This is the drop-in boundary: each entry point replaces what the reference's Cython
+ * layer (src/pyfastani/_fastani.pyx, "pyx" below) does through `cdef extern` bindings to
+ * the skch::/cgi:: C++ headers (vendor/FastANI/src, "FA/" below).  Plain pointers and
+ * sizes only; status-code returns (0 = ok), message via fa_last_error(); no C++
+ * exceptions cross the boundary.  Threading: fa_sketch_* calls on one sketch must be
+ * externally serialised (the reference holds a threading.Lock, pyx:563,715,742);
+ * fa_query* may be called concurrently on one fa_index (pyx:1158-1161).
+ *
+ * There is no CPU fallback: every call that computes runs CUDA kernels and fails with
+ * FA_ERR_CUDA when no device is usable.
+ */
+#ifndef FASTANI_B200_H
+#define FASTANI_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define FA_API __attribute__((visibility("default")))
+#else
+#define FA_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    FA_OK = 0,
+    FA_ERR_INVALID = 1,      /* bad argument (maps to ValueError, pyx:523-539) */
+    FA_ERR_CUDA = 2,         /* CUDA runtime failure / no device */
+    FA_ERR_NOMEM = 3,
+    FA_ERR_UNSUPPORTED = 4,  /* parameter combination not implemented on the device path */
+    FA_ERR_STATE = 5         /* call order (e.g. query on an empty index) */
+};
+
+/* skch::Parameters, FA/map/include/map_parameters.hpp:21-38 (the fields pyfastani sets,
+ * pyx:374-378, 542-560). */
+typedef struct fa_params {
+    int32_t  k;             /* kmerSize */
+    int32_t  window;        /* windowSize (0 = derive with fa_recommended_window) */
+    int32_t  frag_len;      /* minReadLength */
+    int32_t  alphabet;      /* alphabetSize: 4 (nucleotide) */
+    float    min_fraction;  /* minFraction */
+    float    pct_identity;  /* percentageIdentity */
+    double   p_value;       /* p_value */
+    uint64_t ref_size;      /* referenceSize */
+} fa_params;
+
+/* One sequence as the reference receives it (pyx:633-645, 1071-1095): `unit_bytes` is 1
+ * for bytes / UCS1 str, 2 or 4 for UCS2 / UCS4 str.  `on_device` != 0 means `data` is a
+ * device pointer on the index's device (unit_bytes must be 1); used to time the path
+ * with inputs already resident in HBM. */
+typedef struct fa_contig {
+    const void *data;
+    int32_t     unit_bytes;
+    int32_t     on_device;
+    int64_t     len;
+} fa_contig;
+
+/* cgi::CGI_Results, FA/cgi/include/cgid_types.hpp:68-80, after the min-fraction filter
+ * and identity-descending stable sort of pyx:1121-1135. */
+typedef struct fa_hit {
+    int32_t ref_genome;     /* index into the genomes added to the sketch */
+    int32_t matches;        /* countSeq */
+    int32_t fragments;      /* totalQueryFragments */
+    float   identity;
+} fa_hit;
+
+/* Realised workload counters and per-stage device times of one fa_query call
+ * (the figures the roofline is computed from).  Times are CUDA-event
+ * milliseconds on the library's own stream. */
+typedef struct fa_query_info {
+    uint64_t fragments;        /* F: query fragments mapped */
+    uint64_t sketch_sum;       /* sum of per-fragment sketch sizes s */
+    uint64_t seeds;            /* sum H: seed hits */
+    uint64_t candidates;       /* sum C: L1 candidate regions */
+    uint64_t scanned;          /* sum R: reference minimizers visited by L2 */
+    uint64_t mappings;         /* P: L2 mappings that passed the identity filter */
+    int32_t  short_contigs;    /* contigs that raise the "short sequence" warning, pyx:1062-1070 */
+    int32_t  kernel_launches;  /* kernels launched by this call */
+    float    ms_h2d, ms_sketch, ms_lookup, ms_seed_sort, ms_l1, ms_l2, ms_cgi, ms_d2h, ms_total;
+    uint64_t h2d_bytes, d2h_bytes;
+} fa_query_info;
+
+typedef struct fa_sketch fa_sketch;   /* skch::Sketch under construction (pyx:465-470) */
+typedef struct fa_index  fa_index;    /* indexed skch::Sketch owned by a Mapper (pyx:821-824) */
+
+/* -- library -------------------------------------------------------------------------- */
+FA_API const char *fa_last_error(void);                  /* thread-local message of the last failure */
+FA_API int fa_device_count(int32_t *n_out);
+FA_API int fa_version(void);
+
+/* Stat::recommendedWindowSize, FA/map/include/map_stats.hpp:226-256 (pyx:553-560). */
+FA_API int fa_recommended_window(const fa_params *p, int32_t *w_out);
+/* Stat::estimateMinimumHitsRelaxed (map_stats.hpp:142-167) and the identity / 90 % CI
+ * filter of Map::doL2Mapping (computeMap.hpp:371-380); exported for the parity tests. */
+FA_API int fa_stat_minimum_hits(int32_t s, int32_t k, float pct_identity, int32_t *out);
+FA_API int fa_stat_l2(int32_t shared, int32_t s, int32_t k, float pct_identity, float *identity, int32_t *pass);
+
+/* -- Sketch (pyx:449-806) ---------------------------------------------------------------- */
+FA_API int fa_sketch_create(const fa_params *p, int32_t device, fa_sketch **out);            /* pyx:476 */
+FA_API void fa_sketch_free(fa_sketch *s);                                                    /* pyx:569-570 */
+/* One iteration of the contig loop of Sketch._add_draft (pyx:629-683): sketches the contig
+ * on the GPU (if long enough), consumes one sequence id.  *n_added (optional) receives the
+ * number of minimizers appended, or -1 for the "short contig" warning case. */
+FA_API int fa_sketch_add_contig(fa_sketch *s, const void *data, int32_t unit_bytes, int64_t len, int64_t *n_added);
+/* pyx:686-690: closes the current genome; returns its fragment-rounded length. */
+FA_API int fa_sketch_end_genome(fa_sketch *s, uint64_t *genome_len_out);
+/* Batched form of the two calls above for one genome (one H2D + one launch sequence for
+ * all contigs).  *n_short (optional) counts contigs that raise the warning. */
+FA_API int fa_sketch_add_genome(fa_sketch *s, const fa_contig *contigs, int32_t n_contigs,
+                         uint64_t *genome_len_out, int32_t *n_short);
+FA_API int fa_sketch_clear(fa_sketch *s);                                                    /* pyx:746-767 */
+FA_API int fa_sketch_counts(const fa_sketch *s, uint64_t *n_minimizers, uint64_t *n_contigs, uint64_t *n_genomes);
+/* Minimizers view, pyx:1222-1254: copy [first, first+n) of (hash, seqId, wpos). */
+FA_API int fa_sketch_copy_minimizers(const fa_sketch *s, uint64_t first, uint64_t n,
+                              uint32_t *hash, int32_t *seq, int32_t *wpos);
+/* Pickle support (pyx:572-591): bookkeeping out / everything back in. */
+FA_API int fa_sketch_copy_meta(const fa_sketch *s, int32_t *seqs_by_genome, uint64_t *genome_len, int64_t *contig_len);
+FA_API int fa_sketch_restore(fa_sketch *s, const uint32_t *hash, const int32_t *seq, const int32_t *wpos, uint64_t n,
+                      const int32_t *seqs_by_genome, const uint64_t *genome_len, uint64_t n_genomes,
+                      const int64_t *contig_len, uint64_t n_contigs);
+/* Sketch.index(), pyx:769-806 (Sketch::index + computeFreqHist, FA/map/include/
+ * winSketch.hpp:177-244): builds the lookup index on the GPU; the data moves to *out and
+ * the sketch is left empty but usable. */
+FA_API int fa_sketch_index(fa_sketch *s, fa_index **out);
+
+/* -- Mapper (pyx:809-1200) --------------------------------------------------------------- */
+FA_API void fa_index_free(fa_index *ix);                                                     /* pyx:839-840 */
+FA_API int fa_index_counts(const fa_index *ix, uint64_t *n_minimizers, uint64_t *n_unique,
+                    uint64_t *n_contigs, uint64_t *n_genomes);                        /* pyx:1222, 1454-1456 */
+FA_API int fa_index_params(const fa_index *ix, fa_params *out);
+FA_API int fa_index_copy_minimizers(const fa_index *ix, uint64_t first, uint64_t n,
+                             uint32_t *hash, int32_t *seq, int32_t *wpos);           /* pyx:1225-1254 */
+FA_API int fa_index_copy_meta(const fa_index *ix, int32_t *seqs_by_genome, uint64_t *genome_len, int64_t *contig_len);
+/* MinimizerIndex view (pyx:1431-1539): keys in ascending hash order; positions of one hash
+ * in insertion order (winSketch.hpp:180-185).  *n receives the bucket size (0 = KeyError). */
+FA_API int fa_index_copy_keys(const fa_index *ix, uint64_t first, uint64_t n, uint32_t *keys);
+FA_API int fa_index_lookup(const fa_index *ix, uint32_t hash, int32_t *seq, int32_t *wpos, uint64_t cap, uint64_t *n);
+FA_API int fa_index_occurrence_threshold(const fa_index *ix, int32_t *out);                  /* getFreqThreshold, pyx:596-600 */
+/* Mapper._query_draft, pyx:1006-1136: fragments the contigs, sketches them, L1 seeding,
+ * L2 sliding Jaccard, computeCGI, min-fraction filter, sort.  Writes at most `cap` rows;
+ * *n_out receives the number of hits.  `info` is optional. */
+FA_API int fa_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs,
+             fa_hit *out, uint64_t cap, uint64_t *n_out, fa_query_info *info);
+/* Intermediates of the last fa_query on this index, for the bit-exact parity tests
+ * (SURVEY.md 7.1 step 0): L1 candidates as (frag, seq, start, end) rows and L2 mappings as
+ * (frag, seq, refStartPos, shared, sketch, identity-bits) rows of int32. */
+FA_API int fa_debug_last_candidates(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n);
+FA_API int fa_debug_last_mappings(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n);
+/* Device scratch for callers that want inputs resident in HBM before timing. */
+FA_API int fa_device_alloc(fa_index *ix, uint64_t bytes, void **dptr);
+FA_API int fa_device_upload(fa_index *ix, void *dptr, const void *src, uint64_t bytes);
+FA_API int fa_device_free(fa_index *ix, void *dptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTANI_B200_H */

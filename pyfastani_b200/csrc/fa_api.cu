@@ -1,0 +1,456 @@
+// fa_api.cu -- the extern "C" surface declared in include/fastani_b200.h.
+#include <cstdarg>
+#include <cstring>
+#include <algorithm>
+#include <new>
+
+#include "fa_internal.cuh"
+
+namespace fa {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+__global__ void unpack_kernel(const RefMini *ref, uint64_t first, uint64_t n, uint32_t *hash, int32_t *seq, int32_t *wpos)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RefMini e = ref[first + i];
+    hash[i] = e.x; wpos[i] = (int32_t)e.y; seq[i] = (int32_t)e.z;
+}
+
+__global__ void pack_kernel(RefMini *ref, uint64_t n, const uint32_t *hash, const int32_t *seq, const int32_t *wpos)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ref[i] = make_uint4(hash[i], (uint32_t)wpos[i], (uint32_t)seq[i], 0u);
+}
+
+__global__ void lookup_one_kernel(const uint32_t *ukeys, const uint32_t *uoff, uint32_t n_unique, uint32_t h, uint32_t *out)
+{
+    uint32_t lo = 0, hi = n_unique;
+    while (lo < hi) { uint32_t mid = lo + ((hi - lo) >> 1); if (ukeys[mid] < h) lo = mid + 1; else hi = mid; }
+    if (lo < n_unique && ukeys[lo] == h) { out[0] = uoff[lo]; out[1] = uoff[lo + 1] - uoff[lo]; }
+    else { out[0] = 0; out[1] = 0; }
+}
+
+__global__ void gather_kernel(const RefMini *ref, const uint32_t *pos_idx, uint32_t start, uint32_t n, int32_t *seq, int32_t *wpos)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RefMini e = ref[pos_idx[start + i]];
+    seq[i] = (int32_t)e.z; wpos[i] = (int32_t)e.y;
+}
+
+int check_params(const fa_params *p)
+{
+    if (!p) { set_error("params is NULL"); return FA_ERR_INVALID; }
+    if (p->k <= 0 || p->k > 2048) { set_error("k must be in [1, 2048], got %d", p->k); return FA_ERR_INVALID; }
+    if (p->frag_len <= 0) { set_error("fragment_length must be strictly positive, got %d", p->frag_len); return FA_ERR_INVALID; }
+    if (p->min_fraction < 0 || p->min_fraction > 1) { set_error("minimum_fraction must be between 0 and 1"); return FA_ERR_INVALID; }
+    if (!(p->p_value > 0)) { set_error("p_value must be positive"); return FA_ERR_INVALID; }
+    if (p->pct_identity < 0 || p->pct_identity > 100) { set_error("percentage_identity must be between 0 and 100"); return FA_ERR_INVALID; }
+    if (p->alphabet != 4) { set_error("only the nucleotide alphabet (4) is implemented on the device path"); return FA_ERR_UNSUPPORTED; }
+    if (p->window < 0) { set_error("window must be >= 0"); return FA_ERR_INVALID; }
+    return FA_OK;
+}
+
+int copy_minimizers(int device, cudaStream_t st, const RefMini *ref, uint64_t total, uint64_t first, uint64_t n,
+                    uint32_t *hash, int32_t *seq, int32_t *wpos)
+{
+    if (first > total || n > total - first) { set_error("minimizer range out of bounds"); return FA_ERR_INVALID; }
+    if (n == 0) return FA_OK;
+    FA_CUDA(cudaSetDevice(device));
+    DevBuf<uint32_t> dh; DevBuf<int32_t> ds, dw;
+    int rc = dh.reserve(n);
+    if (rc == FA_OK) rc = ds.reserve(n);
+    if (rc == FA_OK) rc = dw.reserve(n);
+    if (rc == FA_OK) {
+        unpack_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(ref, first, n, dh.p, ds.p, dw.p);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hash, dh.p, n * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(seq, ds.p, n * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(wpos, dw.p, n * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_error("copy_minimizers: %s", cudaGetErrorString(e)); rc = FA_ERR_CUDA; }
+    }
+    dh.release(); ds.release(); dw.release();
+    return rc;
+}
+
+// Sketch one batch of contigs (each consumes a sequence id, pyx:683) and append the minimizers.
+int sketch_add_batch(fa_sketch *s, const fa_contig *contigs, int32_t n_contigs, int32_t *n_short, int64_t *n_added)
+{
+    FA_CUDA(cudaSetDevice(s->device));
+    const fa_params &P = s->prm;
+    std::vector<Upload> ups;
+    s->h_seqs.clear();
+    uint64_t off = 0, worst = 0;
+    int64_t tiles = 0;
+    int32_t shorts = 0;
+    for (int32_t c = 0; c < n_contigs; c++) {
+        const fa_contig &ct = contigs[c];
+        if (ct.len < 0 || (ct.len > 0 && !ct.data)) { set_error("contig %d: bad buffer", c); return FA_ERR_INVALID; }
+        if (ct.unit_bytes != 1 && ct.unit_bytes != 2 && ct.unit_bytes != 4) { set_error("unit_bytes must be 1, 2 or 4"); return FA_ERR_INVALID; }
+        if (ct.on_device && ct.unit_bytes != 1) { set_error("device-resident contigs must be bytes"); return FA_ERR_INVALID; }
+        if (ct.len > 0x7FFFFF00ll) { set_error("contigs longer than 2^31 bases are not supported"); return FA_ERR_UNSUPPORTED; }
+    }
+    for (int32_t c = 0; c < n_contigs; c++) {
+        const fa_contig &ct = contigs[c];
+        const int32_t id = (int32_t)s->contig_len.size();
+        if (ct.len >= P.window && ct.len >= P.k) {                                    // pyx:648
+            const int nk = (int)ct.len - P.k + 1;
+            SeqDesc d;
+            d.off = off; d.len = (int32_t)ct.len; d.id = id; d.raw = ct.unit_bytes != 1; d.tile0 = (int32_t)tiles;
+            s->h_seqs.push_back(d);
+            ups.push_back(Upload{ct.data, ct.unit_bytes, ct.on_device, ct.len, off});
+            off += ((uint64_t)ct.len + 15) & ~15ull;
+            tiles += (nk + SK_TILE - 1) / SK_TILE;
+            if (nk >= P.window) worst += (uint64_t)(nk - P.window + 1);
+        } else shorts++;                                                              // pyx:670-677
+        s->cur_len += (uint64_t)(ct.len / P.frag_len) * (uint64_t)P.frag_len;         // pyx:680
+        s->contig_len.push_back(ct.len);
+    }
+    if (n_short) *n_short = shorts;
+    if (n_added) *n_added = shorts == n_contigs && n_contigs == 1 ? -1 : 0;
+    const int n_seqs = (int)s->h_seqs.size();
+    if (n_seqs == 0) return FA_OK;
+    if (tiles > 0x7FFFFF00ll) { set_error("batch too large"); return FA_ERR_UNSUPPORTED; }
+    cudaStream_t st = s->st;
+    int launches = 0;
+    FA_TRY(stage_sequences(st, s->sc, s->stage, ups, off, nullptr));
+    FA_TRY(s->sc.seqs.reserve(n_seqs)); FA_TRY(s->sc.tile_status.reserve((size_t)tiles));
+    FA_TRY(s->sc.counters.reserve(4)); FA_TRY(s->sc.seq_first.reserve(n_seqs)); FA_TRY(s->sc.drops.reserve(n_seqs));
+    FA_TRY(s->ref.reserve(s->n + worst + 1, true, st));
+    FA_CUDA(cudaMemcpyAsync(s->sc.seqs.p, s->h_seqs.data(), (size_t)n_seqs * sizeof(SeqDesc), cudaMemcpyHostToDevice, st));
+    FA_TRY(launch_sketch(st, s->sc, n_seqs, (int)tiles, P.k, P.window, s->ref.p, nullptr, s->n, &launches));
+    FA_TRY(launch_quirk_find(st, s->sc, n_seqs, s->ref.p + s->n, &launches));
+    unsigned long long h_ct[4];
+    FA_CUDA(cudaMemcpyAsync(h_ct, s->sc.counters.p, sizeof h_ct, cudaMemcpyDeviceToHost, st));
+    FA_CUDA(cudaStreamSynchronize(st));
+    uint64_t added = h_ct[1];
+    if (h_ct[2] > 0) FA_TRY(quirk_compact(st, s->sc, (unsigned int)h_ct[2], s->ref.p + s->n, added, &added, &launches));
+    s->n += added;
+    if (n_added) *n_added = (int64_t)added;
+    return FA_OK;
+}
+
+void free_sketch_scratch(SketchScratch &sc)
+{
+    sc.bytes.release(); sc.seqs.release(); sc.tile_status.release(); sc.counters.release(); sc.seq_first.release(); sc.drops.release();
+}
+
+}  // namespace
+}  // namespace fa
+
+using namespace fa;
+
+extern "C" {
+
+const char *fa_last_error(void) { return g_err; }
+int fa_version(void) { return 100; }
+
+int fa_device_count(int32_t *n_out)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e)); if (n_out) *n_out = 0; return FA_ERR_CUDA; }
+    if (n_out) *n_out = n;
+    return FA_OK;
+}
+
+int fa_recommended_window(const fa_params *p, int32_t *w_out)
+{
+    FA_TRY(check_params(p));
+    *w_out = recommended_window(p->p_value, p->k, p->alphabet, p->pct_identity, p->frag_len, p->ref_size);
+    return FA_OK;
+}
+
+int fa_stat_minimum_hits(int32_t s, int32_t k, float pid, int32_t *out) { *out = minimum_hits_relaxed(s, k, pid); return FA_OK; }
+
+int fa_stat_l2(int32_t shared, int32_t s, int32_t k, float pid, float *identity, int32_t *pass)
+{
+    float id = 0;
+    bool ok = l2_pass(shared, s, k, pid, &id);
+    if (identity) *identity = id;
+    if (pass) *pass = ok ? 1 : 0;
+    return FA_OK;
+}
+
+int fa_sketch_create(const fa_params *p, int32_t device, fa_sketch **out)
+{
+    FA_TRY(check_params(p));
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { set_error("no CUDA device is available (%s); libfastani_b200 has no CPU path", cudaGetErrorString(e)); return FA_ERR_CUDA; }
+    if (device < 0 || device >= n) { set_error("device %d out of range (have %d)", device, n); return FA_ERR_INVALID; }
+    FA_CUDA(cudaSetDevice(device));
+    fa_sketch *s = new (std::nothrow) fa_sketch();
+    if (!s) return FA_ERR_NOMEM;
+    s->prm = *p;
+    if (s->prm.window == 0)
+        s->prm.window = recommended_window(p->p_value, p->k, p->alphabet, p->pct_identity, p->frag_len, p->ref_size);
+    s->device = device;
+    e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); delete s; return FA_ERR_CUDA; }
+    *out = s;
+    return FA_OK;
+}
+
+void fa_sketch_free(fa_sketch *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    s->ref.release(); free_sketch_scratch(s->sc); s->stage.release();
+    if (s->st) cudaStreamDestroy(s->st);
+    delete s;
+}
+
+int fa_sketch_add_contig(fa_sketch *s, const void *data, int32_t unit_bytes, int64_t len, int64_t *n_added)
+{
+    if (!s) { set_error("sketch is NULL"); return FA_ERR_INVALID; }
+    fa_contig c{data, unit_bytes, 0, len};
+    int32_t shorts = 0;
+    int64_t added = 0;
+    FA_TRY(sketch_add_batch(s, &c, 1, &shorts, &added));
+    if (n_added) *n_added = shorts ? -1 : added;
+    return FA_OK;
+}
+
+int fa_sketch_end_genome(fa_sketch *s, uint64_t *genome_len_out)
+{
+    if (!s) { set_error("sketch is NULL"); return FA_ERR_INVALID; }
+    s->genome_len.push_back(s->cur_len);                                  // pyx:687
+    s->seqs_by_genome.push_back((int32_t)s->contig_len.size());          // pyx:690
+    if (genome_len_out) *genome_len_out = s->cur_len;
+    s->cur_len = 0;
+    return FA_OK;
+}
+
+int fa_sketch_add_genome(fa_sketch *s, const fa_contig *contigs, int32_t n_contigs, uint64_t *genome_len_out, int32_t *n_short)
+{
+    if (!s || n_contigs < 0 || (n_contigs > 0 && !contigs)) { set_error("bad arguments"); return FA_ERR_INVALID; }
+    FA_TRY(sketch_add_batch(s, contigs, n_contigs, n_short, nullptr));
+    return fa_sketch_end_genome(s, genome_len_out);
+}
+
+int fa_sketch_clear(fa_sketch *s)
+{
+    if (!s) { set_error("sketch is NULL"); return FA_ERR_INVALID; }
+    s->n = 0; s->cur_len = 0;
+    s->seqs_by_genome.clear(); s->genome_len.clear(); s->contig_len.clear();
+    return FA_OK;
+}
+
+int fa_sketch_counts(const fa_sketch *s, uint64_t *n_minimizers, uint64_t *n_contigs, uint64_t *n_genomes)
+{
+    if (!s) { set_error("sketch is NULL"); return FA_ERR_INVALID; }
+    if (n_minimizers) *n_minimizers = s->n;
+    if (n_contigs) *n_contigs = s->contig_len.size();
+    if (n_genomes) *n_genomes = s->genome_len.size();
+    return FA_OK;
+}
+
+int fa_sketch_copy_minimizers(const fa_sketch *s, uint64_t first, uint64_t n, uint32_t *hash, int32_t *seq, int32_t *wpos)
+{
+    if (!s) { set_error("sketch is NULL"); return FA_ERR_INVALID; }
+    return copy_minimizers(s->device, s->st, s->ref.p, s->n, first, n, hash, seq, wpos);
+}
+
+int fa_sketch_copy_meta(const fa_sketch *s, int32_t *seqs_by_genome, uint64_t *genome_len, int64_t *contig_len)
+{
+    if (!s) { set_error("sketch is NULL"); return FA_ERR_INVALID; }
+    if (seqs_by_genome) std::copy(s->seqs_by_genome.begin(), s->seqs_by_genome.end(), seqs_by_genome);
+    if (genome_len) std::copy(s->genome_len.begin(), s->genome_len.end(), genome_len);
+    if (contig_len) std::copy(s->contig_len.begin(), s->contig_len.end(), contig_len);
+    return FA_OK;
+}
+
+int fa_sketch_restore(fa_sketch *s, const uint32_t *hash, const int32_t *seq, const int32_t *wpos, uint64_t n,
+                      const int32_t *seqs_by_genome, const uint64_t *genome_len, uint64_t n_genomes,
+                      const int64_t *contig_len, uint64_t n_contigs)
+{
+    if (!s) { set_error("sketch is NULL"); return FA_ERR_INVALID; }
+    FA_CUDA(cudaSetDevice(s->device));
+    fa_sketch_clear(s);
+    s->seqs_by_genome.assign(seqs_by_genome, seqs_by_genome + n_genomes);
+    s->genome_len.assign(genome_len, genome_len + n_genomes);
+    s->contig_len.assign(contig_len, contig_len + n_contigs);
+    if (n == 0) return FA_OK;
+    FA_TRY(s->ref.reserve(n + 1));
+    DevBuf<uint32_t> dh; DevBuf<int32_t> ds, dw;
+    FA_TRY(dh.reserve(n)); FA_TRY(ds.reserve(n)); FA_TRY(dw.reserve(n));
+    FA_CUDA(cudaMemcpyAsync(dh.p, hash, n * 4, cudaMemcpyHostToDevice, s->st));
+    FA_CUDA(cudaMemcpyAsync(ds.p, seq, n * 4, cudaMemcpyHostToDevice, s->st));
+    FA_CUDA(cudaMemcpyAsync(dw.p, wpos, n * 4, cudaMemcpyHostToDevice, s->st));
+    pack_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, s->st>>>(s->ref.p, n, dh.p, ds.p, dw.p);
+    FA_CUDA(cudaGetLastError());
+    FA_CUDA(cudaStreamSynchronize(s->st));
+    dh.release(); ds.release(); dw.release();
+    s->n = n;
+    return FA_OK;
+}
+
+int fa_sketch_index(fa_sketch *s, fa_index **out)
+{
+    if (!s || !out) { set_error("bad arguments"); return FA_ERR_INVALID; }
+    FA_CUDA(cudaSetDevice(s->device));
+    if (s->prm.frag_len > 32767) { set_error("fragment_length > 32767 is not supported on the device path"); return FA_ERR_UNSUPPORTED; }
+    if (s->prm.frag_len <= 20) { set_error("fragment_length <= 20 is not supported (the reference divides by fragment_length - 20)"); return FA_ERR_UNSUPPORTED; }
+    fa_index *ix = new (std::nothrow) fa_index();
+    if (!ix) return FA_ERR_NOMEM;
+    ix->prm = s->prm; ix->device = s->device;
+    cudaError_t e = cudaStreamCreateWithFlags(&ix->st, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); delete ix; return FA_ERR_CUDA; }
+    // ownership of the minimizers moves to the index; the sketch stays usable but empty (pyx:795-804)
+    ix->ref = s->ref; ix->n = s->n;
+    s->ref = DevBuf<RefMini>();
+    ix->seqs_by_genome.swap(s->seqs_by_genome);
+    ix->genome_len.swap(s->genome_len);
+    ix->contig_len.swap(s->contig_len);
+    fa_sketch_clear(s);
+    FA_CUDA(cudaStreamSynchronize(s->st));
+    if (!ix->ref.p) { int rc = ix->ref.reserve(1); if (rc) { fa_index_free(ix); return rc; } }
+    int launches = 0;
+    int rc = build_index(ix, &launches);
+    if (rc != FA_OK) { fa_index_free(ix); return rc; }
+    *out = ix;
+    return FA_OK;
+}
+
+void fa_index_free(fa_index *ix)
+{
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    ix->ref.release(); ix->pos_idx.release(); ix->ukeys.release(); ix->uoff.release(); ix->dir.release();
+    ix->contig_off.release(); ix->genome_of_seq.release(); ix->bin_base.release(); ix->genome_cell.release();
+    ix->d_min_hits.release(); ix->d_min_shared.release(); ix->d_id_off.release(); ix->d_identity.release();
+    Workspace &w = ix->ws;
+    free_sketch_scratch(w.sk); w.stage.release(); w.qhash.release(); w.qs.release(); w.hit_start.release(); w.hit_cnt.release();
+    w.frag_seeds.release(); w.seeds_a.release(); w.seeds_b.release(); w.cub_tmp.release(); w.frag_cands.release();
+    w.work_base.release(); w.cands.release(); w.maps.release(); w.cells.release(); w.g_identity.release(); w.g_count.release();
+    w.counters.release(); w.hres.release();
+    if (w.ev_ready) for (auto &e : w.ev) cudaEventDestroy(e);
+    if (ix->st) cudaStreamDestroy(ix->st);
+    delete ix;
+}
+
+int fa_index_counts(const fa_index *ix, uint64_t *n_minimizers, uint64_t *n_unique, uint64_t *n_contigs, uint64_t *n_genomes)
+{
+    if (!ix) { set_error("index is NULL"); return FA_ERR_INVALID; }
+    if (n_minimizers) *n_minimizers = ix->n;
+    if (n_unique) *n_unique = ix->n_unique;
+    if (n_contigs) *n_contigs = ix->contig_len.size();
+    if (n_genomes) *n_genomes = ix->genome_len.size();
+    return FA_OK;
+}
+
+int fa_index_params(const fa_index *ix, fa_params *out)
+{
+    if (!ix || !out) { set_error("bad arguments"); return FA_ERR_INVALID; }
+    *out = ix->prm;
+    return FA_OK;
+}
+
+int fa_index_copy_minimizers(const fa_index *ix, uint64_t first, uint64_t n, uint32_t *hash, int32_t *seq, int32_t *wpos)
+{
+    if (!ix) { set_error("index is NULL"); return FA_ERR_INVALID; }
+    return copy_minimizers(ix->device, ix->st, ix->ref.p, ix->n, first, n, hash, seq, wpos);
+}
+
+int fa_index_copy_meta(const fa_index *ix, int32_t *seqs_by_genome, uint64_t *genome_len, int64_t *contig_len)
+{
+    if (!ix) { set_error("index is NULL"); return FA_ERR_INVALID; }
+    if (seqs_by_genome) std::copy(ix->seqs_by_genome.begin(), ix->seqs_by_genome.end(), seqs_by_genome);
+    if (genome_len) std::copy(ix->genome_len.begin(), ix->genome_len.end(), genome_len);
+    if (contig_len) std::copy(ix->contig_len.begin(), ix->contig_len.end(), contig_len);
+    return FA_OK;
+}
+
+int fa_index_copy_keys(const fa_index *ix, uint64_t first, uint64_t n, uint32_t *keys)
+{
+    if (!ix) { set_error("index is NULL"); return FA_ERR_INVALID; }
+    if (first > ix->n_unique || n > ix->n_unique - first) { set_error("key range out of bounds"); return FA_ERR_INVALID; }
+    if (!n) return FA_OK;
+    FA_CUDA(cudaSetDevice(ix->device));
+    FA_CUDA(cudaMemcpy(keys, ix->ukeys.p + first, n * 4, cudaMemcpyDeviceToHost));
+    return FA_OK;
+}
+
+int fa_index_lookup(const fa_index *ix, uint32_t hash, int32_t *seq, int32_t *wpos, uint64_t cap, uint64_t *n)
+{
+    if (!ix || !n) { set_error("bad arguments"); return FA_ERR_INVALID; }
+    *n = 0;
+    if (ix->n_unique == 0) return FA_OK;
+    FA_CUDA(cudaSetDevice(ix->device));
+    uint32_t *d_out = nullptr, h_out[2] = {0, 0};
+    FA_CUDA(cudaMalloc((void **)&d_out, 8));
+    lookup_one_kernel<<<1, 1, 0, ix->st>>>(ix->ukeys.p, ix->uoff.p, (uint32_t)ix->n_unique, hash, d_out);
+    FA_CUDA(cudaMemcpyAsync(h_out, d_out, 8, cudaMemcpyDeviceToHost, ix->st));
+    FA_CUDA(cudaStreamSynchronize(ix->st));
+    cudaFree(d_out);
+    *n = h_out[1];
+    uint32_t m = (uint32_t)std::min<uint64_t>(cap, h_out[1]);
+    if (m && seq && wpos) {
+        DevBuf<int32_t> ds, dw;
+        FA_TRY(ds.reserve(m)); FA_TRY(dw.reserve(m));
+        gather_kernel<<<(m + 127) / 128, 128, 0, ix->st>>>(ix->ref.p, ix->pos_idx.p, h_out[0], m, ds.p, dw.p);
+        FA_CUDA(cudaMemcpyAsync(seq, ds.p, m * 4, cudaMemcpyDeviceToHost, ix->st));
+        FA_CUDA(cudaMemcpyAsync(wpos, dw.p, m * 4, cudaMemcpyDeviceToHost, ix->st));
+        FA_CUDA(cudaStreamSynchronize(ix->st));
+        ds.release(); dw.release();
+    }
+    return FA_OK;
+}
+
+int fa_index_occurrence_threshold(const fa_index *ix, int32_t *out)
+{
+    (void)ix;
+    *out = 2147483647;      // freqThreshold stays INT_MAX: percentageThreshold == 0 (winSketch.hpp:52, 208-231)
+    return FA_OK;
+}
+
+int fa_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *out, uint64_t cap, uint64_t *n_out,
+             fa_query_info *info)
+{
+    if (!ix || n_contigs < 0 || (n_contigs > 0 && !contigs) || !n_out) { set_error("bad arguments"); return FA_ERR_INVALID; }
+    for (int32_t c = 0; c < n_contigs; c++)
+        if (contigs[c].len < 0 || (contigs[c].len > 0 && !contigs[c].data)) { set_error("contig %d: bad buffer", c); return FA_ERR_INVALID; }
+    return run_query(ix, contigs, n_contigs, out, cap, n_out, info);
+}
+
+int fa_debug_last_candidates(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n) { return debug_candidates(ix, rows, cap, n); }
+int fa_debug_last_mappings(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n) { return debug_mappings(ix, rows, cap, n); }
+
+int fa_device_alloc(fa_index *ix, uint64_t bytes, void **dptr)
+{
+    if (!ix || !dptr) { set_error("bad arguments"); return FA_ERR_INVALID; }
+    FA_CUDA(cudaSetDevice(ix->device));
+    FA_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
+    return FA_OK;
+}
+int fa_device_upload(fa_index *ix, void *dptr, const void *src, uint64_t bytes)
+{
+    if (!ix) { set_error("bad arguments"); return FA_ERR_INVALID; }
+    FA_CUDA(cudaSetDevice(ix->device));
+    FA_CUDA(cudaMemcpy(dptr, src, bytes, cudaMemcpyHostToDevice));
+    return FA_OK;
+}
+int fa_device_free(fa_index *ix, void *dptr)
+{
+    if (!ix) { set_error("bad arguments"); return FA_ERR_INVALID; }
+    FA_CUDA(cudaSetDevice(ix->device));
+    FA_CUDA(cudaFree(dptr));
+    return FA_OK;
+}
+
+}  // extern "C"

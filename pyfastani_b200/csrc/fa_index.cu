@@ -1,0 +1,215 @@
+// fa_index.cu -- K2: reference sketch index build on the GPU.
+//
+// Replaces skch::Sketch::index (FA/map/include/winSketch.hpp:177-189: an
+// unordered_map<hash, vector<(seqId, wpos)>> filled one push_back at a time), the lookup
+// side of Sketch::searchIndex (:255-266) and reviseRefIdToGenomeId
+// (FA/cgi/include/computeCoreIdentity.hpp:31-42).  computeFreqHist (:195-244) leaves
+// freqThreshold at INT_MAX because percentageThreshold is 0 (:52), so no histogram is built.
+//
+// Layout: a stable LSD radix sort of (hash, position index) gives
+// `pos_idx` grouped by hash with insertion order kept inside each group; run-length encoding
+// gives the CSR (ukeys, uoff); a directory over the top bits of the hash narrows each lookup
+// to a few keys.  The sort is cub::DeviceRadixSort (library code); the other kernels are ours.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_run_length_encode.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "fa_internal.cuh"
+
+namespace fa {
+
+namespace {
+
+__global__ void extract_keys_kernel(const RefMini *ref, uint64_t n, uint32_t *keys, uint32_t *vals)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { keys[i] = ref[i].x; vals[i] = (uint32_t)i; }
+}
+
+// dir[b] = first unique key whose top `bits` bits are >= b
+__global__ void directory_kernel(const uint32_t *ukeys, uint32_t n_unique, int bits, uint32_t *dir)
+{
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t nb = 1u << bits;
+    if (b > nb) return;
+    if (b == nb) { dir[b] = n_unique; return; }
+    uint32_t target = b << (32 - bits);
+    uint32_t lo = 0, hi = n_unique;
+    while (lo < hi) { uint32_t mid = lo + ((hi - lo) >> 1); if (ukeys[mid] < target) lo = mid + 1; else hi = mid; }
+    dir[b] = lo;
+}
+
+// Neighbouring entries of one hash group that lie in the same contig are duplicates a sliding
+// L2 window may hold at the same time; record their distance on both elements.
+__global__ void dup_delta_kernel(const uint32_t *sorted_keys, const uint32_t *pos_idx, uint64_t n, RefMini *ref)
+{
+    uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (p >= n) return;
+    if (sorted_keys[p] != sorted_keys[p - 1]) return;
+    uint32_t a = pos_idx[p - 1], b = pos_idx[p];
+    if (ref[a].z != ref[b].z) return;
+    uint32_t d = b - a;                        // stable sort: b > a
+    if (d > 65535u) return;
+    atomicOr(&ref[b].w, d);                    // previous duplicate of b
+    atomicOr(&ref[a].w, d << 16);              // next duplicate of a
+}
+
+// contig_off[s] = first ref index with seqId >= s (contigs without minimizers get empty ranges)
+__global__ void contig_off_kernel(const RefMini *ref, uint64_t n, uint32_t n_contigs, uint32_t *contig_off)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    uint32_t cur = i < n ? ref[i].z : n_contigs;
+    uint32_t prev = i == 0 ? 0xFFFFFFFFu : ref[i - 1].z;      // -1: everything up to cur starts here
+    for (uint32_t s = prev + 1; s <= cur && s <= n_contigs; s++) contig_off[s] = (uint32_t)i;
+    if (i == 0) contig_off[0] = 0;
+}
+
+}  // namespace
+
+int build_index(fa_index *ix, int *launches)
+{
+    cudaStream_t st = ix->st;
+    const uint64_t n = ix->n;
+    const uint32_t n_contigs = (uint32_t)ix->contig_len.size();
+    const uint32_t n_genomes = (uint32_t)ix->seqs_by_genome.size();
+    if (n >= 0xFFFFFFF0ull) { set_error("index of %llu minimizers exceeds the 32-bit position index", (unsigned long long)n); return FA_ERR_UNSUPPORTED; }
+
+    // ---- host-side tables: contig -> genome, (contig, bin) cells ---------------------------
+    std::vector<int32_t> genome_of(n_contigs ? n_contigs : 1, 0);
+    {
+        uint32_t g = 0;
+        for (uint32_t s = 0; s < n_contigs; s++) {
+            while (g < n_genomes && (uint32_t)ix->seqs_by_genome[g] <= s) g++;   // upper_bound, computeCoreIdentity.hpp:36-40
+            genome_of[s] = (int32_t)g;
+        }
+    }
+    const int bin_w = ix->prm.frag_len - 20;                                       // computeCoreIdentity.hpp:191
+    std::vector<uint32_t> bin_base(n_contigs + 1, 0), genome_cell(n_genomes + 1, 0);
+    {
+        uint64_t acc = 0;
+        for (uint32_t s = 0; s < n_contigs; s++) {
+            bin_base[s] = (uint32_t)acc;
+            int64_t len = ix->contig_len[s];
+            acc += (bin_w > 0 && len > 0) ? (uint64_t)((len - 1) / bin_w + 1) : 1;
+            if (acc >= 0xFFFFFFF0ull) { set_error("too many reference bins"); return FA_ERR_UNSUPPORTED; }
+        }
+        bin_base[n_contigs] = (uint32_t)acc;
+        ix->n_cells = acc;
+        uint32_t s0 = 0;
+        for (uint32_t g = 0; g < n_genomes; g++) {
+            genome_cell[g] = bin_base[s0 < n_contigs ? s0 : n_contigs];
+            s0 = (uint32_t)ix->seqs_by_genome[g];
+        }
+        genome_cell[n_genomes] = (uint32_t)acc;
+    }
+    FA_TRY(ix->genome_of_seq.reserve(genome_of.size()));
+    FA_TRY(ix->bin_base.reserve(bin_base.size()));
+    FA_TRY(ix->genome_cell.reserve(genome_cell.size()));
+    FA_CUDA(cudaMemcpyAsync(ix->genome_of_seq.p, genome_of.data(), genome_of.size() * 4, cudaMemcpyHostToDevice, st));
+    FA_CUDA(cudaMemcpyAsync(ix->bin_base.p, bin_base.data(), bin_base.size() * 4, cudaMemcpyHostToDevice, st));
+    FA_CUDA(cudaMemcpyAsync(ix->genome_cell.p, genome_cell.data(), genome_cell.size() * 4, cudaMemcpyHostToDevice, st));
+    FA_CUDA(cudaStreamSynchronize(st));       // the host vectors go out of scope
+
+    // ---- statistics tables -------------------------------------------------------------------
+    {
+        int cmw = ix->prm.frag_len - (ix->prm.window - 1) - (ix->prm.k - 1);     // windows per fragment
+        int s_max = cmw < 1 ? 1 : cmw;
+        if (s_max > 4096) s_max = 4096;       // larger sketches are reported as unsupported at query time
+        const StatTable &t = stat_table(ix->prm.k, ix->prm.pct_identity, s_max);
+        ix->s_max = s_max;
+        FA_TRY(ix->d_min_hits.reserve(t.min_hits.size()));
+        FA_TRY(ix->d_min_shared.reserve(t.min_shared.size()));
+        FA_TRY(ix->d_id_off.reserve(t.id_off.size()));
+        FA_TRY(ix->d_identity.reserve(t.identity.size()));
+        FA_CUDA(cudaMemcpyAsync(ix->d_min_hits.p, t.min_hits.data(), t.min_hits.size() * 4, cudaMemcpyHostToDevice, st));
+        FA_CUDA(cudaMemcpyAsync(ix->d_min_shared.p, t.min_shared.data(), t.min_shared.size() * 4, cudaMemcpyHostToDevice, st));
+        FA_CUDA(cudaMemcpyAsync(ix->d_id_off.p, t.id_off.data(), t.id_off.size() * 4, cudaMemcpyHostToDevice, st));
+        FA_CUDA(cudaMemcpyAsync(ix->d_identity.p, t.identity.data(), t.identity.size() * 4, cudaMemcpyHostToDevice, st));
+        FA_CUDA(cudaStreamSynchronize(st));
+    }
+
+    FA_TRY(ix->contig_off.reserve((size_t)n_contigs + 1));
+    {
+        uint64_t m = n + 1;
+        contig_off_kernel<<<(unsigned int)((m + 255) / 256), 256, 0, st>>>(ix->ref.p, n, n_contigs, ix->contig_off.p);
+        FA_CUDA(cudaGetLastError());
+        if (launches) *launches += 1;
+    }
+    ix->n_unique = 0;
+    ix->dir_bits = 0;
+    if (n == 0) {
+        FA_TRY(ix->dir.reserve(2));
+        FA_CUDA(cudaMemsetAsync(ix->dir.p, 0, 8, st));
+        FA_TRY(ix->uoff.reserve(1));
+        FA_CUDA(cudaMemsetAsync(ix->uoff.p, 0, 4, st));
+        FA_CUDA(cudaStreamSynchronize(st));
+        return FA_OK;
+    }
+
+    // ---- sort (hash, index) ------------------------------------------------------------------
+    DevBuf<uint32_t> keys_a, keys_b, vals_a;
+    FA_TRY(keys_a.reserve(n)); FA_TRY(keys_b.reserve(n)); FA_TRY(vals_a.reserve(n));
+    FA_TRY(ix->pos_idx.reserve(n));
+    extract_keys_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(ix->ref.p, n, keys_a.p, vals_a.p);
+    FA_CUDA(cudaGetLastError());
+    if (launches) *launches += 1;
+    size_t tmp_bytes = 0;
+    FA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a.p, keys_b.p, vals_a.p, ix->pos_idx.p, (int64_t)n, 0, 32, st));
+    DevBuf<uint8_t> tmp;
+    FA_TRY(tmp.reserve(tmp_bytes + 16));
+    FA_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_a.p, keys_b.p, vals_a.p, ix->pos_idx.p, (int64_t)n, 0, 32, st));
+    if (launches) *launches += 5;
+    vals_a.release();
+
+    // duplicate distances for the L2 sliding window
+    dup_delta_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(keys_b.p, ix->pos_idx.p, n, ix->ref.p);
+    FA_CUDA(cudaGetLastError());
+    if (launches) *launches += 1;
+
+    // ---- CSR over unique hashes --------------------------------------------------------------
+    DevBuf<uint32_t> run_len;
+    DevBuf<uint64_t> d_nruns;
+    FA_TRY(run_len.reserve(n)); FA_TRY(d_nruns.reserve(1));
+    FA_TRY(ix->ukeys.reserve(n));             // trimmed below
+    size_t rle_bytes = 0;
+    FA_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, rle_bytes, keys_b.p, ix->ukeys.p, run_len.p, d_nruns.p, (int64_t)n, st));
+    FA_TRY(tmp.reserve(rle_bytes + 16));
+    FA_CUDA(cub::DeviceRunLengthEncode::Encode(tmp.p, rle_bytes, keys_b.p, ix->ukeys.p, run_len.p, d_nruns.p, (int64_t)n, st));
+    if (launches) *launches += 2;
+    uint64_t n_unique = 0;
+    FA_CUDA(cudaMemcpyAsync(&n_unique, d_nruns.p, 8, cudaMemcpyDeviceToHost, st));
+    FA_CUDA(cudaStreamSynchronize(st));
+    ix->n_unique = n_unique;
+    keys_a.release(); keys_b.release();
+    FA_TRY(ix->uoff.reserve(n_unique + 1));
+    size_t scan_bytes = 0;
+    FA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, run_len.p, ix->uoff.p, (int64_t)n_unique, st));
+    FA_TRY(tmp.reserve(scan_bytes + 16));
+    FA_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, scan_bytes, run_len.p, ix->uoff.p, (int64_t)n_unique, st));
+    if (launches) *launches += 2;
+    const uint32_t n32 = (uint32_t)n;
+    FA_CUDA(cudaMemcpyAsync(ix->uoff.p + n_unique, &n32, 4, cudaMemcpyHostToDevice, st));
+    {   // trim ukeys to n_unique (the sort buffers above are the transient peak)
+        DevBuf<uint32_t> trimmed;
+        FA_TRY(trimmed.reserve(n_unique ? n_unique : 1));
+        FA_CUDA(cudaMemcpyAsync(trimmed.p, ix->ukeys.p, n_unique * 4, cudaMemcpyDeviceToDevice, st));
+        FA_CUDA(cudaStreamSynchronize(st));
+        ix->ukeys.release();
+        ix->ukeys = trimmed;
+    }
+
+    // ---- directory ---------------------------------------------------------------------------
+    int bits = 1;
+    while (bits < 24 && (1ull << bits) < n_unique) bits++;      // about one key per directory slot, <= 64 MiB
+    ix->dir_bits = bits;
+    FA_TRY(ix->dir.reserve((1u << bits) + 1));
+    directory_kernel<<<((1u << bits) + 1 + 255) / 256, 256, 0, st>>>(ix->ukeys.p, (uint32_t)n_unique, bits, ix->dir.p);
+    FA_CUDA(cudaGetLastError());
+    if (launches) *launches += 1;
+    FA_CUDA(cudaStreamSynchronize(st));
+    run_len.release(); d_nruns.release(); tmp.release();
+    return FA_OK;
+}
+
+}  // namespace fa

@@ -1,0 +1,108 @@
+// fa_internal.cuh -- the two opaque handles of the C ABI and the per-query workspace.
+#pragma once
+#include <mutex>
+
+#include "fa_common.cuh"
+#include "fa_stat.h"
+
+namespace fa {
+
+// L1 candidate region (L1_candidateLocus_t, FA/map/include/computeMap.hpp:40-49) in device form.
+struct Cand {
+    int32_t  frag;     // query fragment (querySeqId)
+    uint32_t hint;     // index of a reference minimizer inside the region (the seed that opened it)
+    int32_t  start;    // rangeStartPos
+    int32_t  end;      // rangeEndPos
+};
+
+// L2 result per candidate slot (L2_mapLocus_t + the MappingResult fields computeCGI reads,
+// computeMap.hpp:52-59, base_types.hpp:89-102); shared < 0 marks "filtered out".
+struct Mapping {
+    int32_t seq;       // refSeqId
+    int32_t ref_start; // refStartPos = meanOptimalPos
+    int32_t shared;    // conservedSketches
+    float   identity;  // nucIdentity
+};
+
+struct Workspace {
+    SketchScratch sk;
+    PinBuf stage;                       // pinned host staging for query bytes
+    std::vector<SeqDesc> h_seqs;
+    DevBuf<uint32_t> qhash;             // per-fragment minimizer hashes -> sorted unique sketches in place
+    DevBuf<int32_t>  qs;                // per-fragment sketch size s
+    DevBuf<uint32_t> hit_start, hit_cnt;   // per query hash: bucket in pos_idx
+    DevBuf<uint64_t> frag_seeds;        // per fragment: seed count, then exclusive prefix (F + 1)
+    DevBuf<uint64_t> seeds_a, seeds_b;  // (frag << 32 | ref index) keys, double buffered for the sort
+    DevBuf<uint8_t>  cub_tmp;
+    DevBuf<uint32_t> frag_cands;        // per fragment: candidate count, then exclusive prefix (F + 1)
+    DevBuf<uint32_t> work_base;         // per fragment: L2 work items, exclusive prefix (F + 1)
+    DevBuf<Cand>     cands;
+    DevBuf<Mapping>  maps;
+    DevBuf<uint32_t> cells;             // per (ref contig, bin): best identity bits (computeCGI pass 2)
+    DevBuf<float>    g_identity;        // per genome
+    DevBuf<int32_t>  g_count;
+    DevBuf<unsigned long long> counters;   // misc device counters (see fa_map.cu)
+    PinBuf hres;                        // pinned result staging
+    cudaEvent_t ev[10] = {};
+    bool ev_ready = false;
+    uint64_t last_cands = 0, last_frags = 0;
+};
+
+}  // namespace fa
+
+struct fa_sketch {
+    fa_params prm;
+    int device = 0;
+    cudaStream_t st = nullptr;
+    fa::DevBuf<fa::RefMini> ref;                 // minimizerIndex, winSketch.hpp:93
+    uint64_t n = 0;
+    std::vector<int32_t>  seqs_by_genome;        // sequencesByFileInfo, winSketch.hpp:75
+    std::vector<uint64_t> genome_len;            // Sketch._lengths, pyx:467
+    std::vector<int64_t>  contig_len;            // one per consumed sequence id (pyx:683)
+    uint64_t cur_len = 0;
+    fa::SketchScratch sc;
+    fa::PinBuf stage;
+    std::vector<fa::SeqDesc> h_seqs;
+};
+
+struct fa_index {
+    fa_params prm;
+    int device = 0;
+    cudaStream_t st = nullptr;
+    // position-ordered minimizers (minimizerIndex) and the hash -> positions table
+    // (minimizerPosLookupIndex, winSketch.hpp:83-84) as CSR over sorted unique hashes
+    fa::DevBuf<fa::RefMini> ref;
+    uint64_t n = 0, n_unique = 0;
+    fa::DevBuf<uint32_t> pos_idx;                // ref indices grouped by hash, insertion order inside a group
+    fa::DevBuf<uint32_t> ukeys, uoff;            // unique hashes, group offsets (n_unique + 1)
+    fa::DevBuf<uint32_t> dir;                    // directory over the top dir_bits of the hash (2^bits + 1)
+    int dir_bits = 0;
+    fa::DevBuf<uint32_t> contig_off;             // first ref index of each contig (n_contigs + 1)
+    fa::DevBuf<int32_t>  genome_of_seq;          // reviseRefIdToGenomeId, computeCoreIdentity.hpp:31-42
+    fa::DevBuf<uint32_t> bin_base;               // first (contig, bin) cell of each contig (n_contigs + 1)
+    fa::DevBuf<uint32_t> genome_cell;            // first cell of each genome (n_genomes + 1)
+    uint64_t n_cells = 0;
+    std::vector<int32_t>  seqs_by_genome;
+    std::vector<uint64_t> genome_len;
+    std::vector<int64_t>  contig_len;
+    // statistics tables (fa_stat.h)
+    int s_max = 0;
+    fa::DevBuf<int32_t>  d_min_hits, d_min_shared;
+    fa::DevBuf<uint32_t> d_id_off;
+    fa::DevBuf<float>    d_identity;
+    std::mutex mtx;                              // serialises queries on the single workspace
+    fa::Workspace ws;
+};
+
+namespace fa {
+int build_index(fa_index *ix, int *launches);
+int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *out, uint64_t cap, uint64_t *n_out,
+              fa_query_info *info);
+// One host or device buffer to place at `off` in the batch byte buffer.
+struct Upload { const void *ptr; int32_t unit; int32_t on_device; int64_t len; uint64_t off; };
+// shared by the sketch and query paths: narrow/copy the uploads into the batch byte buffer
+int stage_sequences(cudaStream_t st, SketchScratch &sc, PinBuf &stage, const std::vector<Upload> &ups, uint64_t total,
+                    uint64_t *h2d_bytes);
+int debug_candidates(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n);
+int debug_mappings(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n);
+}

@@ -1,0 +1,759 @@
+// fa_map.cu -- the query path: K1 on query fragments, K3 (L1 seeding + candidate regions),
+// K4 (L2 sliding-window winnowed-MinHash Jaccard), K5 (core-genome identity).
+//
+// Replaces Mapper._query_draft / _query_fragment / _do_l1_mappings (src/pyfastani/_fastani.pyx:
+// 885-1136), skch::Map::computeL1CandidateRegions / doL2Mapping / computeL2MappedRegions
+// (FA/map/include/computeMap.hpp:310-493), skch::SlideMapper (slidingMap.hpp),
+// skch::MIIteratorL2 (MIIteratorL2.hpp:54-96) and cgi::computeCGI
+// (FA/cgi/include/computeCoreIdentity.hpp:163-295).
+//
+// The reference maps one fragment at a time on a CPU thread; here every stage runs over all
+// fragments of the query at once:
+//   sketch      one tile of k-mers per CTA (fa_sketch.cu), then sort+unique per fragment
+//   lookup      one CTA per fragment: directory + binary search over the unique hashes
+//   seeds       (fragment, reference index) keys, one device-wide radix sort
+//   candidates  one CTA per fragment streaming over its sorted seeds
+//   L2          one THREAD per candidate: the super-window slide with O(1) state updates
+//   CGI         best per (fragment, genome), atomicMax per (contig, bin), ordered float sum
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cstring>
+
+#include "fa_internal.cuh"
+
+namespace fa {
+
+namespace {
+
+// device counters (Workspace::counters)
+enum { CT_MAXS = 0, CT_ERR = 1, CT_WORK = 2, CT_SCANNED = 3, CT_MAPPINGS = 4, CT_SKETCH_SUM = 5, CT_N = 8 };
+enum { ERR_SORT_CAP = 1, ERR_S_MAX = 2 };
+
+constexpr int L2_THREADS = 64;          // candidates per L2 work item (upper bound)
+constexpr int L2_STATE_WORDS = 16384;   // u16 state entries per CTA (32 KiB)
+
+__host__ __device__ inline int l2_threads_for(int s)
+{
+    int t = L2_STATE_WORDS / (s + 1);
+    return t > L2_THREADS ? L2_THREADS : (t < 1 ? 1 : t);
+}
+
+template <int THREADS>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_warp, uint32_t *total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+    __syncthreads();                     // s_warp may still be read from a previous call
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+#pragma unroll
+    for (int q = 0; q < THREADS / 32; q++) { uint32_t t = s_warp[q]; if (q < wid) base += t; tot += t; }
+    *total = tot;
+    return base + incl - v;
+}
+
+// ---- per-fragment sort + unique of the query minimizer hashes (pyx:929-938) -----------------
+__global__ void sort_unique_kernel(uint32_t *qhash, const uint64_t *seq_first, const unsigned long long *sk_counters,
+                                   int n_frags, int cap, int s_max, int32_t *qs, unsigned long long *counters)
+{
+    extern __shared__ uint32_t s_h[];
+    __shared__ uint32_t s_warp[8];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const uint64_t b = seq_first[f];
+    const uint64_t e = (f + 1 < n_frags) ? seq_first[f + 1] : sk_counters[1];
+    const int n = (int)(e - b);
+    if (n > cap) {
+        if (tid == 0) { atomicOr(&counters[CT_ERR], (unsigned long long)ERR_SORT_CAP); qs[f] = 0; }
+        return;
+    }
+    int p2 = 1;
+    while (p2 < n) p2 <<= 1;
+    for (int i = tid; i < p2; i += blockDim.x) s_h[i] = i < n ? qhash[b + i] : 0xFFFFFFFFu;
+    __syncthreads();
+    for (int k = 2; k <= p2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < p2; i += blockDim.x) {
+                int l = i ^ j;
+                if (l > i) {
+                    uint32_t a = s_h[i], c = s_h[l];
+                    bool up = (i & k) == 0;
+                    if ((a > c) == up) { s_h[i] = c; s_h[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    // unique (stable compaction of run heads)
+    uint32_t carry = 0;
+    for (int base = 0; base < n; base += blockDim.x) {
+        int i = base + tid;
+        uint32_t head = (i < n && (i == 0 || s_h[i] != s_h[i - 1])) ? 1u : 0u;
+        uint32_t tot, off = block_excl_scan<256>(head, s_warp, &tot);
+        if (head) qhash[b + carry + off] = s_h[i];
+        carry += tot;
+    }
+    if (tid == 0) {
+        qs[f] = (int32_t)carry;
+        atomicMax(&counters[CT_MAXS], (unsigned long long)carry);
+        atomicAdd(&counters[CT_SKETCH_SUM], (unsigned long long)carry);
+        if ((int)carry > s_max) atomicOr(&counters[CT_ERR], (unsigned long long)ERR_S_MAX);
+    }
+}
+
+// ---- lookup of every sketch hash in the reference index (pyx:941-948) ------------------------
+__global__ void lookup_kernel(const uint32_t *qhash, const uint64_t *seq_first, const int32_t *qs, int n_frags,
+                              const uint32_t *dir, int dir_bits, const uint32_t *ukeys, const uint32_t *uoff,
+                              uint32_t *hit_start, uint32_t *hit_cnt, uint64_t *frag_seeds)
+{
+    __shared__ unsigned long long s_sum;
+    const int f = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) s_sum = 0;
+    __syncthreads();
+    const uint64_t b = seq_first[f];
+    const int s = qs[f];
+    unsigned long long mine = 0;
+    for (int i = tid; i < s; i += blockDim.x) {
+        const uint32_t h = qhash[b + i];
+        const uint32_t d = h >> (32 - dir_bits);
+        uint32_t lo = dir[d], hi = dir[d + 1];
+        while (lo < hi) { uint32_t mid = lo + ((hi - lo) >> 1); if (ukeys[mid] < h) lo = mid + 1; else hi = mid; }
+        uint32_t st = 0, cnt = 0;
+        if (lo < dir[d + 1] && ukeys[lo] == h) { st = uoff[lo]; cnt = uoff[lo + 1] - st; }
+        hit_start[b + i] = st; hit_cnt[b + i] = cnt;
+        mine += cnt;
+    }
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
+    if ((tid & 31) == 0 && mine) atomicAdd(&s_sum, mine);
+    __syncthreads();
+    if (tid == 0) frag_seeds[f] = s_sum;
+    if (f == 0 && tid == 0) frag_seeds[n_frags] = 0;
+}
+
+// ---- seed hits: the concatenated position lists, tagged with the fragment -------------------
+__global__ void fill_seeds_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hit_start,
+                                  const uint32_t *hit_cnt, const uint64_t *seed_base, const uint32_t *pos_idx,
+                                  int shift, uint64_t *seeds)
+{
+    __shared__ uint32_t s_warp[4];
+    __shared__ uint32_t s_off[128], s_st[128], s_cnt[128];
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint64_t b = seq_first[f];
+    const int s = qs[f];
+    uint64_t out = seed_base[f];
+    const uint64_t tag = (uint64_t)f << shift;
+    for (int base = 0; base < s; base += 128) {
+        const int i = base + tid;
+        uint32_t cnt = i < s ? hit_cnt[b + i] : 0, tot;
+        uint32_t off = block_excl_scan<128>(cnt, s_warp, &tot);
+        s_off[tid] = off; s_cnt[tid] = cnt; s_st[tid] = i < s ? hit_start[b + i] : 0;
+        __syncthreads();
+        for (int q = wid; q < 128; q += 4) {
+            const uint32_t c = s_cnt[q], st = s_st[q];
+            const uint64_t o = out + s_off[q];
+            for (uint32_t t = lane; t < c; t += 32) seeds[o + t] = tag | pos_idx[st + t];
+        }
+        out += tot;
+        __syncthreads();
+    }
+}
+
+// ---- L1 candidate regions (computeMap.hpp:310-350) -------------------------------------------
+// Seeds of a fragment are sorted by reference index == (seqId, wpos) order.  For the seed at t
+// and the one m-1 further: same contig and closer than a fragment => raw candidate
+// [max(0, wpos_b - L + 1), wpos_a].  Raw candidates are merged while the previous end reaches the
+// next start; starts and ends are non-decreasing, so a merged region begins exactly where
+// `previous raw end < start` (or the contig changes).
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+candidates_kernel(const uint64_t *seeds, const uint64_t *seed_base, const int32_t *qs, const int32_t *min_hits,
+                  const RefMini *ref, uint64_t idx_mask, int frag_len, uint32_t *frag_cands,
+                  const uint32_t *cand_base, Cand *cands)
+{
+    __shared__ uint32_t s_warp[8];
+    __shared__ int s_wlast[8];
+    __shared__ int s_seq[256], s_end[256];
+    __shared__ int s_carry_seq, s_carry_end, s_carry_valid;
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint64_t b = seed_base[f], e = seed_base[f + 1];
+    const int s = qs[f];
+    if (s <= 0 || b == e) { if (!FILL && tid == 0) frag_cands[f] = 0; return; }
+    const int m = min_hits[s];
+    if (tid == 0) { s_carry_valid = 0; s_carry_seq = -1; s_carry_end = 0; }
+    uint32_t heads_before = 0;
+    const uint32_t out0 = FILL ? cand_base[f] : 0;
+    __syncthreads();
+    for (uint64_t base = b; base < e; base += 256) {
+        const uint64_t t = base + tid;
+        bool valid = false;
+        int seq = -1, start = 0, end = 0;
+        uint32_t ja = 0;
+        if (t + (uint64_t)(m - 1) < e) {
+            ja = (uint32_t)(seeds[t] & idx_mask);
+            const uint32_t jb = (uint32_t)(seeds[t + m - 1] & idx_mask);
+            const RefMini ra = ref[ja], rb = ref[jb];
+            if (ra.z == rb.z && (int)(rb.y - ra.y) < frag_len) {
+                valid = true; seq = (int)ra.z; end = (int)ra.y;
+                start = max(0, (int)rb.y - frag_len + 1);
+            }
+        }
+        s_seq[tid] = seq; s_end[tid] = end;
+        // index (within the chunk) of the last valid raw candidate before this one, -1 = none in chunk
+        int last = valid ? tid : -1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xFFFFFFFFu, last, o); if (lane >= o) last = max(last, v); }
+        if (lane == 31) s_wlast[wid] = last;
+        __syncthreads();
+        int prev = __shfl_up_sync(0xFFFFFFFFu, last, 1);
+        if (lane == 0) prev = -1;
+        for (int q = 0; q < wid; q++) prev = max(prev, s_wlast[q]);
+        bool head = false;
+        if (valid) {
+            int pseq, pend, pvalid;
+            if (prev >= 0) { pseq = s_seq[prev]; pend = s_end[prev]; pvalid = 1; }
+            else { pseq = s_carry_seq; pend = s_carry_end; pvalid = s_carry_valid; }
+            head = !pvalid || pseq != seq || pend < start;
+        }
+        uint32_t tot, off = block_excl_scan<256>(head ? 1u : 0u, s_warp, &tot);
+        if (FILL) {
+            const uint32_t slot = out0 + heads_before + off;            // heads: their own slot
+            if (head) cands[slot] = Cand{f, ja, start, end};
+            __syncthreads();
+            if (valid && !head) atomicMax(&cands[slot - 1].end, end);     // members: the open region
+        }
+        heads_before += tot;
+        __syncthreads();
+        if (tid == 255 || t + 1 == e) {
+            // carry the last valid raw candidate of this chunk into the next one
+            int lastv = max(prev, valid ? tid : -1);
+            if (lastv >= 0) { s_carry_seq = s_seq[lastv]; s_carry_end = s_end[lastv]; s_carry_valid = 1; }
+        }
+        __syncthreads();
+    }
+    if (!FILL && tid == 0) frag_cands[f] = heads_before;
+}
+
+__global__ void work_items_kernel(const uint32_t *frag_cands_counts, const int32_t *qs, int n_frags, uint32_t *work)
+{
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f > n_frags) return;
+    if (f == n_frags) { work[f] = 0; return; }
+    const uint32_t c = frag_cands_counts[f];
+    const int tpc = l2_threads_for(qs[f]);
+    work[f] = (c + tpc - 1) / tpc;
+}
+
+// ---- L2: sliding super-window Jaccard, one thread per candidate --------------------------------
+// State per candidate (SURVEY.md A.5 in incremental form).  Q = sorted query sketch q_1 < ... < q_s.
+// A reference hash that is in Q toggles a match bit M(i); one that is not falls in bucket
+// b = #{q < h} and toggles a distinct-hash count cnt[b].  With
+//   istar = number of query hashes inside the bottom-s of (Q u window),
+//   sigma = number of window-only hashes of bucket `istar` inside it,
+// (istar + sum_{b<istar} cnt[b] + sigma == s), every insert/delete moves (istar, sigma) by one
+// step and `shared` = #{i <= istar : M(i)} is updated in O(1) -- the std::map pivot walk of
+// slidingMap.hpp:137-284 without the tree.  Duplicate hashes inside a window are resolved with
+// the distances stored at index time (RefMini.w), mirroring the wposR bookkeeping of
+// slidingMap.hpp:150-155, 178-205.
+struct SlideState {
+    uint16_t *st;        // st[b * stride]: bit 15 = M(b) (b >= 1), bits 0..14 = cnt[b]
+    int stride, s;
+    int istar, sigma, shared;
+    __device__ __forceinline__ uint16_t &at(int b) { return st[b * stride]; }
+    __device__ __forceinline__ void ins_only(int b)
+    {
+        at(b) += 1;
+        if (b < istar) {
+            if (sigma > 0) sigma--;
+            else { shared -= at(istar) >> 15; istar--; sigma = at(istar) & 0x7FFF; }
+        }
+    }
+    __device__ __forceinline__ void del_only(int b)
+    {
+        at(b) -= 1;
+        const int c = at(istar) & 0x7FFF;
+        if (b < istar) {
+            if (sigma < c) sigma++;
+            else { istar++; shared += at(istar) >> 15; sigma = 0; }
+        } else if (b == istar && sigma > c) { istar++; shared += at(istar) >> 15; sigma = 0; }
+    }
+    __device__ __forceinline__ void ins_match(int i) { at(i) |= 0x8000; if (i <= istar) shared++; }
+    __device__ __forceinline__ void del_match(int i) { at(i) &= 0x7FFF; if (i <= istar) shared--; }
+};
+
+__device__ __forceinline__ uint32_t lb_wpos(const RefMini *ref, uint32_t lo, uint32_t hi, int target)
+{
+    while (lo < hi) { uint32_t mid = lo + ((hi - lo) >> 1); if ((int)ref[mid].y < target) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+__global__ void __launch_bounds__(L2_THREADS)
+l2_kernel(const Cand *cands, const uint32_t *cand_base, const uint32_t *work_base, int n_frags,
+          const uint32_t *qhash, const uint64_t *seq_first, const int32_t *qs,
+          const RefMini *ref, uint32_t n_ref, const uint32_t *contig_off, int frag_len, int cmw,
+          const int32_t *min_shared, const uint32_t *id_off, const float *id_tab,
+          Mapping *maps, unsigned long long *counters, int q_cap)
+{
+    extern __shared__ __align__(16) uint8_t l2_smem[];
+    uint32_t *s_q = reinterpret_cast<uint32_t *>(l2_smem);
+    uint16_t *s_state = reinterpret_cast<uint16_t *>(s_q + q_cap);
+    __shared__ uint32_t s_item;
+    const int tid = threadIdx.x;
+    const uint32_t n_work = work_base[n_frags];
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = (uint32_t)atomicAdd(&counters[CT_WORK], 1ull);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= n_work) break;
+        // work item -> fragment (last f with work_base[f] <= item)
+        int lo = 0, hi = n_frags - 1;
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (work_base[mid] <= item) lo = mid; else hi = mid - 1; }
+        const int f = lo;
+        const int s = qs[f];
+        const int tpc = l2_threads_for(s);
+        const uint32_t c = cand_base[f] + (item - work_base[f]) * tpc + tid;
+        const bool active = tid < tpc && c < cand_base[f + 1];
+        const uint64_t qb = seq_first[f];
+        for (int i = tid; i < s; i += L2_THREADS) s_q[i] = qhash[qb + i];
+        for (int i = tid; i < (s + 1) * tpc; i += L2_THREADS) s_state[i] = 0;
+        __syncthreads();
+        if (!active) continue;
+
+        const Cand cd = cands[c];
+        const int seq = (int)ref[cd.hint].z;
+        const uint32_t c1 = contig_off[seq + 1];
+        // Sketch::searchIndex x3 (computeMap.hpp:421-433), restricted to the candidate's contig
+        const uint32_t beg = lb_wpos(ref, contig_off[seq], cd.hint, cd.start);
+        const RefMini rbeg = ref[beg];
+        const uint32_t end0 = lb_wpos(ref, beg, c1, (int)rbeg.y + cmw);
+        const uint32_t last = lb_wpos(ref, end0, c1, cd.end + frag_len);
+
+        SlideState S;
+        S.st = s_state + tid; S.stride = tpc; S.s = s; S.istar = s; S.sigma = 0; S.shared = 0;
+
+        auto classify = [&](uint32_t h, int &b) -> bool {      // b = #{q < h}; true if q_{b+1} == h
+            int l = 0, r = s;
+            while (l < r) { int mid = (l + r) >> 1; if (s_q[mid] < h) l = mid + 1; else r = mid; }
+            b = l;
+            return l < s && s_q[l] == h;
+        };
+        auto insert = [&](uint32_t j, const RefMini &e, uint32_t win_beg) {      // window is [win_beg, j)
+            const uint32_t dprev = e.w & 0xFFFFu;
+            if (dprev && j >= dprev && j - dprev >= win_beg) return;      // same hash already present (REV)
+            int b;
+            if (classify(e.x, b)) S.ins_match(b + 1); else S.ins_only(b);
+        };
+        auto remove = [&](uint32_t j, const RefMini &e, uint32_t win_end) {      // window is [j, win_end)
+            const uint32_t dnext = e.w >> 16;
+            if (dnext && j + dnext < win_end) return;                     // a later copy keeps the hash present (NOOP)
+            int b;
+            if (classify(e.x, b)) S.del_match(b + 1); else S.del_only(b);
+        };
+
+        for (uint32_t j = beg; j < end0; j++) insert(j, ref[j], beg);     // first super-window, computeMap.hpp:446
+
+        // MIIteratorL2 (MIIteratorL2.hpp:54-96) + the slide loop of computeMap.hpp:453-488
+        uint32_t sw_beg = beg, sw_end = end0, prev_end = end0;
+        int sw_pos = (int)rbeg.y;
+        int best = 0, first_pos = 0, last_pos = 0;
+        const bool runs = end0 < last;
+        RefMini e_b = rbeg, e_b1 = runs ? ref[beg + 1] : rbeg, e_e = runs ? ref[end0] : rbeg, old_b = rbeg, old_e = rbeg;
+        bool adv_b = false, adv_e = false;
+        while (sw_end < last) {
+            if (adv_b) remove(sw_beg - 1, old_b, prev_end);               // :459-460
+            if (adv_e) insert(sw_end - 1, old_e, sw_beg);                 // :463-464
+            const int wb = (int)e_b.y;
+            if (S.shared > best) { best = S.shared; first_pos = last_pos = wb; }     // :467-476
+            else if (S.shared == best) last_pos = wb;                                // :477-481
+            const int d1 = (int)e_b1.y - sw_pos;
+            const int d2 = (int)e_e.y - (sw_pos + cmw - 1);
+            const int adv = min(d1, d2);
+            sw_pos += adv;
+            adv_b = adv == d1; adv_e = adv == d2;
+            prev_end = sw_end;
+            if (adv_b) { old_b = e_b; e_b = e_b1; sw_beg++; if (sw_beg + 1 < n_ref) e_b1 = ref[sw_beg + 1]; }
+            if (adv_e) { old_e = e_e; sw_end++; if (sw_end < last) e_e = ref[sw_end]; }
+        }
+        Mapping mp;
+        mp.seq = seq;
+        mp.ref_start = (first_pos + last_pos) / 2;                        // computeMap.hpp:492
+        const bool pass = s > 0 && best >= min_shared[s];                 // computeMap.hpp:371-380 via the table
+        mp.shared = pass ? best : -1 - best;
+        mp.identity = pass ? id_tab[id_off[s] + best] : 0.0f;
+        maps[c] = mp;
+        // workload counters, one atomic per warp
+        const unsigned am = __activemask();
+        const unsigned sc_sum = __reduce_add_sync(am, (unsigned)(max(end0, last) - beg));
+        const unsigned mp_sum = __reduce_add_sync(am, pass ? 1u : 0u);
+        if ((tid & 31) == __ffs(am) - 1) {
+            atomicAdd(&counters[CT_SCANNED], (unsigned long long)sc_sum);
+            if (mp_sum) atomicAdd(&counters[CT_MAPPINGS], (unsigned long long)mp_sum);
+        }
+    }
+}
+
+// ---- K5: core-genome identity (computeCoreIdentity.hpp:163-295) --------------------------------
+// Pass 1 (:210-231): per (genome, fragment) keep the best mapping by (identity, refSeqId,
+// refStartPos).  Candidates of a fragment are ordered by reference index, genome ids are monotone
+// in it, so each group is a contiguous run of candidate slots; its first slot does the work.
+// Pass 2 (:234-255): per (ref contig, bin) keep the best identity -> atomicMax on the bit
+// pattern (identities are positive floats, so the unsigned order is the float order).
+__global__ void cgi_best_kernel(const Cand *cands, const Mapping *maps, const uint32_t *cand_base, int n_frags,
+                                const int32_t *genome_of_seq, const uint32_t *bin_base, int bin_w, uint32_t *cells)
+{
+    const uint32_t n = cand_base[n_frags];
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        const Mapping m = maps[c];
+        const int f = cands[c].frag;
+        const int g = genome_of_seq[m.seq];
+        const uint32_t cb = cand_base[f], ce = cand_base[f + 1];
+        if (c > cb && genome_of_seq[maps[c - 1].seq] == g) continue;      // not the first slot of its group
+        bool have = false;
+        Mapping best = m;
+        for (uint32_t p = c; p < ce; p++) {
+            const Mapping q = maps[p];
+            if (genome_of_seq[q.seq] != g) break;
+            if (q.shared < 0) continue;
+            if (!have || q.identity > best.identity ||
+                (q.identity == best.identity && (q.seq > best.seq || (q.seq == best.seq && q.ref_start > best.ref_start)))) {
+                best = q; have = true;
+            }
+        }
+        if (have) atomicMax(&cells[bin_base[best.seq] + (uint32_t)(best.ref_start / bin_w)], __float_as_uint(best.identity));
+    }
+}
+
+// Per genome (:268-294): float32 sum of the surviving identities in (refSeqId, bin) order, count,
+// mean.  One warp per genome; the adds are sequential on purpose.  Cells are
+// cleared on the way so the table is ready for the next query.
+__global__ void cgi_sum_kernel(uint32_t *cells, const uint32_t *genome_cell, int n_genomes, int32_t *g_count, float *g_identity)
+{
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g >= n_genomes) return;
+    const uint32_t b = genome_cell[g], e = genome_cell[g + 1];
+    float sum = 0.0f;
+    int cnt = 0;
+    for (uint32_t base = b; base < e; base += 32) {
+        const uint32_t i = base + lane;
+        uint32_t v = i < e ? cells[i] : 0u;
+        if (v) cells[i] = 0u;
+        unsigned nz = __ballot_sync(0xFFFFFFFFu, v != 0u);
+        while (nz) {
+            const int l = __ffs(nz) - 1;
+            nz &= nz - 1;
+            sum += __uint_as_float(__shfl_sync(0xFFFFFFFFu, v, l));
+            cnt++;
+        }
+    }
+    if (lane == 0) { g_count[g] = cnt; g_identity[g] = cnt ? sum / (float)cnt : 0.0f; }
+}
+
+template <typename T>
+int excl_scan(cudaStream_t st, DevBuf<uint8_t> &tmp, const T *in, T *out, int64_t n, int *launches)
+{
+    size_t bytes = 0;
+    FA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, st));
+    FA_TRY(tmp.reserve(bytes + 16));
+    FA_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, n, st));
+    if (launches) *launches += 2;
+    return FA_OK;
+}
+
+inline int bits_for(uint64_t n) { int b = 1; while (b < 63 && (1ull << b) < n) b++; return b; }
+
+}  // namespace
+
+// Narrow / copy the uploads into the pinned staging buffer (host sources), then one H2D for the
+// whole batch and one D2D per device-resident source.
+int stage_sequences(cudaStream_t st, SketchScratch &sc, PinBuf &stage, const std::vector<Upload> &ups, uint64_t total,
+                    uint64_t *h2d_bytes)
+{
+    FA_TRY(sc.bytes.reserve(total + 64));
+    bool any_host = false;
+    for (const Upload &u : ups) any_host |= !u.on_device && u.len > 0;
+    if (any_host) {
+        FA_TRY(stage.reserve(total + 64));
+        for (const Upload &u : ups) {
+            if (u.on_device || u.len <= 0) continue;
+            uint8_t *dst = stage.p + u.off;
+            if (u.unit == 1) memcpy(dst, u.ptr, (size_t)u.len);
+            else {
+                // pyx:147-148: (char)toupper(code point); glibc's toupper leaves values outside
+                // [-128, 255] unchanged
+                for (int64_t i = 0; i < u.len; i++) {
+                    uint32_t cp = u.unit == 2 ? ((const uint16_t *)u.ptr)[i] : ((const uint32_t *)u.ptr)[i];
+                    if (cp >= 'a' && cp <= 'z') cp -= 32;
+                    dst[i] = (uint8_t)cp;
+                }
+            }
+        }
+        FA_CUDA(cudaMemcpyAsync(sc.bytes.p, stage.p, total, cudaMemcpyHostToDevice, st));
+        if (h2d_bytes) *h2d_bytes += total;
+    }
+    for (const Upload &u : ups)
+        if (u.on_device && u.len > 0)
+            FA_CUDA(cudaMemcpyAsync(sc.bytes.p + u.off, u.ptr, (size_t)u.len, cudaMemcpyDeviceToDevice, st));
+    return FA_OK;
+}
+
+int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *out, uint64_t cap, uint64_t *n_out,
+              fa_query_info *info)
+{
+    std::lock_guard<std::mutex> guard(ix->mtx);
+    FA_CUDA(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->st;
+    Workspace &ws = ix->ws;
+    const fa_params &P = ix->prm;
+    fa_query_info qi;
+    memset(&qi, 0, sizeof qi);
+    int launches = 0;
+    if (!ws.ev_ready) {
+        for (auto &e : ws.ev) FA_CUDA(cudaEventCreate(&e));
+        ws.ev_ready = true;
+    }
+    ws.last_cands = 0; ws.last_frags = 0;
+    *n_out = 0;
+
+    // ---- fragments (pyx:1059-1105) -----------------------------------------------------------
+    const int L = P.frag_len, k = P.k, w = P.window;
+    const int lim = std::min(std::min(w, k), L);
+    std::vector<Upload> ups;
+    ws.h_seqs.clear();
+    uint64_t total_len = 0, total_frags = 0, off = 0;
+    const int nk = L - k + 1;
+    const int tiles_per_frag = nk > 0 ? (nk + SK_TILE - 1) / SK_TILE : 0;
+    for (int32_t c = 0; c < n_contigs; c++) {
+        const int64_t slen = contigs[c].len;
+        if (slen < lim) { qi.short_contigs++; continue; }                  // pyx:1062-1070
+        if (contigs[c].unit_bytes != 1 && contigs[c].unit_bytes != 2 && contigs[c].unit_bytes != 4) {
+            set_error("unit_bytes must be 1, 2 or 4"); return FA_ERR_INVALID;
+        }
+        if (contigs[c].on_device && contigs[c].unit_bytes != 1) { set_error("device-resident contigs must be bytes"); return FA_ERR_INVALID; }
+        const int64_t nfrag = slen / L;                                      // pyx:1097
+        if (nfrag > 0) {
+            ups.push_back(Upload{contigs[c].data, contigs[c].unit_bytes, contigs[c].on_device, nfrag * L, off});
+            for (int64_t i = 0; i < nfrag; i++) {
+                SeqDesc d;
+                d.off = off + (uint64_t)i * L; d.len = L; d.id = (int32_t)(total_frags + i);
+                d.raw = contigs[c].unit_bytes != 1; d.tile0 = (int32_t)((total_frags + i) * tiles_per_frag);
+                ws.h_seqs.push_back(d);
+            }
+            off += ((uint64_t)(nfrag * L) + 15) & ~15ull;
+        }
+        total_frags += (uint64_t)nfrag;                                      // pyx:1104
+        total_len += (uint64_t)slen;                                         // pyx:1105
+    }
+    const int F = (int)total_frags;
+    const uint32_t G = (uint32_t)ix->seqs_by_genome.size();
+    qi.fragments = total_frags;
+    if ((uint64_t)F != total_frags || (uint64_t)F * tiles_per_frag > 0x7FFFFFF0ull) { set_error("query too large for one call"); return FA_ERR_UNSUPPORTED; }
+    if (L > 32767) { set_error("fragment_length > 32767 is not supported on the device path"); return FA_ERR_UNSUPPORTED; }
+
+    std::vector<int32_t> h_count;
+    std::vector<float> h_ident;
+    FA_CUDA(cudaEventRecord(ws.ev[0], st));
+    if (F > 0 && tiles_per_frag > 0 && ix->n > 0 && G > 0) {
+        // ---- upload + sketch the fragments ---------------------------------------------------
+        FA_TRY(stage_sequences(st, ws.sk, ws.stage, ups, off, &qi.h2d_bytes));
+        const int n_tiles = F * tiles_per_frag;
+        const int cmw = L - (w - 1) - (k - 1);                                // minimizer windows per fragment
+        const uint64_t emit_cap = (uint64_t)F * (uint64_t)std::max(cmw, 1);
+        FA_TRY(ws.sk.seqs.reserve(F)); FA_TRY(ws.sk.tile_status.reserve(n_tiles));
+        FA_TRY(ws.sk.counters.reserve(4)); FA_TRY(ws.sk.seq_first.reserve(F));
+        FA_TRY(ws.qhash.reserve(emit_cap)); FA_TRY(ws.hit_start.reserve(emit_cap)); FA_TRY(ws.hit_cnt.reserve(emit_cap));
+        FA_TRY(ws.qs.reserve(F)); FA_TRY(ws.frag_seeds.reserve((size_t)F + 1));
+        FA_TRY(ws.frag_cands.reserve((size_t)F + 1)); FA_TRY(ws.work_base.reserve((size_t)F + 1));
+        FA_TRY(ws.counters.reserve(CT_N));
+        if (ws.cells.cap < (ix->n_cells ? ix->n_cells : 1)) {
+            FA_TRY(ws.cells.reserve(ix->n_cells ? ix->n_cells : 1));
+            FA_CUDA(cudaMemsetAsync(ws.cells.p, 0, ws.cells.cap * sizeof(uint32_t), st));   // kept clean by cgi_sum_kernel afterwards
+        }
+        FA_TRY(ws.g_count.reserve(G)); FA_TRY(ws.g_identity.reserve(G));
+        FA_CUDA(cudaMemcpyAsync(ws.sk.seqs.p, ws.h_seqs.data(), (size_t)F * sizeof(SeqDesc), cudaMemcpyHostToDevice, st));
+        qi.h2d_bytes += (uint64_t)F * sizeof(SeqDesc);
+        FA_CUDA(cudaMemsetAsync(ws.counters.p, 0, CT_N * sizeof(unsigned long long), st));
+        FA_CUDA(cudaEventRecord(ws.ev[1], st));
+        FA_TRY(launch_sketch(st, ws.sk, F, n_tiles, k, w, nullptr, ws.qhash.p, 0, &launches));
+        {
+            int p2 = 1; while (p2 < cmw) p2 <<= 1;
+            int sort_cap = std::min(p2, 32768);
+            size_t smem = (size_t)sort_cap * 4;
+            if (smem > 48 * 1024) FA_CUDA(cudaFuncSetAttribute(sort_unique_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            sort_unique_kernel<<<F, 256, smem, st>>>(ws.qhash.p, ws.sk.seq_first.p, ws.sk.counters.p, F, sort_cap, ix->s_max,
+                                                     ws.qs.p, ws.counters.p);
+            FA_CUDA(cudaGetLastError()); launches++;
+        }
+        FA_CUDA(cudaEventRecord(ws.ev[2], st));
+        // ---- lookup + seed counts ------------------------------------------------------------
+        lookup_kernel<<<F, 128, 0, st>>>(ws.qhash.p, ws.sk.seq_first.p, ws.qs.p, F, ix->dir.p, ix->dir_bits, ix->ukeys.p,
+                                         ix->uoff.p, ws.hit_start.p, ws.hit_cnt.p, ws.frag_seeds.p);
+        FA_CUDA(cudaGetLastError()); launches++;
+        FA_TRY(excl_scan<uint64_t>(st, ws.cub_tmp, ws.frag_seeds.p, ws.frag_seeds.p, (int64_t)F + 1, &launches));
+        FA_TRY(ws.hres.reserve(128 + (size_t)G * 8));
+        unsigned long long *h_ct = reinterpret_cast<unsigned long long *>(ws.hres.p);
+        FA_CUDA(cudaMemcpyAsync(h_ct, ws.counters.p, CT_N * 8, cudaMemcpyDeviceToHost, st));
+        FA_CUDA(cudaMemcpyAsync(h_ct + CT_N, ws.frag_seeds.p + F, 8, cudaMemcpyDeviceToHost, st));
+        FA_CUDA(cudaStreamSynchronize(st));                                   // sync 1: seed total, max sketch, errors
+        if (h_ct[CT_ERR] & ERR_SORT_CAP) { set_error("a fragment produced more minimizers than the on-chip sort holds"); return FA_ERR_UNSUPPORTED; }
+        if (h_ct[CT_ERR] & ERR_S_MAX) { set_error("sketch size above %d is not supported on the device path", ix->s_max); return FA_ERR_UNSUPPORTED; }
+        const int max_s = (int)h_ct[CT_MAXS];
+        const uint64_t S = h_ct[CT_N];
+        qi.seeds = S; qi.sketch_sum = h_ct[CT_SKETCH_SUM];
+        FA_CUDA(cudaEventRecord(ws.ev[3], st));
+        uint64_t C = 0;
+        if (S > 0) {
+            // ---- seeds: fill + sort by (fragment, reference index) ----------------------------
+            FA_TRY(ws.seeds_a.reserve(S)); FA_TRY(ws.seeds_b.reserve(S));
+            const int shift = bits_for(ix->n), fbits = bits_for((uint64_t)F);
+            fill_seeds_kernel<<<F, 128, 0, st>>>(ws.sk.seq_first.p, ws.qs.p, ws.hit_start.p, ws.hit_cnt.p, ws.frag_seeds.p,
+                                                 ix->pos_idx.p, shift, ws.seeds_a.p);
+            FA_CUDA(cudaGetLastError()); launches++;
+            size_t sort_bytes = 0;
+            FA_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, ws.seeds_a.p, ws.seeds_b.p, (int64_t)S, 0, shift + fbits, st));
+            FA_TRY(ws.cub_tmp.reserve(sort_bytes + 16));
+            FA_CUDA(cub::DeviceRadixSort::SortKeys(ws.cub_tmp.p, sort_bytes, ws.seeds_a.p, ws.seeds_b.p, (int64_t)S, 0, shift + fbits, st));
+            launches += 2 + (shift + fbits + 7) / 8;
+            FA_CUDA(cudaEventRecord(ws.ev[4], st));
+            // ---- L1 candidates: count, scan, fill ---------------------------------------------
+            const uint64_t idx_mask = (1ull << shift) - 1;
+            candidates_kernel<false><<<F, 256, 0, st>>>(ws.seeds_b.p, ws.frag_seeds.p, ws.qs.p, ix->d_min_hits.p, ix->ref.p,
+                                                        idx_mask, L, ws.frag_cands.p, nullptr, nullptr);
+            FA_CUDA(cudaGetLastError()); launches++;
+            work_items_kernel<<<(F + 1 + 255) / 256, 256, 0, st>>>(ws.frag_cands.p, ws.qs.p, F, ws.work_base.p);
+            FA_CUDA(cudaGetLastError()); launches++;
+            FA_CUDA(cudaMemsetAsync(ws.frag_cands.p + F, 0, 4, st));
+            FA_TRY(excl_scan<uint32_t>(st, ws.cub_tmp, ws.frag_cands.p, ws.frag_cands.p, (int64_t)F + 1, &launches));
+            FA_TRY(excl_scan<uint32_t>(st, ws.cub_tmp, ws.work_base.p, ws.work_base.p, (int64_t)F + 1, &launches));
+            uint32_t *h_u = reinterpret_cast<uint32_t *>(h_ct + CT_N + 1);
+            FA_CUDA(cudaMemcpyAsync(h_u, ws.frag_cands.p + F, 4, cudaMemcpyDeviceToHost, st));
+            FA_CUDA(cudaMemcpyAsync(h_u + 1, ws.work_base.p + F, 4, cudaMemcpyDeviceToHost, st));
+            FA_CUDA(cudaStreamSynchronize(st));                               // sync 2: candidate + work totals
+            C = h_u[0];
+            const uint32_t W = h_u[1];
+            if (C > 0) {
+                FA_TRY(ws.cands.reserve(C)); FA_TRY(ws.maps.reserve(C));
+                candidates_kernel<true><<<F, 256, 0, st>>>(ws.seeds_b.p, ws.frag_seeds.p, ws.qs.p, ix->d_min_hits.p, ix->ref.p,
+                                                           idx_mask, L, nullptr, ws.frag_cands.p, ws.cands.p);
+                FA_CUDA(cudaGetLastError()); launches++;
+                FA_CUDA(cudaEventRecord(ws.ev[5], st));
+                // ---- L2 -----------------------------------------------------------------------
+                const int q_cap = std::max(max_s, 1);
+                const size_t smem = (size_t)q_cap * 4 + (size_t)L2_STATE_WORDS * 2;
+                if (smem > 48 * 1024) FA_CUDA(cudaFuncSetAttribute(l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int dev_sms = 148;
+                cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ix->device);
+                const uint32_t grid = std::min<uint32_t>(W, (uint32_t)dev_sms * 16u);
+                l2_kernel<<<grid, L2_THREADS, smem, st>>>(ws.cands.p, ws.frag_cands.p, ws.work_base.p, F, ws.qhash.p,
+                                                          ws.sk.seq_first.p, ws.qs.p, ix->ref.p, (uint32_t)ix->n, ix->contig_off.p, L, cmw,
+                                                          ix->d_min_shared.p, ix->d_id_off.p, ix->d_identity.p, ws.maps.p,
+                                                          ws.counters.p, q_cap);
+                FA_CUDA(cudaGetLastError()); launches++;
+                FA_CUDA(cudaEventRecord(ws.ev[6], st));
+                // ---- CGI ----------------------------------------------------------------------
+                cgi_best_kernel<<<std::min<uint32_t>((uint32_t)((C + 255) / 256), (uint32_t)dev_sms * 8u), 256, 0, st>>>(
+                    ws.cands.p, ws.maps.p, ws.frag_cands.p, F, ix->genome_of_seq.p, ix->bin_base.p, L - 20, ws.cells.p);
+                FA_CUDA(cudaGetLastError()); launches++;
+            } else {
+                FA_CUDA(cudaEventRecord(ws.ev[5], st));
+                FA_CUDA(cudaEventRecord(ws.ev[6], st));
+            }
+        } else {
+            for (int i = 4; i <= 6; i++) FA_CUDA(cudaEventRecord(ws.ev[i], st));
+        }
+        cgi_sum_kernel<<<(G * 32 + 255) / 256, 256, 0, st>>>(ws.cells.p, ix->genome_cell.p, (int)G, ws.g_count.p, ws.g_identity.p);
+        FA_CUDA(cudaGetLastError()); launches++;
+        FA_CUDA(cudaEventRecord(ws.ev[7], st));
+        // ---- results back ----------------------------------------------------------------------
+        int32_t *h_c = reinterpret_cast<int32_t *>(ws.hres.p + 128);
+        float *h_i = reinterpret_cast<float *>(ws.hres.p + 128 + (size_t)G * 4);
+        FA_CUDA(cudaMemcpyAsync(h_c, ws.g_count.p, (size_t)G * 4, cudaMemcpyDeviceToHost, st));
+        FA_CUDA(cudaMemcpyAsync(h_i, ws.g_identity.p, (size_t)G * 4, cudaMemcpyDeviceToHost, st));
+        FA_CUDA(cudaMemcpyAsync(h_ct, ws.counters.p, CT_N * 8, cudaMemcpyDeviceToHost, st));
+        FA_CUDA(cudaEventRecord(ws.ev[8], st));
+        FA_CUDA(cudaStreamSynchronize(st));                                   // sync 3: results
+        qi.d2h_bytes = (uint64_t)G * 8 + CT_N * 8 * 2 + 16;
+        qi.candidates = C; qi.scanned = h_ct[CT_SCANNED]; qi.mappings = h_ct[CT_MAPPINGS];
+        h_count.assign(h_c, h_c + G); h_ident.assign(h_i, h_i + G);
+        ws.last_cands = C; ws.last_frags = (uint64_t)F;
+        float ms;
+        cudaEventElapsedTime(&ms, ws.ev[0], ws.ev[1]); qi.ms_h2d = ms;
+        cudaEventElapsedTime(&ms, ws.ev[1], ws.ev[2]); qi.ms_sketch = ms;
+        cudaEventElapsedTime(&ms, ws.ev[2], ws.ev[3]); qi.ms_lookup = ms;
+        cudaEventElapsedTime(&ms, ws.ev[3], ws.ev[4]); qi.ms_seed_sort = ms;
+        cudaEventElapsedTime(&ms, ws.ev[4], ws.ev[5]); qi.ms_l1 = ms;
+        cudaEventElapsedTime(&ms, ws.ev[5], ws.ev[6]); qi.ms_l2 = ms;
+        cudaEventElapsedTime(&ms, ws.ev[6], ws.ev[7]); qi.ms_cgi = ms;
+        cudaEventElapsedTime(&ms, ws.ev[7], ws.ev[8]); qi.ms_d2h = ms;
+        cudaEventElapsedTime(&ms, ws.ev[0], ws.ev[8]); qi.ms_total = ms;
+    }
+
+    // ---- hit filter + sort (pyx:1121-1135) ------------------------------------------------------
+    std::vector<fa_hit> hits;
+    for (uint32_t g = 0; g < (uint32_t)h_count.size(); g++) {
+        if (h_count[g] <= 0) continue;
+        const uint64_t ref_len = ix->genome_len[g];
+        const uint64_t min_length = std::min(total_len, ref_len);
+        const uint64_t shared_length = (uint64_t)h_count[g] * (uint64_t)L;
+        if ((float)shared_length >= (float)min_length * P.min_fraction)
+            hits.push_back(fa_hit{(int32_t)g, h_count[g], (int32_t)total_frags, h_ident[g]});
+    }
+    std::stable_sort(hits.begin(), hits.end(), [](const fa_hit &a, const fa_hit &b) { return a.identity > b.identity; });
+    *n_out = hits.size();
+    for (size_t i = 0; i < hits.size() && i < cap; i++) out[i] = hits[i];
+    qi.kernel_launches = launches;
+    if (info) *info = qi;
+    return FA_OK;
+}
+
+int debug_candidates(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n)
+{
+    std::lock_guard<std::mutex> guard(ix->mtx);
+    FA_CUDA(cudaSetDevice(ix->device));
+    Workspace &ws = ix->ws;
+    *n = ws.last_cands;
+    const uint64_t m = std::min(cap, ws.last_cands);
+    if (!m) return FA_OK;
+    std::vector<Cand> h(m);
+    FA_CUDA(cudaMemcpy(h.data(), ws.cands.p, m * sizeof(Cand), cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> hints(m);
+    std::vector<RefMini> e(1);
+    for (uint64_t i = 0; i < m; i++) {
+        FA_CUDA(cudaMemcpy(e.data(), ix->ref.p + h[i].hint, sizeof(RefMini), cudaMemcpyDeviceToHost));
+        rows[4 * i] = h[i].frag; rows[4 * i + 1] = (int32_t)e[0].z; rows[4 * i + 2] = h[i].start; rows[4 * i + 3] = h[i].end;
+    }
+    return FA_OK;
+}
+
+int debug_mappings(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n)
+{
+    std::lock_guard<std::mutex> guard(ix->mtx);
+    FA_CUDA(cudaSetDevice(ix->device));
+    Workspace &ws = ix->ws;
+    const uint64_t C = ws.last_cands;
+    *n = 0;
+    if (!C) return FA_OK;
+    std::vector<Cand> hc(C);
+    std::vector<Mapping> hm(C);
+    std::vector<int32_t> hs(ws.last_frags);
+    FA_CUDA(cudaMemcpy(hc.data(), ws.cands.p, C * sizeof(Cand), cudaMemcpyDeviceToHost));
+    FA_CUDA(cudaMemcpy(hm.data(), ws.maps.p, C * sizeof(Mapping), cudaMemcpyDeviceToHost));
+    FA_CUDA(cudaMemcpy(hs.data(), ws.qs.p, ws.last_frags * 4, cudaMemcpyDeviceToHost));
+    uint64_t k = 0;
+    for (uint64_t i = 0; i < C; i++) {
+        if (hm[i].shared < 0) continue;
+        if (k < cap) {
+            int32_t *r = rows + 6 * k;
+            r[0] = hc[i].frag; r[1] = hm[i].seq; r[2] = hm[i].ref_start; r[3] = hm[i].shared; r[4] = hs[hc[i].frag];
+            memcpy(&r[5], &hm[i].identity, 4);
+        }
+        k++;
+    }
+    *n = k;
+    return FA_OK;
+}
+
+}  // namespace fa

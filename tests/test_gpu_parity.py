@@ -1,0 +1,150 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against (1) golden vectors made by
+the real pyfastani, (2) the CPU oracle on the same seeded inputs, intermediates included.
+
+Bar (BASELINE.json north_star): minimizer hashes/positions, candidate regions, matches and
+fragments bit-exact; identity within 1e-4 absolute -- these tests ask for bit-exact identity too.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+import capi
+import cases
+import golden_io
+import synth
+from oracle.oracle import Oracle
+
+pytestmark = pytest.mark.gpu
+
+IDENTITY_TOL = 1e-4      # the north-star tolerance; asserted bit-exact first, this is the fallback bar
+
+
+def _port():
+    return Oracle("port")
+
+
+@pytest.mark.parametrize("batched", [True, False])
+@pytest.mark.parametrize("idx", range(len(cases.minimizer_cases())))
+def test_minimizers_match_pyfastani(idx, batched):
+    case = cases.minimizer_cases()[idx]
+    man, h, s, w = golden_io.minimizer_golden()[idx]
+    sk = capi.Sketch(batched=batched, **case["params"])
+    sk.add_draft("g", case["contigs"])
+    gh, gs, gw = sk.minimizers()
+    assert len(gh) == man["n"], case["name"]
+    assert np.array_equal(gh, h) and np.array_equal(gs, s) and np.array_equal(gw, w), case["name"]
+    assert sk.warnings == man["warnings"]
+
+
+def _check_hits(hits, names, rows):
+    assert len(hits) == len(rows), (hits, rows)
+    for h, (name, ident, matches, frags) in zip(hits, rows):
+        assert names[h["ref_genome"]] == name
+        assert h["matches"] == matches and h["fragments"] == frags
+        assert abs(float(h["identity"]) - float(golden_io.f32(ident))) <= IDENTITY_TOL
+        assert h["identity"] == golden_io.f32(ident), (float(h["identity"]).hex(), ident)
+
+
+@pytest.mark.parametrize("name", [c["name"] for c in cases.query_cases()])
+def test_queries_match_pyfastani_and_oracle(name):
+    case = next(c for c in cases.query_cases() if c["name"] == name)
+    gold = golden_io.query_golden()[name]
+    sk = capi.Sketch(**case["params"])
+    osk = _port().sketch(**case["params"])
+    for rname, contigs in case["refs"]:
+        sk.add_draft(rname, contigs)
+        osk.add_draft(rname, contigs)
+    assert sk.counts()[0] == gold["minimizers"]
+    assert sk.warnings == gold["ref_warnings"]
+    ix = sk.index()
+    osk.index()
+    assert ix.params().window == gold["window"]
+    assert ix.counts()[:2] == (gold["minimizers"], gold["unique"])
+    for a, b in zip(ix.minimizers(), osk.minimizers()):
+        assert np.array_equal(a, b)
+    for q, res in zip(case["queries"], gold["results"]):
+        hits, out = ix.query_draft(q, dump=True)
+        ohits, oinfo = osk.query_draft(q, dump=True)
+        # L1 candidate regions, bit-exact
+        assert np.array_equal(out["candidates"], oinfo["candidates"])
+        # L2 mappings, every field (the oracle emits them in the same fragment/candidate order)
+        assert np.array_equal(out["mappings"], oinfo["mappings"])
+        st = oinfo["stats"]
+        info = out["info"]
+        assert (info["fragments"], info["seeds"], info["candidates"], info["mappings"], info["sketch_sum"]) == \
+               (st["fragments"], st["seeds"], st["candidates"], st["mappings"], st["sketch_sum"])
+        assert info["scanned"] == st["scanned"]
+        _check_hits(hits, ix.names, res["hits"])
+        assert out["short_contigs"] == res["warnings"]
+        assert info["kernel_launches"] > 0 or st["fragments"] == 0
+
+
+def test_config1_known_answers():
+    """BASELINE config 1 (E. coli query vs Shigella draft reference) and the reference's own
+    known answers (test_ani.py:47-91), both directions plus the self queries."""
+    gold = golden_io.config1_golden()
+    genomes = {n: golden_io.genome(n) for n in ("ecoli", "shigella")}
+    for rname in ("shigella", "ecoli"):
+        sk = capi.Sketch()
+        sk.add_draft(rname, genomes[rname])
+        h, s, w = sk.minimizers()
+        ix = sk.index()
+        for qname in ("ecoli", "shigella"):
+            g = gold["%s_vs_%s" % (qname, rname)]
+            assert ix.counts()[:2] == (g["minimizers"], g["unique"])
+            assert hashlib.sha256(h.tobytes() + s.tobytes() + w.tobytes()).hexdigest() == g["sha256"]
+            hits, _ = ix.query_draft(genomes[qname])
+            _check_hits(hits, ix.names, g["hits"])
+
+
+def test_config1_intermediates_vs_oracle():
+    genomes = {n: golden_io.genome(n) for n in ("ecoli", "shigella")}
+    sk = capi.Sketch(); sk.add_draft("shigella", genomes["shigella"]); ix = sk.index()
+    osk = _port().sketch(); osk.add_draft("shigella", genomes["shigella"]); osk.index()
+    hits, out = ix.query_draft(genomes["ecoli"], dump=True)
+    ohits, oinfo = osk.query_draft(genomes["ecoli"], dump=True)
+    assert len(oinfo["candidates"]) == 5038 and len(oinfo["mappings"]) == 4101
+    assert np.array_equal(out["candidates"], oinfo["candidates"])
+    assert np.array_equal(out["mappings"], oinfo["mappings"])
+    assert np.array_equal(hits, ohits)
+    assert float(hits[0]["identity"]).hex() == "0x1.86a7fa0000000p+6"
+
+
+def test_lookup_index_views():
+    q, refs, _ = synth.one_to_many(5, 3, 60_000)
+    sk = capi.Sketch()
+    for i, r in enumerate(refs):
+        sk.add_genome(i, r)
+    ix = sk.index()
+    h, s, w = ix.minimizers()
+    keys = ix.keys()
+    assert np.array_equal(keys, np.unique(h))
+    for key in list(keys[:20]) + list(keys[-20:]):
+        ps, pw = ix.lookup(int(key))
+        sel = h == key
+        assert np.array_equal(ps, s[sel]) and np.array_equal(pw, w[sel])     # insertion order, winSketch.hpp:180-185
+    ps, pw = ix.lookup(int(keys[0]) + 1 if keys[0] + 1 not in keys else 0xFFFFFFFE)
+    assert len(ps) == 0
+
+
+def test_full_size_properties():
+    """Size-independent properties at a larger scale than the oracle is run on: self-ANI of
+    unrelated genomes hits only itself; reverse complement and contig permutation of the query
+    leave matches/identity of a single-contig reference unchanged."""
+    rng = np.random.default_rng(31)
+    genomes = [synth.to_bytes(synth.random_codes(rng, 1_000_000)) for _ in range(6)]
+    sk = capi.Sketch()
+    for i, g in enumerate(genomes):
+        sk.add_genome(i, g)
+    ix = sk.index()
+    n_min, n_uniq, n_contigs, n_genomes = ix.counts()
+    assert n_contigs == 6 and n_genomes == 6
+    assert abs(n_min / 6e6 - 0.08) < 0.002                 # density 2/(w+1), SURVEY.md section 8
+    for i, g in enumerate(genomes):
+        hits, out = ix.query_genome(g)
+        assert len(hits) == 1 and hits[0]["ref_genome"] == i
+        assert hits[0]["fragments"] == 333 and hits[0]["matches"] >= 331
+        assert hits[0]["identity"] > 99.9
+        rc_hits, _ = ix.query_genome(synth.revcomp(g[:999_000]))
+        assert len(rc_hits) == 1 and rc_hits[0]["ref_genome"] == i and rc_hits[0]["matches"] >= 330
