@@ -120,10 +120,10 @@ FA_API int fa_sketch_counts(const fa_sketch *s, uint64_t *n_minimizers, uint64_t
 FA_API int fa_sketch_copy_minimizers(const fa_sketch *s, uint64_t first, uint64_t n,
                               uint32_t *hash, int32_t *seq, int32_t *wpos);
 /* Pickle support (pyx:572-591): bookkeeping out / everything back in. */
-FA_API int fa_sketch_copy_meta(const fa_sketch *s, int32_t *seqs_by_genome, uint64_t *genome_len, int64_t *contig_len);
+FA_API int fa_sketch_copy_meta(const fa_sketch *s, int32_t *seqs_by_genome, uint64_t *genome_len);
 FA_API int fa_sketch_restore(fa_sketch *s, const uint32_t *hash, const int32_t *seq, const int32_t *wpos, uint64_t n,
                       const int32_t *seqs_by_genome, const uint64_t *genome_len, uint64_t n_genomes,
-                      const int64_t *contig_len, uint64_t n_contigs);
+                      uint64_t n_contigs);
 /* Sketch.index(), pyx:769-806 (Sketch::index + computeFreqHist, FA/map/include/
  * winSketch.hpp:177-244): builds the lookup index on the GPU; the data moves to *out and
  * the sketch is left empty but usable. */
@@ -136,7 +136,7 @@ FA_API int fa_index_counts(const fa_index *ix, uint64_t *n_minimizers, uint64_t 
 FA_API int fa_index_params(const fa_index *ix, fa_params *out);
 FA_API int fa_index_copy_minimizers(const fa_index *ix, uint64_t first, uint64_t n,
                              uint32_t *hash, int32_t *seq, int32_t *wpos);           /* pyx:1225-1254 */
-FA_API int fa_index_copy_meta(const fa_index *ix, int32_t *seqs_by_genome, uint64_t *genome_len, int64_t *contig_len);
+FA_API int fa_index_copy_meta(const fa_index *ix, int32_t *seqs_by_genome, uint64_t *genome_len);
 /* MinimizerIndex view (pyx:1431-1539): keys in ascending hash order; positions of one hash
  * in insertion order (winSketch.hpp:180-185).  *n receives the bucket size (0 = KeyError). */
 FA_API int fa_index_copy_keys(const fa_index *ix, uint64_t first, uint64_t n, uint32_t *keys);
@@ -152,10 +152,12 @@ FA_API int fa_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs,
  * (frag, seq, refStartPos, shared, sketch, identity-bits) rows of int32. */
 FA_API int fa_debug_last_candidates(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n);
 FA_API int fa_debug_last_mappings(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n);
-/* Device scratch for callers that want inputs resident in HBM before timing. */
-FA_API int fa_device_alloc(fa_index *ix, uint64_t bytes, void **dptr);
-FA_API int fa_device_upload(fa_index *ix, void *dptr, const void *src, uint64_t bytes);
-FA_API int fa_device_free(fa_index *ix, void *dptr);
+/* Device buffers for callers that want inputs resident in HBM before the timed region
+ * (fa_contig.on_device). */
+FA_API int fa_device_alloc(int32_t device, uint64_t bytes, void **dptr);
+FA_API int fa_device_upload(int32_t device, void *dptr, const void *src, uint64_t bytes);
+FA_API int fa_device_download(int32_t device, void *dst, const void *dptr, uint64_t bytes);
+FA_API int fa_device_free(int32_t device, void *dptr);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,908 @@
+# coding: utf-8
+# cython: language_level=3, binding=False
+"""Drop-in mirror of ``pyfastani._fastani`` (src/pyfastani/_fastani.pyx in the reference)
+whose every computing call goes to ``libfastani_b200.so`` through the C ABI of
+``include/fastani_b200.h`` -- CUDA kernels for sm_100a, no CPU fallback.
+
+The class surface follows src/pyfastani/_fastani.pyi:1-116: `Sketch.add_genome/add_draft/
+index` -> `Mapper.query_genome/query_draft` -> `Hit(name, identity, matches, fragments)`,
+plus the `Minimizers`, `MinimizerInfo`, `MinimizerIndex`, `Position` views and pickling.
+This module only marshals: input adaptation (str of any kind / any contiguous byte buffer,
+pyx:633-645), warnings (pyx:671-677, 1063-1069), argument errors (pyx:523-539, 1049-1050),
+names and result objects.
+"""
+
+cimport cython
+from cpython.unicode cimport (
+    PyUnicode_DATA,
+    PyUnicode_KIND,
+    PyUnicode_GET_LENGTH,
+    PyUnicode_1BYTE_KIND,
+    PyUnicode_2BYTE_KIND,
+)
+from libc.stdint cimport int32_t, int64_t, uint32_t, uint64_t, uintptr_t
+from libc.stdlib cimport malloc, free
+from libc.string cimport memset
+
+import threading
+import warnings
+
+
+cdef extern from "fastani_b200.h" nogil:
+    ctypedef struct fa_params:
+        int32_t k
+        int32_t window
+        int32_t frag_len
+        int32_t alphabet
+        float min_fraction
+        float pct_identity
+        double p_value
+        uint64_t ref_size
+    ctypedef struct fa_contig:
+        const void* data
+        int32_t unit_bytes
+        int32_t on_device
+        int64_t len
+    ctypedef struct fa_hit:
+        int32_t ref_genome
+        int32_t matches
+        int32_t fragments
+        float identity
+    ctypedef struct fa_query_info:
+        uint64_t fragments
+        uint64_t sketch_sum
+        uint64_t seeds
+        uint64_t candidates
+        uint64_t scanned
+        uint64_t mappings
+        int32_t short_contigs
+        int32_t kernel_launches
+        float ms_h2d
+        float ms_sketch
+        float ms_lookup
+        float ms_seed_sort
+        float ms_l1
+        float ms_l2
+        float ms_cgi
+        float ms_d2h
+        float ms_total
+        uint64_t h2d_bytes
+        uint64_t d2h_bytes
+    ctypedef struct fa_sketch
+    ctypedef struct fa_index
+
+    const char* fa_last_error()
+    int fa_device_count(int32_t* n)
+    int fa_recommended_window(const fa_params* p, int32_t* w)
+    int fa_sketch_create(const fa_params* p, int32_t device, fa_sketch** out)
+    void fa_sketch_free(fa_sketch* s)
+    int fa_sketch_add_genome(fa_sketch* s, const fa_contig* contigs, int32_t n, uint64_t* glen, int32_t* n_short)
+    int fa_sketch_clear(fa_sketch* s)
+    int fa_sketch_counts(const fa_sketch* s, uint64_t* n_min, uint64_t* n_contigs, uint64_t* n_genomes)
+    int fa_sketch_copy_minimizers(const fa_sketch* s, uint64_t first, uint64_t n, uint32_t* h, int32_t* sq, int32_t* w)
+    int fa_sketch_copy_meta(const fa_sketch* s, int32_t* seqs_by_genome, uint64_t* genome_len)
+    int fa_sketch_restore(fa_sketch* s, const uint32_t* h, const int32_t* sq, const int32_t* w, uint64_t n,
+                          const int32_t* seqs_by_genome, const uint64_t* genome_len, uint64_t n_genomes, uint64_t n_contigs)
+    int fa_sketch_index(fa_sketch* s, fa_index** out)
+    void fa_index_free(fa_index* ix)
+    int fa_index_counts(const fa_index* ix, uint64_t* n_min, uint64_t* n_unique, uint64_t* n_contigs, uint64_t* n_genomes)
+    int fa_index_copy_minimizers(const fa_index* ix, uint64_t first, uint64_t n, uint32_t* h, int32_t* sq, int32_t* w)
+    int fa_index_copy_meta(const fa_index* ix, int32_t* seqs_by_genome, uint64_t* genome_len)
+    int fa_index_copy_keys(const fa_index* ix, uint64_t first, uint64_t n, uint32_t* keys)
+    int fa_index_lookup(const fa_index* ix, uint32_t hash, int32_t* sq, int32_t* w, uint64_t cap, uint64_t* n)
+    int fa_index_occurrence_threshold(const fa_index* ix, int32_t* out)
+    int fa_query(fa_index* ix, const fa_contig* contigs, int32_t n, fa_hit* out, uint64_t cap, uint64_t* n_out,
+                 fa_query_info* info)
+    int fa_device_alloc(int32_t device, uint64_t nbytes, void** dptr)
+    int fa_device_upload(int32_t device, void* dptr, const void* src, uint64_t nbytes)
+    int fa_device_free(int32_t device, void* dptr)
+
+
+cdef extern from *:
+    """
+    #define _MAX_KMER_SIZE 2048
+    """
+    const size_t _MAX_KMER_SIZE
+
+MAX_KMER_SIZE = _MAX_KMER_SIZE
+__version__ = "0.1.0"
+
+
+class CudaError(RuntimeError):
+    """Raised when the CUDA library reports a failure (there is no CPU path to fall back to)."""
+
+
+cdef int _check(int rc) except -1:
+    if rc == 0:
+        return 0
+    msg = fa_last_error().decode("utf-8", "replace")
+    if rc == 1:
+        raise ValueError(msg)
+    elif rc == 3:
+        raise MemoryError(msg)
+    elif rc == 4:
+        raise NotImplementedError(msg)
+    raise CudaError(msg)
+
+
+def device_count():
+    """Number of CUDA devices visible to the library."""
+    cdef int32_t n = 0
+    _check(fa_device_count(&n))
+    return n
+
+
+# --- input adaptation ---------------------------------------------------------
+
+cdef class DeviceSequence:
+    """A byte sequence resident in GPU memory, accepted wherever a contig is.
+
+    Not part of the reference API: it lets callers (bench.py) keep inputs in HBM so that
+    the device-only throughput can be timed next to the host-buffer path.
+    """
+    cdef void*          _ptr
+    cdef readonly int64_t length
+    cdef readonly int   device
+    cdef object         _owner
+    cdef bint           _owned
+
+    def __cinit__(self):
+        self._ptr = NULL
+        self._owned = False
+
+    def __dealloc__(self):
+        if self._owned and self._ptr != NULL:
+            fa_device_free(self.device, self._ptr)
+
+    def __len__(self):
+        return self.length
+
+    @property
+    def pointer(self):
+        return <uintptr_t> self._ptr
+
+    @staticmethod
+    def from_host(object data, int device=0):
+        cdef const unsigned char[::1] view = data
+        cdef DeviceSequence d = DeviceSequence.__new__(DeviceSequence)
+        d.device = device
+        d.length = view.shape[0]
+        _check(fa_device_alloc(device, d.length, &d._ptr))
+        d._owned = True
+        if d.length:
+            _check(fa_device_upload(device, d._ptr, &view[0], d.length))
+        return d
+
+    @staticmethod
+    def from_pointer(uintptr_t pointer, int64_t length, int device=0, object owner=None):
+        """Wrap device memory owned by someone else (e.g. a torch tensor's ``data_ptr()``)."""
+        cdef DeviceSequence d = DeviceSequence.__new__(DeviceSequence)
+        d.device = device
+        d.length = length
+        d._ptr = <void*> pointer
+        d._owner = owner
+        return d
+
+
+cdef class _Contigs:
+    """A C array of `fa_contig` built from Python sequences, keeping the buffers alive."""
+    cdef fa_contig* arr
+    cdef int32_t    n
+    cdef list       keep
+
+    def __cinit__(self):
+        self.arr = NULL
+        self.n = 0
+        self.keep = []
+
+    def __dealloc__(self):
+        free(self.arr)
+
+    cdef int fill(self, object contigs) except -1:
+        cdef const unsigned char[::1] view
+        cdef list items = list(contigs)
+        cdef object contig
+        cdef int kind
+        cdef Py_ssize_t i
+        cdef DeviceSequence dev
+        self.n = <int32_t> len(items)
+        self.arr = <fa_contig*> malloc(max(self.n, 1) * sizeof(fa_contig))
+        if self.arr == NULL:
+            raise MemoryError()
+        memset(self.arr, 0, max(self.n, 1) * sizeof(fa_contig))
+        for i, contig in enumerate(items):
+            if isinstance(contig, str):
+                # any unicode kind is read in place (pyx:633-637)
+                kind = PyUnicode_KIND(contig)
+                self.arr[i].data = PyUnicode_DATA(contig)
+                self.arr[i].len = PyUnicode_GET_LENGTH(contig)
+                self.arr[i].unit_bytes = 1 if kind == PyUnicode_1BYTE_KIND else (2 if kind == PyUnicode_2BYTE_KIND else 4)
+                self.keep.append(contig)
+            elif isinstance(contig, DeviceSequence):
+                dev = contig
+                self.arr[i].data = dev._ptr
+                self.arr[i].len = dev.length
+                self.arr[i].unit_bytes = 1
+                self.arr[i].on_device = 1
+                self.keep.append(contig)
+            else:
+                # anything exposing a contiguous byte buffer (pyx:638-645)
+                view = contig
+                self.arr[i].len = view.shape[0]
+                self.arr[i].unit_bytes = 1
+                if view.shape[0] != 0:
+                    self.arr[i].data = <const void*> &view[0]
+                self.keep.append(view)
+        return 0
+
+
+# --- parameters ---------------------------------------------------------------
+
+cdef class _Parameterized:
+    """A base class for types wrapping a `skch::Parameters` equivalent (pyx:364-446)."""
+
+    cdef fa_params _param
+    cdef int       _device
+
+    def __cinit__(self):
+        memset(&self._param, 0, sizeof(fa_params))
+        self._device = 0
+
+    def __getstate__(self):
+        return {
+            "kmerSize": self._param.k,
+            "windowSize": self._param.window,
+            "minReadLength": self._param.frag_len,
+            "minFraction": self._param.min_fraction,
+            "threads": 1,
+            "alphabetSize": self._param.alphabet,
+            "referenceSize": self._param.ref_size,
+            "percentageIdentity": self._param.pct_identity,
+            "p_value": self._param.p_value,
+        }
+
+    def __setstate__(self, state):
+        self._param.k = state["kmerSize"]
+        self._param.window = state["windowSize"]
+        self._param.frag_len = state["minReadLength"]
+        self._param.min_fraction = state["minFraction"]
+        self._param.alphabet = state["alphabetSize"]
+        self._param.ref_size = state["referenceSize"]
+        self._param.pct_identity = state["percentageIdentity"]
+        self._param.p_value = state["p_value"]
+
+    @property
+    def k(self):
+        """`int`: The k-mer size used for sketching."""
+        return self._param.k
+
+    @property
+    def window_size(self):
+        """`int`: The window size used for sketching."""
+        return self._param.window
+
+    @property
+    def fragment_length(self):
+        """`int`: The minimum read length to use for mapping."""
+        return self._param.frag_len
+
+    @property
+    def minimum_fraction(self):
+        """`float`: The minimum genome fraction required to trust ANI values."""
+        return self._param.min_fraction
+
+    @property
+    def percentage_identity(self):
+        """`float`: The identity threshold for similarity when estimating hits."""
+        return self._param.pct_identity
+
+    @property
+    def p_value(self):
+        """`float`: The p-value threshold for similarity when estimating hits."""
+        return self._param.p_value
+
+    @property
+    def protein(self):
+        """`bool`: Whether or not the object expects peptides or nucleotides."""
+        return self._param.alphabet == 20
+
+    @property
+    def device(self):
+        """`int`: The CUDA device holding this object's data (not in the reference)."""
+        return self._device
+
+
+# --- Sketch -------------------------------------------------------------------
+
+@cython.final
+cdef class Sketch(_Parameterized):
+    """An index computing minimizers over the reference genomes (pyx:449-806)."""
+
+    cdef          fa_sketch* _sk
+    cdef          list       _names
+    cdef readonly Minimizers minimizers
+    cdef readonly object     _lock
+
+    def __cinit__(self):
+        self._sk = NULL
+        self._names = []
+        self.minimizers = Minimizers.__new__(Minimizers)
+        self.minimizers._owner = self
+
+    def __init__(
+        self,
+        *,
+        unsigned int k=16,
+        unsigned int fragment_length=3000,
+        float minimum_fraction=0.2,
+        double p_value=1e-03,
+        float percentage_identity=80.0,
+        uint64_t reference_size=5_000_000,
+        bint protein=False,
+        int device=0,
+    ):
+        """__init__(self, *, k=16, fragment_length=3000, minimum_fraction=0.2, p_value=1e-03, percentage_identity=80, reference_size=5e6, protein=False, device=0)\n--
+
+        Create a new FastANI sequence sketch on CUDA device ``device``.  Arguments and
+        errors as in the reference (pyx:484-539).
+        """
+        cdef int32_t w = 0
+        if minimum_fraction > 1 or minimum_fraction < 0:
+            raise ValueError(f"minimum_fraction must be between 0 and 1, got {minimum_fraction!r}")
+        if fragment_length <= 0:
+            raise ValueError(f"fragment_length must be strictly positive, got {fragment_length!r}")
+        if p_value <= 0:
+            raise ValueError(f"p_value must be positive, got {p_value!r}")
+        if percentage_identity > 100 or percentage_identity < 0:
+            raise ValueError(f"percentage_identity must be between 0 and 100, got {percentage_identity!r}")
+        if k <= 0:
+            raise ValueError(f"k must be strictly positive, got {k!r}")
+        elif k > _MAX_KMER_SIZE:
+            raise BufferError(f"k must be smaller than {_MAX_KMER_SIZE}, got {k}")
+        elif k > 16:
+            warnings.warn(
+                f"Using k-mer size greater than 16 ({k!r}), accuracy will be degraded.",
+                UserWarning,
+            )
+        if protein:
+            raise NotImplementedError("protein mode is not implemented on the GPU path")
+
+        self._param.k = k
+        self._param.frag_len = fragment_length
+        self._param.min_fraction = minimum_fraction
+        self._param.p_value = p_value
+        self._param.pct_identity = percentage_identity
+        self._param.ref_size = reference_size
+        self._param.alphabet = 4
+        self._param.window = 0
+        _check(fa_recommended_window(&self._param, &w))
+        self._param.window = w
+        self._device = device
+
+        self._lock = threading.Lock()
+        # (re)create the device-side sketch; __init__ may be called more than once
+        if self._sk != NULL:
+            fa_sketch_free(self._sk)
+            self._sk = NULL
+        _check(fa_sketch_create(&self._param, device, &self._sk))
+        self._names = []
+
+    def __dealloc__(self):
+        if self._sk != NULL:
+            fa_sketch_free(self._sk)
+            self._sk = NULL
+
+    def __getstate__(self):
+        cdef uint64_t n_min = 0, n_contigs = 0, n_genomes = 0
+        _check(fa_sketch_counts(self._sk, &n_min, &n_contigs, &n_genomes))
+        cdef int32_t*  seqs = <int32_t*> malloc(max(n_genomes, 1) * sizeof(int32_t))
+        cdef uint64_t* lens = <uint64_t*> malloc(max(n_genomes, 1) * sizeof(uint64_t))
+        try:
+            _check(fa_sketch_copy_meta(self._sk, seqs, lens))
+            return {
+                "parameters": _Parameterized.__getstate__(self),
+                "counter": n_contigs,
+                "lengths": [lens[i] for i in range(n_genomes)],
+                "names": list(self._names),
+                "device": self._device,
+                "sketch": {
+                    "sequencesByFileInfo": [seqs[i] for i in range(n_genomes)],
+                    "minimizers": self.minimizers.__getstate__(),
+                },
+            }
+        finally:
+            free(seqs)
+            free(lens)
+
+    def __setstate__(self, state):
+        _Parameterized.__setstate__(self, state["parameters"])
+        self._device = state.get("device", 0)
+        self._lock = threading.Lock()
+        if self._sk != NULL:
+            fa_sketch_free(self._sk)
+            self._sk = NULL
+        _check(fa_sketch_create(&self._param, self._device, &self._sk))
+        self._names = list(state["names"])
+        _restore_sketch(self._sk, state["sketch"], state["lengths"], state["counter"])
+
+    @property
+    def occurences_threshold(self):
+        """`int`: The occurence threshold above which minimizers are ignored."""
+        return 2147483647
+
+    @property
+    def names(self):
+        """`list` of `str`: The names of the sequences currently sketched."""
+        return self._names[:]
+
+    cdef int _add_draft(self, object name, object contigs) except 1:
+        cdef _Contigs c = _Contigs.__new__(_Contigs)
+        cdef uint64_t glen = 0
+        cdef int32_t  n_short = 0
+        cdef int      rc
+        c.fill(contigs)
+        with nogil:
+            rc = fa_sketch_add_genome(self._sk, c.arr, c.n, &glen, &n_short)
+        _check(rc)
+        for _ in range(n_short):
+            warnings.warn(
+                (
+                    "Sketch received a short contig relative to parameters, "
+                    "minimizers will not be added."
+                ),
+                UserWarning,
+            )
+        self._names.append(name)
+        return 0
+
+    cpdef Sketch add_draft(self, object name, object contigs):
+        """add_draft(self, name, contigs)\n--
+
+        Add a reference draft genome to the sketcher (pyx:692-717)."""
+        with self._lock:
+            self._add_draft(name, contigs)
+        return self
+
+    cpdef Sketch add_genome(self, object name, object sequence):
+        """add_genome(self, name, sequence)\n--
+
+        Add a reference genome to the sketcher (pyx:719-744)."""
+        with self._lock:
+            self._add_draft(name, (sequence,))
+        return self
+
+    cpdef Sketch clear(self):
+        """clear(self)\n--
+
+        Reset the `Sketch`, removing any reference genome it may contain (pyx:746-767)."""
+        self._names.clear()
+        if self._sk != NULL:
+            _check(fa_sketch_clear(self._sk))
+        return self
+
+    cpdef Mapper index(self):
+        """index(self)\n--
+
+        Index the reference genomes for fast lookups using the minimizers (pyx:769-806).
+        Ownership of the data moves to the returned `Mapper`; the sketch is left empty.
+        """
+        cdef Mapper mapper = Mapper.__new__(Mapper)
+        cdef int rc
+        with nogil:
+            rc = fa_sketch_index(self._sk, &mapper._ix)
+        _check(rc)
+        mapper._param = self._param
+        mapper._device = self._device
+        mapper._names = self._names.copy()
+        self._names = []
+        return mapper
+
+
+cdef int _restore_sketch(fa_sketch* sk, dict sketch_state, object lengths, uint64_t counter) except -1:
+    cdef dict   mins    = sketch_state["minimizers"]
+    cdef list   hashes  = mins["hashes"]
+    cdef list   ids     = mins["ids"]
+    cdef list   offsets = mins["offsets"]
+    cdef size_t n       = mins["length"]
+    cdef list   sbf     = list(sketch_state["sequencesByFileInfo"])
+    cdef list   lens    = list(lengths)
+    cdef size_t g       = len(sbf)
+    cdef size_t i
+    cdef uint32_t* h = <uint32_t*> malloc(max(n, 1) * sizeof(uint32_t))
+    cdef int32_t*  s = <int32_t*> malloc(max(n, 1) * sizeof(int32_t))
+    cdef int32_t*  w = <int32_t*> malloc(max(n, 1) * sizeof(int32_t))
+    cdef int32_t*  q = <int32_t*> malloc(max(g, 1) * sizeof(int32_t))
+    cdef uint64_t* l = <uint64_t*> malloc(max(g, 1) * sizeof(uint64_t))
+    try:
+        for i in range(n):
+            h[i] = hashes[i]
+            s[i] = ids[i]
+            w[i] = offsets[i]
+        for i in range(g):
+            q[i] = sbf[i]
+            l[i] = lens[i] if i < len(lens) else 0
+        if g and counter < <uint64_t> q[g - 1]:
+            counter = q[g - 1]
+        _check(fa_sketch_restore(sk, h, s, w, n, q, l, g, counter))
+    finally:
+        free(h); free(s); free(w); free(q); free(l)
+    return 0
+
+
+# --- Mapper -------------------------------------------------------------------
+
+@cython.final
+cdef class Mapper(_Parameterized):
+    """A genome mapper using Murmur3 hashes and k-mers to compute ANI (pyx:809-1200)."""
+
+    cdef          fa_index*  _ix
+    cdef          list       _names
+    cdef readonly Minimizers minimizers
+    cdef readonly dict       last_query_info
+
+    def __cinit__(self):
+        self._ix = NULL
+        self._names = []
+        self.minimizers = Minimizers.__new__(Minimizers)
+        self.minimizers._owner = self
+        self.last_query_info = {}
+
+    def __init__(self, *args, **kwargs):
+        raise TypeError("Mapper cannot be instantiated, use `Sketch.index` instead.")
+
+    def __dealloc__(self):
+        if self._ix != NULL:
+            fa_index_free(self._ix)
+            self._ix = NULL
+
+    def __getstate__(self):
+        cdef uint64_t n_min = 0, n_unique = 0, n_contigs = 0, n_genomes = 0
+        _check(fa_index_counts(self._ix, &n_min, &n_unique, &n_contigs, &n_genomes))
+        cdef int32_t*  seqs = <int32_t*> malloc(max(n_genomes, 1) * sizeof(int32_t))
+        cdef uint64_t* lens = <uint64_t*> malloc(max(n_genomes, 1) * sizeof(uint64_t))
+        try:
+            _check(fa_index_copy_meta(self._ix, seqs, lens))
+            return {
+                "parameters": _Parameterized.__getstate__(self),
+                "lengths": [lens[i] for i in range(n_genomes)],
+                "names": list(self._names),
+                "device": self._device,
+                "counter": n_contigs,
+                "sketch": {
+                    "sequencesByFileInfo": [seqs[i] for i in range(n_genomes)],
+                    "minimizers": self.minimizers.__getstate__(),
+                },
+            }
+        finally:
+            free(seqs)
+            free(lens)
+
+    def __setstate__(self, state):
+        # restore the minimizers into a scratch sketch, then rebuild the lookup index on the
+        # GPU, like the reference rebuilds its hash table (pyx:853-865)
+        cdef fa_sketch* sk = NULL
+        _Parameterized.__setstate__(self, state["parameters"])
+        self._device = state.get("device", 0)
+        self._names = list(state["names"])
+        _check(fa_sketch_create(&self._param, self._device, &sk))
+        try:
+            _restore_sketch(sk, state["sketch"], state["lengths"], state.get("counter", 0))
+            if self._ix != NULL:
+                fa_index_free(self._ix)
+                self._ix = NULL
+            _check(fa_sketch_index(sk, &self._ix))
+        finally:
+            fa_sketch_free(sk)
+
+    @property
+    def lookup_index(self):
+        """`MinimizerIndex`: The index of initial minimizer positions."""
+        cdef MinimizerIndex index = MinimizerIndex.__new__(MinimizerIndex)
+        index.owner = self
+        return index
+
+    @property
+    def names(self):
+        """`list`: The names of the indexed reference genomes (not in the reference API)."""
+        return self._names[:]
+
+    cdef list _query_draft(self, object contigs, int threads=0):
+        cdef _Contigs      c = _Contigs.__new__(_Contigs)
+        cdef uint64_t      cap = len(self._names)
+        cdef uint64_t      n_out = 0
+        cdef fa_hit*       out
+        cdef fa_query_info info
+        cdef int           rc
+        cdef list          hits = []
+        cdef uint64_t      i
+
+        # `threads` is the reference's CPU worker count (pyx:1043-1050); fragments are mapped
+        # by GPU threads here, so only its validation is kept
+        if threads < 0:
+            raise ValueError(f"`threads` must be positive or null, got {threads!r}")
+        c.fill(contigs)
+        out = <fa_hit*> malloc(max(cap, 1) * sizeof(fa_hit))
+        if out == NULL:
+            raise MemoryError()
+        try:
+            with nogil:
+                rc = fa_query(self._ix, c.arr, c.n, out, cap, &n_out, &info)
+            _check(rc)
+            for _ in range(info.short_contigs):
+                warnings.warn(
+                    (
+                        "Mapper received a short sequence relative to parameters, "
+                        "mapping will not be computed."
+                    ),
+                    UserWarning,
+                )
+            for i in range(min(n_out, cap)):
+                hits.append(Hit(
+                    name=self._names[out[i].ref_genome],
+                    identity=out[i].identity,
+                    matches=out[i].matches,
+                    fragments=out[i].fragments,
+                ))
+            self.last_query_info = {
+                "fragments": info.fragments, "sketch_sum": info.sketch_sum, "seeds": info.seeds,
+                "candidates": info.candidates, "scanned": info.scanned, "mappings": info.mappings,
+                "kernel_launches": info.kernel_launches,
+                "ms_h2d": info.ms_h2d, "ms_sketch": info.ms_sketch, "ms_lookup": info.ms_lookup,
+                "ms_seed_sort": info.ms_seed_sort, "ms_l1": info.ms_l1, "ms_l2": info.ms_l2,
+                "ms_cgi": info.ms_cgi, "ms_d2h": info.ms_d2h, "ms_total": info.ms_total,
+                "h2d_bytes": info.h2d_bytes, "d2h_bytes": info.d2h_bytes,
+            }
+        finally:
+            free(out)
+        return hits
+
+    cpdef list query_draft(self, object contigs, int threads=0):
+        """query_draft(self, contigs, threads=0)\n--
+
+        Query the mapper for a draft genome (pyx:1138-1168).  Reentrant; releases the GIL."""
+        return self._query_draft(contigs, threads=threads)
+
+    cpdef list query_genome(self, object sequence, int threads=0):
+        """query_genome(self, sequence, threads=0)\n--
+
+        Query the mapper for a complete genome (pyx:1170-1200)."""
+        return self._query_draft((sequence,), threads=threads)
+
+
+# --- views ----------------------------------------------------------------------
+
+cdef class Minimizers:
+    """A read-only view over the minimizers of a `Sketch` or a `Mapper` (pyx:1203-1268).
+
+    The data lives in GPU memory; elements are copied to the host on access.
+    """
+
+    cdef object _owner
+
+    def __cinit__(self):
+        self._owner = None
+
+    cdef uint64_t _size(self) except? 0:
+        cdef uint64_t n = 0
+        cdef Sketch sk
+        cdef Mapper mp
+        if isinstance(self._owner, Sketch):
+            sk = self._owner
+            if sk._sk != NULL:
+                _check(fa_sketch_counts(sk._sk, &n, NULL, NULL))
+        elif isinstance(self._owner, Mapper):
+            mp = self._owner
+            if mp._ix != NULL:
+                _check(fa_index_counts(mp._ix, &n, NULL, NULL, NULL))
+        return n
+
+    cdef int _copy(self, uint64_t first, uint64_t n, uint32_t* h, int32_t* s, int32_t* w) except -1:
+        cdef Sketch sk
+        cdef Mapper mp
+        if isinstance(self._owner, Sketch):
+            sk = self._owner
+            _check(fa_sketch_copy_minimizers(sk._sk, first, n, h, s, w))
+        else:
+            mp = self._owner
+            _check(fa_index_copy_minimizers(mp._ix, first, n, h, s, w))
+        return 0
+
+    def __len__(self):
+        return self._size()
+
+    def __getitem__(self, ssize_t index):
+        cdef ssize_t  length = self._size()
+        cdef ssize_t  index_ = index
+        cdef uint32_t h = 0
+        cdef int32_t  s = 0, w = 0
+        if index_ < 0:
+            index_ += length
+        if index_ < 0 or index_ >= length:
+            raise IndexError(index)
+        self._copy(index_, 1, &h, &s, &w)
+        return MinimizerInfo(h, s, w)
+
+    cpdef dict __getstate__(self):
+        cdef uint64_t  n = self._size()
+        cdef uint64_t  i
+        cdef uint32_t* h = <uint32_t*> malloc(max(n, 1) * sizeof(uint32_t))
+        cdef int32_t*  s = <int32_t*> malloc(max(n, 1) * sizeof(int32_t))
+        cdef int32_t*  w = <int32_t*> malloc(max(n, 1) * sizeof(int32_t))
+        try:
+            if n:
+                self._copy(0, n, h, s, w)
+            return {
+                "hashes": [h[i] for i in range(n)],
+                "ids": [s[i] for i in range(n)],
+                "offsets": [w[i] for i in range(n)],
+                "length": n,
+            }
+        finally:
+            free(h); free(s); free(w)
+
+
+cdef class Hit:
+    """A single hit found when querying a `Mapper` with a genome (pyx:1271-1324)."""
+
+    cdef readonly object name
+    cdef readonly int    matches
+    cdef readonly int    fragments
+    cdef readonly float  identity
+
+    def __init__(self, object name, float identity, int matches, int fragments):
+        """__init__(self, name, identity, matches, fragments)\n--
+
+        Create a new `Hit` instance with the given parameters."""
+        self.name = name
+        self.matches = matches
+        self.fragments = fragments
+        self.identity = identity
+
+    def __repr__(self):
+        cdef str ty = type(self).__name__
+        return "{}(name={!r}, identity={!r}, matches={!r}, fragments={!r})".format(
+            ty, self.name, self.identity, self.matches, self.fragments
+        )
+
+    def __eq__(self, Hit other):
+        return (
+                self.name == other.name
+            and self.matches == other.matches
+            and self.fragments == other.fragments
+            and self.identity == other.identity
+        )
+
+    def __reduce__(self):
+        return (Hit, (self.name, self.identity, self.matches, self.fragments))
+
+
+cdef class MinimizerInfo:
+    """The information about a single minimizer (pyx:1327-1379)."""
+
+    cdef readonly uint32_t hash
+    cdef readonly int      sequence_id
+    cdef readonly int      window_position
+
+    def __init__(self, uint32_t hash, int sequence_id, int window_position):
+        """__init__(self, hash, sequence_id, window_position)\n--
+
+        Create a new `MinimizerInfo` with the given parameters."""
+        self.hash = hash
+        self.sequence_id = sequence_id
+        self.window_position = window_position
+
+    def __repr__(self):
+        cdef str ty = type(self).__name__
+        return "{}(hash={!r}, sequence_id={!r}, window_position={!r})".format(
+            ty, self.hash, self.sequence_id, self.window_position
+        )
+
+    def __eq__(self, MinimizerInfo other):
+        return (
+                self.hash == other.hash
+            and self.sequence_id == other.sequence_id
+            and self.window_position == other.window_position
+        )
+
+    def __reduce__(self):
+        return (MinimizerInfo, (self.hash, self.sequence_id, self.window_position))
+
+
+cdef class Position:
+    """A (sequence, window) position of a minimizer in the references (pyx:1382-1428)."""
+
+    cdef readonly int sequence_id
+    cdef readonly int window_position
+
+    def __init__(self, int sequence_id, int window_position):
+        """__init__(self, sequence_id, window_position)\n--
+
+        Create a new `Position` instance with the given parameters."""
+        self.sequence_id = sequence_id
+        self.window_position = window_position
+
+    def __repr__(self):
+        cdef str ty = type(self).__name__
+        return "{}(sequence_id={!r}, window_position={!r})".format(
+            ty, self.sequence_id, self.window_position
+        )
+
+    def __eq__(self, Position other):
+        return (
+                self.sequence_id == other.sequence_id
+            and self.window_position == other.window_position
+        )
+
+    def __reduce__(self):
+        return (Position, (self.sequence_id, self.window_position))
+
+
+cdef class MinimizerIndex:
+    """The index mapping minimizer hash values to their positions (pyx:1431-1539).
+
+    Read-only view over the CSR lookup table held in GPU memory: ``len``, iteration,
+    ``in``, ``[]`` and ``items()`` work as in the reference; item assignment and deletion
+    (which the reference allows on its host hash table) raise `TypeError`.
+    """
+
+    cdef object owner
+
+    def __cinit__(self):
+        self.owner = None
+
+    cdef fa_index* _index(self) except NULL:
+        cdef Mapper mp
+        if self.owner is None:
+            raise ValueError("MinimizerIndex is not attached to a Mapper")
+        mp = self.owner
+        return mp._ix
+
+    def __len__(self):
+        cdef uint64_t n_unique = 0
+        _check(fa_index_counts(self._index(), NULL, &n_unique, NULL, NULL))
+        return n_unique
+
+    def _keys(self):
+        cdef uint64_t  n = len(self)
+        cdef uint64_t  i
+        cdef uint32_t* k = <uint32_t*> malloc(max(n, 1) * sizeof(uint32_t))
+        try:
+            if n:
+                _check(fa_index_copy_keys(self._index(), 0, n, k))
+            return [k[i] for i in range(n)]
+        finally:
+            free(k)
+
+    def __iter__(self):
+        return iter(self._keys())
+
+    def __contains__(self, uint32_t item):
+        cdef uint64_t n = 0
+        _check(fa_index_lookup(self._index(), item, NULL, NULL, 0, &n))
+        return n > 0
+
+    def __getitem__(self, uint32_t item):
+        cdef uint64_t n = 0
+        cdef uint64_t i
+        cdef int32_t* s
+        cdef int32_t* w
+        _check(fa_index_lookup(self._index(), item, NULL, NULL, 0, &n))
+        if n == 0:
+            raise KeyError(item)
+        s = <int32_t*> malloc(n * sizeof(int32_t))
+        w = <int32_t*> malloc(n * sizeof(int32_t))
+        try:
+            _check(fa_index_lookup(self._index(), item, s, w, n, &n))
+            return [Position(s[i], w[i]) for i in range(n)]
+        finally:
+            free(s); free(w)
+
+    def __setitem__(self, uint32_t item, object value):
+        raise TypeError("the lookup index lives in GPU memory and is read-only")
+
+    def __delitem__(self, uint32_t item):
+        raise TypeError("the lookup index lives in GPU memory and is read-only")
+
+    def items(self):
+        for key in self._keys():
+            yield key, self[key]

@@ -106,7 +106,7 @@ int sketch_add_batch(fa_sketch *s, const fa_contig *contigs, int32_t n_contigs, 
     }
     for (int32_t c = 0; c < n_contigs; c++) {
         const fa_contig &ct = contigs[c];
-        const int32_t id = (int32_t)s->contig_len.size();
+        const int32_t id = (int32_t)s->counter;
         if (ct.len >= P.window && ct.len >= P.k) {                                    // pyx:648
             const int nk = (int)ct.len - P.k + 1;
             SeqDesc d;
@@ -118,7 +118,7 @@ int sketch_add_batch(fa_sketch *s, const fa_contig *contigs, int32_t n_contigs, 
             if (nk >= P.window) worst += (uint64_t)(nk - P.window + 1);
         } else shorts++;                                                              // pyx:670-677
         s->cur_len += (uint64_t)(ct.len / P.frag_len) * (uint64_t)P.frag_len;         // pyx:680
-        s->contig_len.push_back(ct.len);
+        s->counter++;                                                                 // pyx:683
     }
     if (n_short) *n_short = shorts;
     if (n_added) *n_added = shorts == n_contigs && n_contigs == 1 ? -1 : 0;
@@ -230,7 +230,7 @@ int fa_sketch_end_genome(fa_sketch *s, uint64_t *genome_len_out)
 {
     if (!s) { set_error("sketch is NULL"); return FA_ERR_INVALID; }
     s->genome_len.push_back(s->cur_len);                                  // pyx:687
-    s->seqs_by_genome.push_back((int32_t)s->contig_len.size());          // pyx:690
+    s->seqs_by_genome.push_back((int32_t)s->counter);                 // pyx:690
     if (genome_len_out) *genome_len_out = s->cur_len;
     s->cur_len = 0;
     return FA_OK;
@@ -247,7 +247,7 @@ int fa_sketch_clear(fa_sketch *s)
 {
     if (!s) { set_error("sketch is NULL"); return FA_ERR_INVALID; }
     s->n = 0; s->cur_len = 0;
-    s->seqs_by_genome.clear(); s->genome_len.clear(); s->contig_len.clear();
+    s->seqs_by_genome.clear(); s->genome_len.clear(); s->counter = 0;
     return FA_OK;
 }
 
@@ -255,7 +255,7 @@ int fa_sketch_counts(const fa_sketch *s, uint64_t *n_minimizers, uint64_t *n_con
 {
     if (!s) { set_error("sketch is NULL"); return FA_ERR_INVALID; }
     if (n_minimizers) *n_minimizers = s->n;
-    if (n_contigs) *n_contigs = s->contig_len.size();
+    if (n_contigs) *n_contigs = s->counter;
     if (n_genomes) *n_genomes = s->genome_len.size();
     return FA_OK;
 }
@@ -266,25 +266,24 @@ int fa_sketch_copy_minimizers(const fa_sketch *s, uint64_t first, uint64_t n, ui
     return copy_minimizers(s->device, s->st, s->ref.p, s->n, first, n, hash, seq, wpos);
 }
 
-int fa_sketch_copy_meta(const fa_sketch *s, int32_t *seqs_by_genome, uint64_t *genome_len, int64_t *contig_len)
+int fa_sketch_copy_meta(const fa_sketch *s, int32_t *seqs_by_genome, uint64_t *genome_len)
 {
     if (!s) { set_error("sketch is NULL"); return FA_ERR_INVALID; }
     if (seqs_by_genome) std::copy(s->seqs_by_genome.begin(), s->seqs_by_genome.end(), seqs_by_genome);
     if (genome_len) std::copy(s->genome_len.begin(), s->genome_len.end(), genome_len);
-    if (contig_len) std::copy(s->contig_len.begin(), s->contig_len.end(), contig_len);
     return FA_OK;
 }
 
 int fa_sketch_restore(fa_sketch *s, const uint32_t *hash, const int32_t *seq, const int32_t *wpos, uint64_t n,
                       const int32_t *seqs_by_genome, const uint64_t *genome_len, uint64_t n_genomes,
-                      const int64_t *contig_len, uint64_t n_contigs)
+                      uint64_t n_contigs)
 {
     if (!s) { set_error("sketch is NULL"); return FA_ERR_INVALID; }
     FA_CUDA(cudaSetDevice(s->device));
     fa_sketch_clear(s);
     s->seqs_by_genome.assign(seqs_by_genome, seqs_by_genome + n_genomes);
     s->genome_len.assign(genome_len, genome_len + n_genomes);
-    s->contig_len.assign(contig_len, contig_len + n_contigs);
+    s->counter = n_contigs;
     if (n == 0) return FA_OK;
     FA_TRY(s->ref.reserve(n + 1));
     DevBuf<uint32_t> dh; DevBuf<int32_t> ds, dw;
@@ -316,7 +315,7 @@ int fa_sketch_index(fa_sketch *s, fa_index **out)
     s->ref = DevBuf<RefMini>();
     ix->seqs_by_genome.swap(s->seqs_by_genome);
     ix->genome_len.swap(s->genome_len);
-    ix->contig_len.swap(s->contig_len);
+    ix->n_contigs = s->counter;
     fa_sketch_clear(s);
     FA_CUDA(cudaStreamSynchronize(s->st));
     if (!ix->ref.p) { int rc = ix->ref.reserve(1); if (rc) { fa_index_free(ix); return rc; } }
@@ -349,7 +348,7 @@ int fa_index_counts(const fa_index *ix, uint64_t *n_minimizers, uint64_t *n_uniq
     if (!ix) { set_error("index is NULL"); return FA_ERR_INVALID; }
     if (n_minimizers) *n_minimizers = ix->n;
     if (n_unique) *n_unique = ix->n_unique;
-    if (n_contigs) *n_contigs = ix->contig_len.size();
+    if (n_contigs) *n_contigs = ix->n_contigs;
     if (n_genomes) *n_genomes = ix->genome_len.size();
     return FA_OK;
 }
@@ -367,12 +366,11 @@ int fa_index_copy_minimizers(const fa_index *ix, uint64_t first, uint64_t n, uin
     return copy_minimizers(ix->device, ix->st, ix->ref.p, ix->n, first, n, hash, seq, wpos);
 }
 
-int fa_index_copy_meta(const fa_index *ix, int32_t *seqs_by_genome, uint64_t *genome_len, int64_t *contig_len)
+int fa_index_copy_meta(const fa_index *ix, int32_t *seqs_by_genome, uint64_t *genome_len)
 {
     if (!ix) { set_error("index is NULL"); return FA_ERR_INVALID; }
     if (seqs_by_genome) std::copy(ix->seqs_by_genome.begin(), ix->seqs_by_genome.end(), seqs_by_genome);
     if (genome_len) std::copy(ix->genome_len.begin(), ix->genome_len.end(), genome_len);
-    if (contig_len) std::copy(ix->contig_len.begin(), ix->contig_len.end(), contig_len);
     return FA_OK;
 }
 
@@ -431,24 +429,28 @@ int fa_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *
 int fa_debug_last_candidates(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n) { return debug_candidates(ix, rows, cap, n); }
 int fa_debug_last_mappings(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n) { return debug_mappings(ix, rows, cap, n); }
 
-int fa_device_alloc(fa_index *ix, uint64_t bytes, void **dptr)
+int fa_device_alloc(int32_t device, uint64_t bytes, void **dptr)
 {
-    if (!ix || !dptr) { set_error("bad arguments"); return FA_ERR_INVALID; }
-    FA_CUDA(cudaSetDevice(ix->device));
+    if (!dptr) { set_error("bad arguments"); return FA_ERR_INVALID; }
+    FA_CUDA(cudaSetDevice(device));
     FA_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
     return FA_OK;
 }
-int fa_device_upload(fa_index *ix, void *dptr, const void *src, uint64_t bytes)
+int fa_device_upload(int32_t device, void *dptr, const void *src, uint64_t bytes)
 {
-    if (!ix) { set_error("bad arguments"); return FA_ERR_INVALID; }
-    FA_CUDA(cudaSetDevice(ix->device));
+    FA_CUDA(cudaSetDevice(device));
     FA_CUDA(cudaMemcpy(dptr, src, bytes, cudaMemcpyHostToDevice));
     return FA_OK;
 }
-int fa_device_free(fa_index *ix, void *dptr)
+int fa_device_download(int32_t device, void *dst, const void *dptr, uint64_t bytes)
 {
-    if (!ix) { set_error("bad arguments"); return FA_ERR_INVALID; }
-    FA_CUDA(cudaSetDevice(ix->device));
+    FA_CUDA(cudaSetDevice(device));
+    FA_CUDA(cudaMemcpy(dst, dptr, bytes, cudaMemcpyDeviceToHost));
+    return FA_OK;
+}
+int fa_device_free(int32_t device, void *dptr)
+{
+    FA_CUDA(cudaSetDevice(device));
     FA_CUDA(cudaFree(dptr));
     return FA_OK;
 }

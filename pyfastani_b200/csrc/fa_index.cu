@@ -65,13 +65,34 @@ __global__ void contig_off_kernel(const RefMini *ref, uint64_t n, uint32_t n_con
     if (i == 0) contig_off[0] = 0;
 }
 
+// (contig, bin) cells of computeCGI's second pass (computeCoreIdentity.hpp:191, 234-255): a mapping
+// starts at the mean of two minimizer positions of its contig, so bins up to the one holding the
+// contig's last minimizer suffice.
+__global__ void contig_bins_kernel(const RefMini *ref, const uint32_t *contig_off, uint32_t n_contigs, int bin_w, uint32_t *nbins)
+{
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n_contigs) return;
+    uint32_t v = 0;
+    if (s < n_contigs) {
+        const uint32_t lo = contig_off[s], hi = contig_off[s + 1];
+        if (hi > lo) v = ref[hi - 1].y / (uint32_t)bin_w + 1;
+    }
+    nbins[s] = v;
+}
+
+__global__ void genome_cells_kernel(const uint32_t *bin_base, const int32_t *first_contig, uint32_t n_genomes, uint32_t *genome_cell)
+{
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g <= n_genomes) genome_cell[g] = bin_base[first_contig[g]];
+}
+
 }  // namespace
 
 int build_index(fa_index *ix, int *launches)
 {
     cudaStream_t st = ix->st;
     const uint64_t n = ix->n;
-    const uint32_t n_contigs = (uint32_t)ix->contig_len.size();
+    const uint32_t n_contigs = (uint32_t)ix->n_contigs;
     const uint32_t n_genomes = (uint32_t)ix->seqs_by_genome.size();
     if (n >= 0xFFFFFFF0ull) { set_error("index of %llu minimizers exceeds the 32-bit position index", (unsigned long long)n); return FA_ERR_UNSUPPORTED; }
 
@@ -84,31 +105,17 @@ int build_index(fa_index *ix, int *launches)
             genome_of[s] = (int32_t)g;
         }
     }
-    const int bin_w = ix->prm.frag_len - 20;                                       // computeCoreIdentity.hpp:191
-    std::vector<uint32_t> bin_base(n_contigs + 1, 0), genome_cell(n_genomes + 1, 0);
-    {
-        uint64_t acc = 0;
-        for (uint32_t s = 0; s < n_contigs; s++) {
-            bin_base[s] = (uint32_t)acc;
-            int64_t len = ix->contig_len[s];
-            acc += (bin_w > 0 && len > 0) ? (uint64_t)((len - 1) / bin_w + 1) : 1;
-            if (acc >= 0xFFFFFFF0ull) { set_error("too many reference bins"); return FA_ERR_UNSUPPORTED; }
-        }
-        bin_base[n_contigs] = (uint32_t)acc;
-        ix->n_cells = acc;
-        uint32_t s0 = 0;
-        for (uint32_t g = 0; g < n_genomes; g++) {
-            genome_cell[g] = bin_base[s0 < n_contigs ? s0 : n_contigs];
-            s0 = (uint32_t)ix->seqs_by_genome[g];
-        }
-        genome_cell[n_genomes] = (uint32_t)acc;
-    }
+    // first contig of each genome (+ the total), for the per-genome cell ranges
+    std::vector<int32_t> first_contig(n_genomes + 1, 0);
+    for (uint32_t g = 0; g < n_genomes; g++) first_contig[g + 1] = std::min<int32_t>(ix->seqs_by_genome[g], (int32_t)n_contigs);
+    first_contig[n_genomes] = (int32_t)n_contigs;
+    DevBuf<int32_t> d_first;
+    FA_TRY(d_first.reserve(first_contig.size()));
     FA_TRY(ix->genome_of_seq.reserve(genome_of.size()));
-    FA_TRY(ix->bin_base.reserve(bin_base.size()));
-    FA_TRY(ix->genome_cell.reserve(genome_cell.size()));
+    FA_TRY(ix->bin_base.reserve((size_t)n_contigs + 1));
+    FA_TRY(ix->genome_cell.reserve((size_t)n_genomes + 1));
     FA_CUDA(cudaMemcpyAsync(ix->genome_of_seq.p, genome_of.data(), genome_of.size() * 4, cudaMemcpyHostToDevice, st));
-    FA_CUDA(cudaMemcpyAsync(ix->bin_base.p, bin_base.data(), bin_base.size() * 4, cudaMemcpyHostToDevice, st));
-    FA_CUDA(cudaMemcpyAsync(ix->genome_cell.p, genome_cell.data(), genome_cell.size() * 4, cudaMemcpyHostToDevice, st));
+    FA_CUDA(cudaMemcpyAsync(d_first.p, first_contig.data(), first_contig.size() * 4, cudaMemcpyHostToDevice, st));
     FA_CUDA(cudaStreamSynchronize(st));       // the host vectors go out of scope
 
     // ---- statistics tables -------------------------------------------------------------------
@@ -135,6 +142,24 @@ int build_index(fa_index *ix, int *launches)
         contig_off_kernel<<<(unsigned int)((m + 255) / 256), 256, 0, st>>>(ix->ref.p, n, n_contigs, ix->contig_off.p);
         FA_CUDA(cudaGetLastError());
         if (launches) *launches += 1;
+    }
+    {
+        const int bin_w = ix->prm.frag_len - 20;                                   // computeCoreIdentity.hpp:191
+        DevBuf<uint8_t> tmp0;
+        contig_bins_kernel<<<(n_contigs + 1 + 255) / 256, 256, 0, st>>>(ix->ref.p, ix->contig_off.p, n_contigs, bin_w, ix->bin_base.p);
+        FA_CUDA(cudaGetLastError());
+        size_t sb = 0;
+        FA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, sb, ix->bin_base.p, ix->bin_base.p, (int64_t)n_contigs + 1, st));
+        FA_TRY(tmp0.reserve(sb + 16));
+        FA_CUDA(cub::DeviceScan::ExclusiveSum(tmp0.p, sb, ix->bin_base.p, ix->bin_base.p, (int64_t)n_contigs + 1, st));
+        genome_cells_kernel<<<(n_genomes + 1 + 255) / 256, 256, 0, st>>>(ix->bin_base.p, d_first.p, n_genomes, ix->genome_cell.p);
+        FA_CUDA(cudaGetLastError());
+        if (launches) *launches += 4;
+        uint32_t cells = 0;
+        FA_CUDA(cudaMemcpyAsync(&cells, ix->bin_base.p + n_contigs, 4, cudaMemcpyDeviceToHost, st));
+        FA_CUDA(cudaStreamSynchronize(st));
+        ix->n_cells = cells;
+        tmp0.release(); d_first.release();
     }
     ix->n_unique = 0;
     ix->dir_bits = 0;

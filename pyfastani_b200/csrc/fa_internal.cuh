@@ -58,7 +58,7 @@ struct fa_sketch {
     uint64_t n = 0;
     std::vector<int32_t>  seqs_by_genome;        // sequencesByFileInfo, winSketch.hpp:75
     std::vector<uint64_t> genome_len;            // Sketch._lengths, pyx:467
-    std::vector<int64_t>  contig_len;            // one per consumed sequence id (pyx:683)
+    uint64_t counter = 0;                        // Sketch._counter: sequence ids consumed (pyx:466, 683)
     uint64_t cur_len = 0;
     fa::SketchScratch sc;
     fa::PinBuf stage;
@@ -84,7 +84,7 @@ struct fa_index {
     uint64_t n_cells = 0;
     std::vector<int32_t>  seqs_by_genome;
     std::vector<uint64_t> genome_len;
-    std::vector<int64_t>  contig_len;
+    uint64_t n_contigs = 0;
     // statistics tables (fa_stat.h)
     int s_max = 0;
     fa::DevBuf<int32_t>  d_min_hits, d_min_shared;

@@ -1,0 +1,164 @@
+"""The reference's own tests (src/pyfastani/tests/test_ani.py, test_sketch.py) re-run against
+pyfastani_b200, with the same adapters (str, bytes, numpy view) and the same expected values."""
+import pickle
+import warnings
+
+import numpy as np
+import pytest
+
+import golden_io
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pf():
+    import pyfastani_b200
+    return pyfastani_b200
+
+
+@pytest.fixture(scope="module")
+def genomes():
+    return {n: golden_io.genome(n) for n in ("ecoli", "shigella")}
+
+
+ADAPTERS = {
+    "str": lambda b: b.decode("ascii"),
+    "bytes": lambda b: b,
+    "numpy": lambda b: np.frombuffer(b, dtype=np.uint8),
+    "bytearray": lambda b: bytearray(b),
+    "memoryview": lambda b: memoryview(b),
+}
+
+
+@pytest.mark.parametrize("adapter", list(ADAPTERS))
+def test_fastani_example(pf, genomes, adapter):          # test_ani.py:29-51
+    get = ADAPTERS[adapter]
+    sketch = pf.Sketch()
+    sketch.add_draft("Escherichia_coli_str_K12_MG1655", [get(c) for c in genomes["ecoli"]])
+    mapper = sketch.index()
+    hits = mapper.query_draft(map(get, genomes["shigella"]))
+    assert len(hits) == 1
+    assert hits[0].name == "Escherichia_coli_str_K12_MG1655"
+    assert hits[0].matches == 1303
+    assert hits[0].fragments == 1608
+    assert round(abs(hits[0].identity - 97.7507), 4) == 0
+
+
+def test_escherichia_minimizers(pf, genomes):           # test_ani.py:54-71
+    sketch = pf.Sketch()
+    assert sketch.window_size == 24
+    sketch.add_draft("Escherichia_coli_str_K12_MG1655", genomes["ecoli"])
+    assert len(sketch.minimizers) == 371301
+    mapper = sketch.index()
+    assert len(mapper.minimizers) == 371301
+    assert len(mapper.lookup_index) == 361568
+    hits = mapper.query_draft(genomes["ecoli"])
+    assert len(hits) == 1
+    assert (hits[0].matches, hits[0].fragments, hits[0].identity) == (1547, 1547, 100.0)
+
+
+def test_shigella_minimizers(pf, genomes):              # test_ani.py:74-91
+    sketch = pf.Sketch()
+    sketch.add_draft("Shigella_flexneri_2a_01", genomes["shigella"])
+    assert len(sketch.minimizers) == 386387
+    first = [(m.hash, m.sequence_id, m.window_position) for m in (sketch.minimizers[i] for i in range(4))]
+    assert first == [(21161528, 0, 0), (25007321, 0, 18), (159674326, 0, 24), (262432603, 0, 25)]
+    assert sketch.minimizers[-1] == sketch.minimizers[386386]
+    with pytest.raises(IndexError):
+        sketch.minimizers[386387]
+    mapper = sketch.index()
+    assert len(mapper.lookup_index) == 347908
+    hits = mapper.query_draft(genomes["shigella"])
+    assert (hits[0].matches, hits[0].fragments, hits[0].identity) == (1600, 1608, 100.0)
+
+
+def test_config1(pf, genomes):
+    sketch = pf.Sketch()
+    sketch.add_draft("shigella", genomes["shigella"])
+    mapper = sketch.index()
+    hits = mapper.query_genome(genomes["ecoli"][0])
+    assert hits == [pf.Hit("shigella", float.fromhex("0x1.86a7fap+6"), 1322, 1547)]
+    info = mapper.last_query_info
+    assert (info["fragments"], info["candidates"], info["mappings"]) == (1547, 5038, 4101)
+    assert mapper.query_genome(genomes["ecoli"][0], threads=4) == hits
+    with pytest.raises(ValueError):
+        mapper.query_genome(genomes["ecoli"][0], threads=-1)
+
+
+def test_sketch_pickling(pf, genomes):                  # test_ani.py:136-153
+    sketch = pf.Sketch()
+    sketch.add_draft("Escherichia_coli_str_K12_MG1655", genomes["ecoli"])
+    sketch = pickle.loads(pickle.dumps(sketch))
+    assert sketch.names == ["Escherichia_coli_str_K12_MG1655"]
+    assert len(sketch.minimizers) == 371301
+    mapper = sketch.index()
+    hits = mapper.query_draft(genomes["shigella"])
+    assert (hits[0].name, hits[0].matches, hits[0].fragments) == ("Escherichia_coli_str_K12_MG1655", 1303, 1608)
+    assert round(abs(hits[0].identity - 97.7507), 4) == 0
+
+
+def test_mapper_pickling(pf, genomes):                  # test_ani.py:156-173
+    sketch = pf.Sketch()
+    sketch.add_draft("Escherichia_coli_str_K12_MG1655", genomes["ecoli"])
+    mapper = pickle.loads(pickle.dumps(sketch.index()))
+    assert len(mapper.lookup_index) == 361568
+    hits = mapper.query_draft(genomes["shigella"])
+    assert (hits[0].name, hits[0].matches, hits[0].fragments) == ("Escherichia_coli_str_K12_MG1655", 1303, 1608)
+    assert round(abs(hits[0].identity - 97.7507), 4) == 0
+
+
+def test_reinit(pf):                                    # test_sketch.py:25-35
+    sketch = pf.Sketch(fragment_length=100)
+    sketch.add_genome("test", "ATGC" * 100)
+    assert sketch.names == ["test"] and sketch.fragment_length == 100
+    sketch.__init__(fragment_length=200)
+    assert sketch.names == [] and sketch.fragment_length == 200
+
+
+def test_add_draft_warnings(pf):                        # test_sketch.py:37-52
+    sketch = pf.Sketch()
+    with warnings.catch_warnings(record=True) as catch:
+        warnings.simplefilter("always")
+        sketch.add_draft("short_seq", ["ATGC" * 1000, "ATGC"])
+        assert len(catch) == 1
+    assert sketch.names == ["short_seq"]
+
+
+def test_pickle_small(pf):                              # test_sketch.py:54-61
+    sketch = pf.Sketch()
+    sketch.add_genome("short_seq", "ATGC" * 1000)
+    sketch2 = pickle.loads(pickle.dumps(sketch))
+    assert sketch2.names == ["short_seq"]
+    assert len(sketch2.minimizers) == len(sketch.minimizers)
+
+
+def test_query_warnings_and_views(pf):
+    rng = np.random.default_rng(3)
+    g = bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), 60_000))
+    sketch = pf.Sketch()
+    sketch.add_genome("g", g)
+    sketch.clear()
+    assert sketch.names == [] and len(sketch.minimizers) == 0
+    sketch.add_genome("g", g)
+    assert sketch.occurences_threshold == 2147483647
+    mapper = sketch.index()
+    assert sketch.names == [] and len(sketch.minimizers) == 0     # ownership moved, pyx:795-804
+    with warnings.catch_warnings(record=True) as catch:
+        warnings.simplefilter("always")
+        hits = mapper.query_draft([g, b"ACGTACGTAC"])
+        assert len(catch) == 1 and len(hits) == 1
+    assert mapper.query_draft([g[:2999]]) == []
+    li = mapper.lookup_index
+    key = next(iter(li))
+    assert key in li and (key + 1 in li) in (True, False)
+    pos = li[key]
+    assert all(isinstance(p, pf.Position) for p in pos)
+    with pytest.raises(KeyError):
+        li[0xFFFFFFFF]
+    with pytest.raises(TypeError):
+        li[key] = pos
+    k2, p2 = next(li.items())
+    assert k2 == key and p2 == pos
+    dev = pf.DeviceSequence.from_host(g)
+    assert mapper.query_genome(dev) == mapper.query_genome(g)
