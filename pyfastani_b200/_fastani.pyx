@@ -68,6 +68,7 @@ cdef extern from "fastani_b200.h" nogil:
         float ms_total
         uint64_t h2d_bytes
         uint64_t d2h_bytes
+        uint64_t l2_fallback
     ctypedef struct fa_sketch
     ctypedef struct fa_index
 
@@ -650,7 +651,7 @@ cdef class Mapper(_Parameterized):
                 "ms_h2d": info.ms_h2d, "ms_sketch": info.ms_sketch, "ms_lookup": info.ms_lookup,
                 "ms_seed_sort": info.ms_seed_sort, "ms_l1": info.ms_l1, "ms_l2": info.ms_l2,
                 "ms_cgi": info.ms_cgi, "ms_d2h": info.ms_d2h, "ms_total": info.ms_total,
-                "h2d_bytes": info.h2d_bytes, "d2h_bytes": info.d2h_bytes,
+                "h2d_bytes": info.h2d_bytes, "d2h_bytes": info.d2h_bytes, "l2_fallback": info.l2_fallback,
             }
         finally:
             free(out)

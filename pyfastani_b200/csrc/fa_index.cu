@@ -54,6 +54,14 @@ __global__ void dup_delta_kernel(const uint32_t *sorted_keys, const uint32_t *po
     atomicOr(&ref[a].w, d << 16);              // next duplicate of a
 }
 
+__global__ void make_hw_kernel(const RefMini *ref, uint64_t n, uint2 *hw)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const RefMini e = ref[i];
+    hw[i] = make_uint2(e.x, e.y | (e.w ? 0x80000000u : 0u));
+}
+
 // contig_off[s] = first ref index with seqId >= s (contigs without minimizers get empty ranges)
 __global__ void contig_off_kernel(const RefMini *ref, uint64_t n, uint32_t n_contigs, uint32_t *contig_off)
 {
@@ -189,6 +197,11 @@ int build_index(fa_index *ix, int *launches)
 
     // duplicate distances for the L2 sliding window
     dup_delta_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(keys_b.p, ix->pos_idx.p, n, ix->ref.p);
+    FA_CUDA(cudaGetLastError());
+    if (launches) *launches += 1;
+
+    FA_TRY(ix->hw.reserve(n + 4));
+    make_hw_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(ix->ref.p, n, ix->hw.p);
     FA_CUDA(cudaGetLastError());
     if (launches) *launches += 1;
 

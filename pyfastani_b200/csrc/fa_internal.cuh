@@ -72,6 +72,7 @@ struct fa_index {
     // position-ordered minimizers (minimizerIndex) and the hash -> positions table
     // (minimizerPosLookupIndex, winSketch.hpp:83-84) as CSR over sorted unique hashes
     fa::DevBuf<fa::RefMini> ref;
+    fa::DevBuf<uint2> hw;                        // (hash, wpos | has-duplicate-nearby << 31): the 8-byte stream L2 reads
     uint64_t n = 0, n_unique = 0;
     fa::DevBuf<uint32_t> pos_idx;                // ref indices grouped by hash, insertion order inside a group
     fa::DevBuf<uint32_t> ukeys, uoff;            // unique hashes, group offsets (n_unique + 1)

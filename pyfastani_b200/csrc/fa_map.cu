@@ -28,15 +28,20 @@ namespace fa {
 namespace {
 
 // device counters (Workspace::counters)
-enum { CT_MAXS = 0, CT_ERR = 1, CT_WORK = 2, CT_SCANNED = 3, CT_MAPPINGS = 4, CT_SKETCH_SUM = 5, CT_N = 8 };
+enum { CT_MAXS = 0, CT_ERR = 1, CT_WORK = 2, CT_SCANNED = 3, CT_MAPPINGS = 4, CT_SKETCH_SUM = 5, CT_REDO = 6, CT_WORK2 = 7, CT_N = 8 };
 enum { ERR_SORT_CAP = 1, ERR_S_MAX = 2 };
 
 constexpr int L2_THREADS = 64;          // candidates per L2 work item (upper bound)
-constexpr int L2_STATE_WORDS = 16384;   // u16 state entries per CTA (32 KiB)
+constexpr int L2_STATE_BYTES = 16384;   // per-CTA slide state of the fast kernel (u8 entries)
+constexpr int L2_STATE_WORDS = 16384;   // u16 entries of the exact fallback kernel (32 KiB)
+constexpr int L2_TAB_BITS = 11;         // classification table over the top bits of the hash
+constexpr int L2_TAB = 1 << L2_TAB_BITS;
+constexpr int32_t L2_REDO = INT32_MIN;  // Mapping.ref_start marker: redo this candidate in the fallback kernel
 
+// candidates per work item for sketch size s: all their state must fit the per-CTA budget
 __host__ __device__ inline int l2_threads_for(int s)
 {
-    int t = L2_STATE_WORDS / (s + 1);
+    int t = L2_STATE_BYTES / (((s + 1) + 3) & ~3);
     return t > L2_THREADS ? L2_THREADS : (t < 1 ? 1 : t);
 }
 
@@ -290,7 +295,7 @@ __device__ __forceinline__ uint32_t lb_wpos(const RefMini *ref, uint32_t lo, uin
 }
 
 __global__ void __launch_bounds__(L2_THREADS)
-l2_kernel(const Cand *cands, const uint32_t *cand_base, const uint32_t *work_base, int n_frags,
+l2_fallback_kernel(const Cand *cands, const uint32_t *cand_base, const uint32_t *work_base, int n_frags,
           const uint32_t *qhash, const uint64_t *seq_first, const int32_t *qs,
           const RefMini *ref, uint32_t n_ref, const uint32_t *contig_off, int frag_len, int cmw,
           const int32_t *min_shared, const uint32_t *id_off, const float *id_tab,
@@ -302,10 +307,11 @@ l2_kernel(const Cand *cands, const uint32_t *cand_base, const uint32_t *work_bas
     __shared__ uint32_t s_item;
     const int tid = threadIdx.x;
     const uint32_t n_work = work_base[n_frags];
+    if (counters[CT_REDO] == 0) return;        // nothing overflowed in the fast kernel (the usual case)
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_item = (uint32_t)atomicAdd(&counters[CT_WORK], 1ull);
+        if (tid == 0) s_item = (uint32_t)atomicAdd(&counters[CT_WORK2], 1ull);
         __syncthreads();
         const uint32_t item = s_item;
         if (item >= n_work) break;
@@ -316,7 +322,8 @@ l2_kernel(const Cand *cands, const uint32_t *cand_base, const uint32_t *work_bas
         const int s = qs[f];
         const int tpc = l2_threads_for(s);
         const uint32_t c = cand_base[f] + (item - work_base[f]) * tpc + tid;
-        const bool active = tid < tpc && c < cand_base[f + 1];
+        const bool active = tid < tpc && c < cand_base[f + 1] && maps[c].ref_start == L2_REDO;
+        if (!__syncthreads_or(active ? 1 : 0)) continue;
         const uint64_t qb = seq_first[f];
         for (int i = tid; i < s; i += L2_THREADS) s_q[i] = qhash[qb + i];
         for (int i = tid; i < (s + 1) * tpc; i += L2_THREADS) s_state[i] = 0;
@@ -389,9 +396,216 @@ l2_kernel(const Cand *cands, const uint32_t *cand_base, const uint32_t *work_bas
         const unsigned am = __activemask();
         const unsigned sc_sum = __reduce_add_sync(am, (unsigned)(max(end0, last) - beg));
         const unsigned mp_sum = __reduce_add_sync(am, pass ? 1u : 0u);
+        (void)sc_sum;                          // already counted by the fast kernel
+        if ((tid & 31) == __ffs(am) - 1 && mp_sum) atomicAdd(&counters[CT_MAPPINGS], (unsigned long long)mp_sum);
+    }
+}
+
+// ---- the fast L2 kernel ---------------------------------------------------------------------
+// Same state machine as SlideState above, reorganised for SIMT execution:
+//  * one EVENT (delete or insert of one reference minimizer) per loop iteration, chosen by
+//    comparing the two stream heads, so all lanes of a warp run the same instruction stream
+//    whatever mix of deletes and inserts their candidates need;
+//  * the reference stream is the 8-byte (hash, wpos) array `hw`, prefetched two elements ahead
+//    on each side; bit 31 of wpos flags the rare elements that have a duplicate hash nearby,
+//    only those fetch the distances from the full record;
+//  * query-hash classification goes through a 2048-entry table over the top hash bits followed
+//    by a fixed number of bisection steps (uniform across the CTA);
+//  * state is one byte per bucket (7-bit count + match bit), four buckets per 32-bit word, with
+//    each thread's words in its own bank.  A count that would pass 127 marks the candidate for
+//    the exact fallback kernel above (never seen outside adversarial sketches).
+struct FastState {
+    uint8_t *base;        // this thread's first byte
+    int stride4;          // tpc * 4: byte distance between consecutive groups of four buckets
+    int istar, sigma, shared;
+    bool overflow;
+    __device__ __forceinline__ uint8_t *at(int b) const { return base + (b >> 2) * stride4 + (b & 3); }
+};
+
+__device__ __forceinline__ void fast_apply(FastState &S, bool is_del, bool match, int lb)
+{
+    if (match) {
+        uint8_t *p = S.at(lb + 1);
+        const uint8_t v = *p;
+        *p = is_del ? (uint8_t)(v & 0x7F) : (uint8_t)(v | 0x80);
+        if (lb + 1 <= S.istar) S.shared += is_del ? -1 : 1;
+        return;
+    }
+    uint8_t *p = S.at(lb);
+    uint8_t v = *p;
+    if (!is_del) {
+        if ((v & 0x7F) == 0x7F) { S.overflow = true; return; }
+        v += 1; *p = v;
+        if (lb < S.istar) {
+            if (S.sigma > 0) S.sigma--;
+            else {
+                const uint8_t a = (lb == S.istar) ? v : *S.at(S.istar);
+                S.shared -= a >> 7;
+                S.istar--;
+                S.sigma = (lb == S.istar) ? (v & 0x7F) : (*S.at(S.istar) & 0x7F);
+            }
+        }
+    } else {
+        v -= 1; *p = v;
+        if (lb <= S.istar) {
+            const int c = (lb == S.istar) ? (v & 0x7F) : (*S.at(S.istar) & 0x7F);
+            const bool grow = (lb < S.istar) ? (S.sigma >= c) : (S.sigma > c);
+            if (grow) { S.istar++; S.shared += *S.at(S.istar) >> 7; S.sigma = 0; }
+            else if (lb < S.istar) S.sigma++;
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t lb_hw(const uint2 *hw, uint32_t lo, uint32_t hi, int target)
+{
+    while (lo < hi) { uint32_t mid = lo + ((hi - lo) >> 1); if ((int)(hw[mid].y & 0x7FFFFFFFu) < target) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+__global__ void __launch_bounds__(L2_THREADS)
+l2_fast_kernel(const Cand *cands, const uint32_t *cand_base, const uint32_t *work_base, int n_frags,
+               const uint32_t *qhash, const uint64_t *seq_first, const int32_t *qs,
+               const RefMini *ref, const uint2 *hw, uint32_t n_ref, const uint32_t *contig_off, int frag_len, int cmw,
+               const int32_t *min_shared, const uint32_t *id_off, const float *id_tab,
+               Mapping *maps, unsigned long long *counters, int q_cap)
+{
+    extern __shared__ __align__(16) uint8_t l2_smem[];
+    uint32_t *s_q = reinterpret_cast<uint32_t *>(l2_smem);
+    uint16_t *s_tab = reinterpret_cast<uint16_t *>(s_q + q_cap);            // L2_TAB + 2 entries
+    uint8_t *s_state = reinterpret_cast<uint8_t *>(s_tab + L2_TAB + 2);       // L2_STATE_BYTES, 4-byte aligned
+    __shared__ uint32_t s_item;
+    __shared__ int s_maxlen, s_cached_f;
+    const int tid = threadIdx.x;
+    const uint32_t n_work = work_base[n_frags];
+    if (tid == 0) s_cached_f = -1;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = (uint32_t)atomicAdd(&counters[CT_WORK], 1ull);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= n_work) break;
+        int lo = 0, hi = n_frags - 1;
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (work_base[mid] <= item) lo = mid; else hi = mid - 1; }
+        const int f = lo;
+        const int s = qs[f];
+        const int tpc = l2_threads_for(s);
+        const uint32_t c = cand_base[f] + (item - work_base[f]) * tpc + tid;
+        const bool active = tid < tpc && c < cand_base[f + 1];
+        if (s_cached_f != f) {
+            // query sketch + classification table: tab[x] = #{q : q < x << (32 - bits)}
+            const uint64_t qb = seq_first[f];
+            for (int i = tid; i < s; i += L2_THREADS) s_q[i] = qhash[qb + i];
+            if (tid == 0) s_maxlen = 0;
+            __syncthreads();
+            for (int x = tid; x <= L2_TAB; x += L2_THREADS) {
+                int l = 0, r = s;
+                if (x == L2_TAB) l = s;
+                else {
+                    const uint32_t target = (uint32_t)x << (32 - L2_TAB_BITS);
+                    while (l < r) { int mid = (l + r) >> 1; if (s_q[mid] < target) l = mid + 1; else r = mid; }
+                }
+                s_tab[x] = (uint16_t)l;
+            }
+            __syncthreads();
+            int ml = 0;
+            for (int x = tid; x < L2_TAB; x += L2_THREADS) ml = max(ml, (int)s_tab[x + 1] - (int)s_tab[x]);
+            atomicMax(&s_maxlen, ml);
+        }
+        {   // clear the state words this work item uses
+            uint32_t *w = reinterpret_cast<uint32_t *>(s_state);
+            const int nwords = ((s + 4) >> 2) * tpc;
+            for (int i = tid; i < nwords; i += L2_THREADS) w[i] = 0;
+        }
+        __syncthreads();
+        if (tid == 0) s_cached_f = f;
+        int nsteps = 0;
+        while ((1 << nsteps) <= s_maxlen) nsteps++;                            // bisection steps inside one table slot
+        if (!active) continue;
+
+        const Cand cd = cands[c];
+        const int seq = (int)ref[cd.hint].z;
+        const uint32_t c1 = contig_off[seq + 1];
+        // Sketch::searchIndex x3 (computeMap.hpp:421-433), restricted to the candidate's contig
+        const uint32_t beg = lb_hw(hw, contig_off[seq], cd.hint, cd.start);
+        const int wpos_beg = (int)(hw[beg].y & 0x7FFFFFFFu);
+        const uint32_t end0 = lb_hw(hw, beg, min(c1, beg + (uint32_t)cmw + 1u), wpos_beg + cmw);
+        const uint32_t last = lb_hw(hw, end0, c1, cd.end + frag_len);
+
+        FastState S;
+        S.base = s_state + tid * 4; S.stride4 = tpc * 4; S.istar = s; S.sigma = 0; S.shared = 0; S.overflow = false;
+
+        // one event: classify the hash, resolve duplicates (rare), update the state
+        auto event = [&](bool is_del, uint32_t j, uint2 e, uint32_t win_beg, uint32_t win_end) {
+            if (e.y & 0x80000000u) {                                           // a same-hash neighbour exists
+                const uint32_t d = ref[j].w;
+                if (is_del) { const uint32_t dn = d >> 16; if (dn && j + dn < win_end) return; }
+                else { const uint32_t dp = d & 0xFFFFu; if (dp && j >= dp && j - dp >= win_beg) return; }
+            }
+            const uint32_t h = e.x;
+            int l = s_tab[h >> (32 - L2_TAB_BITS)], r = s_tab[(h >> (32 - L2_TAB_BITS)) + 1];
+            for (int i = 0; i < nsteps; i++) {
+                const int mid = (l + r) >> 1;
+                const bool go = l < r && s_q[min(mid, s - 1)] < h;
+                const bool shrink = l < r && !go;
+                l = go ? mid + 1 : l;
+                r = shrink ? mid : r;
+            }
+            const bool match = l < s && s_q[min(l, s - 1)] == h;
+            fast_apply(S, is_del, match, l);
+        };
+
+        const uint32_t nmax = n_ref - 1;
+        for (uint32_t j = beg; j < end0; j++) event(false, j, hw[j], beg, j);           // first super-window
+
+        int best = 0, first_pos = 0, last_pos = 0;
+        uint32_t b = beg, e = end0;
+        if (end0 < last) {
+            // stream heads: cur_b = hw[b]; nb = hw[b+1], nb2 = hw[b+2]; ne = hw[e], ne2 = hw[e+1]
+            uint2 cur_b = hw[b], nb = hw[min(b + 1, nmax)], nb2 = hw[min(b + 2, nmax)];
+            uint2 ne = hw[e], ne2 = hw[min(e + 1, nmax)];
+            best = 0; first_pos = last_pos = wpos_beg;                                   // evaluation of the first window (shared >= 0 == best)
+            if (S.shared > 0) best = S.shared;
+            int td = (int)(nb.y & 0x7FFFFFFFu), ti = (int)(ne.y & 0x7FFFFFFFu) - cmw + 1;
+            int T = min(td, ti);
+            bool go_on = !(ti == T && e + 1 >= last);
+            while (go_on) {
+                const bool is_del = td <= ti;                                              // delete first inside a group
+                if (is_del) {
+                    event(true, b, cur_b, b, e);
+                    b++; cur_b = nb; nb = nb2; nb2 = hw[min(b + 2, nmax)];
+                } else {
+                    event(false, e, ne, b, e);
+                    e++; ne = ne2; ne2 = hw[min(e + 1, nmax)];
+                }
+                td = (int)(nb.y & 0x7FFFFFFFu);
+                ti = (e < last) ? (int)(ne.y & 0x7FFFFFFFu) - cmw + 1 : INT32_MAX;
+                const int Tn = min(td, ti);
+                if (Tn != T) {                                                             // group complete: evaluate (computeMap.hpp:467-481)
+                    const int wb = (int)(cur_b.y & 0x7FFFFFFFu);
+                    if (S.shared > best) { best = S.shared; first_pos = last_pos = wb; }
+                    else if (S.shared == best) last_pos = wb;
+                    T = Tn;
+                    go_on = !(ti == Tn && e + 1 >= last);
+                }
+            }
+        }
+        Mapping mp;
+        mp.seq = seq;
+        mp.ref_start = (first_pos + last_pos) / 2;                        // computeMap.hpp:492
+        const bool pass = s > 0 && best >= min_shared[s] && !S.overflow;
+        mp.shared = pass ? best : -1 - best;
+        mp.identity = pass ? id_tab[id_off[s] + best] : 0.0f;
+        if (S.overflow) { mp.ref_start = L2_REDO; mp.shared = -1; }
+        maps[c] = mp;
+        const unsigned am = __activemask();
+        const unsigned sc_sum = __reduce_add_sync(am, (unsigned)(max(end0, last) - beg));
+        const unsigned mp_sum = __reduce_add_sync(am, pass ? 1u : 0u);
+        const unsigned ov_sum = __reduce_add_sync(am, S.overflow ? 1u : 0u);
         if ((tid & 31) == __ffs(am) - 1) {
             atomicAdd(&counters[CT_SCANNED], (unsigned long long)sc_sum);
             if (mp_sum) atomicAdd(&counters[CT_MAPPINGS], (unsigned long long)mp_sum);
+            if (ov_sum) atomicAdd(&counters[CT_REDO], (unsigned long long)ov_sum);
         }
     }
 }
@@ -641,20 +855,32 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
                 FA_CUDA(cudaGetLastError()); launches++;
                 FA_CUDA(cudaEventRecord(ws.ev[5], st));
                 // ---- L2 -----------------------------------------------------------------------
-                const int q_cap = std::max(max_s, 1);
-                const size_t smem = (size_t)q_cap * 4 + (size_t)L2_STATE_WORDS * 2;
-                if (smem > 48 * 1024) FA_CUDA(cudaFuncSetAttribute(l2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                const int q_cap = (std::max(max_s, 1) + 3) & ~3;
                 int dev_sms = 148;
                 cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ix->device);
-                const uint32_t grid = std::min<uint32_t>(W, (uint32_t)dev_sms * 16u);
-                l2_kernel<<<grid, L2_THREADS, smem, st>>>(ws.cands.p, ws.frag_cands.p, ws.work_base.p, F, ws.qhash.p,
-                                                          ws.sk.seq_first.p, ws.qs.p, ix->ref.p, (uint32_t)ix->n, ix->contig_off.p, L, cmw,
-                                                          ix->d_min_shared.p, ix->d_id_off.p, ix->d_identity.p, ws.maps.p,
-                                                          ws.counters.p, q_cap);
-                FA_CUDA(cudaGetLastError()); launches++;
+                {
+                    const size_t smem = (size_t)q_cap * 4 + (size_t)(L2_TAB + 2) * 2 + (size_t)L2_STATE_BYTES;
+                    if (smem > 48 * 1024) FA_CUDA(cudaFuncSetAttribute(l2_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    const uint32_t grid = std::min<uint32_t>(W, (uint32_t)dev_sms * 16u);
+                    l2_fast_kernel<<<grid, L2_THREADS, smem, st>>>(ws.cands.p, ws.frag_cands.p, ws.work_base.p, F, ws.qhash.p,
+                                                                   ws.sk.seq_first.p, ws.qs.p, ix->ref.p, ix->hw.p, (uint32_t)ix->n,
+                                                                   ix->contig_off.p, L, cmw, ix->d_min_shared.p, ix->d_id_off.p,
+                                                                   ix->d_identity.p, ws.maps.p, ws.counters.p, q_cap);
+                    FA_CUDA(cudaGetLastError()); launches++;
+                }
+                {   // exact fallback for candidates whose 7-bit bucket counts overflowed (returns at once if none)
+                    const size_t smem = (size_t)q_cap * 4 + (size_t)L2_STATE_WORDS * 2;
+                    if (smem > 48 * 1024) FA_CUDA(cudaFuncSetAttribute(l2_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    const uint32_t grid = std::min<uint32_t>(W, (uint32_t)dev_sms * 4u);
+                    l2_fallback_kernel<<<grid, L2_THREADS, smem, st>>>(ws.cands.p, ws.frag_cands.p, ws.work_base.p, F, ws.qhash.p,
+                                                                       ws.sk.seq_first.p, ws.qs.p, ix->ref.p, (uint32_t)ix->n, ix->contig_off.p, L, cmw,
+                                                                       ix->d_min_shared.p, ix->d_id_off.p, ix->d_identity.p, ws.maps.p,
+                                                                       ws.counters.p, q_cap);
+                    FA_CUDA(cudaGetLastError()); launches++;
+                }
                 FA_CUDA(cudaEventRecord(ws.ev[6], st));
                 // ---- CGI ----------------------------------------------------------------------
-                cgi_best_kernel<<<std::min<uint32_t>((uint32_t)((C + 255) / 256), (uint32_t)dev_sms * 8u), 256, 0, st>>>(
+                cgi_best_kernel<<<std::min<uint32_t>((uint32_t)((C + 255) / 256), 148u * 8u), 256, 0, st>>>(
                     ws.cands.p, ws.maps.p, ws.frag_cands.p, F, ix->genome_of_seq.p, ix->bin_base.p, L - 20, ws.cells.p);
                 FA_CUDA(cudaGetLastError()); launches++;
             } else {
@@ -676,7 +902,7 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
         FA_CUDA(cudaEventRecord(ws.ev[8], st));
         FA_CUDA(cudaStreamSynchronize(st));                                   // sync 3: results
         qi.d2h_bytes = (uint64_t)G * 8 + CT_N * 8 * 2 + 16;
-        qi.candidates = C; qi.scanned = h_ct[CT_SCANNED]; qi.mappings = h_ct[CT_MAPPINGS];
+        qi.candidates = C; qi.scanned = h_ct[CT_SCANNED]; qi.mappings = h_ct[CT_MAPPINGS]; qi.l2_fallback = h_ct[CT_REDO];
         h_count.assign(h_c, h_c + G); h_ident.assign(h_i, h_i + G);
         ws.last_cands = C; ws.last_frags = (uint64_t)F;
         float ms;

@@ -148,3 +148,25 @@ def test_full_size_properties():
         assert hits[0]["identity"] > 99.9
         rc_hits, _ = ix.query_genome(synth.revcomp(g[:999_000]))
         assert len(rc_hits) == 1 and rc_hits[0]["ref_genome"] == i and rc_hits[0]["matches"] >= 330
+
+
+def test_low_complexity_fragments_take_the_exact_fallback():
+    """Fragments that are mostly poly-A have tiny sketches, so one bucket of the L2 state holds
+    more than 127 reference-only hashes: the fast kernel hands those candidates to the exact
+    fallback kernel.  Results must still equal the oracle's, field by field."""
+    rng = np.random.default_rng(77)
+    ref = synth.to_bytes(synth.random_codes(rng, 40_000))
+    frags = []
+    for i in range(8):
+        off = 2_000 + 4_000 * i
+        frags.append(ref[off:off + 40 + 15 * i] + b"A" * (3000 - 40 - 15 * i))
+    query = b"".join(frags) + ref[1000:7000]
+    sk = capi.Sketch(); sk.add_genome("r", ref); sk.add_genome("r2", synth.revcomp(ref)); ix = sk.index()
+    osk = _port().sketch(); osk.add_genome("r", ref); osk.add_genome("r2", synth.revcomp(ref)); osk.index()
+    hits, out = ix.query_genome(query, dump=True)
+    ohits, oinfo = osk.query_genome(query, dump=True)
+    assert out["info"]["l2_fallback"] > 0
+    assert len(oinfo["candidates"]) > 8
+    assert np.array_equal(out["candidates"], oinfo["candidates"])
+    assert np.array_equal(out["mappings"], oinfo["mappings"])
+    assert np.array_equal(hits, ohits)
