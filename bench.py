@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--seed", type=int, default=12345)
     ap.add_argument("--cpu-sample-refs", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="bracket the device-timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -247,6 +249,9 @@ def run_b200(a):
     stage = {}
     dev_ms = 0.0
     launches = 0
+    if a.profile:
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.start()
     for _ in range(a.steps):
         mapper.query_genome(q_dev)
         inf = mapper.last_query_info
@@ -255,6 +260,9 @@ def run_b200(a):
         for k, v in inf.items():
             if k.startswith("ms_"):
                 stage[k] = stage.get(k, 0.0) + v
+    if a.profile:
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
     barrier()
     dev_ms = max_over_ranks(dev_ms)
     inf = dict(mapper.last_query_info)
