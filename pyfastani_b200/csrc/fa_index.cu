@@ -200,7 +200,8 @@ int build_index(fa_index *ix, int *launches)
     FA_CUDA(cudaGetLastError());
     if (launches) *launches += 1;
 
-    FA_TRY(ix->hw.reserve(n + 4));
+    FA_TRY(ix->hw.reserve(n + 8));            // L2 reads whole 32-byte chunks and one chunk ahead
+    FA_CUDA(cudaMemsetAsync(ix->hw.p + n, 0, 8 * sizeof(uint2), st));
     make_hw_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(ix->ref.p, n, ix->hw.p);
     FA_CUDA(cudaGetLastError());
     if (launches) *launches += 1;

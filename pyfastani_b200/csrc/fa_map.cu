@@ -31,17 +31,25 @@ namespace {
 enum { CT_MAXS = 0, CT_ERR = 1, CT_WORK = 2, CT_SCANNED = 3, CT_MAPPINGS = 4, CT_SKETCH_SUM = 5, CT_REDO = 6, CT_WORK2 = 7, CT_N = 8 };
 enum { ERR_SORT_CAP = 1, ERR_S_MAX = 2 };
 
-constexpr int L2_THREADS = 64;          // candidates per L2 work item (upper bound)
-constexpr int L2_STATE_BYTES = 16384;   // per-CTA slide state of the fast kernel (u8 entries)
-constexpr int L2_STATE_WORDS = 16384;   // u16 entries of the exact fallback kernel (32 KiB)
+constexpr int L2_THREADS = 64;          // lanes per L2 CTA: each lane slides one candidate at a time
+constexpr int L2_ITEM = 128;            // candidates of one fragment per work item (lanes pull them one by one)
+constexpr int L2_STATE_MAX = 96 * 1024; // cap of the per-CTA slide state (larger sketches use fewer lanes)
+constexpr int L2_FB_STATE = 32 * 1024;  // u16 state of the exact fallback kernel
 constexpr int L2_TAB_BITS = 11;         // classification table over the top bits of the hash
 constexpr int L2_TAB = 1 << L2_TAB_BITS;
+constexpr int L2_QPAD = 8;              // sentinel entries behind the staged query sketch
 constexpr int32_t L2_REDO = INT32_MIN;  // Mapping.ref_start marker: redo this candidate in the fallback kernel
 
-// candidates per work item for sketch size s: all their state must fit the per-CTA budget
-__host__ __device__ inline int l2_threads_for(int s)
+// state words (four one-byte buckets each) a sketch of size s needs per lane, and the lanes that fit
+__host__ __device__ inline int l2_words_for(int s) { return (s + 4) >> 2; }
+__host__ __device__ inline int l2_lanes_for(int s, int state_bytes)
 {
-    int t = L2_STATE_BYTES / (((s + 1) + 3) & ~3);
+    int t = state_bytes / (l2_words_for(s) * 4);
+    return t > L2_THREADS ? L2_THREADS : (t < 1 ? 1 : t);
+}
+__host__ __device__ inline int l2_fb_lanes_for(int s)
+{
+    int t = L2_FB_STATE / ((s + 1) * 2);
     return t > L2_THREADS ? L2_THREADS : (t < 1 ? 1 : t);
 }
 
@@ -241,17 +249,14 @@ candidates_kernel(const uint64_t *seeds, const uint64_t *seed_base, const int32_
     if (!FILL && tid == 0) frag_cands[f] = heads_before;
 }
 
-__global__ void work_items_kernel(const uint32_t *frag_cands_counts, const int32_t *qs, int n_frags, uint32_t *work)
+__global__ void work_items_kernel(const uint32_t *frag_cands_counts, int n_frags, uint32_t *work)
 {
     int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f > n_frags) return;
-    if (f == n_frags) { work[f] = 0; return; }
-    const uint32_t c = frag_cands_counts[f];
-    const int tpc = l2_threads_for(qs[f]);
-    work[f] = (c + tpc - 1) / tpc;
+    work[f] = f == n_frags ? 0u : (frag_cands_counts[f] + L2_ITEM - 1) / L2_ITEM;
 }
 
-// ---- L2: sliding super-window Jaccard, one thread per candidate --------------------------------
+// ---- L2: sliding super-window Jaccard, one lane per candidate ----------------------------------
 // State per candidate (SURVEY.md A.5 in incremental form).  Q = sorted query sketch q_1 < ... < q_s.
 // A reference hash that is in Q toggles a match bit M(i); one that is not falls in bucket
 // b = #{q < h} and toggles a distinct-hash count cnt[b].  With
@@ -262,6 +267,55 @@ __global__ void work_items_kernel(const uint32_t *frag_cands_counts, const int32
 // slidingMap.hpp:137-284 without the tree.  Duplicate hashes inside a window are resolved with
 // the distances stored at index time (RefMini.w), mirroring the wposR bookkeeping of
 // slidingMap.hpp:150-155, 178-205.
+
+__device__ __forceinline__ uint32_t lb_hw(const uint2 *hw, uint32_t lo, uint32_t hi, int target)
+{
+    while (lo < hi) { uint32_t mid = lo + ((hi - lo) >> 1); if ((int)(hw[mid].y & 0x7FFFFFFFu) < target) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// The three Sketch::searchIndex calls of computeL2MappedRegions (computeMap.hpp:421-433) for every
+// candidate, restricted to the candidate's contig.  Minimizer positions grow strictly inside a
+// contig (one minimizer per window at most), so an index distance never exceeds the position
+// distance and each search runs over a short range.
+struct Prep {
+    uint32_t beg, end0, last;   // first super-window [beg, end0); the slide stops when its end reaches `last`
+    int32_t  seq;               // refSeqId
+};
+
+__global__ void __launch_bounds__(256)
+l2_prep_kernel(const Cand *cands, const uint32_t *cand_base, int n_frags, const RefMini *ref, const uint2 *hw,
+               const uint32_t *contig_off, int frag_len, int cmw, Prep *prep, unsigned long long *counters)
+{
+    const uint32_t n = cand_base[n_frags];
+    unsigned long long scanned = 0;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        const Cand cd = cands[c];
+        const RefMini rh = ref[cd.hint];
+        const int seq = (int)rh.z;
+        const uint32_t c0 = contig_off[seq], c1 = contig_off[seq + 1];
+        const uint32_t back = (uint32_t)((int)rh.y - cd.start);               // wpos[hint] >= start
+        uint32_t lo = cd.hint - min(back, cd.hint - c0);
+        if (lo > c0 && (int)(hw[lo].y & 0x7FFFFFFFu) >= cd.start) lo = c0;     // positions not strictly increasing: full range
+        const uint32_t beg = lb_hw(hw, lo, cd.hint, cd.start);
+        const int wpos_beg = (int)(hw[beg].y & 0x7FFFFFFFu);
+        const uint32_t end0 = lb_hw(hw, beg, min(c1, beg + (uint32_t)cmw + 1u), wpos_beg + cmw);
+        uint32_t hi = c1;
+        const int target = cd.end + frag_len;
+        if (end0 < c1) {
+            const int d = target - (int)(hw[end0].y & 0x7FFFFFFFu);
+            hi = d <= 0 ? end0 : (uint32_t)min((unsigned long long)c1, (unsigned long long)end0 + (unsigned long long)d);
+            if (hi < c1 && (int)(hw[hi].y & 0x7FFFFFFFu) < target) hi = c1;
+        }
+        const uint32_t last = lb_hw(hw, end0, hi, target);
+        prep[c] = Prep{beg, end0, last, seq};
+        scanned += max(end0, last) - beg;
+    }
+    for (int o = 16; o > 0; o >>= 1) scanned += __shfl_xor_sync(0xFFFFFFFFu, scanned, o);
+    if ((threadIdx.x & 31) == 0 && scanned) atomicAdd(&counters[CT_SCANNED], scanned);
+}
+
+// ---- exact fallback (16-bit bucket counts, binary-search classification) -------------------------
 struct SlideState {
     uint16_t *st;        // st[b * stride]: bit 15 = M(b) (b >= 1), bits 0..14 = cnt[b]
     int stride, s;
@@ -288,16 +342,10 @@ struct SlideState {
     __device__ __forceinline__ void del_match(int i) { at(i) &= 0x7FFF; if (i <= istar) shared--; }
 };
 
-__device__ __forceinline__ uint32_t lb_wpos(const RefMini *ref, uint32_t lo, uint32_t hi, int target)
-{
-    while (lo < hi) { uint32_t mid = lo + ((hi - lo) >> 1); if ((int)ref[mid].y < target) lo = mid + 1; else hi = mid; }
-    return lo;
-}
-
 __global__ void __launch_bounds__(L2_THREADS)
-l2_fallback_kernel(const Cand *cands, const uint32_t *cand_base, const uint32_t *work_base, int n_frags,
+l2_fallback_kernel(const Prep *prep, const uint32_t *cand_base, const uint32_t *work_base, int n_frags,
           const uint32_t *qhash, const uint64_t *seq_first, const int32_t *qs,
-          const RefMini *ref, uint32_t n_ref, const uint32_t *contig_off, int frag_len, int cmw,
+          const RefMini *ref, uint32_t n_ref, int cmw,
           const int32_t *min_shared, const uint32_t *id_off, const float *id_tab,
           Mapping *maps, unsigned long long *counters, int q_cap)
 {
@@ -320,161 +368,306 @@ l2_fallback_kernel(const Cand *cands, const uint32_t *cand_base, const uint32_t 
         while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (work_base[mid] <= item) lo = mid; else hi = mid - 1; }
         const int f = lo;
         const int s = qs[f];
-        const int tpc = l2_threads_for(s);
-        const uint32_t c = cand_base[f] + (item - work_base[f]) * tpc + tid;
-        const bool active = tid < tpc && c < cand_base[f + 1] && maps[c].ref_start == L2_REDO;
-        if (!__syncthreads_or(active ? 1 : 0)) continue;
-        const uint64_t qb = seq_first[f];
-        for (int i = tid; i < s; i += L2_THREADS) s_q[i] = qhash[qb + i];
-        for (int i = tid; i < (s + 1) * tpc; i += L2_THREADS) s_state[i] = 0;
-        __syncthreads();
-        if (!active) continue;
+        const int tpc = l2_fb_lanes_for(s);
+        const uint32_t c_lo = cand_base[f] + (item - work_base[f]) * L2_ITEM;
+        const uint32_t c_hi = min(c_lo + (uint32_t)L2_ITEM, cand_base[f + 1]);
+        bool staged = false;
+        for (uint32_t c0 = c_lo; c0 < c_hi; c0 += tpc) {
+            const uint32_t c = c0 + tid;
+            const bool active = tid < tpc && c < c_hi && maps[c].ref_start == L2_REDO;
+            if (!__syncthreads_or(active ? 1 : 0)) continue;
+            if (!staged) {
+                const uint64_t qb = seq_first[f];
+                for (int i = tid; i < s; i += L2_THREADS) s_q[i] = qhash[qb + i];
+                staged = true;
+            }
+            for (int i = tid; i < (s + 1) * tpc; i += L2_THREADS) s_state[i] = 0;
+            __syncthreads();
+            if (!active) continue;
 
-        const Cand cd = cands[c];
-        const int seq = (int)ref[cd.hint].z;
-        const uint32_t c1 = contig_off[seq + 1];
-        // Sketch::searchIndex x3 (computeMap.hpp:421-433), restricted to the candidate's contig
-        const uint32_t beg = lb_wpos(ref, contig_off[seq], cd.hint, cd.start);
-        const RefMini rbeg = ref[beg];
-        const uint32_t end0 = lb_wpos(ref, beg, c1, (int)rbeg.y + cmw);
-        const uint32_t last = lb_wpos(ref, end0, c1, cd.end + frag_len);
+            const Prep pp = prep[c];
+            const uint32_t beg = pp.beg, end0 = pp.end0, last = pp.last;
+            const RefMini rbeg = ref[beg];
 
-        SlideState S;
-        S.st = s_state + tid; S.stride = tpc; S.s = s; S.istar = s; S.sigma = 0; S.shared = 0;
+            SlideState S;
+            S.st = s_state + tid; S.stride = tpc; S.s = s; S.istar = s; S.sigma = 0; S.shared = 0;
 
-        auto classify = [&](uint32_t h, int &b) -> bool {      // b = #{q < h}; true if q_{b+1} == h
-            int l = 0, r = s;
-            while (l < r) { int mid = (l + r) >> 1; if (s_q[mid] < h) l = mid + 1; else r = mid; }
-            b = l;
-            return l < s && s_q[l] == h;
-        };
-        auto insert = [&](uint32_t j, const RefMini &e, uint32_t win_beg) {      // window is [win_beg, j)
-            const uint32_t dprev = e.w & 0xFFFFu;
-            if (dprev && j >= dprev && j - dprev >= win_beg) return;      // same hash already present (REV)
-            int b;
-            if (classify(e.x, b)) S.ins_match(b + 1); else S.ins_only(b);
-        };
-        auto remove = [&](uint32_t j, const RefMini &e, uint32_t win_end) {      // window is [j, win_end)
-            const uint32_t dnext = e.w >> 16;
-            if (dnext && j + dnext < win_end) return;                     // a later copy keeps the hash present (NOOP)
-            int b;
-            if (classify(e.x, b)) S.del_match(b + 1); else S.del_only(b);
-        };
+            auto classify = [&](uint32_t h, int &b) -> bool {      // b = #{q < h}; true if q_{b+1} == h
+                int l = 0, r = s;
+                while (l < r) { int mid = (l + r) >> 1; if (s_q[mid] < h) l = mid + 1; else r = mid; }
+                b = l;
+                return l < s && s_q[l] == h;
+            };
+            auto insert = [&](uint32_t j, const RefMini &e, uint32_t win_beg) {      // window is [win_beg, j)
+                const uint32_t dprev = e.w & 0xFFFFu;
+                if (dprev && j >= dprev && j - dprev >= win_beg) return;      // same hash already present (REV)
+                int b;
+                if (classify(e.x, b)) S.ins_match(b + 1); else S.ins_only(b);
+            };
+            auto remove = [&](uint32_t j, const RefMini &e, uint32_t win_end) {      // window is [j, win_end)
+                const uint32_t dnext = e.w >> 16;
+                if (dnext && j + dnext < win_end) return;                     // a later copy keeps the hash present (NOOP)
+                int b;
+                if (classify(e.x, b)) S.del_match(b + 1); else S.del_only(b);
+            };
 
-        for (uint32_t j = beg; j < end0; j++) insert(j, ref[j], beg);     // first super-window, computeMap.hpp:446
+            for (uint32_t j = beg; j < end0; j++) insert(j, ref[j], beg);     // first super-window, computeMap.hpp:446
 
-        // MIIteratorL2 (MIIteratorL2.hpp:54-96) + the slide loop of computeMap.hpp:453-488
-        uint32_t sw_beg = beg, sw_end = end0, prev_end = end0;
-        int sw_pos = (int)rbeg.y;
-        int best = 0, first_pos = 0, last_pos = 0;
-        const bool runs = end0 < last;
-        RefMini e_b = rbeg, e_b1 = runs ? ref[beg + 1] : rbeg, e_e = runs ? ref[end0] : rbeg, old_b = rbeg, old_e = rbeg;
-        bool adv_b = false, adv_e = false;
-        while (sw_end < last) {
-            if (adv_b) remove(sw_beg - 1, old_b, prev_end);               // :459-460
-            if (adv_e) insert(sw_end - 1, old_e, sw_beg);                 // :463-464
-            const int wb = (int)e_b.y;
-            if (S.shared > best) { best = S.shared; first_pos = last_pos = wb; }     // :467-476
-            else if (S.shared == best) last_pos = wb;                                // :477-481
-            const int d1 = (int)e_b1.y - sw_pos;
-            const int d2 = (int)e_e.y - (sw_pos + cmw - 1);
-            const int adv = min(d1, d2);
-            sw_pos += adv;
-            adv_b = adv == d1; adv_e = adv == d2;
-            prev_end = sw_end;
-            if (adv_b) { old_b = e_b; e_b = e_b1; sw_beg++; if (sw_beg + 1 < n_ref) e_b1 = ref[sw_beg + 1]; }
-            if (adv_e) { old_e = e_e; sw_end++; if (sw_end < last) e_e = ref[sw_end]; }
+            // MIIteratorL2 (MIIteratorL2.hpp:54-96) + the slide loop of computeMap.hpp:453-488
+            uint32_t sw_beg = beg, sw_end = end0, prev_end = end0;
+            int sw_pos = (int)rbeg.y;
+            int best = 0, first_pos = 0, last_pos = 0;
+            const bool runs = end0 < last;
+            RefMini e_b = rbeg, e_b1 = runs ? ref[beg + 1] : rbeg, e_e = runs ? ref[end0] : rbeg, old_b = rbeg, old_e = rbeg;
+            bool adv_b = false, adv_e = false;
+            while (sw_end < last) {
+                if (adv_b) remove(sw_beg - 1, old_b, prev_end);               // :459-460
+                if (adv_e) insert(sw_end - 1, old_e, sw_beg);                 // :463-464
+                const int wb = (int)e_b.y;
+                if (S.shared > best) { best = S.shared; first_pos = last_pos = wb; }     // :467-476
+                else if (S.shared == best) last_pos = wb;                                // :477-481
+                const int d1 = (int)e_b1.y - sw_pos;
+                const int d2 = (int)e_e.y - (sw_pos + cmw - 1);
+                const int adv = min(d1, d2);
+                sw_pos += adv;
+                adv_b = adv == d1; adv_e = adv == d2;
+                prev_end = sw_end;
+                if (adv_b) { old_b = e_b; e_b = e_b1; sw_beg++; if (sw_beg + 1 < n_ref) e_b1 = ref[sw_beg + 1]; }
+                if (adv_e) { old_e = e_e; sw_end++; if (sw_end < last) e_e = ref[sw_end]; }
+            }
+            Mapping mp;
+            mp.seq = pp.seq;
+            mp.ref_start = (first_pos + last_pos) / 2;                        // computeMap.hpp:492
+            const bool pass = s > 0 && best >= min_shared[s];                 // computeMap.hpp:371-380 via the table
+            mp.shared = pass ? best : -1 - best;
+            mp.identity = pass ? id_tab[id_off[s] + best] : 0.0f;
+            maps[c] = mp;
         }
-        Mapping mp;
-        mp.seq = seq;
-        mp.ref_start = (first_pos + last_pos) / 2;                        // computeMap.hpp:492
-        const bool pass = s > 0 && best >= min_shared[s];                 // computeMap.hpp:371-380 via the table
-        mp.shared = pass ? best : -1 - best;
-        mp.identity = pass ? id_tab[id_off[s] + best] : 0.0f;
-        maps[c] = mp;
-        // workload counters, one atomic per warp
-        const unsigned am = __activemask();
-        const unsigned sc_sum = __reduce_add_sync(am, (unsigned)(max(end0, last) - beg));
-        const unsigned mp_sum = __reduce_add_sync(am, pass ? 1u : 0u);
-        (void)sc_sum;                          // already counted by the fast kernel
-        if ((tid & 31) == __ffs(am) - 1 && mp_sum) atomicAdd(&counters[CT_MAPPINGS], (unsigned long long)mp_sum);
     }
 }
 
 // ---- the fast L2 kernel ---------------------------------------------------------------------
 // Same state machine as SlideState above, reorganised for SIMT execution:
 //  * one EVENT (delete or insert of one reference minimizer) per loop iteration, chosen by
-//    comparing the two stream heads, so all lanes of a warp run the same instruction stream
-//    whatever mix of deletes and inserts their candidates need;
-//  * the reference stream is the 8-byte (hash, wpos) array `hw`, prefetched two elements ahead
-//    on each side; bit 31 of wpos flags the rare elements that have a duplicate hash nearby,
-//    only those fetch the distances from the full record;
-//  * query-hash classification goes through a 2048-entry table over the top hash bits followed
-//    by a fixed number of bisection steps (uniform across the CTA);
+//    comparing the two stream heads, and applied with selects only, so all lanes of a warp run
+//    the same instruction stream whatever mix of deletes / inserts / matches their candidates
+//    need.  The first super-window is built by the same loop (its inserts all carry a time
+//    <= the first window position);
+//  * lanes pull candidates of the work item one by one: a lane that finishes a candidate starts
+//    the next without waiting for the rest of its warp;
+//  * the reference stream is the 8-byte (hash, wpos) array `hw`, read with 16-byte loads one
+//    chunk ahead on each side; bit 31 of wpos flags the rare elements that have a duplicate
+//    hash nearby, only those fetch the distances from the full record;
+//  * the next event is classified (table over the top hash bits + MAXN compares against the
+//    staged query sketch) while the state update of the current one is in flight;
 //  * state is one byte per bucket (7-bit count + match bit), four buckets per 32-bit word, with
-//    each thread's words in its own bank.  A count that would pass 127 marks the candidate for
+//    each lane's words in its own bank.  A count that would pass 127 marks the candidate for
 //    the exact fallback kernel above (never seen outside adversarial sketches).
-struct FastState {
-    uint8_t *base;        // this thread's first byte
-    int stride4;          // tpc * 4: byte distance between consecutive groups of four buckets
-    int istar, sigma, shared;
-    bool overflow;
-    __device__ __forceinline__ uint8_t *at(int b) const { return base + (b >> 2) * stride4 + (b & 3); }
+
+// One side of the window: element j of `hw` with the pair holding it and the pair after it.
+struct HwStream {
+    uint64_t c0, c1, n0, n1;
+    __device__ __forceinline__ void init(const uint2 *hw, uint32_t j)
+    {
+        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(hw) + (j >> 1);
+        asm("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(c0), "=l"(c1) : "l"(p));
+        asm("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(n0), "=l"(n1) : "l"(p + 1));
+    }
+    __device__ __forceinline__ uint64_t get(uint32_t j) const { return (j & 1) ? c1 : c0; }
+    // called with the new index j after an advance by one, under predicate `adv`
+    __device__ __forceinline__ void advance(const uint2 *hw, uint32_t j, bool adv)
+    {
+        const bool roll = adv && (j & 1) == 0;
+        c0 = roll ? n0 : c0; c1 = roll ? n1 : c1;
+        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(hw) + (j >> 1) + 1;
+        asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.global.nc.v2.u64 {%0, %1}, [%2];\n\t}"
+            : "+l"(n0), "+l"(n1) : "l"(p), "r"((uint32_t)roll));
+    }
 };
 
-__device__ __forceinline__ void fast_apply(FastState &S, bool is_del, bool match, int lb)
+struct L2Args {
+    const Prep *prep; const RefMini *ref; const uint2 *hw;
+    const uint32_t *s_q; const uint16_t *s_tab; uint8_t *st;
+    uint32_t *s_next; uint32_t c_hi;
+    int s, stride4, cmw, msh, nsteps;
+    const float *id_row; Mapping *maps; unsigned long long *counters;
+};
+
+// MAXN > 0: every table slot holds at most MAXN sketch hashes (compare against all of them);
+// MAXN == 0: bisect between the slot's bounds.
+template <int MAXN>
+__device__ __forceinline__ void l2_classify(const L2Args &A, uint32_t h, int &lb, bool &match)
 {
-    if (match) {
-        uint8_t *p = S.at(lb + 1);
-        const uint8_t v = *p;
-        *p = is_del ? (uint8_t)(v & 0x7F) : (uint8_t)(v | 0x80);
-        if (lb + 1 <= S.istar) S.shared += is_del ? -1 : 1;
-        return;
-    }
-    uint8_t *p = S.at(lb);
-    uint8_t v = *p;
-    if (!is_del) {
-        if ((v & 0x7F) == 0x7F) { S.overflow = true; return; }
-        v += 1; *p = v;
-        if (lb < S.istar) {
-            if (S.sigma > 0) S.sigma--;
-            else {
-                const uint8_t a = (lb == S.istar) ? v : *S.at(S.istar);
-                S.shared -= a >> 7;
-                S.istar--;
-                S.sigma = (lb == S.istar) ? (v & 0x7F) : (*S.at(S.istar) & 0x7F);
-            }
+    const uint32_t slot = h >> (32 - L2_TAB_BITS);
+    int l = (int)A.s_tab[slot];
+    if (MAXN > 0) {
+        // the slot's entries are sorted and everything behind them (next slots, sentinels) is larger than h
+        bool m = false;
+        int add = 0;
+#pragma unroll
+        for (int i = 0; i < MAXN; i++) {
+            const uint32_t qv = A.s_q[l + i];
+            add += qv < h ? 1 : 0;
+            m |= qv == h;
         }
+        lb = l + add;
+        match = m && lb < A.s;
     } else {
-        v -= 1; *p = v;
-        if (lb <= S.istar) {
-            const int c = (lb == S.istar) ? (v & 0x7F) : (*S.at(S.istar) & 0x7F);
-            const bool grow = (lb < S.istar) ? (S.sigma >= c) : (S.sigma > c);
-            if (grow) { S.istar++; S.shared += *S.at(S.istar) >> 7; S.sigma = 0; }
-            else if (lb < S.istar) S.sigma++;
+        int r = (int)A.s_tab[slot + 1];
+        for (int i = 0; i < A.nsteps; i++) {
+            const int mid = (l + r) >> 1;
+            const bool go = l < r && A.s_q[min(mid, A.s - 1)] < h;
+            const bool shrink = l < r && !go;
+            l = go ? mid + 1 : l;
+            r = shrink ? mid : r;
         }
+        lb = l;
+        match = l < A.s && A.s_q[min(l, A.s - 1)] == h;
     }
 }
 
-__device__ __forceinline__ uint32_t lb_hw(const uint2 *hw, uint32_t lo, uint32_t hi, int target)
+template <int MAXN>
+__device__ __forceinline__ void l2_slide_lanes(const L2Args &A)
 {
-    while (lo < hi) { uint32_t mid = lo + ((hi - lo) >> 1); if ((int)(hw[mid].y & 0x7FFFFFFFu) < target) lo = mid + 1; else hi = mid; }
-    return lo;
+    const int s = A.s, stride4 = A.stride4, cmw = A.cmw;
+    uint8_t *const st = A.st;
+    const uint2 *const hw = A.hw;
+    const int nwords = l2_words_for(s);
+
+    bool alive = true, have = false;
+    uint32_t c = 0, b = 0, e = 0, last = 0;
+    int seq = 0, pos0 = 0, wb_cur = 0, T = 0, best = 0, first_pos = 0, last_pos = 0;
+    int istar = 0, sigma = 0, shared = 0, td = 0, ti = 0;
+    uint32_t a = 0, hb = 0, wfb = 0;
+    bool overflow = false;
+    HwStream D, I;                     // D: element b + 1 (its position is the next delete time), I: element e
+    uint64_t xd = 0;
+    bool p_del = false, p_match = false, p_skip = false;      // pending (classified) event
+    int p_lb = 0;
+
+    auto pick = [&]() {
+        xd = D.get(b + 1);
+        const uint64_t xi = I.get(e);
+        td = (int)((uint32_t)(xd >> 32) & 0x7FFFFFFFu);
+        ti = e < last ? (int)((uint32_t)(xi >> 32) & 0x7FFFFFFFu) - cmw + 1 : INT32_MAX;
+        p_del = td <= ti;                                                  // delete first inside a group
+        const uint32_t h = p_del ? hb : (uint32_t)xi;
+        const uint32_t wf = p_del ? wfb : (uint32_t)(xi >> 32);
+        p_skip = false;
+        if (wf & 0x80000000u) {                                            // a same-hash neighbour exists (rare)
+            const uint32_t j = p_del ? b : e;
+            const uint32_t d = A.ref[j].w;
+            if (p_del) { const uint32_t dn = d >> 16; p_skip = dn && j + dn < e; }            // a later copy stays (NOOP)
+            else { const uint32_t dp = d & 0xFFFFu; p_skip = dp && j >= dp && j - dp >= b; }  // already present (REV)
+        }
+        l2_classify<MAXN>(A, h, p_lb, p_match);
+    };
+
+    for (;;) {
+        if (!have && alive) {
+            // ---- next candidate of the work item ------------------------------------------------
+            for (;;) {
+                c = atomicAdd(A.s_next, 1u);
+                if (c >= A.c_hi) { alive = false; break; }
+                const Prep pp = A.prep[c];
+                if (pp.end0 >= pp.last) {                                  // no window to evaluate
+                    A.maps[c] = Mapping{pp.seq, 0, -1, 0.0f};
+                    continue;
+                }
+#pragma unroll 4
+                for (int wd = 0; wd < nwords; wd++) *reinterpret_cast<uint32_t *>(st + wd * stride4) = 0u;
+                seq = pp.seq; b = pp.beg; e = pp.beg; last = pp.last;
+                I.init(hw, e);
+                D.init(hw, b + 1);
+                const uint64_t x0 = I.get(e);
+                hb = (uint32_t)x0; wfb = (uint32_t)(x0 >> 32);
+                pos0 = (int)(wfb & 0x7FFFFFFFu);
+                wb_cur = pos0; T = pos0; best = 0; first_pos = pos0; last_pos = pos0;
+                istar = s; sigma = 0; shared = 0; a = 0; overflow = false;
+                pick();
+                have = true;
+                break;
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, alive)) break;
+        if (alive) {
+            // 1. state bytes the pending event touches: its own bucket and the pivot's neighbour
+            const bool c_del = p_del;
+            const bool c_match = p_match && !p_skip, c_only = !p_match && !p_skip;
+            const int idx = p_lb + (p_match ? 1 : 0);
+            uint8_t *const pa = st + (idx >> 2) * stride4 + (idx & 3);
+            const uint32_t v = *pa;
+            const int nbi = istar + (c_del ? 1 : -1);                           // one word of slack on both sides
+            const uint32_t pn = st[(nbi >> 2) * stride4 + (nbi & 3)];
+            // 2. advance the stream the event came from, pick + classify the next event
+            hb = c_del ? (uint32_t)xd : hb;
+            wfb = c_del ? (uint32_t)(xd >> 32) : wfb;
+            wb_cur = c_del ? td : wb_cur;
+            b += c_del ? 1u : 0u;
+            e += c_del ? 0u : 1u;
+            D.advance(hw, b + 1, c_del);
+            I.advance(hw, e, !c_del);
+            pick();
+            // 3. apply the event
+            const bool ovf = c_only && !c_del && (v & 0x7Fu) == 0x7Fu;
+            const bool ins_o = c_only && !c_del && !ovf, del_o = c_only && c_del;
+            overflow |= ovf;
+            uint32_t v2 = c_match ? (c_del ? (v & 0x7Fu) : (v | 0x80u)) : v;
+            v2 = ins_o ? v + 1u : v2;
+            v2 = del_o ? v - 1u : v2;
+            *pa = (uint8_t)v2;
+            const bool below = idx < istar, at_p = idx == istar;
+            a = at_p ? v2 : a;
+            const int cc = (int)(a & 0x7Fu);
+            const bool mv_dn = ins_o && below && sigma == 0;
+            const bool dec_s = ins_o && below && sigma > 0;
+            const bool mv_up = del_o && (below ? sigma >= cc : (at_p && sigma > cc));
+            const bool inc_s = del_o && below && !mv_up;
+            shared += (c_match && idx <= istar) ? (c_del ? -1 : 1) : 0;
+            shared -= mv_dn ? (int)(a >> 7) : 0;
+            const uint32_t a_dn = (idx == istar - 1) ? v2 : pn;
+            a = mv_dn ? a_dn : (mv_up ? pn : a);
+            shared += mv_up ? (int)(a >> 7) : 0;
+            istar += mv_up ? 1 : (mv_dn ? -1 : 0);
+            sigma = mv_dn ? (int)(a & 0x7Fu) : (mv_up ? 0 : sigma + (inc_s ? 1 : 0) - (dec_s ? 1 : 0));
+            // 4. a change of event time completes a group of simultaneous events: evaluate the
+            //    window (computeMap.hpp:467-481), then stop before the insert that would make
+            //    the window end reach `last` (the loop condition of :453)
+            const int Tn = max(min(td, ti), pos0);
+            const bool grp = Tn != T;
+            const bool gt = grp && shared > best, ge = grp && shared >= best;
+            best = gt ? shared : best;
+            first_pos = gt ? wb_cur : first_pos;
+            last_pos = ge ? wb_cur : last_pos;
+            T = Tn;
+            if (grp && ((ti == Tn && e + 1 >= last) || overflow)) {
+                Mapping mp;
+                mp.seq = seq;
+                mp.ref_start = (first_pos + last_pos) / 2;                        // computeMap.hpp:492
+                const bool pass = best >= A.msh && !overflow;                       // computeMap.hpp:371-380 via the table
+                mp.shared = pass ? best : -1 - best;
+                mp.identity = pass ? A.id_row[best] : 0.0f;
+                if (overflow) { mp.ref_start = L2_REDO; mp.shared = -1; atomicAdd(&A.counters[CT_REDO], 1ull); }
+                A.maps[c] = mp;
+                have = false;
+            }
+        }
+    }
 }
 
 __global__ void __launch_bounds__(L2_THREADS)
-l2_fast_kernel(const Cand *cands, const uint32_t *cand_base, const uint32_t *work_base, int n_frags,
-               const uint32_t *qhash, const uint64_t *seq_first, const int32_t *qs,
-               const RefMini *ref, const uint2 *hw, uint32_t n_ref, const uint32_t *contig_off, int frag_len, int cmw,
-               const int32_t *min_shared, const uint32_t *id_off, const float *id_tab,
-               Mapping *maps, unsigned long long *counters, int q_cap)
+l2_slide_kernel(const Prep *prep, const uint32_t *cand_base, const uint32_t *work_base, int n_frags,
+                const uint32_t *qhash, const uint64_t *seq_first, const int32_t *qs,
+                const RefMini *ref, const uint2 *hw, int cmw,
+                const int32_t *min_shared, const uint32_t *id_off, const float *id_tab,
+                Mapping *maps, unsigned long long *counters, int q_cap, int state_bytes)
 {
     extern __shared__ __align__(16) uint8_t l2_smem[];
-    uint32_t *s_q = reinterpret_cast<uint32_t *>(l2_smem);
+    uint32_t *s_q = reinterpret_cast<uint32_t *>(l2_smem);                  // q_cap entries: sketch + sentinels
     uint16_t *s_tab = reinterpret_cast<uint16_t *>(s_q + q_cap);            // L2_TAB + 2 entries
-    uint8_t *s_state = reinterpret_cast<uint8_t *>(s_tab + L2_TAB + 2);       // L2_STATE_BYTES, 4-byte aligned
-    __shared__ uint32_t s_item;
-    __shared__ int s_maxlen, s_cached_f;
+    uint8_t *s_state = reinterpret_cast<uint8_t *>(s_tab + L2_TAB + 2);       // slack row + state_bytes + slack row
+    __shared__ uint32_t s_item, s_next;
+    __shared__ int s_maxn, s_cached_f;
     const int tid = threadIdx.x;
     const uint32_t n_work = work_base[n_frags];
     if (tid == 0) s_cached_f = -1;
@@ -485,128 +678,54 @@ l2_fast_kernel(const Cand *cands, const uint32_t *cand_base, const uint32_t *wor
         __syncthreads();
         const uint32_t item = s_item;
         if (item >= n_work) break;
-        int lo = 0, hi = n_frags - 1;
-        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (work_base[mid] <= item) lo = mid; else hi = mid - 1; }
-        const int f = lo;
+        int flo = 0, fhi = n_frags - 1;
+        while (flo < fhi) { int mid = (flo + fhi + 1) >> 1; if (work_base[mid] <= item) flo = mid; else fhi = mid - 1; }
+        const int f = flo;
         const int s = qs[f];
-        const int tpc = l2_threads_for(s);
-        const uint32_t c = cand_base[f] + (item - work_base[f]) * tpc + tid;
-        const bool active = tid < tpc && c < cand_base[f + 1];
+        const uint32_t c_lo = cand_base[f] + (item - work_base[f]) * L2_ITEM;
+        const uint32_t c_hi = min(c_lo + (uint32_t)L2_ITEM, cand_base[f + 1]);
         if (s_cached_f != f) {
-            // query sketch + classification table: tab[x] = #{q : q < x << (32 - bits)}
+            // query sketch + classification table: slot x of the top hash bits -> first sketch index of the slot
             const uint64_t qb = seq_first[f];
-            for (int i = tid; i < s; i += L2_THREADS) s_q[i] = qhash[qb + i];
-            if (tid == 0) s_maxlen = 0;
+            for (int i = tid; i < s + L2_QPAD; i += L2_THREADS) s_q[i] = i < s ? qhash[qb + i] : 0xFFFFFFFFu;
+            if (tid == 0) s_maxn = 0;
             __syncthreads();
-            for (int x = tid; x <= L2_TAB; x += L2_THREADS) {
-                int l = 0, r = s;
-                if (x == L2_TAB) l = s;
-                else {
-                    const uint32_t target = (uint32_t)x << (32 - L2_TAB_BITS);
-                    while (l < r) { int mid = (l + r) >> 1; if (s_q[mid] < target) l = mid + 1; else r = mid; }
-                }
-                s_tab[x] = (uint16_t)l;
-            }
-            __syncthreads();
+            constexpr int PER = L2_TAB / L2_THREADS;
+            const uint32_t x0 = (uint32_t)tid * PER;
+            int l = 0, r = s;
+            const uint32_t t0 = x0 << (32 - L2_TAB_BITS);
+            while (l < r) { int mid = (l + r) >> 1; if (s_q[mid] < t0) l = mid + 1; else r = mid; }
             int ml = 0;
-            for (int x = tid; x < L2_TAB; x += L2_THREADS) ml = max(ml, (int)s_tab[x + 1] - (int)s_tab[x]);
-            atomicMax(&s_maxlen, ml);
+#pragma unroll 1
+            for (int i = 0; i < PER; i++) {
+                s_tab[x0 + i] = (uint16_t)l;
+                const int l0 = l;
+                const uint32_t x = x0 + i + 1;
+                if (x == L2_TAB) l = s;
+                else { const uint32_t t = x << (32 - L2_TAB_BITS); while (s_q[l] < t) l++; }     // the sentinels stop the walk
+                ml = max(ml, l - l0);
+            }
+            if (tid == L2_THREADS - 1) s_tab[L2_TAB] = (uint16_t)s;
+            atomicMax(&s_maxn, ml);
         }
-        {   // clear the state words this work item uses
-            uint32_t *w = reinterpret_cast<uint32_t *>(s_state);
-            const int nwords = ((s + 4) >> 2) * tpc;
-            for (int i = tid; i < nwords; i += L2_THREADS) w[i] = 0;
-        }
+        if (tid == 0) { s_next = c_lo; s_cached_f = f; }
         __syncthreads();
-        if (tid == 0) s_cached_f = f;
-        int nsteps = 0;
-        while ((1 << nsteps) <= s_maxlen) nsteps++;                            // bisection steps inside one table slot
-        if (!active) continue;
+        const int maxn = s_maxn;
+        const int nl = l2_lanes_for(s, state_bytes);
+        if (tid >= nl) continue;
 
-        const Cand cd = cands[c];
-        const int seq = (int)ref[cd.hint].z;
-        const uint32_t c1 = contig_off[seq + 1];
-        // Sketch::searchIndex x3 (computeMap.hpp:421-433), restricted to the candidate's contig
-        const uint32_t beg = lb_hw(hw, contig_off[seq], cd.hint, cd.start);
-        const int wpos_beg = (int)(hw[beg].y & 0x7FFFFFFFu);
-        const uint32_t end0 = lb_hw(hw, beg, min(c1, beg + (uint32_t)cmw + 1u), wpos_beg + cmw);
-        const uint32_t last = lb_hw(hw, end0, c1, cd.end + frag_len);
-
-        FastState S;
-        S.base = s_state + tid * 4; S.stride4 = tpc * 4; S.istar = s; S.sigma = 0; S.shared = 0; S.overflow = false;
-
-        // one event: classify the hash, resolve duplicates (rare), update the state
-        auto event = [&](bool is_del, uint32_t j, uint2 e, uint32_t win_beg, uint32_t win_end) {
-            if (e.y & 0x80000000u) {                                           // a same-hash neighbour exists
-                const uint32_t d = ref[j].w;
-                if (is_del) { const uint32_t dn = d >> 16; if (dn && j + dn < win_end) return; }
-                else { const uint32_t dp = d & 0xFFFFu; if (dp && j >= dp && j - dp >= win_beg) return; }
-            }
-            const uint32_t h = e.x;
-            int l = s_tab[h >> (32 - L2_TAB_BITS)], r = s_tab[(h >> (32 - L2_TAB_BITS)) + 1];
-            for (int i = 0; i < nsteps; i++) {
-                const int mid = (l + r) >> 1;
-                const bool go = l < r && s_q[min(mid, s - 1)] < h;
-                const bool shrink = l < r && !go;
-                l = go ? mid + 1 : l;
-                r = shrink ? mid : r;
-            }
-            const bool match = l < s && s_q[min(l, s - 1)] == h;
-            fast_apply(S, is_del, match, l);
-        };
-
-        const uint32_t nmax = n_ref - 1;
-        for (uint32_t j = beg; j < end0; j++) event(false, j, hw[j], beg, j);           // first super-window
-
-        int best = 0, first_pos = 0, last_pos = 0;
-        uint32_t b = beg, e = end0;
-        if (end0 < last) {
-            // stream heads: cur_b = hw[b]; nb = hw[b+1], nb2 = hw[b+2]; ne = hw[e], ne2 = hw[e+1]
-            uint2 cur_b = hw[b], nb = hw[min(b + 1, nmax)], nb2 = hw[min(b + 2, nmax)];
-            uint2 ne = hw[e], ne2 = hw[min(e + 1, nmax)];
-            best = 0; first_pos = last_pos = wpos_beg;                                   // evaluation of the first window (shared >= 0 == best)
-            if (S.shared > 0) best = S.shared;
-            int td = (int)(nb.y & 0x7FFFFFFFu), ti = (int)(ne.y & 0x7FFFFFFFu) - cmw + 1;
-            int T = min(td, ti);
-            bool go_on = !(ti == T && e + 1 >= last);
-            while (go_on) {
-                const bool is_del = td <= ti;                                              // delete first inside a group
-                if (is_del) {
-                    event(true, b, cur_b, b, e);
-                    b++; cur_b = nb; nb = nb2; nb2 = hw[min(b + 2, nmax)];
-                } else {
-                    event(false, e, ne, b, e);
-                    e++; ne = ne2; ne2 = hw[min(e + 1, nmax)];
-                }
-                td = (int)(nb.y & 0x7FFFFFFFu);
-                ti = (e < last) ? (int)(ne.y & 0x7FFFFFFFu) - cmw + 1 : INT32_MAX;
-                const int Tn = min(td, ti);
-                if (Tn != T) {                                                             // group complete: evaluate (computeMap.hpp:467-481)
-                    const int wb = (int)(cur_b.y & 0x7FFFFFFFu);
-                    if (S.shared > best) { best = S.shared; first_pos = last_pos = wb; }
-                    else if (S.shared == best) last_pos = wb;
-                    T = Tn;
-                    go_on = !(ti == Tn && e + 1 >= last);
-                }
-            }
-        }
-        Mapping mp;
-        mp.seq = seq;
-        mp.ref_start = (first_pos + last_pos) / 2;                        // computeMap.hpp:492
-        const bool pass = s > 0 && best >= min_shared[s] && !S.overflow;
-        mp.shared = pass ? best : -1 - best;
-        mp.identity = pass ? id_tab[id_off[s] + best] : 0.0f;
-        if (S.overflow) { mp.ref_start = L2_REDO; mp.shared = -1; }
-        maps[c] = mp;
-        const unsigned am = __activemask();
-        const unsigned sc_sum = __reduce_add_sync(am, (unsigned)(max(end0, last) - beg));
-        const unsigned mp_sum = __reduce_add_sync(am, pass ? 1u : 0u);
-        const unsigned ov_sum = __reduce_add_sync(am, S.overflow ? 1u : 0u);
-        if ((tid & 31) == __ffs(am) - 1) {
-            atomicAdd(&counters[CT_SCANNED], (unsigned long long)sc_sum);
-            if (mp_sum) atomicAdd(&counters[CT_MAPPINGS], (unsigned long long)mp_sum);
-            if (ov_sum) atomicAdd(&counters[CT_REDO], (unsigned long long)ov_sum);
-        }
+        L2Args A;
+        A.prep = prep; A.ref = ref; A.hw = hw; A.s_q = s_q; A.s_tab = s_tab;
+        A.st = s_state + L2_THREADS * 4 + tid * 4;
+        A.s_next = &s_next; A.c_hi = c_hi;
+        A.s = s; A.stride4 = nl * 4; A.cmw = cmw; A.msh = min_shared[s];
+        A.nsteps = 0;
+        while ((1 << A.nsteps) <= maxn) A.nsteps++;
+        A.id_row = id_tab + id_off[s]; A.maps = maps; A.counters = counters;
+        if (maxn <= 2) l2_slide_lanes<2>(A);
+        else if (maxn == 3) l2_slide_lanes<3>(A);
+        else if (maxn == 4) l2_slide_lanes<4>(A);
+        else l2_slide_lanes<0>(A);
     }
 }
 
@@ -617,11 +736,14 @@ l2_fast_kernel(const Cand *cands, const uint32_t *cand_base, const uint32_t *wor
 // Pass 2 (:234-255): per (ref contig, bin) keep the best identity -> atomicMax on the bit
 // pattern (identities are positive floats, so the unsigned order is the float order).
 __global__ void cgi_best_kernel(const Cand *cands, const Mapping *maps, const uint32_t *cand_base, int n_frags,
-                                const int32_t *genome_of_seq, const uint32_t *bin_base, int bin_w, uint32_t *cells)
+                                const int32_t *genome_of_seq, const uint32_t *bin_base, int bin_w, uint32_t *cells,
+                                unsigned long long *counters)
 {
     const uint32_t n = cand_base[n_frags];
+    unsigned int passed = 0;
     for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
         const Mapping m = maps[c];
+        passed += m.shared >= 0 ? 1u : 0u;
         const int f = cands[c].frag;
         const int g = genome_of_seq[m.seq];
         const uint32_t cb = cand_base[f], ce = cand_base[f + 1];
@@ -639,6 +761,8 @@ __global__ void cgi_best_kernel(const Cand *cands, const Mapping *maps, const ui
         }
         if (have) atomicMax(&cells[bin_base[best.seq] + (uint32_t)(best.ref_start / bin_w)], __float_as_uint(best.identity));
     }
+    passed = __reduce_add_sync(0xFFFFFFFFu, passed);
+    if ((threadIdx.x & 31) == 0 && passed) atomicAdd(&counters[CT_MAPPINGS], (unsigned long long)passed);
 }
 
 // Per genome (:268-294): float32 sum of the surviving identities in (refSeqId, bin) order, count,
@@ -837,7 +961,7 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
             candidates_kernel<false><<<F, 256, 0, st>>>(ws.seeds_b.p, ws.frag_seeds.p, ws.qs.p, ix->d_min_hits.p, ix->ref.p,
                                                         idx_mask, L, ws.frag_cands.p, nullptr, nullptr);
             FA_CUDA(cudaGetLastError()); launches++;
-            work_items_kernel<<<(F + 1 + 255) / 256, 256, 0, st>>>(ws.frag_cands.p, ws.qs.p, F, ws.work_base.p);
+            work_items_kernel<<<(F + 1 + 255) / 256, 256, 0, st>>>(ws.frag_cands.p, F, ws.work_base.p);
             FA_CUDA(cudaGetLastError()); launches++;
             FA_CUDA(cudaMemsetAsync(ws.frag_cands.p + F, 0, 4, st));
             FA_TRY(excl_scan<uint32_t>(st, ws.cub_tmp, ws.frag_cands.p, ws.frag_cands.p, (int64_t)F + 1, &launches));
@@ -855,25 +979,33 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
                 FA_CUDA(cudaGetLastError()); launches++;
                 FA_CUDA(cudaEventRecord(ws.ev[5], st));
                 // ---- L2 -----------------------------------------------------------------------
-                const int q_cap = (std::max(max_s, 1) + 3) & ~3;
+                FA_TRY(ws.prep.reserve(C));
                 int dev_sms = 148;
                 cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ix->device);
+                l2_prep_kernel<<<std::min<uint32_t>((uint32_t)((C + 255) / 256), (uint32_t)dev_sms * 8u), 256, 0, st>>>(
+                    ws.cands.p, ws.frag_cands.p, F, ix->ref.p, ix->hw.p, ix->contig_off.p, L, cmw,
+                    reinterpret_cast<Prep *>(ws.prep.p), ws.counters.p);
+                FA_CUDA(cudaGetLastError()); launches++;
+                const int q_cap = (std::max(max_s, 1) + L2_QPAD + 3) & ~3;
                 {
-                    const size_t smem = (size_t)q_cap * 4 + (size_t)(L2_TAB + 2) * 2 + (size_t)L2_STATE_BYTES;
-                    if (smem > 48 * 1024) FA_CUDA(cudaFuncSetAttribute(l2_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    const uint32_t grid = std::min<uint32_t>(W, (uint32_t)dev_sms * 16u);
-                    l2_fast_kernel<<<grid, L2_THREADS, smem, st>>>(ws.cands.p, ws.frag_cands.p, ws.work_base.p, F, ws.qhash.p,
-                                                                   ws.sk.seq_first.p, ws.qs.p, ix->ref.p, ix->hw.p, (uint32_t)ix->n,
-                                                                   ix->contig_off.p, L, cmw, ix->d_min_shared.p, ix->d_id_off.p,
-                                                                   ix->d_identity.p, ws.maps.p, ws.counters.p, q_cap);
+                    const int state_bytes = std::min(l2_words_for(std::max(max_s, 1)) * 4 * L2_THREADS, L2_STATE_MAX);
+                    const size_t smem = (size_t)q_cap * 4 + (size_t)(L2_TAB + 2) * 2 + (size_t)state_bytes + 2 * L2_THREADS * 4;
+                    if (smem > 48 * 1024) FA_CUDA(cudaFuncSetAttribute(l2_slide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    int per_sm = 1;
+                    FA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l2_slide_kernel, L2_THREADS, smem));
+                    const uint32_t grid = std::min<uint32_t>(W, (uint32_t)dev_sms * (uint32_t)std::max(per_sm, 1));
+                    l2_slide_kernel<<<grid, L2_THREADS, smem, st>>>(reinterpret_cast<const Prep *>(ws.prep.p), ws.frag_cands.p, ws.work_base.p, F,
+                                                                    ws.qhash.p, ws.sk.seq_first.p, ws.qs.p, ix->ref.p, ix->hw.p,
+                                                                    cmw, ix->d_min_shared.p, ix->d_id_off.p,
+                                                                    ix->d_identity.p, ws.maps.p, ws.counters.p, q_cap, state_bytes);
                     FA_CUDA(cudaGetLastError()); launches++;
                 }
                 {   // exact fallback for candidates whose 7-bit bucket counts overflowed (returns at once if none)
-                    const size_t smem = (size_t)q_cap * 4 + (size_t)L2_STATE_WORDS * 2;
+                    const size_t smem = (size_t)q_cap * 4 + (size_t)L2_FB_STATE + 64;
                     if (smem > 48 * 1024) FA_CUDA(cudaFuncSetAttribute(l2_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     const uint32_t grid = std::min<uint32_t>(W, (uint32_t)dev_sms * 4u);
-                    l2_fallback_kernel<<<grid, L2_THREADS, smem, st>>>(ws.cands.p, ws.frag_cands.p, ws.work_base.p, F, ws.qhash.p,
-                                                                       ws.sk.seq_first.p, ws.qs.p, ix->ref.p, (uint32_t)ix->n, ix->contig_off.p, L, cmw,
+                    l2_fallback_kernel<<<grid, L2_THREADS, smem, st>>>(reinterpret_cast<const Prep *>(ws.prep.p), ws.frag_cands.p, ws.work_base.p, F,
+                                                                       ws.qhash.p, ws.sk.seq_first.p, ws.qs.p, ix->ref.p, (uint32_t)ix->n, cmw,
                                                                        ix->d_min_shared.p, ix->d_id_off.p, ix->d_identity.p, ws.maps.p,
                                                                        ws.counters.p, q_cap);
                     FA_CUDA(cudaGetLastError()); launches++;
@@ -881,7 +1013,7 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
                 FA_CUDA(cudaEventRecord(ws.ev[6], st));
                 // ---- CGI ----------------------------------------------------------------------
                 cgi_best_kernel<<<std::min<uint32_t>((uint32_t)((C + 255) / 256), 148u * 8u), 256, 0, st>>>(
-                    ws.cands.p, ws.maps.p, ws.frag_cands.p, F, ix->genome_of_seq.p, ix->bin_base.p, L - 20, ws.cells.p);
+                    ws.cands.p, ws.maps.p, ws.frag_cands.p, F, ix->genome_of_seq.p, ix->bin_base.p, L - 20, ws.cells.p, ws.counters.p);
                 FA_CUDA(cudaGetLastError()); launches++;
             } else {
                 FA_CUDA(cudaEventRecord(ws.ev[5], st));
