@@ -37,6 +37,7 @@ constexpr int L2_STATE_MAX = 96 * 1024; // cap of the per-CTA slide state (large
 constexpr int L2_FB_STATE = 32 * 1024;  // u16 state of the exact fallback kernel
 constexpr int L2_TAB_BITS = 11;         // classification table over the top bits of the hash
 constexpr int L2_TAB = 1 << L2_TAB_BITS;
+static_assert(L2_TAB_BITS == 11, "l2_slot() is written for 2048 slots");
 constexpr int L2_QPAD = 8;              // sentinel entries behind the staged query sketch
 constexpr int32_t L2_REDO = INT32_MIN;  // Mapping.ref_start marker: redo this candidate in the fallback kernel
 
@@ -485,33 +486,51 @@ struct HwStream {
     }
 };
 
+// Minimizer hashes are window minima, so they crowd towards zero (density ~ (1 - u)^(2w - 1)): a
+// table over the plain top bits would put most of a sketch into a few slots.  The slot function is
+// piecewise linear instead: the hash range is cut into equal pieces of 2^p (about the half-life of
+// that density) and piece k gets 1024 >> k slots, which spreads a sketch about evenly.  Monotone.
+__host__ __device__ inline int l2_tab_shift(int w)
+{
+    const double half = 4294967296.0 * 0.6931471805599453 / (2.0 * (w < 1 ? 1 : w));
+    int p = 10;
+    while (p < 30 && (double)(1u << p) < half) p++;
+    return p;
+}
+__device__ __forceinline__ uint32_t l2_slot(uint32_t h, int p)
+{
+    const uint32_t k = min(h >> p, 11u);
+    return 2048u - (2048u >> k) + ((h & ((1u << p) - 1u)) >> (p - 10 + k));
+}
+
 struct L2Args {
     const Prep *prep; const RefMini *ref; const uint2 *hw;
     const uint32_t *s_q; const uint16_t *s_tab; uint8_t *st;
     uint32_t *s_next; uint32_t c_hi;
-    int s, stride4, cmw, msh, nsteps;
+    int s, stride4, cmw, msh, nsteps, tab_p;
     const float *id_row; Mapping *maps; unsigned long long *counters;
 };
 
 // MAXN > 0: every table slot holds at most MAXN sketch hashes (compare against all of them);
-// MAXN == 0: bisect between the slot's bounds.
+// MAXN == 0: bisect between the slot's bounds.  Returns idx = lb + match where lb = #{q < h} and
+// match = (q_{lb+1} == h): the state byte the event touches.
 template <int MAXN>
-__device__ __forceinline__ void l2_classify(const L2Args &A, uint32_t h, int &lb, bool &match)
+__device__ __forceinline__ void l2_classify(const L2Args &A, uint32_t h, int &idx, int &match)
 {
-    const uint32_t slot = h >> (32 - L2_TAB_BITS);
+    const uint32_t slot = l2_slot(h, A.tab_p);
     int l = (int)A.s_tab[slot];
     if (MAXN > 0) {
         // the slot's entries are sorted and everything behind them (next slots, sentinels) is larger than h
-        bool m = false;
-        int add = 0;
+        int lt = 0, eq = 0;
 #pragma unroll
         for (int i = 0; i < MAXN; i++) {
             const uint32_t qv = A.s_q[l + i];
-            add += qv < h ? 1 : 0;
-            m |= qv == h;
+            lt += qv < h ? 1 : 0;
+            eq |= qv == h ? 1 : 0;
         }
-        lb = l + add;
-        match = m && lb < A.s;
+        l += lt;
+        match = l < A.s ? eq : 0;                 // (a sentinel equals h only for h == 0xFFFFFFFF)
+        idx = l + match;
     } else {
         int r = (int)A.s_tab[slot + 1];
         for (int i = 0; i < A.nsteps; i++) {
@@ -521,46 +540,51 @@ __device__ __forceinline__ void l2_classify(const L2Args &A, uint32_t h, int &lb
             l = go ? mid + 1 : l;
             r = shrink ? mid : r;
         }
-        lb = l;
-        match = l < A.s && A.s_q[min(l, A.s - 1)] == h;
+        match = (l < A.s && A.s_q[min(l, A.s - 1)] == h) ? 1 : 0;
+        idx = l + match;
     }
 }
 
-template <int MAXN>
+// FULL: all 64 lanes of the CTA are in use, so the lane-interleaved state has a constant row pitch.
+template <int MAXN, bool FULL>
 __device__ __forceinline__ void l2_slide_lanes(const L2Args &A)
 {
-    const int s = A.s, stride4 = A.stride4, cmw = A.cmw;
+    const int s = A.s, stride4 = A.stride4, cmw1 = A.cmw - 1;
     uint8_t *const st = A.st;
     const uint2 *const hw = A.hw;
     const int nwords = l2_words_for(s);
+    auto at = [&](int idx) -> uint8_t * {
+        return FULL ? st + ((idx & ~3) << 6) + (idx & 3) : st + (idx >> 2) * stride4 + (idx & 3);
+    };
 
     bool alive = true, have = false;
     uint32_t c = 0, b = 0, e = 0, last = 0;
     int seq = 0, pos0 = 0, wb_cur = 0, T = 0, best = 0, first_pos = 0, last_pos = 0;
-    int istar = 0, sigma = 0, shared = 0, td = 0, ti = 0;
+    int istar = 0, sigma = 0, shared = 0, td = 0, ti = 0, overflow = 0;
     uint32_t a = 0, hb = 0, wfb = 0;
-    bool overflow = false;
     HwStream D, I;                     // D: element b + 1 (its position is the next delete time), I: element e
     uint64_t xd = 0;
-    bool p_del = false, p_match = false, p_skip = false;      // pending (classified) event
-    int p_lb = 0;
+    int p_del = 0, p_match = 0, p_skip = 0, p_idx = 0;        // pending (classified) event
 
     auto pick = [&]() {
         xd = D.get(b + 1);
         const uint64_t xi = I.get(e);
+        const uint32_t wi = (uint32_t)(xi >> 32);
         td = (int)((uint32_t)(xd >> 32) & 0x7FFFFFFFu);
-        ti = e < last ? (int)((uint32_t)(xi >> 32) & 0x7FFFFFFFu) - cmw + 1 : INT32_MAX;
-        p_del = td <= ti;                                                  // delete first inside a group
-        const uint32_t h = p_del ? hb : (uint32_t)xi;
-        const uint32_t wf = p_del ? wfb : (uint32_t)(xi >> 32);
-        p_skip = false;
+        ti = max((int)(wi & 0x7FFFFFFFu) - cmw1, pos0);                     // the first window's inserts share its time
+        ti = e < last ? ti : INT32_MAX;
+        const bool del = td <= ti;                                         // delete first inside a group
+        p_del = del ? 1 : 0;
+        const uint32_t h = del ? hb : (uint32_t)xi;
+        const uint32_t wf = del ? wfb : wi;
+        p_skip = 0;
         if (wf & 0x80000000u) {                                            // a same-hash neighbour exists (rare)
-            const uint32_t j = p_del ? b : e;
+            const uint32_t j = del ? b : e;
             const uint32_t d = A.ref[j].w;
-            if (p_del) { const uint32_t dn = d >> 16; p_skip = dn && j + dn < e; }            // a later copy stays (NOOP)
-            else { const uint32_t dp = d & 0xFFFFu; p_skip = dp && j >= dp && j - dp >= b; }  // already present (REV)
+            if (del) { const uint32_t dn = d >> 16; p_skip = (dn && j + dn < e) ? 1 : 0; }            // a later copy stays (NOOP)
+            else { const uint32_t dp = d & 0xFFFFu; p_skip = (dp && j >= dp && j - dp >= b) ? 1 : 0; }  // already present (REV)
         }
-        l2_classify<MAXN>(A, h, p_lb, p_match);
+        l2_classify<MAXN>(A, h, p_idx, p_match);
     };
 
     for (;;) {
@@ -583,7 +607,7 @@ __device__ __forceinline__ void l2_slide_lanes(const L2Args &A)
                 hb = (uint32_t)x0; wfb = (uint32_t)(x0 >> 32);
                 pos0 = (int)(wfb & 0x7FFFFFFFu);
                 wb_cur = pos0; T = pos0; best = 0; first_pos = pos0; last_pos = pos0;
-                istar = s; sigma = 0; shared = 0; a = 0; overflow = false;
+                istar = s; sigma = 0; shared = 0; a = 0; overflow = 0;
                 pick();
                 have = true;
                 break;
@@ -592,48 +616,47 @@ __device__ __forceinline__ void l2_slide_lanes(const L2Args &A)
         if (!__any_sync(0xFFFFFFFFu, alive)) break;
         if (alive) {
             // 1. state bytes the pending event touches: its own bucket and the pivot's neighbour
-            const bool c_del = p_del;
-            const bool c_match = p_match && !p_skip, c_only = !p_match && !p_skip;
-            const int idx = p_lb + (p_match ? 1 : 0);
-            uint8_t *const pa = st + (idx >> 2) * stride4 + (idx & 3);
+            const int del = p_del, idx = p_idx;
+            const int act = (p_skip | overflow) ^ 1;
+            int mt = p_match & act, on = (p_match ^ 1) & act;
+            const int sgn = 1 - 2 * del;
+            uint8_t *const pa = at(idx);
             const uint32_t v = *pa;
-            const int nbi = istar + (c_del ? 1 : -1);                           // one word of slack on both sides
-            const uint32_t pn = st[(nbi >> 2) * stride4 + (nbi & 3)];
+            const uint32_t pn = *at(istar - sgn);                           // one row of slack on both sides
             // 2. advance the stream the event came from, pick + classify the next event
-            hb = c_del ? (uint32_t)xd : hb;
-            wfb = c_del ? (uint32_t)(xd >> 32) : wfb;
-            wb_cur = c_del ? td : wb_cur;
-            b += c_del ? 1u : 0u;
-            e += c_del ? 0u : 1u;
-            D.advance(hw, b + 1, c_del);
-            I.advance(hw, e, !c_del);
+            hb = del ? (uint32_t)xd : hb;
+            wfb = del ? (uint32_t)(xd >> 32) : wfb;
+            wb_cur = del ? td : wb_cur;
+            b += (uint32_t)del;
+            e += (uint32_t)(del ^ 1);
+            D.advance(hw, b + 1, del != 0);
+            I.advance(hw, e, del == 0);
             pick();
             // 3. apply the event
-            const bool ovf = c_only && !c_del && (v & 0x7Fu) == 0x7Fu;
-            const bool ins_o = c_only && !c_del && !ovf, del_o = c_only && c_del;
+            const int ovf = (on & (del ^ 1) & ((v & 0x7Fu) == 0x7Fu ? 1 : 0));
             overflow |= ovf;
-            uint32_t v2 = c_match ? (c_del ? (v & 0x7Fu) : (v | 0x80u)) : v;
-            v2 = ins_o ? v + 1u : v2;
-            v2 = del_o ? v - 1u : v2;
+            on &= ovf ^ 1;
+            const uint32_t v2 = (v + (uint32_t)(sgn * ((mt << 7) + on))) & 0xFFu;
             *pa = (uint8_t)v2;
             const bool below = idx < istar, at_p = idx == istar;
             a = at_p ? v2 : a;
             const int cc = (int)(a & 0x7Fu);
-            const bool mv_dn = ins_o && below && sigma == 0;
-            const bool dec_s = ins_o && below && sigma > 0;
-            const bool mv_up = del_o && (below ? sigma >= cc : (at_p && sigma > cc));
-            const bool inc_s = del_o && below && !mv_up;
-            shared += (c_match && idx <= istar) ? (c_del ? -1 : 1) : 0;
+            const bool in_ins = (on & (del ^ 1)) && below;
+            const bool in_del = (on & del) && (below || (at_p && sigma > cc));
+            const bool mv_dn = in_ins && sigma == 0;
+            const bool mv_up = in_del && (at_p || sigma >= cc);
+            shared += (mt && idx <= istar) ? sgn : 0;
             shared -= mv_dn ? (int)(a >> 7) : 0;
             const uint32_t a_dn = (idx == istar - 1) ? v2 : pn;
             a = mv_dn ? a_dn : (mv_up ? pn : a);
             shared += mv_up ? (int)(a >> 7) : 0;
-            istar += mv_up ? 1 : (mv_dn ? -1 : 0);
-            sigma = mv_dn ? (int)(a & 0x7Fu) : (mv_up ? 0 : sigma + (inc_s ? 1 : 0) - (dec_s ? 1 : 0));
+            istar += (mv_up ? 1 : 0) - (mv_dn ? 1 : 0);
+            const int sig_n = sigma + (in_del ? 1 : 0) - (in_ins ? 1 : 0);
+            sigma = mv_dn ? (int)(a & 0x7Fu) : (mv_up ? 0 : sig_n);
             // 4. a change of event time completes a group of simultaneous events: evaluate the
             //    window (computeMap.hpp:467-481), then stop before the insert that would make
             //    the window end reach `last` (the loop condition of :453)
-            const int Tn = max(min(td, ti), pos0);
+            const int Tn = min(td, ti);
             const bool grp = Tn != T;
             const bool gt = grp && shared > best, ge = grp && shared >= best;
             best = gt ? shared : best;
@@ -655,12 +678,13 @@ __device__ __forceinline__ void l2_slide_lanes(const L2Args &A)
     }
 }
 
-__global__ void __launch_bounds__(L2_THREADS)
+template <int MINB>
+__global__ void __launch_bounds__(L2_THREADS, MINB)
 l2_slide_kernel(const Prep *prep, const uint32_t *cand_base, const uint32_t *work_base, int n_frags,
                 const uint32_t *qhash, const uint64_t *seq_first, const int32_t *qs,
                 const RefMini *ref, const uint2 *hw, int cmw,
                 const int32_t *min_shared, const uint32_t *id_off, const float *id_tab,
-                Mapping *maps, unsigned long long *counters, int q_cap, int state_bytes)
+                Mapping *maps, unsigned long long *counters, int q_cap, int state_bytes, int tab_p)
 {
     extern __shared__ __align__(16) uint8_t l2_smem[];
     uint32_t *s_q = reinterpret_cast<uint32_t *>(l2_smem);                  // q_cap entries: sketch + sentinels
@@ -690,22 +714,15 @@ l2_slide_kernel(const Prep *prep, const uint32_t *cand_base, const uint32_t *wor
             for (int i = tid; i < s + L2_QPAD; i += L2_THREADS) s_q[i] = i < s ? qhash[qb + i] : 0xFFFFFFFFu;
             if (tid == 0) s_maxn = 0;
             __syncthreads();
-            constexpr int PER = L2_TAB / L2_THREADS;
-            const uint32_t x0 = (uint32_t)tid * PER;
-            int l = 0, r = s;
-            const uint32_t t0 = x0 << (32 - L2_TAB_BITS);
-            while (l < r) { int mid = (l + r) >> 1; if (s_q[mid] < t0) l = mid + 1; else r = mid; }
-            int ml = 0;
-#pragma unroll 1
-            for (int i = 0; i < PER; i++) {
-                s_tab[x0 + i] = (uint16_t)l;
-                const int l0 = l;
-                const uint32_t x = x0 + i + 1;
-                if (x == L2_TAB) l = s;
-                else { const uint32_t t = x << (32 - L2_TAB_BITS); while (s_q[l] < t) l++; }     // the sentinels stop the walk
-                ml = max(ml, l - l0);
+            // tab[x] = first sketch index whose slot is >= x (tab[L2_TAB] = s)
+            for (int i = tid; i <= s; i += L2_THREADS) {
+                const uint32_t lo = i == 0 ? 0u : l2_slot(s_q[i - 1], tab_p) + 1u;
+                const uint32_t hi = i == s ? (uint32_t)L2_TAB : l2_slot(s_q[i], tab_p);
+                for (uint32_t x = lo; x <= hi; x++) s_tab[x] = (uint16_t)i;
             }
-            if (tid == L2_THREADS - 1) s_tab[L2_TAB] = (uint16_t)s;
+            __syncthreads();
+            int ml = 0;
+            for (int x = tid; x < L2_TAB; x += L2_THREADS) ml = max(ml, (int)s_tab[x + 1] - (int)s_tab[x]);
             atomicMax(&s_maxn, ml);
         }
         if (tid == 0) { s_next = c_lo; s_cached_f = f; }
@@ -718,14 +735,14 @@ l2_slide_kernel(const Prep *prep, const uint32_t *cand_base, const uint32_t *wor
         A.prep = prep; A.ref = ref; A.hw = hw; A.s_q = s_q; A.s_tab = s_tab;
         A.st = s_state + L2_THREADS * 4 + tid * 4;
         A.s_next = &s_next; A.c_hi = c_hi;
-        A.s = s; A.stride4 = nl * 4; A.cmw = cmw; A.msh = min_shared[s];
+        A.s = s; A.stride4 = nl * 4; A.cmw = cmw; A.msh = min_shared[s]; A.tab_p = tab_p;
         A.nsteps = 0;
         while ((1 << A.nsteps) <= maxn) A.nsteps++;
         A.id_row = id_tab + id_off[s]; A.maps = maps; A.counters = counters;
-        if (maxn <= 2) l2_slide_lanes<2>(A);
-        else if (maxn == 3) l2_slide_lanes<3>(A);
-        else if (maxn == 4) l2_slide_lanes<4>(A);
-        else l2_slide_lanes<0>(A);
+        if (nl == L2_THREADS && maxn <= 2) l2_slide_lanes<2, true>(A);
+        else if (nl == L2_THREADS && maxn == 3) l2_slide_lanes<3, true>(A);
+        else if (maxn <= 4) l2_slide_lanes<4, false>(A);
+        else l2_slide_lanes<0, false>(A);
     }
 }
 
@@ -990,14 +1007,16 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
                 {
                     const int state_bytes = std::min(l2_words_for(std::max(max_s, 1)) * 4 * L2_THREADS, L2_STATE_MAX);
                     const size_t smem = (size_t)q_cap * 4 + (size_t)(L2_TAB + 2) * 2 + (size_t)state_bytes + 2 * L2_THREADS * 4;
-                    if (smem > 48 * 1024) FA_CUDA(cudaFuncSetAttribute(l2_slide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    static const int variant = getenv("FA_L2_VARIANT") ? atoi(getenv("FA_L2_VARIANT")) : 0;
+                    auto slide_fn = variant == 1 ? l2_slide_kernel<10> : (variant == 2 ? l2_slide_kernel<12> : l2_slide_kernel<8>);
+                    if (smem > 48 * 1024) FA_CUDA(cudaFuncSetAttribute(slide_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     int per_sm = 1;
-                    FA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l2_slide_kernel, L2_THREADS, smem));
+                    FA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, slide_fn, L2_THREADS, smem));
                     const uint32_t grid = std::min<uint32_t>(W, (uint32_t)dev_sms * (uint32_t)std::max(per_sm, 1));
-                    l2_slide_kernel<<<grid, L2_THREADS, smem, st>>>(reinterpret_cast<const Prep *>(ws.prep.p), ws.frag_cands.p, ws.work_base.p, F,
+                    slide_fn<<<grid, L2_THREADS, smem, st>>>(reinterpret_cast<const Prep *>(ws.prep.p), ws.frag_cands.p, ws.work_base.p, F,
                                                                     ws.qhash.p, ws.sk.seq_first.p, ws.qs.p, ix->ref.p, ix->hw.p,
                                                                     cmw, ix->d_min_shared.p, ix->d_id_off.p,
-                                                                    ix->d_identity.p, ws.maps.p, ws.counters.p, q_cap, state_bytes);
+                                                                    ix->d_identity.p, ws.maps.p, ws.counters.p, q_cap, state_bytes, l2_tab_shift(w));
                     FA_CUDA(cudaGetLastError()); launches++;
                 }
                 {   // exact fallback for candidates whose 7-bit bucket counts overflowed (returns at once if none)
