@@ -28,7 +28,7 @@ namespace fa {
 namespace {
 
 // device counters (Workspace::counters)
-enum { CT_MAXS = 0, CT_ERR = 1, CT_WORK = 2, CT_SCANNED = 3, CT_MAPPINGS = 4, CT_SKETCH_SUM = 5, CT_REDO = 6, CT_WORK2 = 7, CT_N = 8 };
+enum { CT_MAXS = 0, CT_ERR = 1, CT_WORK = 2, CT_SCANNED = 3, CT_MAPPINGS = 4, CT_SKETCH_SUM = 5, CT_REDO = 6, CT_WORK2 = 7, CT_WORK3 = 8, CT_N = 9 };
 enum { ERR_SORT_CAP = 1, ERR_S_MAX = 2 };
 
 constexpr int L2_THREADS = 64;          // lanes per L2 CTA: each lane slides one candidate at a time
@@ -43,11 +43,6 @@ constexpr int32_t L2_REDO = INT32_MIN;  // Mapping.ref_start marker: redo this c
 
 // state words (four one-byte buckets each) a sketch of size s needs per lane, and the lanes that fit
 __host__ __device__ inline int l2_words_for(int s) { return (s + 4) >> 2; }
-__host__ __device__ inline int l2_lanes_for(int s, int state_bytes)
-{
-    int t = state_bytes / (l2_words_for(s) * 4);
-    return t > L2_THREADS ? L2_THREADS : (t < 1 ? 1 : t);
-}
 __host__ __device__ inline int l2_fb_lanes_for(int s)
 {
     int t = L2_FB_STATE / ((s + 1) * 2);
@@ -257,7 +252,7 @@ __global__ void work_items_kernel(const uint32_t *frag_cands_counts, int n_frags
     work[f] = f == n_frags ? 0u : (frag_cands_counts[f] + L2_ITEM - 1) / L2_ITEM;
 }
 
-// ---- L2: sliding super-window Jaccard, one lane per candidate ----------------------------------
+// ---- L2: sliding super-window Jaccard -------------------------------------------------------
 // State per candidate (SURVEY.md A.5 in incremental form).  Q = sorted query sketch q_1 < ... < q_s.
 // A reference hash that is in Q toggles a match bit M(i); one that is not falls in bucket
 // b = #{q < h} and toggles a distinct-hash count cnt[b].  With
@@ -268,6 +263,15 @@ __global__ void work_items_kernel(const uint32_t *frag_cands_counts, int n_frags
 // slidingMap.hpp:137-284 without the tree.  Duplicate hashes inside a window are resolved with
 // the distances stored at index time (RefMini.w), mirroring the wposR bookkeeping of
 // slidingMap.hpp:150-155, 178-205.
+//
+// The work is split so that only the inherently sequential part runs one lane per candidate:
+//   l2_prep_kernel    per candidate: the index searches of computeMap.hpp:421-433, event counts
+//   l2_events_kernel  per candidate (one warp): classify every reference minimizer of the region
+//                     against the query sketch, merge the insert and delete streams by event time
+//                     (merge path), resolve duplicates, mark the ends of the time groups
+//                     -> a list of 16-bit events in HBM
+//   l2_slide_kernel   one lane per candidate replays its event list through the state machine
+//   l2_fallback_kernel  exact, slow variant for the candidates the fast path does not take
 
 __device__ __forceinline__ uint32_t lb_hw(const uint2 *hw, uint32_t lo, uint32_t hi, int target)
 {
@@ -275,22 +279,41 @@ __device__ __forceinline__ uint32_t lb_hw(const uint2 *hw, uint32_t lo, uint32_t
     return lo;
 }
 
+// Events: bits 0-1 and 8-14 hold the state byte the event touches, already in the lane-
+// interleaved layout of the slide kernel (four one-byte buckets per word, words of one lane 256
+// bytes apart): offset = (idx >> 2) << 8 | (idx & 3) with idx = #{q < h} + match.
+constexpr uint32_t EV_MATCH = 4;      // the hash is in the query sketch: toggles M(idx)
+constexpr uint32_t EV_ONLY = 8;       // the hash is not in the sketch: counts in bucket idx (neither bit: no state change)
+constexpr uint32_t EV_DEL = 16;       // delete (window begin advances) / insert
+constexpr uint32_t EV_GRP = 32;       // last event of its time group: evaluate the window after it
+constexpr uint32_t EV_DUP = 0x8000;   // (events kernel only) a same-hash neighbour exists: resolve against the window
+constexpr uint32_t EV_AOFF = 0x7F03;
+constexpr int EV_MAX_S = 508;         // largest sketch the 16-bit events address
+constexpr int EV_RMAX = 1024;         // most reference minimizers of a candidate region on the event path
+constexpr int EVK_THREADS = 128;
+
+__host__ __device__ inline uint32_t ev_aoff(int idx) { return ((uint32_t)(idx & ~3) << 6) | (uint32_t)(idx & 3); }
+
 // The three Sketch::searchIndex calls of computeL2MappedRegions (computeMap.hpp:421-433) for every
 // candidate, restricted to the candidate's contig.  Minimizer positions grow strictly inside a
 // contig (one minimizer per window at most), so an index distance never exceeds the position
 // distance and each search runs over a short range.
 struct Prep {
-    uint32_t beg, end0, last;   // first super-window [beg, end0); the slide stops when its end reaches `last`
+    uint32_t beg, last;         // first reference minimizer of the region; the slide stops when the window end reaches `last`
     int32_t  seq;               // refSeqId
+    uint32_t n_del;             // delete events before the slide stops (insert events: last - 1 - beg)
 };
 
 __global__ void __launch_bounds__(256)
-l2_prep_kernel(const Cand *cands, const uint32_t *cand_base, int n_frags, const RefMini *ref, const uint2 *hw,
-               const uint32_t *contig_off, int frag_len, int cmw, Prep *prep, unsigned long long *counters)
+l2_prep_kernel(const Cand *cands, const uint32_t *cand_base, int n_frags, const int32_t *qs, const RefMini *ref, const uint2 *hw,
+               const uint32_t *contig_off, int frag_len, int cmw, Prep *prep, unsigned long long *ev_cnt, Mapping *maps,
+               unsigned long long *counters)
 {
     const uint32_t n = cand_base[n_frags];
     unsigned long long scanned = 0;
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+    unsigned int redo = 0;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c <= n; c += gridDim.x * blockDim.x) {
+        if (c == n) { ev_cnt[c] = 0; break; }
         const Cand cd = cands[c];
         const RefMini rh = ref[cd.hint];
         const int seq = (int)rh.z;
@@ -309,11 +332,359 @@ l2_prep_kernel(const Cand *cands, const uint32_t *cand_base, int n_frags, const 
             if (hi < c1 && (int)(hw[hi].y & 0x7FFFFFFFu) < target) hi = c1;
         }
         const uint32_t last = lb_hw(hw, end0, hi, target);
-        prep[c] = Prep{beg, end0, last, seq};
         scanned += max(end0, last) - beg;
+        Prep pp{beg, last, seq, 0u};
+        unsigned long long cnt = 0;
+        Mapping mp{seq, 0, -1, 0.0f};
+        if (end0 < last) {
+            // the slide stops before the insert of element last - 1; deletes at or after that time are not reached
+            const int t_stop = (int)(hw[last - 1].y & 0x7FFFFFFFu) - cmw + 1;
+            const uint32_t dstop = lb_hw(hw, beg + 1, last, t_stop);
+            pp.n_del = dstop - 1 - beg;
+            const bool fast = last - beg <= (uint32_t)EV_RMAX && qs[cd.frag] <= EV_MAX_S;
+            if (fast) cnt = ((unsigned long long)(last - 1 - beg) + pp.n_del + 7ull) & ~7ull;      // padded to whole 16-byte chunks
+            else { mp.ref_start = L2_REDO; redo++; }
+        }
+        prep[c] = pp;
+        ev_cnt[c] = cnt;
+        maps[c] = mp;                         // final for candidates without a window; overwritten by the slide otherwise
     }
     for (int o = 16; o > 0; o >>= 1) scanned += __shfl_xor_sync(0xFFFFFFFFu, scanned, o);
-    if ((threadIdx.x & 31) == 0 && scanned) atomicAdd(&counters[CT_SCANNED], scanned);
+    redo = __reduce_add_sync(0xFFFFFFFFu, redo);
+    if ((threadIdx.x & 31) == 0) {
+        if (scanned) atomicAdd(&counters[CT_SCANNED], scanned);
+        if (redo) atomicAdd(&counters[CT_REDO], (unsigned long long)redo);
+    }
+}
+
+// Minimizer hashes are window minima, so they crowd towards zero (density ~ (1 - u)^(2w - 1)): a
+// table over the plain top bits would put most of a sketch into a few slots.  The slot function is
+// piecewise linear instead: the hash range is cut into equal pieces of 2^p (about the half-life of
+// that density) and piece k gets 1024 >> k slots, which spreads a sketch about evenly.  Monotone.
+__host__ __device__ inline int l2_tab_shift(int w)
+{
+    const double half = 4294967296.0 * 0.6931471805599453 / (2.0 * (w < 1 ? 1 : w));
+    int p = 10;
+    while (p < 30 && (double)(1u << p) < half) p++;
+    return p;
+}
+__device__ __forceinline__ uint32_t l2_slot(uint32_t h, int p)
+{
+    const uint32_t k = min(h >> p, 11u);
+    return 2048u - (2048u >> k) + ((h & ((1u << p) - 1u)) >> (p - 10 + k));
+}
+
+// Per candidate descriptor for the slide kernel.
+struct SlideJob {
+    unsigned long long ev_off;  // first event
+    uint32_t n_events;          // unpadded; 0 = nothing to slide
+    int32_t  s;                 // sketch size of the fragment
+};
+
+// ---- events --------------------------------------------------------------------------------
+// One CTA per work item (<= L2_ITEM candidates of one fragment): the fragment's sketch and the
+// classification table are staged once, then each warp takes candidates one by one.
+//   classification: slot table (above) + a few compares against the staged sketch
+//   merge: delete m (time wpos[beg + m + 1]) and insert m (time max(wpos[beg + m] - cmw + 1, first
+//          window position)) are two sorted sequences; every lane finds its split on the merge path
+//          and emits a contiguous run of whole 16-byte chunks, deletes first inside a time group
+//          (MIIteratorL2.hpp:74-96)
+__global__ void __launch_bounds__(EVK_THREADS)
+l2_events_kernel(const Prep *prep, const unsigned long long *ev_off, const uint32_t *cand_base, const uint32_t *work_base,
+                 int n_frags, const uint32_t *qhash, const uint64_t *seq_first, const int32_t *qs,
+                 const RefMini *ref, const uint2 *hw, int cmw, int tab_p, uint16_t *ev, SlideJob *jobs,
+                 unsigned long long *counters, int q_cap)
+{
+    extern __shared__ __align__(16) uint8_t ev_smem[];
+    uint32_t *s_q = reinterpret_cast<uint32_t *>(ev_smem);                  // q_cap entries: sketch + sentinels
+    uint16_t *s_tab = reinterpret_cast<uint16_t *>(s_q + q_cap);            // L2_TAB + 2 entries
+    uint8_t *s_warp = reinterpret_cast<uint8_t *>(s_tab + L2_TAB + 2) + 12;   // 16-byte aligned (q_cap is a multiple of 4)
+    __shared__ uint32_t s_item, s_next;
+    __shared__ int s_maxn, s_cached_f;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int WARP_BYTES = EV_RMAX * 4 + EV_RMAX * 2;
+    int *w_pos = reinterpret_cast<int *>(s_warp + wid * WARP_BYTES);              // wpos of the region's elements
+    uint16_t *w_cls = reinterpret_cast<uint16_t *>(w_pos + EV_RMAX);              // their event codes
+    const uint32_t n_work = work_base[n_frags];
+    const int cmw1 = cmw - 1;
+    if (tid == 0) s_cached_f = -1;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = (uint32_t)atomicAdd(&counters[CT_WORK3], 1ull);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= n_work) break;
+        int flo = 0, fhi = n_frags - 1;
+        while (flo < fhi) { int mid = (flo + fhi + 1) >> 1; if (work_base[mid] <= item) flo = mid; else fhi = mid - 1; }
+        const int f = flo;
+        const int s = qs[f];
+        const uint32_t c_lo = cand_base[f] + (item - work_base[f]) * L2_ITEM;
+        const uint32_t c_hi = min(c_lo + (uint32_t)L2_ITEM, cand_base[f + 1]);
+        if (s_cached_f != f && s <= EV_MAX_S) {
+            const uint64_t qb = seq_first[f];
+            for (int i = tid; i < s + L2_QPAD; i += EVK_THREADS) s_q[i] = i < s ? qhash[qb + i] : 0xFFFFFFFFu;
+            if (tid == 0) s_maxn = 0;
+            __syncthreads();
+            // tab[x] = first sketch index whose slot is >= x (tab[L2_TAB] = s)
+            for (int i = tid; i <= s; i += EVK_THREADS) {
+                const uint32_t lo = i == 0 ? 0u : l2_slot(s_q[i - 1], tab_p) + 1u;
+                const uint32_t hi = i == s ? (uint32_t)L2_TAB : l2_slot(s_q[i], tab_p);
+                for (uint32_t x = lo; x <= hi; x++) s_tab[x] = (uint16_t)i;
+            }
+            __syncthreads();
+            int ml = 0;
+            for (int x = tid; x < L2_TAB; x += EVK_THREADS) ml = max(ml, (int)s_tab[x + 1] - (int)s_tab[x]);
+            atomicMax(&s_maxn, ml);
+        }
+        if (tid == 0) { s_next = c_lo + EVK_THREADS / 32; s_cached_f = s <= EV_MAX_S ? f : -1; }
+        __syncthreads();
+        const int maxn = s_maxn;
+        const bool linear = maxn <= L2_QPAD - 1;          // compare against every entry of the slot; else bisect
+
+        // candidates are handed out one ahead, so the next descriptor is in flight while this one is processed
+        uint32_t c = c_lo + (uint32_t)wid;
+        Prep pp{};
+        unsigned long long off = 0, off1 = 0;
+        if (c < c_hi) { pp = prep[c]; off = ev_off[c]; off1 = ev_off[c + 1]; }
+        while (c < c_hi) {
+            uint32_t c_nx = 0;
+            if (lane == 0) c_nx = atomicAdd(&s_next, 1u);
+            c_nx = __shfl_sync(0xFFFFFFFFu, c_nx, 0);
+            Prep pp_nx{};
+            unsigned long long off_nx = 0, off1_nx = 0;
+            if (c_nx < c_hi) { pp_nx = prep[c_nx]; off_nx = ev_off[c_nx]; off1_nx = ev_off[c_nx + 1]; }
+
+            const uint32_t n_pad = (uint32_t)(off1 - off);
+            const int R = (int)(pp.last - pp.beg), nI = R - 1, nD = (int)pp.n_del;
+            const int N = n_pad ? nI + nD : 0;
+            if (lane == 0) jobs[c] = SlideJob{off, (uint32_t)N, s};
+            if (N) {
+                // 1. load + classify the region, eight independent loads per lane in flight
+                for (int i0 = 0; i0 < R; i0 += 256) {
+                    uint2 xs[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i = i0 + u * 32 + lane;
+                        xs[u] = i < R ? __ldg(hw + pp.beg + i) : make_uint2(0u, 0u);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i = i0 + u * 32 + lane;
+                        if (i < R) {
+                            const uint32_t h = xs[u].x;
+                            const uint32_t slot = l2_slot(h, tab_p);
+                            int l = (int)s_tab[slot], match;
+                            if (linear) {
+                                int lt = 0, eq = 0;
+                                for (int q = 0; q < maxn; q++) { const uint32_t qv = s_q[l + q]; lt += qv < h ? 1 : 0; eq |= qv == h ? 1 : 0; }
+                                l += lt;
+                                match = l < s ? eq : 0;
+                            } else {
+                                int r = (int)s_tab[slot + 1];
+                                while (l < r) { const int mid = (l + r) >> 1; if (s_q[mid] < h) l = mid + 1; else r = mid; }
+                                match = (l < s && s_q[l] == h) ? 1 : 0;
+                            }
+                            w_pos[i] = (int)(xs[u].y & 0x7FFFFFFFu);
+                            w_cls[i] = (uint16_t)(ev_aoff(l + match) | (match ? EV_MATCH : EV_ONLY) | ((xs[u].y >> 31) ? EV_DUP : 0u));
+                        }
+                    }
+                }
+                __syncwarp();
+                // 2. merge path: lane -> events [t_lo, t_hi), whole chunks of eight
+                const int pos0 = w_pos[0];
+                const int per = (((N + 31) >> 5) + 7) & ~7;
+                const int t_lo = min(N, lane * per), t_hi = min((int)n_pad, lane * per + per);
+                int x;                                             // deletes among the first t_lo events
+                {
+                    int lo = max(0, t_lo - nI), hi = min(t_lo, nD);
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (w_pos[mid + 1] <= max(w_pos[t_lo - mid - 1] - cmw1, pos0)) lo = mid + 1; else hi = mid;
+                    }
+                    x = lo;
+                }
+                int y = t_lo - x;
+                int kdx = x < nD ? w_pos[x + 1] : INT32_MAX;
+                int kiy = y < nI ? max(w_pos[y] - cmw1, pos0) : INT32_MAX;
+                uint4 *dst = reinterpret_cast<uint4 *>(ev + off) + (lane * per >> 3);
+                for (int t0 = lane * per; t0 < t_hi; t0 += 8) {
+                    uint32_t pk[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const bool live = t0 + u < N;                  // (the tail of the last chunk is padding: no-ops)
+                        const bool del = kdx <= kiy;                   // delete first inside a group
+                        const int key = min(kdx, kiy);
+                        const int m = del ? x : y;
+                        uint32_t code = live ? w_cls[m] : 0u;
+                        if (code & EV_DUP) {                           // a same-hash neighbour exists (rare)
+                            const uint32_t j = pp.beg + (uint32_t)m, b = pp.beg + (uint32_t)x, e = pp.beg + (uint32_t)y;
+                            const uint32_t d = ref[j].w;
+                            bool skip;
+                            if (del) { const uint32_t dn = d >> 16; skip = dn && j + dn < e; }              // a later copy stays (NOOP)
+                            else { const uint32_t dp = d & 0xFFFFu; skip = dp && j >= dp && j - dp >= b; }   // already present (REV)
+                            code &= skip ? ~(EV_DUP | EV_MATCH | EV_ONLY | EV_AOFF) : ~EV_DUP;
+                        }
+                        code |= (live && del) ? EV_DEL : 0u;
+                        x += (live && del) ? 1 : 0;
+                        y += (live && !del) ? 1 : 0;
+                        const int lim = del ? nD : nI, cur = del ? x : y;
+                        const int val = w_pos[min(del ? x + 1 : y, R - 1)];
+                        int nk = del ? val : max(val - cmw1, pos0);
+                        nk = cur < lim ? nk : INT32_MAX;
+                        kdx = (live && del) ? nk : kdx;
+                        kiy = (live && !del) ? nk : kiy;
+                        code |= (live && min(kdx, kiy) != key) ? EV_GRP : 0u;      // (both exhausted: the unreached final group)
+                        pk[u >> 1] |= code << (16 * (u & 1));
+                    }
+                    *dst++ = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+                __syncwarp();
+            }
+            c = c_nx; pp = pp_nx; off = off_nx; off1 = off1_nx;
+        }
+    }
+}
+
+// ---- slide ---------------------------------------------------------------------------------
+// One lane per candidate, eight events (one 16-byte chunk) per loop trip, the next chunk in
+// flight.  Every event is applied with selects only, so lanes do not diverge whatever mix of
+// inserts / deletes / matches they replay.  Lanes take candidates from one global counter: a lane
+// that finishes starts the next candidate at the next trip.  State is one byte per bucket (7-bit
+// count + match bit), four buckets per 32-bit word, words interleaved by lane so that every lane
+// owns a shared-memory bank.  A count that would pass 127 sends the candidate to the fallback.
+struct SlideLane {
+    int istar, sigma, shared, best, nb, first_nb, last_nb, overflow;
+    uint32_t a;                // cached state byte of bucket istar
+    uint32_t ioff;             // ev_aoff(istar)
+};
+
+template <bool FULL>
+__device__ __forceinline__ void slide_event(SlideLane &L, uint8_t *st, int pitch, uint32_t ev)
+{
+    const uint32_t aoff = ev & EV_AOFF;
+    const int del = (int)((ev >> 4) & 1u);
+    const int sgn = 1 - 2 * del;
+    uint8_t *const pa = FULL ? st + aoff : st + (aoff >> 8) * pitch + (aoff & 3u);
+    const uint32_t v = *pa;
+    const int nbi = L.istar - sgn;                                   // the bucket the pivot would move to
+    const uint32_t noff = ev_aoff(nbi);
+    const uint32_t pn = FULL ? st[(int)noff] : st[(nbi >> 2) * pitch + (nbi & 3)];   // one row of slack below bucket 0
+    const int act = L.overflow ^ 1;
+    const int mt = (int)((ev >> 2) & 1u) & act;
+    int on = (int)((ev >> 3) & 1u) & act;
+    const int ovf = on & (del ^ 1) & ((v & 0x7Fu) == 0x7Fu ? 1 : 0);
+    L.overflow |= ovf;
+    on &= ovf ^ 1;
+    const uint32_t v2 = (v + (uint32_t)(sgn * ((mt << 7) + on))) & 0xFFu;
+    *pa = (uint8_t)v2;
+    const bool below = aoff < L.ioff, at_p = aoff == L.ioff;
+    L.a = at_p ? v2 : L.a;
+    const int cc = (int)(L.a & 0x7Fu);
+    const bool in_ins = (on & (del ^ 1)) && below;
+    const bool in_del = (on & del) && (below || (at_p && L.sigma > cc));
+    const bool mv_dn = in_ins && L.sigma == 0;
+    const bool mv_up = in_del && (at_p || L.sigma >= cc);
+    const bool mv = mv_dn || mv_up;
+    L.shared += (mt && aoff <= L.ioff) ? sgn : 0;
+    L.shared -= mv_dn ? (int)(L.a >> 7) : 0;
+    const uint32_t a_nb = (aoff == noff) ? v2 : pn;                  // (only possible when moving down)
+    L.a = mv ? a_nb : L.a;
+    L.shared += mv_up ? (int)(L.a >> 7) : 0;
+    L.istar = mv ? nbi : L.istar;
+    L.ioff = mv ? noff : L.ioff;
+    const int sig_n = L.sigma + (in_del ? 1 : 0) - (in_ins ? 1 : 0);
+    L.sigma = mv_dn ? (int)(L.a & 0x7Fu) : (mv_up ? 0 : sig_n);
+    // window evaluation at the end of a time group (computeMap.hpp:467-481), by begin index
+    L.nb += del;
+    const bool grp = (ev & EV_GRP) != 0;
+    const bool gt = grp && L.shared > L.best, ge = grp && L.shared >= L.best;
+    L.best = gt ? L.shared : L.best;
+    L.first_nb = gt ? L.nb : L.first_nb;
+    L.last_nb = ge ? L.nb : L.last_nb;
+}
+
+template <bool FULL>
+__global__ void __launch_bounds__(L2_THREADS)
+l2_slide_kernel(const SlideJob *jobs, const Prep *prep, uint32_t n_cands, const uint2 *hw, const uint16_t *ev,
+                const int32_t *min_shared, const uint32_t *id_off, const float *id_tab,
+                Mapping *maps, unsigned long long *counters, int n_lanes)
+{
+    extern __shared__ __align__(16) uint8_t l2_smem[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int pitch = n_lanes * 4;
+    uint8_t *const st = l2_smem + pitch + tid * 4;                 // one row of slack below bucket 0
+    if (tid >= n_lanes) return;
+    const int in_warp = n_lanes - (tid & ~31);                     // lanes of this warp that slide
+    const unsigned wmask = in_warp >= 32 ? 0xFFFFFFFFu : (1u << in_warp) - 1u;
+
+    bool alive = true, have = false;
+    uint32_t c = 0, k = 0, n_pad = 0;
+    int s = 0;
+    const uint4 *evp = nullptr;
+    uint4 nxt = make_uint4(0, 0, 0, 0);
+    SlideLane L{};
+
+    for (;;) {
+        // ---- lanes without a candidate take the next ones of the global queue ------------------
+        const unsigned need = __ballot_sync(wmask, !have && alive);
+        if (need) {
+            const int leader = __ffs(need) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(&counters[CT_WORK], (unsigned long long)__popc(need));
+            base = __shfl_sync(wmask, base, leader);
+            if (!have && alive) {
+                const unsigned long long cc64 = base + (unsigned long long)__popc(need & ((1u << lane) - 1u));
+                if (cc64 >= (unsigned long long)n_cands) alive = false;
+                else {
+                    c = (uint32_t)cc64;
+                    const SlideJob jb = jobs[c];
+                    if (jb.n_events) {                               // (else: nothing to slide, ask again next trip)
+                        s = jb.s;
+                        const int nwords = l2_words_for(s);
+                        for (int wd = 0; wd < nwords; wd++) *reinterpret_cast<uint32_t *>(st + wd * pitch) = 0u;
+                        evp = reinterpret_cast<const uint4 *>(ev + jb.ev_off);
+                        n_pad = (jb.n_events + 7u) & ~7u;
+                        k = 0;
+                        nxt = __ldg(evp);
+                        L.istar = s; L.ioff = ev_aoff(s); L.sigma = 0; L.shared = 0; L.a = 0; L.overflow = 0;
+                        L.best = 0; L.nb = 0; L.first_nb = 0; L.last_nb = 0;
+                        have = true;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(wmask, alive)) break;
+        if (have) {
+            const uint4 cur = nxt;
+            nxt = __ldg(evp + (k >> 3) + 1);                         // (one chunk of slack behind the last list)
+            slide_event<FULL>(L, st, pitch, cur.x & 0xFFFFu);
+            slide_event<FULL>(L, st, pitch, cur.x >> 16);
+            slide_event<FULL>(L, st, pitch, cur.y & 0xFFFFu);
+            slide_event<FULL>(L, st, pitch, cur.y >> 16);
+            slide_event<FULL>(L, st, pitch, cur.z & 0xFFFFu);
+            slide_event<FULL>(L, st, pitch, cur.z >> 16);
+            slide_event<FULL>(L, st, pitch, cur.w & 0xFFFFu);
+            slide_event<FULL>(L, st, pitch, cur.w >> 16);
+            k += 8;
+            if (k >= n_pad || L.overflow) {
+                const Prep pp = prep[c];
+                Mapping mp;
+                mp.seq = pp.seq;
+                if (L.overflow) { mp.ref_start = L2_REDO; mp.shared = -1; mp.identity = 0.0f; atomicAdd(&counters[CT_REDO], 1ull); }
+                else {
+                    const int first_pos = (int)(hw[pp.beg + (uint32_t)L.first_nb].y & 0x7FFFFFFFu);
+                    const int last_pos = (int)(hw[pp.beg + (uint32_t)L.last_nb].y & 0x7FFFFFFFu);
+                    mp.ref_start = (first_pos + last_pos) / 2;                        // computeMap.hpp:492
+                    const bool pass = L.best >= min_shared[s];                          // computeMap.hpp:371-380 via the table
+                    mp.shared = pass ? L.best : -1 - L.best;
+                    mp.identity = pass ? id_tab[id_off[s] + L.best] : 0.0f;
+                }
+                maps[c] = mp;
+                have = false;
+            }
+        }
+    }
 }
 
 // ---- exact fallback (16-bit bucket counts, binary-search classification) -------------------------
@@ -356,7 +727,7 @@ l2_fallback_kernel(const Prep *prep, const uint32_t *cand_base, const uint32_t *
     __shared__ uint32_t s_item;
     const int tid = threadIdx.x;
     const uint32_t n_work = work_base[n_frags];
-    if (counters[CT_REDO] == 0) return;        // nothing overflowed in the fast kernel (the usual case)
+    if (counters[CT_REDO] == 0) return;        // nothing left for the exact path (the usual case)
 
     for (;;) {
         __syncthreads();
@@ -387,8 +758,14 @@ l2_fallback_kernel(const Prep *prep, const uint32_t *cand_base, const uint32_t *
             if (!active) continue;
 
             const Prep pp = prep[c];
-            const uint32_t beg = pp.beg, end0 = pp.end0, last = pp.last;
+            const uint32_t beg = pp.beg, last = pp.last;
             const RefMini rbeg = ref[beg];
+            uint32_t end0 = beg;                                              // first index with wpos >= wpos[beg] + cmw
+            {
+                uint32_t l = beg, r = last;
+                while (l < r) { uint32_t mid = l + ((r - l) >> 1); if ((int)ref[mid].y < (int)rbeg.y + cmw) l = mid + 1; else r = mid; }
+                end0 = l;
+            }
 
             SlideState S;
             S.st = s_state + tid; S.stride = tpc; S.s = s; S.istar = s; S.sigma = 0; S.shared = 0;
@@ -444,305 +821,6 @@ l2_fallback_kernel(const Prep *prep, const uint32_t *cand_base, const uint32_t *
             mp.identity = pass ? id_tab[id_off[s] + best] : 0.0f;
             maps[c] = mp;
         }
-    }
-}
-
-// ---- the fast L2 kernel ---------------------------------------------------------------------
-// Same state machine as SlideState above, reorganised for SIMT execution:
-//  * one EVENT (delete or insert of one reference minimizer) per loop iteration, chosen by
-//    comparing the two stream heads, and applied with selects only, so all lanes of a warp run
-//    the same instruction stream whatever mix of deletes / inserts / matches their candidates
-//    need.  The first super-window is built by the same loop (its inserts all carry a time
-//    <= the first window position);
-//  * lanes pull candidates of the work item one by one: a lane that finishes a candidate starts
-//    the next without waiting for the rest of its warp;
-//  * the reference stream is the 8-byte (hash, wpos) array `hw`, read with 16-byte loads one
-//    chunk ahead on each side; bit 31 of wpos flags the rare elements that have a duplicate
-//    hash nearby, only those fetch the distances from the full record;
-//  * the next event is classified (table over the top hash bits + MAXN compares against the
-//    staged query sketch) while the state update of the current one is in flight;
-//  * state is one byte per bucket (7-bit count + match bit), four buckets per 32-bit word, with
-//    each lane's words in its own bank.  A count that would pass 127 marks the candidate for
-//    the exact fallback kernel above (never seen outside adversarial sketches).
-
-// One side of the window: element j of `hw` with the pair holding it and the pair after it.
-struct HwStream {
-    uint64_t c0, c1, n0, n1;
-    __device__ __forceinline__ void init(const uint2 *hw, uint32_t j)
-    {
-        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(hw) + (j >> 1);
-        asm("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(c0), "=l"(c1) : "l"(p));
-        asm("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(n0), "=l"(n1) : "l"(p + 1));
-    }
-    __device__ __forceinline__ uint64_t get(uint32_t j) const { return (j & 1) ? c1 : c0; }
-    // called with the new index j after an advance by one, under predicate `adv`
-    __device__ __forceinline__ void advance(const uint2 *hw, uint32_t j, bool adv)
-    {
-        const bool roll = adv && (j & 1) == 0;
-        c0 = roll ? n0 : c0; c1 = roll ? n1 : c1;
-        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(hw) + (j >> 1) + 1;
-        asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.global.nc.v2.u64 {%0, %1}, [%2];\n\t}"
-            : "+l"(n0), "+l"(n1) : "l"(p), "r"((uint32_t)roll));
-    }
-};
-
-// Minimizer hashes are window minima, so they crowd towards zero (density ~ (1 - u)^(2w - 1)): a
-// table over the plain top bits would put most of a sketch into a few slots.  The slot function is
-// piecewise linear instead: the hash range is cut into equal pieces of 2^p (about the half-life of
-// that density) and piece k gets 1024 >> k slots, which spreads a sketch about evenly.  Monotone.
-__host__ __device__ inline int l2_tab_shift(int w)
-{
-    const double half = 4294967296.0 * 0.6931471805599453 / (2.0 * (w < 1 ? 1 : w));
-    int p = 10;
-    while (p < 30 && (double)(1u << p) < half) p++;
-    return p;
-}
-__device__ __forceinline__ uint32_t l2_slot(uint32_t h, int p)
-{
-    const uint32_t k = min(h >> p, 11u);
-    return 2048u - (2048u >> k) + ((h & ((1u << p) - 1u)) >> (p - 10 + k));
-}
-
-struct L2Args {
-    const Prep *prep; const RefMini *ref; const uint2 *hw;
-    const uint32_t *s_q; const uint16_t *s_tab; uint8_t *st;
-    uint32_t *s_next; uint32_t c_hi;
-    int s, stride4, cmw, msh, nsteps, tab_p;
-    const float *id_row; Mapping *maps; unsigned long long *counters;
-};
-
-// MAXN > 0: every table slot holds at most MAXN sketch hashes (compare against all of them);
-// MAXN == 0: bisect between the slot's bounds.  Returns idx = lb + match where lb = #{q < h} and
-// match = (q_{lb+1} == h): the state byte the event touches.
-template <int MAXN>
-__device__ __forceinline__ void l2_classify(const L2Args &A, uint32_t h, int &idx, int &match)
-{
-    const uint32_t slot = l2_slot(h, A.tab_p);
-    int l = (int)A.s_tab[slot];
-    if (MAXN > 0) {
-        // the slot's entries are sorted and everything behind them (next slots, sentinels) is larger than h
-        int lt = 0, eq = 0;
-#pragma unroll
-        for (int i = 0; i < MAXN; i++) {
-            const uint32_t qv = A.s_q[l + i];
-            lt += qv < h ? 1 : 0;
-            eq |= qv == h ? 1 : 0;
-        }
-        l += lt;
-        match = l < A.s ? eq : 0;                 // (a sentinel equals h only for h == 0xFFFFFFFF)
-        idx = l + match;
-    } else {
-        int r = (int)A.s_tab[slot + 1];
-        for (int i = 0; i < A.nsteps; i++) {
-            const int mid = (l + r) >> 1;
-            const bool go = l < r && A.s_q[min(mid, A.s - 1)] < h;
-            const bool shrink = l < r && !go;
-            l = go ? mid + 1 : l;
-            r = shrink ? mid : r;
-        }
-        match = (l < A.s && A.s_q[min(l, A.s - 1)] == h) ? 1 : 0;
-        idx = l + match;
-    }
-}
-
-// FULL: all 64 lanes of the CTA are in use, so the lane-interleaved state has a constant row pitch.
-template <int MAXN, bool FULL>
-__device__ __forceinline__ void l2_slide_lanes(const L2Args &A)
-{
-    const int s = A.s, stride4 = A.stride4, cmw1 = A.cmw - 1;
-    uint8_t *const st = A.st;
-    const uint2 *const hw = A.hw;
-    const int nwords = l2_words_for(s);
-    auto at = [&](int idx) -> uint8_t * {
-        return FULL ? st + ((idx & ~3) << 6) + (idx & 3) : st + (idx >> 2) * stride4 + (idx & 3);
-    };
-
-    bool alive = true, have = false;
-    uint32_t c = 0, b = 0, e = 0, last = 0;
-    int seq = 0, pos0 = 0, wb_cur = 0, T = 0, best = 0, first_pos = 0, last_pos = 0;
-    int istar = 0, sigma = 0, shared = 0, td = 0, ti = 0, overflow = 0;
-    uint32_t a = 0, hb = 0, wfb = 0;
-    HwStream D, I;                     // D: element b + 1 (its position is the next delete time), I: element e
-    uint64_t xd = 0;
-    int p_del = 0, p_match = 0, p_skip = 0, p_idx = 0;        // pending (classified) event
-
-    auto pick = [&]() {
-        xd = D.get(b + 1);
-        const uint64_t xi = I.get(e);
-        const uint32_t wi = (uint32_t)(xi >> 32);
-        td = (int)((uint32_t)(xd >> 32) & 0x7FFFFFFFu);
-        ti = max((int)(wi & 0x7FFFFFFFu) - cmw1, pos0);                     // the first window's inserts share its time
-        ti = e < last ? ti : INT32_MAX;
-        const bool del = td <= ti;                                         // delete first inside a group
-        p_del = del ? 1 : 0;
-        const uint32_t h = del ? hb : (uint32_t)xi;
-        const uint32_t wf = del ? wfb : wi;
-        p_skip = 0;
-        if (wf & 0x80000000u) {                                            // a same-hash neighbour exists (rare)
-            const uint32_t j = del ? b : e;
-            const uint32_t d = A.ref[j].w;
-            if (del) { const uint32_t dn = d >> 16; p_skip = (dn && j + dn < e) ? 1 : 0; }            // a later copy stays (NOOP)
-            else { const uint32_t dp = d & 0xFFFFu; p_skip = (dp && j >= dp && j - dp >= b) ? 1 : 0; }  // already present (REV)
-        }
-        l2_classify<MAXN>(A, h, p_idx, p_match);
-    };
-
-    for (;;) {
-        if (!have && alive) {
-            // ---- next candidate of the work item ------------------------------------------------
-            for (;;) {
-                c = atomicAdd(A.s_next, 1u);
-                if (c >= A.c_hi) { alive = false; break; }
-                const Prep pp = A.prep[c];
-                if (pp.end0 >= pp.last) {                                  // no window to evaluate
-                    A.maps[c] = Mapping{pp.seq, 0, -1, 0.0f};
-                    continue;
-                }
-#pragma unroll 4
-                for (int wd = 0; wd < nwords; wd++) *reinterpret_cast<uint32_t *>(st + wd * stride4) = 0u;
-                seq = pp.seq; b = pp.beg; e = pp.beg; last = pp.last;
-                I.init(hw, e);
-                D.init(hw, b + 1);
-                const uint64_t x0 = I.get(e);
-                hb = (uint32_t)x0; wfb = (uint32_t)(x0 >> 32);
-                pos0 = (int)(wfb & 0x7FFFFFFFu);
-                wb_cur = pos0; T = pos0; best = 0; first_pos = pos0; last_pos = pos0;
-                istar = s; sigma = 0; shared = 0; a = 0; overflow = 0;
-                pick();
-                have = true;
-                break;
-            }
-        }
-        if (!__any_sync(0xFFFFFFFFu, alive)) break;
-        if (alive) {
-            // 1. state bytes the pending event touches: its own bucket and the pivot's neighbour
-            const int del = p_del, idx = p_idx;
-            const int act = (p_skip | overflow) ^ 1;
-            int mt = p_match & act, on = (p_match ^ 1) & act;
-            const int sgn = 1 - 2 * del;
-            uint8_t *const pa = at(idx);
-            const uint32_t v = *pa;
-            const uint32_t pn = *at(istar - sgn);                           // one row of slack on both sides
-            // 2. advance the stream the event came from, pick + classify the next event
-            hb = del ? (uint32_t)xd : hb;
-            wfb = del ? (uint32_t)(xd >> 32) : wfb;
-            wb_cur = del ? td : wb_cur;
-            b += (uint32_t)del;
-            e += (uint32_t)(del ^ 1);
-            D.advance(hw, b + 1, del != 0);
-            I.advance(hw, e, del == 0);
-            pick();
-            // 3. apply the event
-            const int ovf = (on & (del ^ 1) & ((v & 0x7Fu) == 0x7Fu ? 1 : 0));
-            overflow |= ovf;
-            on &= ovf ^ 1;
-            const uint32_t v2 = (v + (uint32_t)(sgn * ((mt << 7) + on))) & 0xFFu;
-            *pa = (uint8_t)v2;
-            const bool below = idx < istar, at_p = idx == istar;
-            a = at_p ? v2 : a;
-            const int cc = (int)(a & 0x7Fu);
-            const bool in_ins = (on & (del ^ 1)) && below;
-            const bool in_del = (on & del) && (below || (at_p && sigma > cc));
-            const bool mv_dn = in_ins && sigma == 0;
-            const bool mv_up = in_del && (at_p || sigma >= cc);
-            shared += (mt && idx <= istar) ? sgn : 0;
-            shared -= mv_dn ? (int)(a >> 7) : 0;
-            const uint32_t a_dn = (idx == istar - 1) ? v2 : pn;
-            a = mv_dn ? a_dn : (mv_up ? pn : a);
-            shared += mv_up ? (int)(a >> 7) : 0;
-            istar += (mv_up ? 1 : 0) - (mv_dn ? 1 : 0);
-            const int sig_n = sigma + (in_del ? 1 : 0) - (in_ins ? 1 : 0);
-            sigma = mv_dn ? (int)(a & 0x7Fu) : (mv_up ? 0 : sig_n);
-            // 4. a change of event time completes a group of simultaneous events: evaluate the
-            //    window (computeMap.hpp:467-481), then stop before the insert that would make
-            //    the window end reach `last` (the loop condition of :453)
-            const int Tn = min(td, ti);
-            const bool grp = Tn != T;
-            const bool gt = grp && shared > best, ge = grp && shared >= best;
-            best = gt ? shared : best;
-            first_pos = gt ? wb_cur : first_pos;
-            last_pos = ge ? wb_cur : last_pos;
-            T = Tn;
-            if (grp && ((ti == Tn && e + 1 >= last) || overflow)) {
-                Mapping mp;
-                mp.seq = seq;
-                mp.ref_start = (first_pos + last_pos) / 2;                        // computeMap.hpp:492
-                const bool pass = best >= A.msh && !overflow;                       // computeMap.hpp:371-380 via the table
-                mp.shared = pass ? best : -1 - best;
-                mp.identity = pass ? A.id_row[best] : 0.0f;
-                if (overflow) { mp.ref_start = L2_REDO; mp.shared = -1; atomicAdd(&A.counters[CT_REDO], 1ull); }
-                A.maps[c] = mp;
-                have = false;
-            }
-        }
-    }
-}
-
-template <int MINB>
-__global__ void __launch_bounds__(L2_THREADS, MINB)
-l2_slide_kernel(const Prep *prep, const uint32_t *cand_base, const uint32_t *work_base, int n_frags,
-                const uint32_t *qhash, const uint64_t *seq_first, const int32_t *qs,
-                const RefMini *ref, const uint2 *hw, int cmw,
-                const int32_t *min_shared, const uint32_t *id_off, const float *id_tab,
-                Mapping *maps, unsigned long long *counters, int q_cap, int state_bytes, int tab_p)
-{
-    extern __shared__ __align__(16) uint8_t l2_smem[];
-    uint32_t *s_q = reinterpret_cast<uint32_t *>(l2_smem);                  // q_cap entries: sketch + sentinels
-    uint16_t *s_tab = reinterpret_cast<uint16_t *>(s_q + q_cap);            // L2_TAB + 2 entries
-    uint8_t *s_state = reinterpret_cast<uint8_t *>(s_tab + L2_TAB + 2);       // slack row + state_bytes + slack row
-    __shared__ uint32_t s_item, s_next;
-    __shared__ int s_maxn, s_cached_f;
-    const int tid = threadIdx.x;
-    const uint32_t n_work = work_base[n_frags];
-    if (tid == 0) s_cached_f = -1;
-
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_item = (uint32_t)atomicAdd(&counters[CT_WORK], 1ull);
-        __syncthreads();
-        const uint32_t item = s_item;
-        if (item >= n_work) break;
-        int flo = 0, fhi = n_frags - 1;
-        while (flo < fhi) { int mid = (flo + fhi + 1) >> 1; if (work_base[mid] <= item) flo = mid; else fhi = mid - 1; }
-        const int f = flo;
-        const int s = qs[f];
-        const uint32_t c_lo = cand_base[f] + (item - work_base[f]) * L2_ITEM;
-        const uint32_t c_hi = min(c_lo + (uint32_t)L2_ITEM, cand_base[f + 1]);
-        if (s_cached_f != f) {
-            // query sketch + classification table: slot x of the top hash bits -> first sketch index of the slot
-            const uint64_t qb = seq_first[f];
-            for (int i = tid; i < s + L2_QPAD; i += L2_THREADS) s_q[i] = i < s ? qhash[qb + i] : 0xFFFFFFFFu;
-            if (tid == 0) s_maxn = 0;
-            __syncthreads();
-            // tab[x] = first sketch index whose slot is >= x (tab[L2_TAB] = s)
-            for (int i = tid; i <= s; i += L2_THREADS) {
-                const uint32_t lo = i == 0 ? 0u : l2_slot(s_q[i - 1], tab_p) + 1u;
-                const uint32_t hi = i == s ? (uint32_t)L2_TAB : l2_slot(s_q[i], tab_p);
-                for (uint32_t x = lo; x <= hi; x++) s_tab[x] = (uint16_t)i;
-            }
-            __syncthreads();
-            int ml = 0;
-            for (int x = tid; x < L2_TAB; x += L2_THREADS) ml = max(ml, (int)s_tab[x + 1] - (int)s_tab[x]);
-            atomicMax(&s_maxn, ml);
-        }
-        if (tid == 0) { s_next = c_lo; s_cached_f = f; }
-        __syncthreads();
-        const int maxn = s_maxn;
-        const int nl = l2_lanes_for(s, state_bytes);
-        if (tid >= nl) continue;
-
-        L2Args A;
-        A.prep = prep; A.ref = ref; A.hw = hw; A.s_q = s_q; A.s_tab = s_tab;
-        A.st = s_state + L2_THREADS * 4 + tid * 4;
-        A.s_next = &s_next; A.c_hi = c_hi;
-        A.s = s; A.stride4 = nl * 4; A.cmw = cmw; A.msh = min_shared[s]; A.tab_p = tab_p;
-        A.nsteps = 0;
-        while ((1 << A.nsteps) <= maxn) A.nsteps++;
-        A.id_row = id_tab + id_off[s]; A.maps = maps; A.counters = counters;
-        if (nl == L2_THREADS && maxn <= 2) l2_slide_lanes<2, true>(A);
-        else if (nl == L2_THREADS && maxn == 3) l2_slide_lanes<3, true>(A);
-        else if (maxn <= 4) l2_slide_lanes<4, false>(A);
-        else l2_slide_lanes<0, false>(A);
     }
 }
 
@@ -996,30 +1074,51 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
                 FA_CUDA(cudaGetLastError()); launches++;
                 FA_CUDA(cudaEventRecord(ws.ev[5], st));
                 // ---- L2 -----------------------------------------------------------------------
-                FA_TRY(ws.prep.reserve(C));
+                FA_TRY(ws.prep.reserve(C)); FA_TRY(ws.ev_off.reserve(C + 1)); FA_TRY(ws.jobs.reserve(C));
                 int dev_sms = 148;
                 cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ix->device);
-                l2_prep_kernel<<<std::min<uint32_t>((uint32_t)((C + 255) / 256), (uint32_t)dev_sms * 8u), 256, 0, st>>>(
-                    ws.cands.p, ws.frag_cands.p, F, ix->ref.p, ix->hw.p, ix->contig_off.p, L, cmw,
-                    reinterpret_cast<Prep *>(ws.prep.p), ws.counters.p);
+                l2_prep_kernel<<<std::min<uint32_t>((uint32_t)((C + 256) / 256), (uint32_t)dev_sms * 8u), 256, 0, st>>>(
+                    ws.cands.p, ws.frag_cands.p, F, ws.qs.p, ix->ref.p, ix->hw.p, ix->contig_off.p, L, cmw,
+                    reinterpret_cast<Prep *>(ws.prep.p), reinterpret_cast<unsigned long long *>(ws.ev_off.p), ws.maps.p, ws.counters.p);
                 FA_CUDA(cudaGetLastError()); launches++;
+                FA_TRY(excl_scan<uint64_t>(st, ws.cub_tmp, ws.ev_off.p, ws.ev_off.p, (int64_t)C + 1, &launches));
+                uint64_t *h_ev = reinterpret_cast<uint64_t *>(h_u + 2);
+                FA_CUDA(cudaMemcpyAsync(h_ev, ws.ev_off.p + C, 8, cudaMemcpyDeviceToHost, st));
+                FA_CUDA(cudaStreamSynchronize(st));                           // sync 3: size of the event lists
+                const uint64_t n_ev = h_ev[0];
+                FA_TRY(ws.events.reserve(n_ev + 64));
                 const int q_cap = (std::max(max_s, 1) + L2_QPAD + 3) & ~3;
-                {
-                    const int state_bytes = std::min(l2_words_for(std::max(max_s, 1)) * 4 * L2_THREADS, L2_STATE_MAX);
-                    const size_t smem = (size_t)q_cap * 4 + (size_t)(L2_TAB + 2) * 2 + (size_t)state_bytes + 2 * L2_THREADS * 4;
-                    static const int variant = getenv("FA_L2_VARIANT") ? atoi(getenv("FA_L2_VARIANT")) : 0;
-                    auto slide_fn = variant == 1 ? l2_slide_kernel<10> : (variant == 2 ? l2_slide_kernel<12> : l2_slide_kernel<8>);
-                    if (smem > 48 * 1024) FA_CUDA(cudaFuncSetAttribute(slide_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    int per_sm = 1;
-                    FA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, slide_fn, L2_THREADS, smem));
-                    const uint32_t grid = std::min<uint32_t>(W, (uint32_t)dev_sms * (uint32_t)std::max(per_sm, 1));
-                    slide_fn<<<grid, L2_THREADS, smem, st>>>(reinterpret_cast<const Prep *>(ws.prep.p), ws.frag_cands.p, ws.work_base.p, F,
-                                                                    ws.qhash.p, ws.sk.seq_first.p, ws.qs.p, ix->ref.p, ix->hw.p,
-                                                                    cmw, ix->d_min_shared.p, ix->d_id_off.p,
-                                                                    ix->d_identity.p, ws.maps.p, ws.counters.p, q_cap, state_bytes, l2_tab_shift(w));
-                    FA_CUDA(cudaGetLastError()); launches++;
+                if (n_ev > 0) {
+                    {
+                        const size_t smem = (size_t)q_cap * 4 + (size_t)(L2_TAB + 2) * 2 + 12 +
+                                            (size_t)(EVK_THREADS / 32) * (EV_RMAX * 4 + EV_RMAX * 2);
+                        FA_CUDA(cudaFuncSetAttribute(l2_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        int per_sm = 1;
+                        FA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l2_events_kernel, EVK_THREADS, smem));
+                        const uint32_t grid = std::min<uint32_t>(W, (uint32_t)dev_sms * (uint32_t)std::max(per_sm, 1));
+                        l2_events_kernel<<<grid, EVK_THREADS, smem, st>>>(
+                            reinterpret_cast<const Prep *>(ws.prep.p), reinterpret_cast<const unsigned long long *>(ws.ev_off.p),
+                            ws.frag_cands.p, ws.work_base.p, F, ws.qhash.p, ws.sk.seq_first.p, ws.qs.p, ix->ref.p, ix->hw.p, cmw,
+                            l2_tab_shift(w), ws.events.p, reinterpret_cast<SlideJob *>(ws.jobs.p), ws.counters.p, q_cap);
+                        FA_CUDA(cudaGetLastError()); launches++;
+                    }
+                    {
+                        const int rows = l2_words_for(std::min(std::max(max_s, 1), EV_MAX_S)) + 2;     // + one row of slack on each side
+                        const int n_lanes = std::max(1, std::min(L2_THREADS, L2_STATE_MAX / (rows * 4)));
+                        const size_t smem = (size_t)rows * n_lanes * 4;
+                        auto slide_fn = n_lanes == L2_THREADS ? l2_slide_kernel<true> : l2_slide_kernel<false>;
+                        if (smem > 48 * 1024) FA_CUDA(cudaFuncSetAttribute(slide_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        int per_sm = 1;
+                        FA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, slide_fn, L2_THREADS, smem));
+                        const uint64_t want = (C + n_lanes - 1) / n_lanes;
+                        const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)dev_sms * (uint64_t)std::max(per_sm, 1));
+                        slide_fn<<<grid, L2_THREADS, smem, st>>>(
+                            reinterpret_cast<const SlideJob *>(ws.jobs.p), reinterpret_cast<const Prep *>(ws.prep.p), (uint32_t)C, ix->hw.p,
+                            ws.events.p, ix->d_min_shared.p, ix->d_id_off.p, ix->d_identity.p, ws.maps.p, ws.counters.p, n_lanes);
+                        FA_CUDA(cudaGetLastError()); launches++;
+                    }
                 }
-                {   // exact fallback for candidates whose 7-bit bucket counts overflowed (returns at once if none)
+                {   // exact path for what the event path did not take: long regions, very large sketches, bucket overflow
                     const size_t smem = (size_t)q_cap * 4 + (size_t)L2_FB_STATE + 64;
                     if (smem > 48 * 1024) FA_CUDA(cudaFuncSetAttribute(l2_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     const uint32_t grid = std::min<uint32_t>(W, (uint32_t)dev_sms * 4u);
