@@ -33,7 +33,6 @@ enum { ERR_SORT_CAP = 1, ERR_S_MAX = 2 };
 
 constexpr int L2_THREADS = 64;          // lanes per L2 CTA: each lane slides one candidate at a time
 constexpr int L2_ITEM = 128;            // candidates of one fragment per work item (lanes pull them one by one)
-constexpr int L2_STATE_MAX = 96 * 1024; // cap of the per-CTA slide state (larger sketches use fewer lanes)
 constexpr int L2_FB_STATE = 32 * 1024;  // u16 state of the exact fallback kernel
 constexpr int L2_TAB_BITS = 11;         // classification table over the top bits of the hash
 constexpr int L2_TAB = 1 << L2_TAB_BITS;
@@ -389,72 +388,20 @@ struct SlideJob {
 //          window position)) are two sorted sequences; every lane finds its split on the merge path
 //          and emits a contiguous run of whole 16-byte chunks, deletes first inside a time group
 //          (MIIteratorL2.hpp:74-96)
-__global__ void __launch_bounds__(EVK_THREADS)
-l2_events_kernel(const Prep *prep, const unsigned long long *ev_off, const uint32_t *cand_base, const uint32_t *work_base,
-                 int n_frags, const uint32_t *qhash, const uint64_t *seq_first, const int32_t *qs,
-                 const RefMini *ref, const uint2 *hw, int cmw, int tab_p, uint16_t *ev, SlideJob *jobs,
-                 unsigned long long *counters, int q_cap)
+struct EvCtx {
+    const uint32_t *s_q; const uint16_t *s_tab; int *w_pos; uint16_t *w_cls;
+    const RefMini *ref; const uint2 *hw; uint16_t *ev; SlideJob *jobs;
+    int s, cmw1, tab_p, maxn;
+};
+
+// MAXN > 0: every table slot holds at most MAXN sketch hashes; MAXN == 0: bisect inside the slot.
+template <int MAXN>
+__device__ __forceinline__ void ev_candidate(const EvCtx &X, uint32_t c, const Prep &pp, unsigned long long off,
+                                             unsigned long long off1, int lane)
 {
-    extern __shared__ __align__(16) uint8_t ev_smem[];
-    uint32_t *s_q = reinterpret_cast<uint32_t *>(ev_smem);                  // q_cap entries: sketch + sentinels
-    uint16_t *s_tab = reinterpret_cast<uint16_t *>(s_q + q_cap);            // L2_TAB + 2 entries
-    uint8_t *s_warp = reinterpret_cast<uint8_t *>(s_tab + L2_TAB + 2) + 12;   // 16-byte aligned (q_cap is a multiple of 4)
-    __shared__ uint32_t s_item, s_next;
-    __shared__ int s_maxn, s_cached_f;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    constexpr int WARP_BYTES = EV_RMAX * 4 + EV_RMAX * 2;
-    int *w_pos = reinterpret_cast<int *>(s_warp + wid * WARP_BYTES);              // wpos of the region's elements
-    uint16_t *w_cls = reinterpret_cast<uint16_t *>(w_pos + EV_RMAX);              // their event codes
-    const uint32_t n_work = work_base[n_frags];
-    const int cmw1 = cmw - 1;
-    if (tid == 0) s_cached_f = -1;
-
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_item = (uint32_t)atomicAdd(&counters[CT_WORK3], 1ull);
-        __syncthreads();
-        const uint32_t item = s_item;
-        if (item >= n_work) break;
-        int flo = 0, fhi = n_frags - 1;
-        while (flo < fhi) { int mid = (flo + fhi + 1) >> 1; if (work_base[mid] <= item) flo = mid; else fhi = mid - 1; }
-        const int f = flo;
-        const int s = qs[f];
-        const uint32_t c_lo = cand_base[f] + (item - work_base[f]) * L2_ITEM;
-        const uint32_t c_hi = min(c_lo + (uint32_t)L2_ITEM, cand_base[f + 1]);
-        if (s_cached_f != f && s <= EV_MAX_S) {
-            const uint64_t qb = seq_first[f];
-            for (int i = tid; i < s + L2_QPAD; i += EVK_THREADS) s_q[i] = i < s ? qhash[qb + i] : 0xFFFFFFFFu;
-            if (tid == 0) s_maxn = 0;
-            __syncthreads();
-            // tab[x] = first sketch index whose slot is >= x (tab[L2_TAB] = s)
-            for (int i = tid; i <= s; i += EVK_THREADS) {
-                const uint32_t lo = i == 0 ? 0u : l2_slot(s_q[i - 1], tab_p) + 1u;
-                const uint32_t hi = i == s ? (uint32_t)L2_TAB : l2_slot(s_q[i], tab_p);
-                for (uint32_t x = lo; x <= hi; x++) s_tab[x] = (uint16_t)i;
-            }
-            __syncthreads();
-            int ml = 0;
-            for (int x = tid; x < L2_TAB; x += EVK_THREADS) ml = max(ml, (int)s_tab[x + 1] - (int)s_tab[x]);
-            atomicMax(&s_maxn, ml);
-        }
-        if (tid == 0) { s_next = c_lo + EVK_THREADS / 32; s_cached_f = s <= EV_MAX_S ? f : -1; }
-        __syncthreads();
-        const int maxn = s_maxn;
-        const bool linear = maxn <= L2_QPAD - 1;          // compare against every entry of the slot; else bisect
-
-        // candidates are handed out one ahead, so the next descriptor is in flight while this one is processed
-        uint32_t c = c_lo + (uint32_t)wid;
-        Prep pp{};
-        unsigned long long off = 0, off1 = 0;
-        if (c < c_hi) { pp = prep[c]; off = ev_off[c]; off1 = ev_off[c + 1]; }
-        while (c < c_hi) {
-            uint32_t c_nx = 0;
-            if (lane == 0) c_nx = atomicAdd(&s_next, 1u);
-            c_nx = __shfl_sync(0xFFFFFFFFu, c_nx, 0);
-            Prep pp_nx{};
-            unsigned long long off_nx = 0, off1_nx = 0;
-            if (c_nx < c_hi) { pp_nx = prep[c_nx]; off_nx = ev_off[c_nx]; off1_nx = ev_off[c_nx + 1]; }
-
+    const uint32_t *s_q = X.s_q; const uint16_t *s_tab = X.s_tab; int *w_pos = X.w_pos; uint16_t *w_cls = X.w_cls;
+    const RefMini *ref = X.ref; const uint2 *hw = X.hw; uint16_t *ev = X.ev; SlideJob *jobs = X.jobs;
+    const int s = X.s, cmw1 = X.cmw1, tab_p = X.tab_p;
             const uint32_t n_pad = (uint32_t)(off1 - off);
             const int R = (int)(pp.last - pp.beg), nI = R - 1, nD = (int)pp.n_del;
             const int N = n_pad ? nI + nD : 0;
@@ -475,9 +422,10 @@ l2_events_kernel(const Prep *prep, const unsigned long long *ev_off, const uint3
                             const uint32_t h = xs[u].x;
                             const uint32_t slot = l2_slot(h, tab_p);
                             int l = (int)s_tab[slot], match;
-                            if (linear) {
+                            if (MAXN > 0) {
                                 int lt = 0, eq = 0;
-                                for (int q = 0; q < maxn; q++) { const uint32_t qv = s_q[l + q]; lt += qv < h ? 1 : 0; eq |= qv == h ? 1 : 0; }
+#pragma unroll
+                                for (int q = 0; q < MAXN; q++) { const uint32_t qv = s_q[l + q]; lt += qv < h ? 1 : 0; eq |= qv == h ? 1 : 0; }
                                 l += lt;
                                 match = l < s ? eq : 0;
                             } else {
@@ -541,6 +489,82 @@ l2_events_kernel(const Prep *prep, const unsigned long long *ev_off, const uint3
                 }
                 __syncwarp();
             }
+}
+
+__global__ void __launch_bounds__(EVK_THREADS)
+l2_events_kernel(const Prep *prep, const unsigned long long *ev_off, const uint32_t *cand_base, const uint32_t *work_base,
+                 int n_frags, const uint32_t *qhash, const uint64_t *seq_first, const int32_t *qs,
+                 const RefMini *ref, const uint2 *hw, int cmw, int tab_p, uint16_t *ev, SlideJob *jobs,
+                 unsigned long long *counters, int q_cap)
+{
+    extern __shared__ __align__(16) uint8_t ev_smem[];
+    uint32_t *s_q = reinterpret_cast<uint32_t *>(ev_smem);                  // q_cap entries: sketch + sentinels
+    uint16_t *s_tab = reinterpret_cast<uint16_t *>(s_q + q_cap);            // L2_TAB + 2 entries
+    uint8_t *s_warp = reinterpret_cast<uint8_t *>(s_tab + L2_TAB + 2) + 12;   // 16-byte aligned (q_cap is a multiple of 4)
+    __shared__ uint32_t s_item, s_next;
+    __shared__ int s_maxn, s_cached_f;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int WARP_BYTES = EV_RMAX * 4 + EV_RMAX * 2;
+    int *w_pos = reinterpret_cast<int *>(s_warp + wid * WARP_BYTES);              // wpos of the region's elements
+    uint16_t *w_cls = reinterpret_cast<uint16_t *>(w_pos + EV_RMAX);              // their event codes
+    const uint32_t n_work = work_base[n_frags];
+    const int cmw1 = cmw - 1;
+    if (tid == 0) s_cached_f = -1;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = (uint32_t)atomicAdd(&counters[CT_WORK3], 1ull);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= n_work) break;
+        int flo = 0, fhi = n_frags - 1;
+        while (flo < fhi) { int mid = (flo + fhi + 1) >> 1; if (work_base[mid] <= item) flo = mid; else fhi = mid - 1; }
+        const int f = flo;
+        const int s = qs[f];
+        const uint32_t c_lo = cand_base[f] + (item - work_base[f]) * L2_ITEM;
+        const uint32_t c_hi = min(c_lo + (uint32_t)L2_ITEM, cand_base[f + 1]);
+        if (s_cached_f != f && s <= EV_MAX_S) {
+            const uint64_t qb = seq_first[f];
+            for (int i = tid; i < s + L2_QPAD; i += EVK_THREADS) s_q[i] = i < s ? qhash[qb + i] : 0xFFFFFFFFu;
+            if (tid == 0) s_maxn = 0;
+            __syncthreads();
+            // tab[x] = first sketch index whose slot is >= x (tab[L2_TAB] = s)
+            for (int i = tid; i <= s; i += EVK_THREADS) {
+                const uint32_t lo = i == 0 ? 0u : l2_slot(s_q[i - 1], tab_p) + 1u;
+                const uint32_t hi = i == s ? (uint32_t)L2_TAB : l2_slot(s_q[i], tab_p);
+                for (uint32_t x = lo; x <= hi; x++) s_tab[x] = (uint16_t)i;
+            }
+            __syncthreads();
+            int ml = 0;
+            for (int x = tid; x < L2_TAB; x += EVK_THREADS) ml = max(ml, (int)s_tab[x + 1] - (int)s_tab[x]);
+            atomicMax(&s_maxn, ml);
+        }
+        if (tid == 0) { s_next = c_lo + EVK_THREADS / 32; s_cached_f = s <= EV_MAX_S ? f : -1; }
+        __syncthreads();
+        const int maxn = s_maxn;
+        EvCtx X;
+        X.s_q = s_q; X.s_tab = s_tab; X.w_pos = w_pos; X.w_cls = w_cls; X.ref = ref; X.hw = hw; X.ev = ev; X.jobs = jobs;
+        X.s = s; X.cmw1 = cmw1; X.tab_p = tab_p; X.maxn = maxn;
+
+        // candidates are handed out one ahead, so the next descriptor is in flight while this one is processed
+        uint32_t c = c_lo + (uint32_t)wid;
+        Prep pp{};
+        unsigned long long off = 0, off1 = 0;
+        if (c < c_hi) { pp = prep[c]; off = ev_off[c]; off1 = ev_off[c + 1]; }
+        while (c < c_hi) {
+            uint32_t c_nx = 0;
+            if (lane == 0) c_nx = atomicAdd(&s_next, 1u);
+            c_nx = __shfl_sync(0xFFFFFFFFu, c_nx, 0);
+            Prep pp_nx{};
+            unsigned long long off_nx = 0, off1_nx = 0;
+            if (c_nx < c_hi) { pp_nx = prep[c_nx]; off_nx = ev_off[c_nx]; off1_nx = ev_off[c_nx + 1]; }
+
+            switch (maxn <= 2 ? 2 : (maxn <= 4 ? 4 : (maxn <= L2_QPAD - 1 ? L2_QPAD - 1 : 0))) {
+            case 2: ev_candidate<2>(X, c, pp, off, off1, lane); break;
+            case 4: ev_candidate<4>(X, c, pp, off, off1, lane); break;
+            case L2_QPAD - 1: ev_candidate<L2_QPAD - 1>(X, c, pp, off, off1, lane); break;
+            default: ev_candidate<0>(X, c, pp, off, off1, lane); break;
+            }
             c = c_nx; pp = pp_nx; off = off_nx; off1 = off1_nx;
         }
     }
@@ -554,49 +578,53 @@ l2_events_kernel(const Prep *prep, const unsigned long long *ev_off, const uint3
 // count + match bit), four buckets per 32-bit word, words interleaved by lane so that every lane
 // owns a shared-memory bank.  A count that would pass 127 sends the candidate to the fallback.
 struct SlideLane {
-    int istar, sigma, shared, best, nb, first_nb, last_nb, overflow;
+    int sigma, shared, best, nb, first_nb, last_nb;
     uint32_t a;                // cached state byte of bucket istar
     uint32_t ioff;             // ev_aoff(istar)
+    uint32_t mx;               // largest state byte written (> 255: a bucket count overflowed)
 };
 
-template <bool FULL>
-__device__ __forceinline__ void slide_event(SlideLane &L, uint8_t *st, int pitch, uint32_t ev)
+// shared-memory bytes by 32-bit shared address (keeps the window base out of the per-event code)
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v)); }
+
+// state byte of a bucket: count << 1 | match bit, so an event adds +-(EV_MATCH ? 1 : EV_ONLY ? 2 : 0)
+__device__ __forceinline__ void slide_event(SlideLane &L, uint32_t st, uint32_t ev)
 {
     const uint32_t aoff = ev & EV_AOFF;
-    const int del = (int)((ev >> 4) & 1u);
-    const int sgn = 1 - 2 * del;
-    uint8_t *const pa = FULL ? st + aoff : st + (aoff >> 8) * pitch + (aoff & 3u);
-    const uint32_t v = *pa;
-    const int nbi = L.istar - sgn;                                   // the bucket the pivot would move to
-    const uint32_t noff = ev_aoff(nbi);
-    const uint32_t pn = FULL ? st[(int)noff] : st[(nbi >> 2) * pitch + (nbi & 3)];   // one row of slack below bucket 0
-    const int act = L.overflow ^ 1;
-    const int mt = (int)((ev >> 2) & 1u) & act;
-    int on = (int)((ev >> 3) & 1u) & act;
-    const int ovf = on & (del ^ 1) & ((v & 0x7Fu) == 0x7Fu ? 1 : 0);
-    L.overflow |= ovf;
-    on &= ovf ^ 1;
-    const uint32_t v2 = (v + (uint32_t)(sgn * ((mt << 7) + on))) & 0xFFu;
-    *pa = (uint8_t)v2;
+    const uint32_t pa = st + aoff;
+    const uint32_t v = lds_u8(pa);
+    const bool del = (ev & EV_DEL) != 0;
+    const int sgn = del ? -1 : 1;
+    const uint32_t noff = (L.ioff + (del ? 0xFDu : 0xFFFFFFFFu)) & ~0xFCu;       // bucket istar + 1 / istar - 1
+    const uint32_t pn = lds_u8(st + noff);                                      // (slack rows on both sides)
+    const uint32_t v2 = v + (uint32_t)(sgn * (int)((ev >> 2) & 3u));
+    sts_u8(pa, v2);
+    L.mx = max(L.mx, v2);
     const bool below = aoff < L.ioff, at_p = aoff == L.ioff;
     L.a = at_p ? v2 : L.a;
-    const int cc = (int)(L.a & 0x7Fu);
-    const bool in_ins = (on & (del ^ 1)) && below;
-    const bool in_del = (on & del) && (below || (at_p && L.sigma > cc));
+    const int cc = (int)(L.a >> 1);
+    const bool on = (ev & EV_ONLY) != 0;
+    const bool in_ins = on && !del && below;
+    const bool in_del = on && del && (below || (at_p && L.sigma > cc));
     const bool mv_dn = in_ins && L.sigma == 0;
     const bool mv_up = in_del && (at_p || L.sigma >= cc);
     const bool mv = mv_dn || mv_up;
-    L.shared += (mt && aoff <= L.ioff) ? sgn : 0;
-    L.shared -= mv_dn ? (int)(L.a >> 7) : 0;
+    L.shared += ((ev & EV_MATCH) != 0 && aoff <= L.ioff) ? sgn : 0;
     const uint32_t a_nb = (aoff == noff) ? v2 : pn;                  // (only possible when moving down)
+    const int dsh = mv_up ? (int)(a_nb & 1u) : (mv_dn ? -(int)(L.a & 1u) : 0);
+    L.shared += dsh;
     L.a = mv ? a_nb : L.a;
-    L.shared += mv_up ? (int)(L.a >> 7) : 0;
-    L.istar = mv ? nbi : L.istar;
     L.ioff = mv ? noff : L.ioff;
     const int sig_n = L.sigma + (in_del ? 1 : 0) - (in_ins ? 1 : 0);
-    L.sigma = mv_dn ? (int)(L.a & 0x7Fu) : (mv_up ? 0 : sig_n);
+    L.sigma = mv_dn ? (int)(L.a >> 1) : (mv_up ? 0 : sig_n);
     // window evaluation at the end of a time group (computeMap.hpp:467-481), by begin index
-    L.nb += del;
+    L.nb += del ? 1 : 0;
     const bool grp = (ev & EV_GRP) != 0;
     const bool gt = grp && L.shared > L.best, ge = grp && L.shared >= L.best;
     L.best = gt ? L.shared : L.best;
@@ -604,19 +632,17 @@ __device__ __forceinline__ void slide_event(SlideLane &L, uint8_t *st, int pitch
     L.last_nb = ge ? L.nb : L.last_nb;
 }
 
-template <bool FULL>
 __global__ void __launch_bounds__(L2_THREADS)
 l2_slide_kernel(const SlideJob *jobs, const Prep *prep, uint32_t n_cands, const uint2 *hw, const uint16_t *ev,
                 const int32_t *min_shared, const uint32_t *id_off, const float *id_tab,
-                Mapping *maps, unsigned long long *counters, int n_lanes)
+                Mapping *maps, unsigned long long *counters)
 {
     extern __shared__ __align__(16) uint8_t l2_smem[];
     const int tid = threadIdx.x, lane = tid & 31;
-    const int pitch = n_lanes * 4;
+    constexpr int pitch = L2_THREADS * 4;
     uint8_t *const st = l2_smem + pitch + tid * 4;                 // one row of slack below bucket 0
-    if (tid >= n_lanes) return;
-    const int in_warp = n_lanes - (tid & ~31);                     // lanes of this warp that slide
-    const unsigned wmask = in_warp >= 32 ? 0xFFFFFFFFu : (1u << in_warp) - 1u;
+    const uint32_t st_sh = (uint32_t)__cvta_generic_to_shared(st);
+    constexpr unsigned wmask = 0xFFFFFFFFu;
 
     bool alive = true, have = false;
     uint32_t c = 0, k = 0, n_pad = 0;
@@ -647,7 +673,7 @@ l2_slide_kernel(const SlideJob *jobs, const Prep *prep, uint32_t n_cands, const 
                         n_pad = (jb.n_events + 7u) & ~7u;
                         k = 0;
                         nxt = __ldg(evp);
-                        L.istar = s; L.ioff = ev_aoff(s); L.sigma = 0; L.shared = 0; L.a = 0; L.overflow = 0;
+                        L.ioff = ev_aoff(s); L.sigma = 0; L.shared = 0; L.a = 0; L.mx = 0;
                         L.best = 0; L.nb = 0; L.first_nb = 0; L.last_nb = 0;
                         have = true;
                     }
@@ -658,20 +684,21 @@ l2_slide_kernel(const SlideJob *jobs, const Prep *prep, uint32_t n_cands, const 
         if (have) {
             const uint4 cur = nxt;
             nxt = __ldg(evp + (k >> 3) + 1);                         // (one chunk of slack behind the last list)
-            slide_event<FULL>(L, st, pitch, cur.x & 0xFFFFu);
-            slide_event<FULL>(L, st, pitch, cur.x >> 16);
-            slide_event<FULL>(L, st, pitch, cur.y & 0xFFFFu);
-            slide_event<FULL>(L, st, pitch, cur.y >> 16);
-            slide_event<FULL>(L, st, pitch, cur.z & 0xFFFFu);
-            slide_event<FULL>(L, st, pitch, cur.z >> 16);
-            slide_event<FULL>(L, st, pitch, cur.w & 0xFFFFu);
-            slide_event<FULL>(L, st, pitch, cur.w >> 16);
+            slide_event(L, st_sh, cur.x & 0xFFFFu);
+            slide_event(L, st_sh, cur.x >> 16);
+            slide_event(L, st_sh, cur.y & 0xFFFFu);
+            slide_event(L, st_sh, cur.y >> 16);
+            slide_event(L, st_sh, cur.z & 0xFFFFu);
+            slide_event(L, st_sh, cur.z >> 16);
+            slide_event(L, st_sh, cur.w & 0xFFFFu);
+            slide_event(L, st_sh, cur.w >> 16);
             k += 8;
-            if (k >= n_pad || L.overflow) {
+            const bool overflow = L.mx > 255u;                       // (checked once per chunk: the pivot strays at most eight buckets)
+            if (k >= n_pad || overflow) {
                 const Prep pp = prep[c];
                 Mapping mp;
                 mp.seq = pp.seq;
-                if (L.overflow) { mp.ref_start = L2_REDO; mp.shared = -1; mp.identity = 0.0f; atomicAdd(&counters[CT_REDO], 1ull); }
+                if (overflow) { mp.ref_start = L2_REDO; mp.shared = -1; mp.identity = 0.0f; atomicAdd(&counters[CT_REDO], 1ull); }
                 else {
                     const int first_pos = (int)(hw[pp.beg + (uint32_t)L.first_nb].y & 0x7FFFFFFFu);
                     const int last_pos = (int)(hw[pp.beg + (uint32_t)L.last_nb].y & 0x7FFFFFFFu);
@@ -1103,18 +1130,17 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
                         FA_CUDA(cudaGetLastError()); launches++;
                     }
                     {
-                        const int rows = l2_words_for(std::min(std::max(max_s, 1), EV_MAX_S)) + 2;     // + one row of slack on each side
-                        const int n_lanes = std::max(1, std::min(L2_THREADS, L2_STATE_MAX / (rows * 4)));
-                        const size_t smem = (size_t)rows * n_lanes * 4;
-                        auto slide_fn = n_lanes == L2_THREADS ? l2_slide_kernel<true> : l2_slide_kernel<false>;
+                        const int rows = l2_words_for(std::min(std::max(max_s, 1), EV_MAX_S) + 9) + 1;  // slack: one row below, the pivot may stray eight buckets above
+                        const size_t smem = (size_t)rows * L2_THREADS * 4;
+                        auto slide_fn = l2_slide_kernel;
                         if (smem > 48 * 1024) FA_CUDA(cudaFuncSetAttribute(slide_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                         int per_sm = 1;
                         FA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, slide_fn, L2_THREADS, smem));
-                        const uint64_t want = (C + n_lanes - 1) / n_lanes;
+                        const uint64_t want = (C + L2_THREADS - 1) / L2_THREADS;
                         const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)dev_sms * (uint64_t)std::max(per_sm, 1));
                         slide_fn<<<grid, L2_THREADS, smem, st>>>(
                             reinterpret_cast<const SlideJob *>(ws.jobs.p), reinterpret_cast<const Prep *>(ws.prep.p), (uint32_t)C, ix->hw.p,
-                            ws.events.p, ix->d_min_shared.p, ix->d_id_off.p, ix->d_identity.p, ws.maps.p, ws.counters.p, n_lanes);
+                            ws.events.p, ix->d_min_shared.p, ix->d_id_off.p, ix->d_identity.p, ws.maps.p, ws.counters.p);
                         FA_CUDA(cudaGetLastError()); launches++;
                     }
                 }
