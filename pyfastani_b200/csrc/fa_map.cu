@@ -278,6 +278,25 @@ __device__ __forceinline__ uint32_t lb_hw(const uint2 *hw, uint32_t lo, uint32_t
     return lo;
 }
 
+// lower bound near a guess: gallop from the guess, then bisect the bracket -- the probes stay within a few
+// sectors of the answer instead of walking a wide range (the searches below are DRAM-sector bound)
+__device__ __forceinline__ uint32_t lb_near(const uint2 *hw, uint32_t lo, uint32_t hi, int target, long long guess)
+{
+    if (lo >= hi) return lo;
+    const uint32_t g = (uint32_t)min(max(guess, (long long)lo), (long long)hi - 1);
+    uint32_t l, r, step = 4;
+    if ((int)(hw[g].y & 0x7FFFFFFFu) < target) {                      // answer in (g, hi]
+        l = g + 1;
+        r = min(hi, g + step);
+        while (r < hi && (int)(hw[r].y & 0x7FFFFFFFu) < target) { l = r + 1; step *= 2; r = (hi - r > step) ? r + step : hi; }
+    } else {                                                          // answer in [lo, g]
+        r = g;
+        l = (g - lo > step) ? g - step : lo;
+        while (l > lo && (int)(hw[l].y & 0x7FFFFFFFu) >= target) { r = l; step *= 2; l = (l - lo > step) ? l - step : lo; }
+    }
+    return lb_hw(hw, l, r, target);
+}
+
 // Events: bits 0-1 and 8-14 hold the state byte the event touches, already in the lane-
 // interleaved layout of the slide kernel (four one-byte buckets per word, words of one lane 256
 // bytes apart): offset = (idx >> 2) << 8 | (idx & 3) with idx = #{q < h} + match.
@@ -305,8 +324,8 @@ struct Prep {
 
 __global__ void __launch_bounds__(256)
 l2_prep_kernel(const Cand *cands, const uint32_t *cand_base, int n_frags, const int32_t *qs, const RefMini *ref, const uint2 *hw,
-               const uint32_t *contig_off, int frag_len, int cmw, Prep *prep, unsigned long long *ev_cnt, Mapping *maps,
-               unsigned long long *counters)
+               const uint32_t *contig_off, int frag_len, int cmw, int dens_num, int dens_den, Prep *prep,
+               unsigned long long *ev_cnt, Mapping *maps, unsigned long long *counters)
 {
     const uint32_t n = cand_base[n_frags];
     unsigned long long scanned = 0;
@@ -317,20 +336,17 @@ l2_prep_kernel(const Cand *cands, const uint32_t *cand_base, int n_frags, const 
         const RefMini rh = ref[cd.hint];
         const int seq = (int)rh.z;
         const uint32_t c0 = contig_off[seq], c1 = contig_off[seq + 1];
-        const uint32_t back = (uint32_t)((int)rh.y - cd.start);               // wpos[hint] >= start
-        uint32_t lo = cd.hint - min(back, cd.hint - c0);
-        if (lo > c0 && (int)(hw[lo].y & 0x7FFFFFFFu) >= cd.start) lo = c0;     // positions not strictly increasing: full range
-        const uint32_t beg = lb_hw(hw, lo, cd.hint, cd.start);
+        // expected index distance of a position distance: 2 / (w + 1) minimizers per base
+        const int back = (int)rh.y - cd.start;                                  // wpos[hint] >= start
+        const uint32_t beg = lb_near(hw, c0, cd.hint, cd.start, (long long)cd.hint - (long long)back * dens_num / dens_den);
         const int wpos_beg = (int)(hw[beg].y & 0x7FFFFFFFu);
-        const uint32_t end0 = lb_hw(hw, beg, min(c1, beg + (uint32_t)cmw + 1u), wpos_beg + cmw);
-        uint32_t hi = c1;
+        const uint32_t end0 = lb_near(hw, beg, c1, wpos_beg + cmw, (long long)beg + (long long)cmw * dens_num / dens_den);
         const int target = cd.end + frag_len;
+        uint32_t last = end0;
         if (end0 < c1) {
             const int d = target - (int)(hw[end0].y & 0x7FFFFFFFu);
-            hi = d <= 0 ? end0 : (uint32_t)min((unsigned long long)c1, (unsigned long long)end0 + (unsigned long long)d);
-            if (hi < c1 && (int)(hw[hi].y & 0x7FFFFFFFu) < target) hi = c1;
+            if (d > 0) last = lb_near(hw, end0, c1, target, (long long)end0 + (long long)d * dens_num / dens_den);
         }
-        const uint32_t last = lb_hw(hw, end0, hi, target);
         scanned += max(end0, last) - beg;
         Prep pp{beg, last, seq, 0u};
         unsigned long long cnt = 0;
@@ -338,7 +354,7 @@ l2_prep_kernel(const Cand *cands, const uint32_t *cand_base, int n_frags, const 
         if (end0 < last) {
             // the slide stops before the insert of element last - 1; deletes at or after that time are not reached
             const int t_stop = (int)(hw[last - 1].y & 0x7FFFFFFFu) - cmw + 1;
-            const uint32_t dstop = lb_hw(hw, beg + 1, last, t_stop);
+            const uint32_t dstop = lb_near(hw, beg + 1, last, t_stop, (long long)last - 1 - (long long)cmw * dens_num / dens_den);
             pp.n_del = dstop - 1 - beg;
             const bool fast = last - beg <= (uint32_t)EV_RMAX && qs[cd.frag] <= EV_MAX_S;
             if (fast) cnt = ((unsigned long long)(last - 1 - beg) + pp.n_del + 7ull) & ~7ull;      // padded to whole 16-byte chunks
@@ -1105,7 +1121,7 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
                 int dev_sms = 148;
                 cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ix->device);
                 l2_prep_kernel<<<std::min<uint32_t>((uint32_t)((C + 256) / 256), (uint32_t)dev_sms * 8u), 256, 0, st>>>(
-                    ws.cands.p, ws.frag_cands.p, F, ws.qs.p, ix->ref.p, ix->hw.p, ix->contig_off.p, L, cmw,
+                    ws.cands.p, ws.frag_cands.p, F, ws.qs.p, ix->ref.p, ix->hw.p, ix->contig_off.p, L, cmw, 2, w + 1,
                     reinterpret_cast<Prep *>(ws.prep.p), reinterpret_cast<unsigned long long *>(ws.ev_off.p), ws.maps.p, ws.counters.p);
                 FA_CUDA(cudaGetLastError()); launches++;
                 FA_TRY(excl_scan<uint64_t>(st, ws.cub_tmp, ws.ev_off.p, ws.ev_off.p, (int64_t)C + 1, &launches));
