@@ -293,7 +293,11 @@ def run_b200(a):
         "ms_lookup": 36.0 * inf["sketch_sum"],
         "ms_seed_sort": 8.0 * inf["seeds"] * 2,
         "ms_l1": 8.0 * inf["seeds"] + 12.0 * inf["candidates"],
-        "ms_l2": 8.0 * inf["scanned"] + (4.0 * s_mean + 16.0) * inf["candidates"],
+        # L2 = prep (index searches) + events (classify + merge: reads the (hash, wpos) stream once, writes
+        # 2-byte events) + slide (replays the events, writes 16-byte results)
+        "ms_l2_prep": 56.0 * inf["candidates"],
+        "ms_l2_events": 8.0 * inf["scanned"] + 2.0 * inf["events"] + (4.0 * s_mean + 16.0) * inf["candidates"],
+        "ms_l2_slide": 2.0 * inf["events"] + 32.0 * inf["candidates"],
         "ms_cgi": 16.0 * inf["candidates"],
     }
     per_step = {k: v / a.steps for k, v in stage.items()}
@@ -301,7 +305,8 @@ def run_b200(a):
     top_ms = per_step[top]
     achieved = alg[top] / (top_ms * 1e-3) / 1e9 if top_ms > 0 else 0.0
     kernel_names = {"ms_sketch": "sketch_kernel", "ms_lookup": "lookup_kernel", "ms_seed_sort": "fill_seeds+DeviceRadixSort",
-                    "ms_l1": "candidates_kernel", "ms_l2": "l2_kernel", "ms_cgi": "cgi_best_kernel"}
+                    "ms_l1": "candidates_kernel", "ms_l2_prep": "l2_prep_kernel", "ms_l2_events": "l2_events_kernel",
+                    "ms_l2_slide": "l2_slide_kernel", "ms_cgi": "cgi_best_kernel"}
     roofline = {"bound": "hbm", "kernel": kernel_names[top], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
                 "algorithmic_bytes_per_launch": alg[top], "ms_per_launch": top_ms,
@@ -341,7 +346,8 @@ def run_b200(a):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "stages": stage_roofline,
-        "counters": {k: inf[k] for k in ("fragments", "sketch_sum", "seeds", "candidates", "scanned", "mappings")},
+        "counters": {k: inf[k] for k in ("fragments", "sketch_sum", "seeds", "candidates", "scanned", "events", "mappings",
+                                         "l2_fallback")},
         "hits": len(hits),
         "parity": parity,
         "index_build": {"sketch_s": t_sketch, "index_s": t_index, "minimizers": n_min,

@@ -84,7 +84,10 @@ typedef struct fa_query_info {
     int32_t  kernel_launches;  /* kernels launched by this call */
     float    ms_h2d, ms_sketch, ms_lookup, ms_seed_sort, ms_l1, ms_l2, ms_cgi, ms_d2h, ms_total;
     uint64_t h2d_bytes, d2h_bytes;
-    uint64_t l2_fallback;      /* candidates re-run by the exact fallback L2 kernel (bucket count overflow) */
+    uint64_t l2_fallback;      /* candidates taken by the exact fallback L2 kernel (long regions, huge sketches, bucket overflow) */
+    uint64_t events;           /* insert/delete events replayed by the L2 slide kernel */
+    float    ms_l2_prep, ms_l2_events, ms_l2_slide;   /* the three kernels inside ms_l2 */
+    float    reserved_;
 } fa_query_info;
 
 typedef struct fa_sketch fa_sketch;   /* skch::Sketch under construction (pyx:465-470) */

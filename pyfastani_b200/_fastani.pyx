@@ -69,6 +69,11 @@ cdef extern from "fastani_b200.h" nogil:
         uint64_t h2d_bytes
         uint64_t d2h_bytes
         uint64_t l2_fallback
+        uint64_t events
+        float ms_l2_prep
+        float ms_l2_events
+        float ms_l2_slide
+        float reserved_
     ctypedef struct fa_sketch
     ctypedef struct fa_index
 
@@ -651,7 +656,8 @@ cdef class Mapper(_Parameterized):
                 "ms_h2d": info.ms_h2d, "ms_sketch": info.ms_sketch, "ms_lookup": info.ms_lookup,
                 "ms_seed_sort": info.ms_seed_sort, "ms_l1": info.ms_l1, "ms_l2": info.ms_l2,
                 "ms_cgi": info.ms_cgi, "ms_d2h": info.ms_d2h, "ms_total": info.ms_total,
-                "h2d_bytes": info.h2d_bytes, "d2h_bytes": info.d2h_bytes, "l2_fallback": info.l2_fallback,
+                "h2d_bytes": info.h2d_bytes, "d2h_bytes": info.d2h_bytes, "l2_fallback": info.l2_fallback, "events": info.events,
+                "ms_l2_prep": info.ms_l2_prep, "ms_l2_events": info.ms_l2_events, "ms_l2_slide": info.ms_l2_slide,
             }
         finally:
             free(out)

@@ -47,7 +47,7 @@ struct Workspace {
     DevBuf<int32_t>  g_count;
     DevBuf<unsigned long long> counters;   // misc device counters (see fa_map.cu)
     PinBuf hres;                        // pinned result staging
-    cudaEvent_t ev[10] = {};
+    cudaEvent_t ev[12] = {};
     bool ev_ready = false;
     uint64_t last_cands = 0, last_frags = 0;
 };

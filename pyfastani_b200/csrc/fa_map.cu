@@ -1125,10 +1125,12 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
                     reinterpret_cast<Prep *>(ws.prep.p), reinterpret_cast<unsigned long long *>(ws.ev_off.p), ws.maps.p, ws.counters.p);
                 FA_CUDA(cudaGetLastError()); launches++;
                 FA_TRY(excl_scan<uint64_t>(st, ws.cub_tmp, ws.ev_off.p, ws.ev_off.p, (int64_t)C + 1, &launches));
+                FA_CUDA(cudaEventRecord(ws.ev[9], st));
                 uint64_t *h_ev = reinterpret_cast<uint64_t *>(h_u + 2);
                 FA_CUDA(cudaMemcpyAsync(h_ev, ws.ev_off.p + C, 8, cudaMemcpyDeviceToHost, st));
                 FA_CUDA(cudaStreamSynchronize(st));                           // sync 3: size of the event lists
                 const uint64_t n_ev = h_ev[0];
+                qi.events = n_ev;
                 FA_TRY(ws.events.reserve(n_ev + 64));
                 const int q_cap = (std::max(max_s, 1) + L2_QPAD + 3) & ~3;
                 if (n_ev > 0) {
@@ -1145,6 +1147,7 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
                             l2_tab_shift(w), ws.events.p, reinterpret_cast<SlideJob *>(ws.jobs.p), ws.counters.p, q_cap);
                         FA_CUDA(cudaGetLastError()); launches++;
                     }
+                    FA_CUDA(cudaEventRecord(ws.ev[10], st));
                     {
                         const int rows = l2_words_for(std::min(std::max(max_s, 1), EV_MAX_S) + 9) + 1;  // slack: one row below, the pivot may stray eight buckets above
                         const size_t smem = (size_t)rows * L2_THREADS * 4;
@@ -1204,6 +1207,11 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
         cudaEventElapsedTime(&ms, ws.ev[3], ws.ev[4]); qi.ms_seed_sort = ms;
         cudaEventElapsedTime(&ms, ws.ev[4], ws.ev[5]); qi.ms_l1 = ms;
         cudaEventElapsedTime(&ms, ws.ev[5], ws.ev[6]); qi.ms_l2 = ms;
+        if (qi.events) {
+            cudaEventElapsedTime(&ms, ws.ev[5], ws.ev[9]); qi.ms_l2_prep = ms;
+            cudaEventElapsedTime(&ms, ws.ev[9], ws.ev[10]); qi.ms_l2_events = ms;
+            cudaEventElapsedTime(&ms, ws.ev[10], ws.ev[6]); qi.ms_l2_slide = ms;
+        }
         cudaEventElapsedTime(&ms, ws.ev[6], ws.ev[7]); qi.ms_cgi = ms;
         cudaEventElapsedTime(&ms, ws.ev[7], ws.ev[8]); qi.ms_d2h = ms;
         cudaEventElapsedTime(&ms, ws.ev[0], ws.ev[8]); qi.ms_total = ms;

@@ -29,7 +29,8 @@ class QueryInfo(C.Structure):
                 + [("short_contigs", C.c_int32), ("kernel_launches", C.c_int32)]
                 + [(n, C.c_float) for n in ("ms_h2d", "ms_sketch", "ms_lookup", "ms_seed_sort", "ms_l1", "ms_l2",
                                             "ms_cgi", "ms_d2h", "ms_total")]
-                + [("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("l2_fallback", C.c_uint64)])
+                + [("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("l2_fallback", C.c_uint64), ("events", C.c_uint64)]
+                + [(n, C.c_float) for n in ("ms_l2_prep", "ms_l2_events", "ms_l2_slide", "reserved_")])
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
