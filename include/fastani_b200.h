@@ -87,7 +87,7 @@ typedef struct fa_query_info {
     uint64_t l2_fallback;      /* candidates taken by the exact fallback L2 kernel (long regions, huge sketches, bucket overflow) */
     uint64_t events;           /* insert/delete events replayed by the L2 slide kernel */
     float    ms_l2_prep, ms_l2_events, ms_l2_slide;   /* the three kernels inside ms_l2 */
-    float    reserved_;
+    uint32_t l1_sorted_fragments;                     /* fragments whose seeds took the device-wide radix sort instead of the on-chip L1 */
 } fa_query_info;
 
 typedef struct fa_sketch fa_sketch;   /* skch::Sketch under construction (pyx:465-470) */
@@ -156,6 +156,9 @@ FA_API int fa_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs,
  * (frag, seq, refStartPos, shared, sketch, identity-bits) rows of int32. */
 FA_API int fa_debug_last_candidates(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n);
 FA_API int fa_debug_last_mappings(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n);
+/* Test hook: cap on the seeds per fragment the on-chip L1 kernel accepts (fragments above it take the
+ * device-wide radix-sort path); -1 restores the default (whatever fits in shared memory). */
+FA_API int fa_debug_set_l1_seed_cap(fa_index *ix, int64_t cap);
 /* Device buffers for callers that want inputs resident in HBM before the timed region
  * (fa_contig.on_device). */
 FA_API int fa_device_alloc(int32_t device, uint64_t bytes, void **dptr);

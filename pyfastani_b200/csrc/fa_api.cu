@@ -330,12 +330,12 @@ void fa_index_free(fa_index *ix)
 {
     if (!ix) return;
     cudaSetDevice(ix->device);
-    ix->ref.release(); ix->hw.release(); ix->pos_idx.release(); ix->ukeys.release(); ix->uoff.release(); ix->dir.release();
+    ix->ref.release(); ix->hw.release(); ix->gpos.release(); ix->pos_idx.release(); ix->ukeys.release(); ix->uoff.release(); ix->dir.release();
     ix->contig_off.release(); ix->genome_of_seq.release(); ix->bin_base.release(); ix->genome_cell.release();
     ix->d_min_hits.release(); ix->d_min_shared.release(); ix->d_id_off.release(); ix->d_identity.release();
     Workspace &w = ix->ws;
     free_sketch_scratch(w.sk); w.stage.release(); w.qhash.release(); w.qs.release(); w.hit_start.release(); w.hit_cnt.release();
-    w.frag_seeds.release(); w.seeds_a.release(); w.seeds_b.release(); w.cub_tmp.release(); w.frag_cands.release();
+    w.frag_seeds.release(); w.seeds_a.release(); w.seeds_b.release(); w.fb_seeds.release(); w.cand_tmp.release(); w.hfs.release(); w.cub_tmp.release(); w.frag_cands.release();
     w.work_base.release(); w.cands.release(); w.maps.release(); w.cells.release(); w.g_identity.release(); w.g_count.release();
     w.counters.release(); w.hres.release();
     if (w.ev_ready) for (auto &e : w.ev) cudaEventDestroy(e);
@@ -428,6 +428,13 @@ int fa_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *
 
 int fa_debug_last_candidates(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n) { return debug_candidates(ix, rows, cap, n); }
 int fa_debug_last_mappings(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n) { return debug_mappings(ix, rows, cap, n); }
+int fa_debug_set_l1_seed_cap(fa_index *ix, int64_t cap)
+{
+    if (!ix) { set_error("index is NULL"); return FA_ERR_INVALID; }
+    std::lock_guard<std::mutex> guard(ix->mtx);
+    ix->l1_seed_cap = cap < 0 ? -1 : (long long)cap;
+    return FA_OK;
+}
 
 int fa_device_alloc(int32_t device, uint64_t bytes, void **dptr)
 {

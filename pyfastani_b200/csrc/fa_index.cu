@@ -62,6 +62,25 @@ __global__ void make_hw_kernel(const RefMini *ref, uint64_t n, uint2 *hw)
     hw[i] = make_uint2(e.x, e.y | (e.w ? 0x80000000u : 0u));
 }
 
+// gpos: a 32-bit running coordinate over the position-ordered minimizers in which two elements are
+// closer than a fragment exactly when they lie in the same contig less than frag_len apart.  Every
+// step adds min(wpos difference, frag_len) (frag_len across a contig border), so the test of
+// computeL1CandidateRegions (computeMap.hpp:325-330: same seqId, wpos distance < fragment length)
+// becomes one unsigned subtraction of two 4-byte gathers (fa_map.cu l1_fused_kernel).  Sums wrap
+// mod 2^32; differences of elements fewer than frag_len indices apart never do.
+__global__ void gpos_delta_kernel(const RefMini *ref, uint64_t n, uint32_t frag_len, uint32_t *gpos)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t d = 0;
+    if (i > 0) {
+        const RefMini a = ref[i - 1], b = ref[i];
+        d = frag_len;
+        if (a.z == b.z) d = min(b.y - a.y, frag_len);          // (an unordered pair wraps to a huge value: frag_len)
+    }
+    gpos[i] = d;
+}
+
 // contig_off[s] = first ref index with seqId >= s (contigs without minimizers get empty ranges)
 __global__ void contig_off_kernel(const RefMini *ref, uint64_t n, uint32_t n_contigs, uint32_t *contig_off)
 {
@@ -133,6 +152,8 @@ int build_index(fa_index *ix, int *launches)
         if (s_max > 4096) s_max = 4096;       // larger sketches are reported as unsupported at query time
         const StatTable &t = stat_table(ix->prm.k, ix->prm.pct_identity, s_max);
         ix->s_max = s_max;
+        ix->max_min_hits = 1;
+        for (int32_t v : t.min_hits) ix->max_min_hits = std::max(ix->max_min_hits, (int)v);
         FA_TRY(ix->d_min_hits.reserve(t.min_hits.size()));
         FA_TRY(ix->d_min_shared.reserve(t.min_shared.size()));
         FA_TRY(ix->d_id_off.reserve(t.id_off.size()));
@@ -205,6 +226,17 @@ int build_index(fa_index *ix, int *launches)
     make_hw_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(ix->ref.p, n, ix->hw.p);
     FA_CUDA(cudaGetLastError());
     if (launches) *launches += 1;
+
+    FA_TRY(ix->gpos.reserve(n));
+    gpos_delta_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(ix->ref.p, n, (uint32_t)ix->prm.frag_len, ix->gpos.p);
+    FA_CUDA(cudaGetLastError());
+    {
+        size_t sb = 0;
+        FA_CUDA(cub::DeviceScan::InclusiveSum(nullptr, sb, ix->gpos.p, ix->gpos.p, (int64_t)n, st));
+        FA_TRY(tmp.reserve(sb + 16));
+        FA_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, sb, ix->gpos.p, ix->gpos.p, (int64_t)n, st));
+    }
+    if (launches) *launches += 3;
 
     // ---- CSR over unique hashes --------------------------------------------------------------
     DevBuf<uint32_t> run_len;

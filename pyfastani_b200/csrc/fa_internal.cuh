@@ -32,7 +32,10 @@ struct Workspace {
     DevBuf<int32_t>  qs;                // per-fragment sketch size s
     DevBuf<uint32_t> hit_start, hit_cnt;   // per query hash: bucket in pos_idx
     DevBuf<uint64_t> frag_seeds;        // per fragment: seed count, then exclusive prefix (F + 1)
-    DevBuf<uint64_t> seeds_a, seeds_b;  // (frag << 32 | ref index) keys, double buffered for the sort
+    DevBuf<uint64_t> seeds_a, seeds_b;  // (frag << bits | ref index) keys of the radix-sort L1 path, double buffered
+    DevBuf<uint64_t> fb_seeds;          // seed prefix (F + 1) over the fragments that take the radix-sort path
+    DevBuf<Cand>     cand_tmp;          // l1_fused_kernel: regions of fragment f at its seed offset
+    PinBuf hfs;                         // host copy of the seed prefixes
     DevBuf<uint8_t>  cub_tmp;
     DevBuf<uint32_t> frag_cands;        // per fragment: candidate count, then exclusive prefix (F + 1)
     DevBuf<uint32_t> work_base;         // per fragment: L2 work items, exclusive prefix (F + 1)
@@ -77,6 +80,7 @@ struct fa_index {
     // (minimizerPosLookupIndex, winSketch.hpp:83-84) as CSR over sorted unique hashes
     fa::DevBuf<fa::RefMini> ref;
     fa::DevBuf<uint2> hw;                        // (hash, wpos | has-duplicate-nearby << 31): the 8-byte stream L2 reads
+    fa::DevBuf<uint32_t> gpos;                   // running coordinate for the L1 proximity test (fa_index.cu gpos_delta_kernel)
     uint64_t n = 0, n_unique = 0;
     fa::DevBuf<uint32_t> pos_idx;                // ref indices grouped by hash, insertion order inside a group
     fa::DevBuf<uint32_t> ukeys, uoff;            // unique hashes, group offsets (n_unique + 1)
@@ -92,9 +96,11 @@ struct fa_index {
     uint64_t n_contigs = 0;
     // statistics tables (fa_stat.h)
     int s_max = 0;
+    int max_min_hits = 1;                        // largest entry of d_min_hits
     fa::DevBuf<int32_t>  d_min_hits, d_min_shared;
     fa::DevBuf<uint32_t> d_id_off;
     fa::DevBuf<float>    d_identity;
+    long long l1_seed_cap = -1;                  // test hook: most seeds per fragment for the on-chip L1 (-1 = what fits)
     std::mutex mtx;                              // serialises queries on the single workspace
     fa::Workspace ws;
 };

@@ -152,6 +152,7 @@ __global__ void fill_seeds_kernel(const uint64_t *seq_first, const int32_t *qs, 
     const uint64_t b = seq_first[f];
     const int s = qs[f];
     uint64_t out = seed_base[f];
+    if (seed_base[f + 1] == out) return;                 // not a fragment of this path (or no seeds)
     const uint64_t tag = (uint64_t)f << shift;
     for (int base = 0; base < s; base += 128) {
         const int i = base + tid;
@@ -188,7 +189,7 @@ candidates_kernel(const uint64_t *seeds, const uint64_t *seed_base, const int32_
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint64_t b = seed_base[f], e = seed_base[f + 1];
     const int s = qs[f];
-    if (s <= 0 || b == e) { if (!FILL && tid == 0) frag_cands[f] = 0; return; }
+    if (s <= 0 || b == e) return;                         // fragments without seeds here belong to l1_fused_kernel
     const int m = min_hits[s];
     if (tid == 0) { s_carry_valid = 0; s_carry_seq = -1; s_carry_end = 0; }
     uint32_t heads_before = 0;
@@ -242,6 +243,277 @@ candidates_kernel(const uint64_t *seeds, const uint64_t *seed_base, const int32_
         __syncthreads();
     }
     if (!FILL && tid == 0) frag_cands[f] = heads_before;
+}
+
+
+// ---- L1 on chip: seeds -> candidate regions without leaving the SM -----------------------------
+// The seed hits of one fragment (pyx:941-948: the concatenated position lists of its sketch
+// hashes) must be visited in (seqId, wpos) = reference-index order (computeMap.hpp:316).  Each
+// position list is already sorted and the hits of a fragment cluster in a few hundred loci, so a
+// device-wide 64-bit radix sort (the general path above) moves far more bytes than needed.  Here
+// one CTA owns a fragment:
+//   A  count the hits per chunk of 2^16 reference minimizers (shared-memory histogram)
+//   B  scatter them, as 16-bit offsets, into chunk order (the histogram becomes the cursors)
+//   C  sort every chunk bucket by one warp: a 1024-bit bitmap when the bucket spans < 1024
+//      indices (a locus: ~50 hits over ~250 minimizers), an in-place bitonic network otherwise
+//   D  tiles of 4096 sorted hits: gather the running coordinate gpos (fa_index.cu), test the
+//      pairs (t, t + minHits - 1) of computeMap.hpp:320-334, find region heads / ends of the
+//      merge step (:338-347) from the bitmap of valid pairs -- no sequential carry but one
+//      (index, gpos) pair per tile -- and write the regions to a per-fragment scratch range.
+// Seeds never touch HBM; the only traffic is pos_idx (twice, the second time from L2) and the
+// gathers of gpos / hw.  Fragments whose hits do not fit the CTA's shared memory take the
+// radix-sort path.
+constexpr int L1_THREADS = 1024;
+constexpr int L1_SHIFT = 16;
+constexpr int L1_TILE = 4096;                 // sorted hits per phase-D tile
+constexpr int L1_PER = L1_TILE / L1_THREADS;
+constexpr int L1_EXTRA = 1024;                // look-ahead of the pair test: minHits - 1 <= L1_EXTRA
+constexpr int L1_BM = 32;                     // bitmap words per warp in phase C
+constexpr int L1_STAGE = L1_TILE + L1_EXTRA;
+
+__host__ __device__ inline size_t l1_fixed_smem(uint32_t n_chunks)
+{
+    return (size_t)((n_chunks + 1 + 3) & ~3u) * 4 + (size_t)L1_STAGE * 8;
+}
+
+// in-place sort of k[0, n) by one warp
+__device__ __forceinline__ void l1_sort_bucket(uint16_t *k, int n, uint32_t *bm, int lane)
+{
+    uint32_t lo = 0xFFFFu, hi = 0u;
+    for (int i = lane; i < n; i += 32) { const uint32_t v = k[i]; lo = min(lo, v); hi = max(hi, v); }
+    lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+    hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+    if (hi - lo < (uint32_t)(32 * L1_BM)) {
+        bm[lane] = 0u;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) { const uint32_t d = (uint32_t)k[i] - lo; atomicOr(&bm[d >> 5], 1u << (d & 31u)); }
+        __syncwarp();
+        uint32_t wv = bm[lane];
+        const uint32_t cnt = __popc(wv);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+        int pos = (int)(incl - cnt);
+        const uint32_t base = lo + (uint32_t)lane * 32u;
+        while (wv) { const int bit = __ffs(wv) - 1; wv &= wv - 1u; k[pos++] = (uint16_t)(base + (uint32_t)bit); }
+        __syncwarp();
+        return;
+    }
+    // bitonic network with ascending comparators only (first step of every merge mirrors the
+    // upper half), so slots at or beyond n act as +infinity and are never touched
+    int lg = 1;
+    while ((1 << lg) < n) lg++;
+    const int half = 1 << (lg - 1);
+    for (int ks = 1; ks <= lg; ks++) {                       // merge size 2^ks
+        const int hs = ks - 1, hm = (1 << hs) - 1;
+        for (int idx = lane; idx < half; idx += 32) {
+            const int blk = idx >> hs, off = idx & hm;
+            const int i = (blk << ks) + off, l = (blk << ks) + (1 << ks) - 1 - off;
+            if (l < n) { const uint16_t a = k[i], b = k[l]; if (a > b) { k[i] = b; k[l] = a; } }
+        }
+        __syncwarp();
+        for (int js = hs - 1; js >= 0; js--) {               // half-cleaners of distance 2^js
+            const int jm = (1 << js) - 1;
+            for (int idx = lane; idx < half; idx += 32) {
+                const int i = ((idx >> js) << (js + 1)) + (idx & jm), l = i + (1 << js);
+                if (l < n) { const uint16_t a = k[i], b = k[l]; if (a > b) { k[i] = b; k[l] = a; } }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(L1_THREADS, 1)
+l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hit_start, const uint32_t *hit_cnt,
+                const uint64_t *seed_base, const uint32_t *pos_idx, const uint32_t *gpos, const uint2 *hw,
+                const int32_t *min_hits, int frag_len, uint32_t n_chunks, uint32_t seed_cap,
+                Cand *tmp, uint32_t *frag_cands)
+{
+    extern __shared__ __align__(16) uint8_t l1_smem[];
+    uint32_t *hist = reinterpret_cast<uint32_t *>(l1_smem);                 // [n_chunks]: counts -> cursors -> bucket ends
+    uint32_t *s_j = hist + ((n_chunks + 1 + 3) & ~3u);                       // phase D: reference index per staged hit
+    uint32_t *s_g = s_j + L1_STAGE;                                          //          its gpos
+    uint32_t *s_bm = s_j;                                                    // phase C: per-warp bitmaps (aliases s_j)
+    uint16_t *keys = reinterpret_cast<uint16_t *>(s_g + L1_STAGE);
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_valid[L1_TILE / 32], s_head[L1_TILE / 32], s_hpre[L1_TILE / 32 + 1];
+    __shared__ uint32_t s_blk, s_cj, s_cg;
+    __shared__ int s_cvalid;
+
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint64_t sb = seed_base[f];
+    const uint64_t nf64 = seed_base[f + 1] - sb;
+    if (nf64 > (uint64_t)seed_cap) return;                                   // the radix-sort path takes this fragment
+    const int s = qs[f];
+    if (s <= 0 || nf64 == 0) { if (tid == 0) frag_cands[f] = 0; return; }
+    const uint32_t n = (uint32_t)nf64;
+    const uint64_t qb = seq_first[f];
+
+    for (uint32_t i = tid; i <= n_chunks; i += L1_THREADS) hist[i] = 0u;
+    if (tid == 0) { s_blk = 0u; s_cvalid = 0; s_cj = 0u; s_cg = 0u; }
+    __syncthreads();
+
+    // ---- A: histogram over chunks ------------------------------------------------------------
+    for (int q = wid; q < s; q += L1_THREADS / 32) {
+        const uint32_t st = hit_start[qb + q], c = hit_cnt[qb + q];
+        for (uint32_t t0 = 0; t0 < c; t0 += 128) {
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const uint32_t t = t0 + u * 32 + lane; v[u] = t < c ? __ldg(pos_idx + st + t) : 0xFFFFFFFFu; }
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (v[u] != 0xFFFFFFFFu) atomicAdd(&hist[v[u] >> L1_SHIFT], 1u);
+        }
+    }
+    __syncthreads();
+    // ---- exclusive scan: hist[c] = first slot of bucket c --------------------------------------
+    {
+        const uint32_t per = (n_chunks + L1_THREADS - 1) / L1_THREADS;
+        const uint32_t i0 = min((uint32_t)tid * per, n_chunks), i1 = min(i0 + per, n_chunks);
+        uint32_t sum = 0;
+        for (uint32_t i = i0; i < i1; i++) sum += hist[i];
+        uint32_t tot, x = block_excl_scan<L1_THREADS>(sum, s_warp, &tot);
+        for (uint32_t i = i0; i < i1; i++) { const uint32_t v = hist[i]; hist[i] = x; x += v; }
+    }
+    __syncthreads();
+    // ---- B: scatter the low 16 bits into chunk order; afterwards hist[c] = end of bucket c -------
+    for (int q = wid; q < s; q += L1_THREADS / 32) {
+        const uint32_t st = hit_start[qb + q], c = hit_cnt[qb + q];
+        for (uint32_t t0 = 0; t0 < c; t0 += 128) {
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { const uint32_t t = t0 + u * 32 + lane; v[u] = t < c ? __ldg(pos_idx + st + t) : 0xFFFFFFFFu; }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (v[u] != 0xFFFFFFFFu) { const uint32_t slot = atomicAdd(&hist[v[u] >> L1_SHIFT], 1u); keys[slot] = (uint16_t)v[u]; }
+        }
+    }
+    __syncthreads();
+    // ---- C: sort the buckets (warps take blocks of 32 chunks) ----------------------------------
+    for (;;) {
+        uint32_t blk = 0;
+        if (lane == 0) blk = atomicAdd(&s_blk, 1u);
+        blk = __shfl_sync(0xFFFFFFFFu, blk, 0);
+        const uint32_t c = blk * 32u + (uint32_t)lane;
+        if (blk * 32u >= n_chunks) break;
+        uint32_t b0 = 0, sz = 0;
+        if (c < n_chunks) { b0 = c ? hist[c - 1] : 0u; sz = hist[c] - b0; }
+        unsigned todo = __ballot_sync(0xFFFFFFFFu, sz >= 2u);
+        while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            l1_sort_bucket(keys + __shfl_sync(0xFFFFFFFFu, b0, l), (int)__shfl_sync(0xFFFFFFFFu, sz, l), s_bm + wid * L1_BM, lane);
+        }
+    }
+    __syncthreads();
+
+    // ---- D: candidate regions -------------------------------------------------------------------
+    const int m = min_hits[s];
+    const uint32_t L = (uint32_t)frag_len;
+    Cand *out = tmp + sb;
+    uint32_t heads_before = 0;
+    for (uint32_t base = 0; base < n; base += L1_TILE) {
+        // D1: stage (reference index, gpos) of the tile and of the m - 1 hits behind it
+        for (int e0 = wid * 32; e0 < L1_TILE + m - 1; e0 += L1_THREADS) {
+            const uint32_t t0 = base + (uint32_t)e0;
+            if (t0 >= n) break;
+            uint32_t lo = 0, hi = n_chunks - 1;                           // first chunk whose end is beyond t0
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (hist[mid] <= t0) lo = mid + 1; else hi = mid; }
+            const uint32_t t = t0 + (uint32_t)lane;
+            if (t < n) {
+                uint32_t c = lo;
+                while (hist[c] <= t) c++;
+                const uint32_t j = (c << L1_SHIFT) | (uint32_t)keys[t];
+                s_j[e0 + lane] = j;
+                s_g[e0 + lane] = __ldg(gpos + j);
+            }
+        }
+        __syncthreads();
+        // D2: valid pairs (computeMap.hpp:325-330) as a bitmap
+        uint32_t ja[L1_PER], jb[L1_PER], gb[L1_PER];
+        bool valid[L1_PER];
+#pragma unroll
+        for (int u = 0; u < L1_PER; u++) {
+            const int e = u * L1_THREADS + tid;
+            const uint32_t t = base + (uint32_t)e;
+            valid[u] = false; ja[u] = 0; jb[u] = 0; gb[u] = 0;
+            if (t + (uint32_t)(m - 1) < n) {
+                ja[u] = s_j[e]; jb[u] = s_j[e + m - 1]; gb[u] = s_g[e + m - 1];
+                valid[u] = (jb[u] - ja[u] < L) && (gb[u] - s_g[e] < L);
+            }
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, valid[u]);
+            if (lane == 0) s_valid[e >> 5] = bal;
+        }
+        __syncthreads();
+        // D3: heads: a valid pair whose predecessor among the valid pairs ends before its start (:338-340)
+        uint32_t pj[L1_PER];
+        bool head[L1_PER], pv[L1_PER];
+#pragma unroll
+        for (int u = 0; u < L1_PER; u++) {
+            const int e = u * L1_THREADS + tid;
+            head[u] = false; pv[u] = false; pj[u] = 0;
+            if (valid[u]) {
+                int w = e >> 5;
+                uint32_t x = s_valid[w] & ((1u << lane) - 1u);
+                while (x == 0u && w > 0) x = s_valid[--w];
+                uint32_t pg;
+                if (x) { const int p = w * 32 + 31 - __clz(x); pj[u] = s_j[p]; pg = s_g[p]; pv[u] = true; }
+                else { pj[u] = s_cj; pg = s_cg; pv[u] = s_cvalid != 0; }
+                head[u] = !pv[u] || (jb[u] - pj[u] >= L) || (gb[u] - pg >= L);
+            }
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, head[u]);
+            if (lane == 0) s_head[e >> 5] = bal;
+        }
+        __syncthreads();
+        if (wid == 0) {                                                   // exclusive prefix of the head counts per word
+            uint32_t c4[L1_TILE / 1024], sum = 0;
+#pragma unroll
+            for (int q = 0; q < L1_TILE / 1024; q++) { c4[q] = __popc(s_head[lane * (L1_TILE / 1024) + q]); sum += c4[q]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+            uint32_t x = incl - sum;
+#pragma unroll
+            for (int q = 0; q < L1_TILE / 1024; q++) { s_hpre[lane * (L1_TILE / 1024) + q] = x; x += c4[q]; }
+            if (lane == 31) s_hpre[L1_TILE / 32] = incl;
+        }
+        __syncthreads();
+        // D4: write the heads; a head also closes the region before it (its end is the last member's wpos, :341-346)
+#pragma unroll
+        for (int u = 0; u < L1_PER; u++) {
+            if (head[u]) {
+                const int e = u * L1_THREADS + tid;
+                const uint32_t slot = heads_before + s_hpre[e >> 5] + __popc(s_head[e >> 5] & ((1u << lane) - 1u));
+                const int wb = (int)(__ldg(&hw[jb[u]].y) & 0x7FFFFFFFu);
+                Cand *o = out + slot;
+                o->frag = f; o->hint = ja[u]; o->start = max(0, wb - frag_len + 1);
+                if (pv[u]) out[slot - 1].end = (int)(__ldg(&hw[pj[u]].y) & 0x7FFFFFFFu);
+            }
+        }
+        heads_before += s_hpre[L1_TILE / 32];
+        // carry: the last valid pair of the tile
+        if (tid == 0) {
+            int w = L1_TILE / 32 - 1;
+            while (w >= 0 && s_valid[w] == 0u) w--;
+            if (w >= 0) { const int p = w * 32 + 31 - __clz(s_valid[w]); s_cj = s_j[p]; s_cg = s_g[p]; s_cvalid = 1; }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (heads_before) out[heads_before - 1].end = (int)(hw[s_cj].y & 0x7FFFFFFFu);
+        frag_cands[f] = heads_before;
+    }
+}
+
+// scratch ranges of l1_fused_kernel -> the candidate array in fragment order
+__global__ void compact_cands_kernel(const Cand *tmp, const uint64_t *seed_base, const uint32_t *cand_base, uint32_t seed_cap, Cand *cands)
+{
+    const int f = blockIdx.x;
+    const uint64_t sb = seed_base[f];
+    if (seed_base[f + 1] - sb > (uint64_t)seed_cap) return;
+    const uint32_t c0 = cand_base[f], n = cand_base[f + 1] - c0;
+    const uint4 *src = reinterpret_cast<const uint4 *>(tmp + sb);
+    uint4 *dst = reinterpret_cast<uint4 *>(cands + c0);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
 __global__ void work_items_kernel(const uint32_t *frag_cands_counts, int n_frags, uint32_t *work)
@@ -1070,35 +1342,77 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
         FA_CUDA(cudaGetLastError()); launches++;
         FA_TRY(excl_scan<uint64_t>(st, ws.cub_tmp, ws.frag_seeds.p, ws.frag_seeds.p, (int64_t)F + 1, &launches));
         FA_TRY(ws.hres.reserve(128 + (size_t)G * 8));
+        FA_TRY(ws.hfs.reserve(((size_t)F + 1) * 16));
         unsigned long long *h_ct = reinterpret_cast<unsigned long long *>(ws.hres.p);
+        uint64_t *h_fs = reinterpret_cast<uint64_t *>(ws.hfs.p);              // per-fragment seed prefix (F + 1), then the slow-path prefix
         FA_CUDA(cudaMemcpyAsync(h_ct, ws.counters.p, CT_N * 8, cudaMemcpyDeviceToHost, st));
-        FA_CUDA(cudaMemcpyAsync(h_ct + CT_N, ws.frag_seeds.p + F, 8, cudaMemcpyDeviceToHost, st));
-        FA_CUDA(cudaStreamSynchronize(st));                                   // sync 1: seed total, max sketch, errors
+        FA_CUDA(cudaMemcpyAsync(h_fs, ws.frag_seeds.p, ((size_t)F + 1) * 8, cudaMemcpyDeviceToHost, st));
+        FA_CUDA(cudaStreamSynchronize(st));                                   // sync 1: seed counts, max sketch, errors
+        qi.d2h_bytes += ((uint64_t)F + 1) * 8;
         if (h_ct[CT_ERR] & ERR_SORT_CAP) { set_error("a fragment produced more minimizers than the on-chip sort holds"); return FA_ERR_UNSUPPORTED; }
         if (h_ct[CT_ERR] & ERR_S_MAX) { set_error("sketch size above %d is not supported on the device path", ix->s_max); return FA_ERR_UNSUPPORTED; }
         const int max_s = (int)h_ct[CT_MAXS];
-        const uint64_t S = h_ct[CT_N];
+        const uint64_t S = h_fs[F];
         qi.seeds = S; qi.sketch_sum = h_ct[CT_SKETCH_SUM];
         FA_CUDA(cudaEventRecord(ws.ev[3], st));
         uint64_t C = 0;
         if (S > 0) {
-            // ---- seeds: fill + sort by (fragment, reference index) ----------------------------
-            FA_TRY(ws.seeds_a.reserve(S)); FA_TRY(ws.seeds_b.reserve(S));
+            int dev_sms = 148, smem_optin = 48 * 1024;
+            cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ix->device);
+            cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ix->device);
+            // ---- which fragments fit the on-chip L1 (l1_fused_kernel), which take the radix sort ----
+            const uint32_t n_chunks = (uint32_t)((ix->n + (1ull << L1_SHIFT) - 1) >> L1_SHIFT);
+            cudaFuncAttributes l1_attr;
+            FA_CUDA(cudaFuncGetAttributes(&l1_attr, l1_fused_kernel));
+            const size_t l1_fixed = l1_fixed_smem(n_chunks), l1_room = (size_t)smem_optin - l1_attr.sharedSizeBytes;
+            uint64_t seed_cap = 0;
+            if (l1_fixed + 64 < l1_room && ix->max_min_hits - 1 <= L1_EXTRA) seed_cap = (l1_room - l1_fixed - 16) / 2;
+            if (ix->l1_seed_cap >= 0) seed_cap = std::min<uint64_t>(seed_cap, (uint64_t)ix->l1_seed_cap);
+            seed_cap = std::min<uint64_t>(seed_cap, 0x7FFFFFFFull);
+            uint64_t max_fast = 0, S_slow = 0;
+            uint32_t n_slow = 0;
+            uint64_t *h_fb = h_fs + F + 1;
+            h_fb[0] = 0;
+            for (int f = 0; f < F; f++) {
+                const uint64_t nf = h_fs[f + 1] - h_fs[f];
+                const bool slow = nf > seed_cap;
+                if (slow) { n_slow++; S_slow += nf; } else max_fast = std::max(max_fast, nf);
+                h_fb[f + 1] = h_fb[f] + (slow ? nf : 0);
+            }
+            qi.l1_sorted_fragments = n_slow;
             const int shift = bits_for(ix->n), fbits = bits_for((uint64_t)F);
-            fill_seeds_kernel<<<F, 128, 0, st>>>(ws.sk.seq_first.p, ws.qs.p, ws.hit_start.p, ws.hit_cnt.p, ws.frag_seeds.p,
-                                                 ix->pos_idx.p, shift, ws.seeds_a.p);
-            FA_CUDA(cudaGetLastError()); launches++;
-            size_t sort_bytes = 0;
-            FA_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, ws.seeds_a.p, ws.seeds_b.p, (int64_t)S, 0, shift + fbits, st));
-            FA_TRY(ws.cub_tmp.reserve(sort_bytes + 16));
-            FA_CUDA(cub::DeviceRadixSort::SortKeys(ws.cub_tmp.p, sort_bytes, ws.seeds_a.p, ws.seeds_b.p, (int64_t)S, 0, shift + fbits, st));
-            launches += 2 + (shift + fbits + 7) / 8;
-            FA_CUDA(cudaEventRecord(ws.ev[4], st));
-            // ---- L1 candidates: count, scan, fill ---------------------------------------------
             const uint64_t idx_mask = (1ull << shift) - 1;
-            candidates_kernel<false><<<F, 256, 0, st>>>(ws.seeds_b.p, ws.frag_seeds.p, ws.qs.p, ix->d_min_hits.p, ix->ref.p,
-                                                        idx_mask, L, ws.frag_cands.p, nullptr, nullptr);
-            FA_CUDA(cudaGetLastError()); launches++;
+            if (n_slow) {
+                // ---- general path: fill + sort by (fragment, reference index) -------------------
+                FA_TRY(ws.fb_seeds.reserve((size_t)F + 1));
+                FA_CUDA(cudaMemcpyAsync(ws.fb_seeds.p, h_fb, ((size_t)F + 1) * 8, cudaMemcpyHostToDevice, st));
+                qi.h2d_bytes += ((uint64_t)F + 1) * 8;
+                FA_TRY(ws.seeds_a.reserve(S_slow)); FA_TRY(ws.seeds_b.reserve(S_slow));
+                fill_seeds_kernel<<<F, 128, 0, st>>>(ws.sk.seq_first.p, ws.qs.p, ws.hit_start.p, ws.hit_cnt.p, ws.fb_seeds.p,
+                                                     ix->pos_idx.p, shift, ws.seeds_a.p);
+                FA_CUDA(cudaGetLastError()); launches++;
+                size_t sort_bytes = 0;
+                FA_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, ws.seeds_a.p, ws.seeds_b.p, (int64_t)S_slow, 0, shift + fbits, st));
+                FA_TRY(ws.cub_tmp.reserve(sort_bytes + 16));
+                FA_CUDA(cub::DeviceRadixSort::SortKeys(ws.cub_tmp.p, sort_bytes, ws.seeds_a.p, ws.seeds_b.p, (int64_t)S_slow, 0, shift + fbits, st));
+                launches += 2 + (shift + fbits + 7) / 8;
+            }
+            FA_CUDA(cudaEventRecord(ws.ev[4], st));
+            // ---- L1 candidates -------------------------------------------------------------------
+            if (n_slow < (uint32_t)F) {
+                FA_TRY(ws.cand_tmp.reserve(S));
+                const size_t smem = l1_fixed + 2 * ((max_fast + 7) & ~7ull);
+                FA_CUDA(cudaFuncSetAttribute(l1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                l1_fused_kernel<<<F, L1_THREADS, smem, st>>>(ws.sk.seq_first.p, ws.qs.p, ws.hit_start.p, ws.hit_cnt.p, ws.frag_seeds.p,
+                                                             ix->pos_idx.p, ix->gpos.p, ix->hw.p, ix->d_min_hits.p, L, n_chunks,
+                                                             (uint32_t)seed_cap, ws.cand_tmp.p, ws.frag_cands.p);
+                FA_CUDA(cudaGetLastError()); launches++;
+            }
+            if (n_slow) {
+                candidates_kernel<false><<<F, 256, 0, st>>>(ws.seeds_b.p, ws.fb_seeds.p, ws.qs.p, ix->d_min_hits.p, ix->ref.p,
+                                                            idx_mask, L, ws.frag_cands.p, nullptr, nullptr);
+                FA_CUDA(cudaGetLastError()); launches++;
+            }
             work_items_kernel<<<(F + 1 + 255) / 256, 256, 0, st>>>(ws.frag_cands.p, F, ws.work_base.p);
             FA_CUDA(cudaGetLastError()); launches++;
             FA_CUDA(cudaMemsetAsync(ws.frag_cands.p + F, 0, 4, st));
@@ -1112,14 +1426,18 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
             const uint32_t W = h_u[1];
             if (C > 0) {
                 FA_TRY(ws.cands.reserve(C)); FA_TRY(ws.maps.reserve(C));
-                candidates_kernel<true><<<F, 256, 0, st>>>(ws.seeds_b.p, ws.frag_seeds.p, ws.qs.p, ix->d_min_hits.p, ix->ref.p,
-                                                           idx_mask, L, nullptr, ws.frag_cands.p, ws.cands.p);
-                FA_CUDA(cudaGetLastError()); launches++;
+                if (n_slow < (uint32_t)F) {
+                    compact_cands_kernel<<<F, 128, 0, st>>>(ws.cand_tmp.p, ws.frag_seeds.p, ws.frag_cands.p, (uint32_t)seed_cap, ws.cands.p);
+                    FA_CUDA(cudaGetLastError()); launches++;
+                }
+                if (n_slow) {
+                    candidates_kernel<true><<<F, 256, 0, st>>>(ws.seeds_b.p, ws.fb_seeds.p, ws.qs.p, ix->d_min_hits.p, ix->ref.p,
+                                                               idx_mask, L, nullptr, ws.frag_cands.p, ws.cands.p);
+                    FA_CUDA(cudaGetLastError()); launches++;
+                }
                 FA_CUDA(cudaEventRecord(ws.ev[5], st));
                 // ---- L2 -----------------------------------------------------------------------
                 FA_TRY(ws.prep.reserve(C)); FA_TRY(ws.ev_off.reserve(C + 1)); FA_TRY(ws.jobs.reserve(C));
-                int dev_sms = 148;
-                cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, ix->device);
                 l2_prep_kernel<<<std::min<uint32_t>((uint32_t)((C + 256) / 256), (uint32_t)dev_sms * 8u), 256, 0, st>>>(
                     ws.cands.p, ws.frag_cands.p, F, ws.qs.p, ix->ref.p, ix->hw.p, ix->contig_off.p, L, cmw, 2, w + 1,
                     reinterpret_cast<Prep *>(ws.prep.p), reinterpret_cast<unsigned long long *>(ws.ev_off.p), ws.maps.p, ws.counters.p);

@@ -30,7 +30,8 @@ class QueryInfo(C.Structure):
                 + [(n, C.c_float) for n in ("ms_h2d", "ms_sketch", "ms_lookup", "ms_seed_sort", "ms_l1", "ms_l2",
                                             "ms_cgi", "ms_d2h", "ms_total")]
                 + [("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("l2_fallback", C.c_uint64), ("events", C.c_uint64)]
-                + [(n, C.c_float) for n in ("ms_l2_prep", "ms_l2_events", "ms_l2_slide", "reserved_")])
+                + [(n, C.c_float) for n in ("ms_l2_prep", "ms_l2_events", "ms_l2_slide")]
+                + [("l1_sorted_fragments", C.c_uint32)])
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -205,6 +206,10 @@ class Index:
             check(lib().fa_index_lookup(self.h, C.c_uint32(hash_), s.ctypes.data_as(C.c_void_p),
                                         w.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
         return s, w
+
+    def set_l1_seed_cap(self, cap):
+        """Test hook: fragments with more seeds than `cap` take the radix-sort L1 path (-1 = default)."""
+        check(lib().fa_debug_set_l1_seed_cap(self.h, C.c_int64(cap)))
 
     def query_draft(self, contigs, dump=False):
         contigs = list(contigs)

@@ -46,8 +46,11 @@ def _check_hits(hits, names, rows):
         assert h["identity"] == golden_io.f32(ident), (float(h["identity"]).hex(), ident)
 
 
+@pytest.mark.parametrize("l1", ["chip", "sort", "mixed"])
 @pytest.mark.parametrize("name", [c["name"] for c in cases.query_cases()])
-def test_queries_match_pyfastani_and_oracle(name):
+def test_queries_match_pyfastani_and_oracle(name, l1):
+    """`l1` selects the L1 path: all fragments through the on-chip kernel (the default), all through
+    the device-wide radix sort, or split by seed count."""
     case = next(c for c in cases.query_cases() if c["name"] == name)
     gold = golden_io.query_golden()[name]
     sk = capi.Sketch(**case["params"])
@@ -64,13 +67,18 @@ def test_queries_match_pyfastani_and_oracle(name):
     for a, b in zip(ix.minimizers(), osk.minimizers()):
         assert np.array_equal(a, b)
     for q, res in zip(case["queries"], gold["results"]):
-        hits, out = ix.query_draft(q, dump=True)
         ohits, oinfo = osk.query_draft(q, dump=True)
+        st = oinfo["stats"]
+        ix.set_l1_seed_cap({"chip": -1, "sort": 0, "mixed": st["seeds"] // max(st["fragments"], 1) - 1}[l1])
+        hits, out = ix.query_draft(q, dump=True)
+        if l1 == "chip":
+            assert out["info"]["l1_sorted_fragments"] == 0
+        elif st["seeds"]:
+            assert out["info"]["l1_sorted_fragments"] > 0
         # L1 candidate regions, bit-exact
         assert np.array_equal(out["candidates"], oinfo["candidates"])
         # L2 mappings, every field (the oracle emits them in the same fragment/candidate order)
         assert np.array_equal(out["mappings"], oinfo["mappings"])
-        st = oinfo["stats"]
         info = out["info"]
         assert (info["fragments"], info["seeds"], info["candidates"], info["mappings"], info["sketch_sum"]) == \
                (st["fragments"], st["seeds"], st["candidates"], st["mappings"], st["sketch_sum"])
@@ -78,6 +86,32 @@ def test_queries_match_pyfastani_and_oracle(name):
         _check_hits(hits, ix.names, res["hits"])
         assert out["short_contigs"] == res["warnings"]
         assert info["kernel_launches"] > 0 or st["fragments"] == 0
+
+
+@pytest.mark.parametrize("l1", ["chip", "sort", "mixed"])
+def test_l1_many_references(l1):
+    """120 related references: every fragment has several thousand seed hits (more than one 4096-hit
+    tile of the on-chip L1 kernel) spread over nine 2^16-minimizer chunks of the index, plus a
+    reverse-complemented and a shuffled-contig query.  Candidates, mappings and hits vs the oracle."""
+    q, refs, _ = synth.one_to_many(808, 120, 60_000, lo=0.85, hi=0.995)
+    sk, osk = capi.Sketch(), _port().sketch()
+    for i, r in enumerate(refs):
+        contigs = [r] if i % 3 else [r[:25_000], r[25_000:25_900], r[25_900:]]
+        sk.add_draft(i, contigs)
+        osk.add_draft(i, contigs)
+    ix = sk.index()
+    osk.index()
+    assert ix.counts()[0] > 8 * 65536
+    for query in ([q], [synth.revcomp(q)], [q[30_000:], q[:30_000]]):
+        ohits, oinfo = osk.query_draft(query, dump=True)
+        st = oinfo["stats"]
+        assert st["seeds"] // st["fragments"] > 4096
+        ix.set_l1_seed_cap({"chip": -1, "sort": 0, "mixed": st["seeds"] // st["fragments"] - 1}[l1])
+        hits, out = ix.query_draft(query, dump=True)
+        assert (out["info"]["l1_sorted_fragments"] == 0) == (l1 == "chip")
+        assert np.array_equal(out["candidates"], oinfo["candidates"])
+        assert np.array_equal(out["mappings"], oinfo["mappings"])
+        assert np.array_equal(hits, ohits)
 
 
 def test_config1_known_answers():
