@@ -268,7 +268,7 @@ constexpr int L1_SHIFT = 16;
 constexpr int L1_TILE = 4096;                 // sorted hits per phase-D tile
 constexpr int L1_PER = L1_TILE / L1_THREADS;
 constexpr int L1_EXTRA = 1024;                // look-ahead of the pair test: minHits - 1 <= L1_EXTRA
-constexpr int L1_BM = 32;                     // bitmap words per warp in phase C
+constexpr int L1_BM = 32;                     // bitmap words per warp in phase C (+ as many prefix words)
 constexpr int L1_STAGE = L1_TILE + L1_EXTRA;
 
 __host__ __device__ inline size_t l1_fixed_smem(uint32_t n_chunks)
@@ -279,25 +279,50 @@ __host__ __device__ inline size_t l1_fixed_smem(uint32_t n_chunks)
 // in-place sort of k[0, n) by one warp
 __device__ __forceinline__ void l1_sort_bucket(uint16_t *k, int n, uint32_t *bm, int lane)
 {
-    uint32_t lo = 0xFFFFu, hi = 0u;
-    for (int i = lane; i < n; i += 32) { const uint32_t v = k[i]; lo = min(lo, v); hi = max(hi, v); }
-    lo = __reduce_min_sync(0xFFFFFFFFu, lo);
-    hi = __reduce_max_sync(0xFFFFFFFFu, hi);
-    if (hi - lo < (uint32_t)(32 * L1_BM)) {
-        bm[lane] = 0u;
-        __syncwarp();
-        for (int i = lane; i < n; i += 32) { const uint32_t d = (uint32_t)k[i] - lo; atomicOr(&bm[d >> 5], 1u << (d & 31u)); }
-        __syncwarp();
-        uint32_t wv = bm[lane];
-        const uint32_t cnt = __popc(wv);
-        uint32_t incl = cnt;
+    if (n <= 64) {
+        // the usual bucket (one locus): both keys of a lane stay in registers; rank = set bits below in a 1024-bit map
+        const uint32_t v0 = lane < n ? (uint32_t)k[lane] : 0xFFFFFFFFu, v1 = lane + 32 < n ? (uint32_t)k[lane + 32] : 0xFFFFFFFFu;
+        const uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, min(v0, v1));
+        const uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, max(lane < n ? v0 : 0u, lane + 32 < n ? v1 : 0u));
+        if (hi - lo < (uint32_t)(32 * L1_BM)) {
+            bm[lane] = 0u;
+            __syncwarp();
+            const uint32_t d0 = v0 - lo, d1 = v1 - lo;
+            if (lane < n) atomicOr(&bm[d0 >> 5], 1u << (d0 & 31u));
+            if (lane + 32 < n) atomicOr(&bm[d1 >> 5], 1u << (d1 & 31u));
+            __syncwarp();
+            const uint32_t wv = bm[lane], cnt = __popc(wv);
+            uint32_t incl = cnt;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
-        int pos = (int)(incl - cnt);
-        const uint32_t base = lo + (uint32_t)lane * 32u;
-        while (wv) { const int bit = __ffs(wv) - 1; wv &= wv - 1u; k[pos++] = (uint16_t)(base + (uint32_t)bit); }
-        __syncwarp();
-        return;
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+            bm[L1_BM + lane] = incl - cnt;
+            __syncwarp();
+            if (lane < n) k[bm[L1_BM + (d0 >> 5)] + __popc(bm[d0 >> 5] & ((1u << (d0 & 31u)) - 1u))] = (uint16_t)v0;
+            if (lane + 32 < n) k[bm[L1_BM + (d1 >> 5)] + __popc(bm[d1 >> 5] & ((1u << (d1 & 31u)) - 1u))] = (uint16_t)v1;
+            __syncwarp();
+            return;
+        }
+    } else {
+        uint32_t lo = 0xFFFFu, hi = 0u;
+        for (int i = lane; i < n; i += 32) { const uint32_t v = k[i]; lo = min(lo, v); hi = max(hi, v); }
+        lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+        hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+        if (hi - lo < (uint32_t)(32 * L1_BM)) {
+            bm[lane] = 0u;
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) { const uint32_t d = (uint32_t)k[i] - lo; atomicOr(&bm[d >> 5], 1u << (d & 31u)); }
+            __syncwarp();
+            uint32_t wv = bm[lane];
+            const uint32_t cnt = __popc(wv);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+            int pos = (int)(incl - cnt);
+            const uint32_t base = lo + (uint32_t)lane * 32u;
+            while (wv) { const int bit = __ffs(wv) - 1; wv &= wv - 1u; k[pos++] = (uint16_t)(base + (uint32_t)bit); }
+            __syncwarp();
+            return;
+        }
     }
     // bitonic network with ascending comparators only (first step of every merge mirrors the
     // upper half), so slots at or beyond n act as +infinity and are never touched
@@ -326,7 +351,7 @@ __device__ __forceinline__ void l1_sort_bucket(uint16_t *k, int n, uint32_t *bm,
 __global__ void __launch_bounds__(L1_THREADS, 1)
 l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hit_start, const uint32_t *hit_cnt,
                 const uint64_t *seed_base, const uint32_t *pos_idx, const uint32_t *gpos, const uint2 *hw,
-                const int32_t *min_hits, int frag_len, uint32_t n_chunks, uint32_t seed_cap,
+                const int32_t *min_hits, int frag_len, uint32_t n_chunks, uint32_t seed_cap, uint32_t key_cap,
                 Cand *tmp, uint32_t *frag_cands)
 {
     extern __shared__ __align__(16) uint8_t l1_smem[];
@@ -334,7 +359,9 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
     uint32_t *s_j = hist + ((n_chunks + 1 + 3) & ~3u);                       // phase D: reference index per staged hit
     uint32_t *s_g = s_j + L1_STAGE;                                          //          its gpos
     uint32_t *s_bm = s_j;                                                    // phase C: per-warp bitmaps (aliases s_j)
-    uint16_t *keys = reinterpret_cast<uint16_t *>(s_g + L1_STAGE);
+    uint32_t *s_lst = s_j, *s_lcnt = s_g;                                    // phases A, B: the position lists (alias)
+    uint16_t *keys = reinterpret_cast<uint16_t *>(s_g + L1_STAGE);           // [key_cap], key_cap a multiple of 32
+    uint16_t *blk_chunk = keys + key_cap;                                    // chunk holding sorted hit 32 * q
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_valid[L1_TILE / 32], s_head[L1_TILE / 32], s_hpre[L1_TILE / 32 + 1];
     __shared__ uint32_t s_blk, s_cj, s_cg;
@@ -350,12 +377,13 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
     const uint64_t qb = seq_first[f];
 
     for (uint32_t i = tid; i <= n_chunks; i += L1_THREADS) hist[i] = 0u;
+    for (int q = tid; q < s; q += L1_THREADS) { s_lst[q] = hit_start[qb + q]; s_lcnt[q] = hit_cnt[qb + q]; }
     if (tid == 0) { s_blk = 0u; s_cvalid = 0; s_cj = 0u; s_cg = 0u; }
     __syncthreads();
 
     // ---- A: histogram over chunks ------------------------------------------------------------
     for (int q = wid; q < s; q += L1_THREADS / 32) {
-        const uint32_t st = hit_start[qb + q], c = hit_cnt[qb + q];
+        const uint32_t st = s_lst[q], c = s_lcnt[q];
         for (uint32_t t0 = 0; t0 < c; t0 += 128) {
             uint32_t v[4];
 #pragma unroll
@@ -377,7 +405,7 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
     __syncthreads();
     // ---- B: scatter the low 16 bits into chunk order; afterwards hist[c] = end of bucket c -------
     for (int q = wid; q < s; q += L1_THREADS / 32) {
-        const uint32_t st = hit_start[qb + q], c = hit_cnt[qb + q];
+        const uint32_t st = s_lst[q], c = s_lcnt[q];
         for (uint32_t t0 = 0; t0 < c; t0 += 128) {
             uint32_t v[4];
 #pragma unroll
@@ -397,11 +425,12 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
         if (blk * 32u >= n_chunks) break;
         uint32_t b0 = 0, sz = 0;
         if (c < n_chunks) { b0 = c ? hist[c - 1] : 0u; sz = hist[c] - b0; }
+        for (uint32_t t0 = (b0 + 31u) & ~31u; t0 < b0 + sz; t0 += 32u) blk_chunk[t0 >> 5] = (uint16_t)c;
         unsigned todo = __ballot_sync(0xFFFFFFFFu, sz >= 2u);
         while (todo) {
             const int l = __ffs(todo) - 1;
             todo &= todo - 1u;
-            l1_sort_bucket(keys + __shfl_sync(0xFFFFFFFFu, b0, l), (int)__shfl_sync(0xFFFFFFFFu, sz, l), s_bm + wid * L1_BM, lane);
+            l1_sort_bucket(keys + __shfl_sync(0xFFFFFFFFu, b0, l), (int)__shfl_sync(0xFFFFFFFFu, sz, l), s_bm + wid * (2 * L1_BM), lane);
         }
     }
     __syncthreads();
@@ -412,20 +441,25 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
     Cand *out = tmp + sb;
     uint32_t heads_before = 0;
     for (uint32_t base = 0; base < n; base += L1_TILE) {
-        // D1: stage (reference index, gpos) of the tile and of the m - 1 hits behind it
-        for (int e0 = wid * 32; e0 < L1_TILE + m - 1; e0 += L1_THREADS) {
-            const uint32_t t0 = base + (uint32_t)e0;
-            if (t0 >= n) break;
-            uint32_t lo = 0, hi = n_chunks - 1;                           // first chunk whose end is beyond t0
-            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (hist[mid] <= t0) lo = mid + 1; else hi = mid; }
-            const uint32_t t = t0 + (uint32_t)lane;
-            if (t < n) {
-                uint32_t c = lo;
-                while (hist[c] <= t) c++;
-                const uint32_t j = (c << L1_SHIFT) | (uint32_t)keys[t];
-                s_j[e0 + lane] = j;
-                s_g[e0 + lane] = __ldg(gpos + j);
+        // D1: stage (reference index, gpos) of the tile and of the m - 1 hits behind it; all gathers of a thread in flight
+        {
+            uint32_t jv[L1_PER + 1], gv[L1_PER + 1];
+#pragma unroll
+            for (int u = 0; u <= L1_PER; u++) {
+                const int e0 = u * L1_THREADS + wid * 32;
+                const uint32_t t = base + (uint32_t)(e0 + lane);
+                jv[u] = 0xFFFFFFFFu;
+                if (e0 < L1_TILE + m - 1 && t < n) {
+                    uint32_t c = blk_chunk[(base + (uint32_t)e0) >> 5];
+                    while (hist[c] <= t) c++;
+                    jv[u] = (c << L1_SHIFT) | (uint32_t)keys[t];
+                }
             }
+#pragma unroll
+            for (int u = 0; u <= L1_PER; u++) gv[u] = jv[u] != 0xFFFFFFFFu ? __ldg(gpos + jv[u]) : 0u;
+#pragma unroll
+            for (int u = 0; u <= L1_PER; u++)
+                if (jv[u] != 0xFFFFFFFFu) { const int e = u * L1_THREADS + tid; s_j[e] = jv[u]; s_g[e] = gv[u]; }
         }
         __syncthreads();
         // D2: valid pairs (computeMap.hpp:325-330) as a bitmap
@@ -1366,7 +1400,7 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
             FA_CUDA(cudaFuncGetAttributes(&l1_attr, l1_fused_kernel));
             const size_t l1_fixed = l1_fixed_smem(n_chunks), l1_room = (size_t)smem_optin - l1_attr.sharedSizeBytes;
             uint64_t seed_cap = 0;
-            if (l1_fixed + 64 < l1_room && ix->max_min_hits - 1 <= L1_EXTRA) seed_cap = (l1_room - l1_fixed - 16) / 2;
+            if (l1_fixed + 256 < l1_room && ix->max_min_hits - 1 <= L1_EXTRA) seed_cap = ((l1_room - l1_fixed - 128) * 16 / 33) & ~31ull;   // 2 + 1/16 bytes per hit
             if (ix->l1_seed_cap >= 0) seed_cap = std::min<uint64_t>(seed_cap, (uint64_t)ix->l1_seed_cap);
             seed_cap = std::min<uint64_t>(seed_cap, 0x7FFFFFFFull);
             uint64_t max_fast = 0, S_slow = 0;
@@ -1401,11 +1435,12 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
             // ---- L1 candidates -------------------------------------------------------------------
             if (n_slow < (uint32_t)F) {
                 FA_TRY(ws.cand_tmp.reserve(S));
-                const size_t smem = l1_fixed + 2 * ((max_fast + 7) & ~7ull);
+                const uint64_t key_cap = (max_fast + 31) & ~31ull;
+                const size_t smem = l1_fixed + 2 * key_cap + 2 * (key_cap / 32 + 8);
                 FA_CUDA(cudaFuncSetAttribute(l1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 l1_fused_kernel<<<F, L1_THREADS, smem, st>>>(ws.sk.seq_first.p, ws.qs.p, ws.hit_start.p, ws.hit_cnt.p, ws.frag_seeds.p,
                                                              ix->pos_idx.p, ix->gpos.p, ix->hw.p, ix->d_min_hits.p, L, n_chunks,
-                                                             (uint32_t)seed_cap, ws.cand_tmp.p, ws.frag_cands.p);
+                                                             (uint32_t)seed_cap, (uint32_t)key_cap, ws.cand_tmp.p, ws.frag_cands.p);
                 FA_CUDA(cudaGetLastError()); launches++;
             }
             if (n_slow) {
