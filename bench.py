@@ -58,6 +58,18 @@ def peaks():
         return 6650.0, "fallback"
 
 
+def measured_traffic(kernel, a):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed `ncu --set full` capture
+    of this workload (profiles/traffic.json, written by profiles/summarize_ncu.py); None for any other workload."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if t.get("refs") == a.refs and t.get("length") == a.length:
+            return t["kernels"].get(kernel)
+    except Exception:
+        pass
+    return None
+
+
 def workload_name(a):
     return ("configs[1] 1-to-many: one synthetic %.1f Mbp query vs %d synthetic %.1f Mbp references at 80-99%% identity"
             % (a.length / 1e6, a.refs, a.length / 1e6))
@@ -296,10 +308,10 @@ def run_b200(a):
         "ms_seed_sort": 16.0 * inf["seeds"] * inf["l1_sorted_fragments"] / max(inf["fragments"], 1),
         "ms_l1": 8.0 * inf["seeds"] + 16.0 * inf["candidates"],
         # L2 = prep (index searches) + events (classify + merge: reads the (hash, wpos) stream once, writes
-        # 2-byte events) + slide (replays the events, writes 16-byte results)
+        # 2-byte events) + slide (replays the events up to its early stop, writes 16-byte results)
         "ms_l2_prep": 56.0 * inf["candidates"],
         "ms_l2_events": 8.0 * inf["scanned"] + 2.0 * inf["events"] + (4.0 * s_mean + 16.0) * inf["candidates"],
-        "ms_l2_slide": 2.0 * inf["events"] + 32.0 * inf["candidates"],
+        "ms_l2_slide": 2.0 * inf["events_replayed"] + 34.0 * inf["candidates"],
         "ms_cgi": 16.0 * inf["candidates"],
     }
     per_step = {k: v / a.steps for k, v in stage.items()}
@@ -310,7 +322,8 @@ def run_b200(a):
                     "ms_l1": "l1_fused_kernel", "ms_l2_prep": "l2_prep_kernel", "ms_l2_events": "l2_events_kernel",
                     "ms_l2_slide": "l2_slide_kernel", "ms_cgi": "cgi_best_kernel"}
     roofline = {"bound": "hbm", "kernel": kernel_names[top], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
+                "frac": achieved / peak, "traffic": measured_traffic(kernel_names[top], a),
+                "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
                 "algorithmic_bytes_per_launch": alg[top], "ms_per_launch": top_ms,
                 "share_of_step": top_ms / (dev_ms / a.steps)}
     stage_roofline = {k: {"ms": per_step.get(k, 0.0), "alg_bytes": alg[k],
@@ -349,7 +362,7 @@ def run_b200(a):
         "cpu_baseline": cpu,
         "stages": stage_roofline,
         "counters": {k: inf[k] for k in ("fragments", "sketch_sum", "seeds", "candidates", "scanned", "events", "mappings",
-                                         "l2_fallback", "l1_sorted_fragments")},
+                                         "l2_fallback", "l1_sorted_fragments", "events_replayed")},
         "hits": len(hits),
         "parity": parity,
         "index_build": {"sketch_s": t_sketch, "index_s": t_index, "minimizers": n_min,

@@ -88,6 +88,8 @@ typedef struct fa_query_info {
     uint64_t events;           /* insert/delete events replayed by the L2 slide kernel */
     float    ms_l2_prep, ms_l2_events, ms_l2_slide;   /* the three kernels inside ms_l2 */
     uint32_t l1_sorted_fragments;                     /* fragments whose seeds took the device-wide radix sort instead of the on-chip L1 */
+    uint32_t reserved0;
+    uint64_t events_replayed;  /* events the slide kernel went through before its early stop (<= events) */
 } fa_query_info;
 
 typedef struct fa_sketch fa_sketch;   /* skch::Sketch under construction (pyx:465-470) */

@@ -44,6 +44,7 @@ struct Workspace {
     DevBuf<uint4>    prep;              // per candidate: the index searches of L2 (fa_map.cu Prep)
     DevBuf<uint64_t> ev_off;            // per candidate: padded event count, then exclusive prefix (C + 1)
     DevBuf<uint4>    jobs;              // per candidate: slide descriptor (fa_map.cu SlideJob)
+    DevBuf<uint16_t> room;              // per candidate: elements of its region that are in the sketch (early stop of the slide)
     DevBuf<uint16_t> events;            // the merged, classified insert/delete events of all candidates
     DevBuf<uint32_t> cells;             // per (ref contig, bin): best identity bits (computeCGI pass 2)
     DevBuf<float>    g_identity;        // per genome

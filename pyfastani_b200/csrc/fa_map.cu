@@ -28,7 +28,7 @@ namespace fa {
 namespace {
 
 // device counters (Workspace::counters)
-enum { CT_MAXS = 0, CT_ERR = 1, CT_WORK = 2, CT_SCANNED = 3, CT_MAPPINGS = 4, CT_SKETCH_SUM = 5, CT_REDO = 6, CT_WORK2 = 7, CT_WORK3 = 8, CT_N = 9 };
+enum { CT_MAXS = 0, CT_ERR = 1, CT_WORK = 2, CT_SCANNED = 3, CT_MAPPINGS = 4, CT_SKETCH_SUM = 5, CT_REDO = 6, CT_WORK2 = 7, CT_WORK3 = 8, CT_REPLAYED = 9, CT_N = 10 };
 enum { ERR_SORT_CAP = 1, ERR_S_MAX = 2 };
 
 constexpr int L2_THREADS = 64;          // lanes per L2 CTA: each lane slides one candidate at a time
@@ -615,6 +615,7 @@ constexpr uint32_t EV_AOFF = 0x7F03;
 constexpr int EV_MAX_S = 508;         // largest sketch the 16-bit events address
 constexpr int EV_RMAX = 1024;         // most reference minimizers of a candidate region on the event path
 constexpr int EVK_THREADS = 128;
+constexpr int EV_UNROLL = 8;          // independent loads per lane in the classification loop
 
 __host__ __device__ inline uint32_t ev_aoff(int idx) { return ((uint32_t)(idx & ~3) << 6) | (uint32_t)(idx & 3); }
 
@@ -712,7 +713,7 @@ struct SlideJob {
 //          (MIIteratorL2.hpp:74-96)
 struct EvCtx {
     const uint32_t *s_q; const uint16_t *s_tab; int *w_pos; uint16_t *w_cls;
-    const RefMini *ref; const uint2 *hw; uint16_t *ev; SlideJob *jobs;
+    const RefMini *ref; const uint2 *hw; uint16_t *ev; SlideJob *jobs; uint16_t *room;
     int s, cmw1, tab_p, maxn;
 };
 
@@ -729,16 +730,17 @@ __device__ __forceinline__ void ev_candidate(const EvCtx &X, uint32_t c, const P
             const int N = n_pad ? nI + nD : 0;
             if (lane == 0) jobs[c] = SlideJob{off, (uint32_t)N, s};
             if (N) {
-                // 1. load + classify the region, eight independent loads per lane in flight
-                for (int i0 = 0; i0 < R; i0 += 256) {
-                    uint2 xs[8];
+                // 1. load + classify the region, EV_UNROLL independent loads per lane in flight
+                int n_mi = 0;                                      // elements that are in the sketch
+                for (int i0 = 0; i0 < R; i0 += 32 * EV_UNROLL) {
+                    uint2 xs[EV_UNROLL];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) {
+                    for (int u = 0; u < EV_UNROLL; u++) {
                         const int i = i0 + u * 32 + lane;
                         xs[u] = i < R ? __ldg(hw + pp.beg + i) : make_uint2(0u, 0u);
                     }
 #pragma unroll
-                    for (int u = 0; u < 8; u++) {
+                    for (int u = 0; u < EV_UNROLL; u++) {
                         const int i = i0 + u * 32 + lane;
                         if (i < R) {
                             const uint32_t h = xs[u].x;
@@ -757,10 +759,15 @@ __device__ __forceinline__ void ev_candidate(const EvCtx &X, uint32_t c, const P
                             }
                             w_pos[i] = (int)(xs[u].y & 0x7FFFFFFFu);
                             w_cls[i] = (uint16_t)(ev_aoff(l + match) | (match ? EV_MATCH : EV_ONLY) | ((xs[u].y >> 31) ? EV_DUP : 0u));
+                            n_mi += match;
                         }
                     }
                 }
                 __syncwarp();
+                // (an upper bound of the inserts that set a match bit -- same-hash copies and the last element are counted,
+                // too -- is all the early stop of the slide needs)
+                n_mi = __reduce_add_sync(0xFFFFFFFFu, n_mi);
+                if (lane == 0) X.room[c] = (uint16_t)n_mi;
                 // 2. merge path: lane -> events [t_lo, t_hi), whole chunks of eight
                 const int pos0 = w_pos[0];
                 const int per = (((N + 31) >> 5) + 7) & ~7;
@@ -816,7 +823,7 @@ __device__ __forceinline__ void ev_candidate(const EvCtx &X, uint32_t c, const P
 __global__ void __launch_bounds__(EVK_THREADS)
 l2_events_kernel(const Prep *prep, const unsigned long long *ev_off, const uint32_t *cand_base, const uint32_t *work_base,
                  int n_frags, const uint32_t *qhash, const uint64_t *seq_first, const int32_t *qs,
-                 const RefMini *ref, const uint2 *hw, int cmw, int tab_p, uint16_t *ev, SlideJob *jobs,
+                 const RefMini *ref, const uint2 *hw, int cmw, int tab_p, uint16_t *ev, SlideJob *jobs, uint16_t *room,
                  unsigned long long *counters, int q_cap)
 {
     extern __shared__ __align__(16) uint8_t ev_smem[];
@@ -865,7 +872,7 @@ l2_events_kernel(const Prep *prep, const unsigned long long *ev_off, const uint3
         __syncthreads();
         const int maxn = s_maxn;
         EvCtx X;
-        X.s_q = s_q; X.s_tab = s_tab; X.w_pos = w_pos; X.w_cls = w_cls; X.ref = ref; X.hw = hw; X.ev = ev; X.jobs = jobs;
+        X.s_q = s_q; X.s_tab = s_tab; X.w_pos = w_pos; X.w_cls = w_cls; X.ref = ref; X.hw = hw; X.ev = ev; X.jobs = jobs; X.room = room;
         X.s = s; X.cmw1 = cmw1; X.tab_p = tab_p; X.maxn = maxn;
 
         // candidates are handed out one ahead, so the next descriptor is in flight while this one is processed
@@ -904,6 +911,7 @@ struct SlideLane {
     uint32_t a;                // cached state byte of bucket istar
     uint32_t ioff;             // ev_aoff(istar)
     uint32_t mx;               // largest state byte written (> 255: a bucket count overflowed)
+    int room;                  // match inserts of the list less the match deletes so far: no later window shares more
 };
 
 // shared-memory bytes by 32-bit shared address (keeps the window base out of the per-event code)
@@ -938,6 +946,7 @@ __device__ __forceinline__ void slide_event(SlideLane &L, uint32_t st, uint32_t 
     const bool mv_up = in_del && (at_p || L.sigma >= cc);
     const bool mv = mv_dn || mv_up;
     L.shared += ((ev & EV_MATCH) != 0 && aoff <= L.ioff) ? sgn : 0;
+    L.room -= (ev & (EV_MATCH | EV_DEL)) == (EV_MATCH | EV_DEL) ? 1 : 0;
     const uint32_t a_nb = (aoff == noff) ? v2 : pn;                  // (only possible when moving down)
     const int dsh = mv_up ? (int)(a_nb & 1u) : (mv_dn ? -(int)(L.a & 1u) : 0);
     L.shared += dsh;
@@ -955,7 +964,7 @@ __device__ __forceinline__ void slide_event(SlideLane &L, uint32_t st, uint32_t 
 }
 
 __global__ void __launch_bounds__(L2_THREADS)
-l2_slide_kernel(const SlideJob *jobs, const Prep *prep, uint32_t n_cands, const uint2 *hw, const uint16_t *ev,
+l2_slide_kernel(const SlideJob *jobs, const uint16_t *room, const Prep *prep, uint32_t n_cands, const uint2 *hw, const uint16_t *ev,
                 const int32_t *min_shared, const uint32_t *id_off, const float *id_tab,
                 Mapping *maps, unsigned long long *counters)
 {
@@ -969,6 +978,7 @@ l2_slide_kernel(const SlideJob *jobs, const Prep *prep, uint32_t n_cands, const 
     bool alive = true, have = false;
     uint32_t c = 0, k = 0, n_pad = 0;
     int s = 0;
+    unsigned long long replayed = 0;
     const uint4 *evp = nullptr;
     uint4 nxt = make_uint4(0, 0, 0, 0);
     SlideLane L{};
@@ -989,6 +999,7 @@ l2_slide_kernel(const SlideJob *jobs, const Prep *prep, uint32_t n_cands, const 
                     const SlideJob jb = jobs[c];
                     if (jb.n_events) {                               // (else: nothing to slide, ask again next trip)
                         s = jb.s;
+                        L.room = (int)room[c];
                         const int nwords = l2_words_for(s);
                         for (int wd = 0; wd < nwords; wd++) *reinterpret_cast<uint32_t *>(st + wd * pitch) = 0u;
                         evp = reinterpret_cast<const uint4 *>(ev + jb.ev_off);
@@ -1016,7 +1027,10 @@ l2_slide_kernel(const SlideJob *jobs, const Prep *prep, uint32_t n_cands, const 
             slide_event(L, st_sh, cur.w >> 16);
             k += 8;
             const bool overflow = L.mx > 255u;                       // (checked once per chunk: the pivot strays at most eight buckets)
-            if (k >= n_pad || overflow) {
+            // early stop: the shared count of a window is at most its number of matches, and the windows still to
+            // come hold at most `room` of them -- below the best so far they change neither the optimum nor its
+            // first / last position (computeMap.hpp:467-481)
+            if (k >= n_pad || overflow || L.room < L.best) {
                 const Prep pp = prep[c];
                 Mapping mp;
                 mp.seq = pp.seq;
@@ -1030,10 +1044,13 @@ l2_slide_kernel(const SlideJob *jobs, const Prep *prep, uint32_t n_cands, const 
                     mp.identity = pass ? id_tab[id_off[s] + L.best] : 0.0f;
                 }
                 maps[c] = mp;
+                replayed += k;
                 have = false;
             }
         }
     }
+    for (int o = 16; o > 0; o >>= 1) replayed += __shfl_xor_sync(wmask, replayed, o);
+    if (lane == 0 && replayed) atomicAdd(&counters[CT_REPLAYED], replayed);
 }
 
 // ---- exact fallback (16-bit bucket counts, binary-search classification) -------------------------
@@ -1472,7 +1489,7 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
                 }
                 FA_CUDA(cudaEventRecord(ws.ev[5], st));
                 // ---- L2 -----------------------------------------------------------------------
-                FA_TRY(ws.prep.reserve(C)); FA_TRY(ws.ev_off.reserve(C + 1)); FA_TRY(ws.jobs.reserve(C));
+                FA_TRY(ws.prep.reserve(C)); FA_TRY(ws.ev_off.reserve(C + 1)); FA_TRY(ws.jobs.reserve(C)); FA_TRY(ws.room.reserve(C));
                 l2_prep_kernel<<<std::min<uint32_t>((uint32_t)((C + 256) / 256), (uint32_t)dev_sms * 8u), 256, 0, st>>>(
                     ws.cands.p, ws.frag_cands.p, F, ws.qs.p, ix->ref.p, ix->hw.p, ix->contig_off.p, L, cmw, 2, w + 1,
                     reinterpret_cast<Prep *>(ws.prep.p), reinterpret_cast<unsigned long long *>(ws.ev_off.p), ws.maps.p, ws.counters.p);
@@ -1497,7 +1514,7 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
                         l2_events_kernel<<<grid, EVK_THREADS, smem, st>>>(
                             reinterpret_cast<const Prep *>(ws.prep.p), reinterpret_cast<const unsigned long long *>(ws.ev_off.p),
                             ws.frag_cands.p, ws.work_base.p, F, ws.qhash.p, ws.sk.seq_first.p, ws.qs.p, ix->ref.p, ix->hw.p, cmw,
-                            l2_tab_shift(w), ws.events.p, reinterpret_cast<SlideJob *>(ws.jobs.p), ws.counters.p, q_cap);
+                            l2_tab_shift(w), ws.events.p, reinterpret_cast<SlideJob *>(ws.jobs.p), ws.room.p, ws.counters.p, q_cap);
                         FA_CUDA(cudaGetLastError()); launches++;
                     }
                     FA_CUDA(cudaEventRecord(ws.ev[10], st));
@@ -1511,7 +1528,7 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
                         const uint64_t want = (C + L2_THREADS - 1) / L2_THREADS;
                         const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)dev_sms * (uint64_t)std::max(per_sm, 1));
                         slide_fn<<<grid, L2_THREADS, smem, st>>>(
-                            reinterpret_cast<const SlideJob *>(ws.jobs.p), reinterpret_cast<const Prep *>(ws.prep.p), (uint32_t)C, ix->hw.p,
+                            reinterpret_cast<const SlideJob *>(ws.jobs.p), ws.room.p, reinterpret_cast<const Prep *>(ws.prep.p), (uint32_t)C, ix->hw.p,
                             ws.events.p, ix->d_min_shared.p, ix->d_id_off.p, ix->d_identity.p, ws.maps.p, ws.counters.p);
                         FA_CUDA(cudaGetLastError()); launches++;
                     }
@@ -1551,6 +1568,7 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
         FA_CUDA(cudaStreamSynchronize(st));                                   // sync 3: results
         qi.d2h_bytes = (uint64_t)G * 8 + CT_N * 8 * 2 + 16;
         qi.candidates = C; qi.scanned = h_ct[CT_SCANNED]; qi.mappings = h_ct[CT_MAPPINGS]; qi.l2_fallback = h_ct[CT_REDO];
+        qi.events_replayed = h_ct[CT_REPLAYED];
         h_count.assign(h_c, h_c + G); h_ident.assign(h_i, h_i + G);
         ws.last_cands = C; ws.last_frags = (uint64_t)F;
         float ms;
