@@ -204,3 +204,35 @@ def test_low_complexity_fragments_take_the_exact_fallback():
     assert np.array_equal(out["candidates"], oinfo["candidates"])
     assert np.array_equal(out["mappings"], oinfo["mappings"])
     assert np.array_equal(hits, ohits)
+
+
+def test_l2_early_stop_keeps_first_and_last_optimum():
+    """The slide kernel stops once the sketch matches still to come cannot reach the best window.
+    Cases built to catch a stop that comes too soon: tandem copies of the query fragments inside one
+    candidate region (the last optimum lies in the second copy), a diverged copy behind an exact
+    one, and an exact copy behind a diverged one.  Mappings field by field against the oracle,
+    and the stop must really have fired (fewer events replayed than the lists hold)."""
+    rng = np.random.default_rng(4242)
+    base = synth.random_codes(rng, 30_000)
+    q = synth.to_bytes(base)
+    filler = lambda n: synth.to_bytes(synth.random_codes(rng, n))
+    mut = lambda ident: synth.to_bytes(synth.mutate_codes(rng, base, ident))
+    refs = [
+        filler(5_000) + q + filler(700) + q + filler(5_000),                   # tandem exact copies, 700 bp apart
+        filler(3_000) + q[:9_000] + filler(1_200) + mut(0.93)[:9_000] + filler(3_000),
+        filler(3_000) + mut(0.90)[3_000:15_000] + filler(900) + q[3_000:15_000] + filler(8_000),
+        mut(0.97), mut(0.85),
+    ]
+    sk, osk = capi.Sketch(), _port().sketch()
+    for i, r in enumerate(refs):
+        sk.add_genome(i, r)
+        osk.add_genome(i, r)
+    ix = sk.index()
+    osk.index()
+    for query in (q, synth.revcomp(q), q[1_234:28_000]):
+        hits, out = ix.query_genome(query, dump=True)
+        ohits, oinfo = osk.query_genome(query, dump=True)
+        assert np.array_equal(out["candidates"], oinfo["candidates"])
+        assert np.array_equal(out["mappings"], oinfo["mappings"])
+        assert np.array_equal(hits, ohits)
+        assert 0 < out["info"]["events_replayed"] < out["info"]["events"]
