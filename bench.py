@@ -46,6 +46,10 @@ def parse():
     ap.add_argument("--seed", type=int, default=12345)
     ap.add_argument("--cpu-sample-refs", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="queries", choices=["queries", "references"],
+                    help="N > 1: 'queries' = replicated index, one query stream per GPU (weak scaling, the default); "
+                         "'references' = whole reference genomes split over the GPUs, every GPU maps the same query, hit rows "
+                         "all-gathered over NCCL and merged (SURVEY.md 8(e), BASELINE config 5 layout; strong scaling)")
     ap.add_argument("--profile", action="store_true",
                     help="bracket the device-timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     return ap.parse_args()
@@ -226,9 +230,13 @@ def run_b200(a):
     keep = set(sample_ids(a)) if (rank == 0 and world == 1 and not a.no_cpu_baseline) else set()
     sample_refs = []
     sketch = pf.Sketch(device=local)
+    by_refs = a.shard == "references" and world > 1
+    from pyfastani_b200 import sharding
+    offsets = sharding.reference_shards([a.length] * a.refs, world) if by_refs else [0, a.refs]
+    my_refs = range(offsets[rank], offsets[rank + 1]) if by_refs else range(a.refs)
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
-    for i in range(a.refs):
+    for i in my_refs:
         ref = reference_on_device(torch, base_dev, lut, float(idents[i]), a.seed, i)
         torch.cuda.synchronize(dev)
         sketch.add_genome(i, pf.DeviceSequence.from_pointer(ref.data_ptr(), ref.numel(), local, ref))
@@ -249,9 +257,20 @@ def run_b200(a):
 
     # ---- warm-up ------------------------------------------------------------------------------
     hits = None
+    name_to_local = {n: j for j, n in enumerate(mapper.names)}
+
+    def map_query(q):
+        """One step.  Reference-sharded: this rank's hits (local genome ids) are all-gathered as 16-byte rows over
+        NCCL and merged into the global order on every rank."""
+        hs = mapper.query_genome(q)
+        if not by_refs:
+            return hs
+        rows = sharding.hits_to_rows(hs, name_to_local)
+        return sharding.merge_hits(sharding.gather_hits([rows], device=dev)[0], offsets)
+
     for _ in range(max(a.warmup, 1)):
-        hits = mapper.query_genome(q_dev)
-        mapper.query_genome(query)
+        hits = map_query(q_dev)
+        map_query(query)
     info0 = dict(mapper.last_query_info)
 
     # ---- timed: K steps, query resident in HBM (CUDA events inside the library) -----------------
@@ -264,8 +283,9 @@ def run_b200(a):
     if a.profile:
         torch.cuda.synchronize(dev)
         torch.cuda.profiler.start()
+    t_wall = time.perf_counter()
     for _ in range(a.steps):
-        mapper.query_genome(q_dev)
+        map_query(q_dev)
         inf = mapper.last_query_info
         dev_ms += inf["ms_total"]
         launches += inf["kernel_launches"]
@@ -276,6 +296,8 @@ def run_b200(a):
         torch.cuda.synchronize(dev)
         torch.cuda.profiler.stop()
     barrier()
+    if by_refs:     # the gather is part of the step: wall clock between the barriers instead of the library's kernel timers
+        dev_ms = (time.perf_counter() - t_wall) * 1e3
     dev_ms = max_over_ranks(dev_ms)
     inf = dict(mapper.last_query_info)
 
@@ -284,13 +306,17 @@ def run_b200(a):
     t0 = time.perf_counter()
     h2d = d2h = 0
     for _ in range(a.steps):
-        hits_e2e = mapper.query_genome(query)
+        hits_e2e = map_query(query)
         h2d += mapper.last_query_info["h2d_bytes"]
         d2h += mapper.last_query_info["d2h_bytes"]
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.summary()
-    assert [(h.name, h.matches, h.identity) for h in hits_e2e] == [(h.name, h.matches, h.identity) for h in hits]
+    if by_refs:
+        assert np.array_equal(hits_e2e, hits) and len(hits) <= a.refs
+        assert np.all(np.diff(hits["identity"].astype(np.float64)) <= 0)
+    else:
+        assert [(h.name, h.matches, h.identity) for h in hits_e2e] == [(h.name, h.matches, h.identity) for h in hits]
 
     if rank != 0:
         if world > 1:
@@ -345,18 +371,23 @@ def run_b200(a):
         assert ok == len(ohits), "GPU hits differ from the CPU reference on the sampled pairs"
 
     ms_per_step = dev_ms / a.steps
+    jobs = 1 if by_refs else world          # whole-job units per step: one query vs all references, or one query per GPU
     line = {
-        "metric": METRIC, "value": world * pairs / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
-        "warmup": max(a.warmup, 1), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": jobs * pairs / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 1), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if by_refs else "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": workload_name(a), "refs": a.refs, "length": a.length, "fragment_length": FRAG, "k": 16,
-                   "window": mapper.window_size, "parallelism": "replicated index, one query stream per GPU",
+                   "window": mapper.window_size,
+                   "parallelism": ("reference genomes sharded over the GPUs (%s per rank), same query on every GPU, NCCL all-gather "
+                                   "of the hit rows inside the step" % [offsets[r + 1] - offsets[r] for r in range(world)]) if by_refs
+                                  else "replicated index, one query stream per GPU",
                    "l2_policy": "inputs larger than L2: the index is %.1f GB, every step streams it" % (n_min * 28 / 1e9)},
-        "fragments_per_s": world * frags / (ms_per_step * 1e-3),
+        "fragments_per_s": jobs * frags / (ms_per_step * 1e-3),
         "clocks": clocks,
-        "e2e": {"value": world * pairs * a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d // a.steps,
+        "e2e": {"value": jobs * pairs * a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d // a.steps,
                 "d2h_bytes_per_step": d2h // a.steps, "ms_per_step": e2e_s / a.steps * 1e3,
-                "fragments_per_s": world * frags * a.steps / e2e_s},
+                "fragments_per_s": jobs * frags * a.steps / e2e_s},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,
