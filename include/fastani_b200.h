@@ -153,6 +153,13 @@ FA_API int fa_index_occurrence_threshold(const fa_index *ix, int32_t *out);     
  * *n_out receives the number of hits.  `info` is optional. */
 FA_API int fa_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs,
              fa_hit *out, uint64_t cap, uint64_t *n_out, fa_query_info *info);
+/* Many queries in one call -- the throughput entry for many-to-many runs (BASELINE configs 3-5; the reference loops
+ * over queries in Python, benches/mapping/bench.py:55-66): query q owns the next contigs_per_query[q] entries of
+ * `contigs`; its hits are out[hit_offsets[q] .. hit_offsets[q + 1]) (hit_offsets has n_queries + 1 entries), in
+ * the order fa_query returns them.  FA_ERR_INVALID if `cap` rows do not hold all hits (n_queries x genomes always
+ * do).  `info` (may be NULL) receives the counters and stage times summed over the queries. */
+FA_API int fa_query_batch(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_per_query, int32_t n_queries,
+                   fa_hit *out, uint64_t cap, uint64_t *hit_offsets, fa_query_info *info);
 /* Intermediates of the last fa_query on this index, for the bit-exact parity tests
  * (SURVEY.md 7.1 step 0): L1 candidates as (frag, seq, start, end) rows and L2 mappings as
  * (frag, seq, refStartPos, shared, sketch, identity-bits) rows of int32. */

@@ -101,6 +101,8 @@ cdef extern from "fastani_b200.h" nogil:
     int fa_index_occurrence_threshold(const fa_index* ix, int32_t* out)
     int fa_query(fa_index* ix, const fa_contig* contigs, int32_t n, fa_hit* out, uint64_t cap, uint64_t* n_out,
                  fa_query_info* info)
+    int fa_query_batch(fa_index* ix, const fa_contig* contigs, const int32_t* contigs_per_query, int32_t n_queries,
+                       fa_hit* out, uint64_t cap, uint64_t* hit_offsets, fa_query_info* info)
     int fa_device_alloc(int32_t device, uint64_t nbytes, void** dptr)
     int fa_device_upload(int32_t device, void* dptr, const void* src, uint64_t nbytes)
     int fa_device_free(int32_t device, void* dptr)
@@ -665,6 +667,77 @@ cdef class Mapper(_Parameterized):
         finally:
             free(out)
         return hits
+
+    cpdef list query_many(self, object queries, int threads=0):
+        """query_many(self, queries, threads=0)\n--
+
+        Map many queries with one call into the library (`fa_query_batch`; not in the reference
+        API, which loops over `query_draft` in Python).  Each item of `queries` is either one
+        sequence (`str`, bytes-like, `DeviceSequence`: a complete genome) or a list / tuple of
+        contigs (a draft).  Returns one list of `Hit` per query, each exactly what
+        `query_genome` / `query_draft` returns for that item.  Releases the GIL for the whole batch."""
+        cdef _Contigs      c = _Contigs.__new__(_Contigs)
+        cdef list          flat = []
+        cdef list          items = list(queries)
+        cdef int32_t       nq = <int32_t> len(items)
+        cdef uint64_t      cap = <uint64_t> max(len(self._names), 1) * <uint64_t> max(nq, 1)
+        cdef int32_t*      counts = NULL
+        cdef uint64_t*     offs = NULL
+        cdef fa_hit*       out = NULL
+        cdef fa_query_info info
+        cdef int           rc
+        cdef list          result = []
+        cdef list          hits
+        cdef uint64_t      i
+        cdef int32_t       q
+
+        if threads < 0:
+            raise ValueError(f"`threads` must be positive or null, got {threads!r}")
+        counts = <int32_t*> malloc(max(nq, 1) * sizeof(int32_t))
+        offs = <uint64_t*> malloc((nq + 1) * sizeof(uint64_t))
+        out = <fa_hit*> malloc(cap * sizeof(fa_hit))
+        try:
+            if counts == NULL or offs == NULL or out == NULL:
+                raise MemoryError()
+            for q in range(nq):
+                if isinstance(items[q], (list, tuple)):
+                    counts[q] = <int32_t> len(items[q])
+                    flat.extend(items[q])
+                else:
+                    counts[q] = 1
+                    flat.append(items[q])
+            c.fill(flat)
+            with nogil:
+                rc = fa_query_batch(self._ix, c.arr, counts, nq, out, cap, offs, &info)
+            _check(rc)
+            for _ in range(info.short_contigs):
+                warnings.warn(
+                    (
+                        "Mapper received a short sequence relative to parameters, "
+                        "mapping will not be computed."
+                    ),
+                    UserWarning,
+                )
+            for q in range(nq):
+                hits = []
+                for i in range(offs[q], offs[q + 1]):
+                    hits.append(Hit(
+                        name=self._names[out[i].ref_genome],
+                        identity=out[i].identity,
+                        matches=out[i].matches,
+                        fragments=out[i].fragments,
+                    ))
+                result.append(hits)
+            self.last_query_info = {
+                "fragments": info.fragments, "seeds": info.seeds, "candidates": info.candidates, "mappings": info.mappings,
+                "kernel_launches": info.kernel_launches, "ms_total": info.ms_total, "h2d_bytes": info.h2d_bytes,
+                "d2h_bytes": info.d2h_bytes, "events": info.events, "events_replayed": info.events_replayed, "queries": nq,
+            }
+        finally:
+            free(counts)
+            free(offs)
+            free(out)
+        return result
 
     cpdef list query_draft(self, object contigs, int threads=0):
         """query_draft(self, contigs, threads=0)\n--

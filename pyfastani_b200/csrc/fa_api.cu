@@ -426,6 +426,42 @@ int fa_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *
     return run_query(ix, contigs, n_contigs, out, cap, n_out, info);
 }
 
+// Many queries in one call (no host language between them): query q owns contigs
+// [sum(contigs_per_query[:q]), +contigs_per_query[q]); its hits are out[hit_offsets[q] .. hit_offsets[q + 1]).
+// Counters and stage times of `info` are summed over the queries.
+int fa_query_batch(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_per_query, int32_t n_queries,
+                   fa_hit *out, uint64_t cap, uint64_t *hit_offsets, fa_query_info *info)
+{
+    if (!ix || n_queries < 0 || !hit_offsets || (n_queries > 0 && !contigs_per_query)) { set_error("bad arguments"); return FA_ERR_INVALID; }
+    fa_query_info sum;
+    memset(&sum, 0, sizeof sum);
+    uint64_t used = 0;
+    int64_t first = 0;
+    hit_offsets[0] = 0;
+    for (int32_t q = 0; q < n_queries; q++) {
+        const int32_t nc = contigs_per_query[q];
+        if (nc < 0) { set_error("query %d: negative contig count", q); return FA_ERR_INVALID; }
+        fa_query_info qi;
+        uint64_t n = 0;
+        const int rc = fa_query(ix, nc ? contigs + first : nullptr, nc, out ? out + used : nullptr, cap - used, &n, &qi);
+        if (rc != FA_OK) return rc;
+        if (n > cap - used) { set_error("query %d: %llu hits do not fit the output (capacity %llu)", q, (unsigned long long)n, (unsigned long long)cap); return FA_ERR_INVALID; }
+        used += n;
+        first += nc;
+        hit_offsets[q + 1] = used;
+        sum.fragments += qi.fragments; sum.sketch_sum += qi.sketch_sum; sum.seeds += qi.seeds; sum.candidates += qi.candidates;
+        sum.scanned += qi.scanned; sum.mappings += qi.mappings; sum.short_contigs += qi.short_contigs;
+        sum.kernel_launches += qi.kernel_launches; sum.h2d_bytes += qi.h2d_bytes; sum.d2h_bytes += qi.d2h_bytes;
+        sum.l2_fallback += qi.l2_fallback; sum.events += qi.events; sum.events_replayed += qi.events_replayed;
+        sum.l1_sorted_fragments += qi.l1_sorted_fragments;
+        sum.ms_h2d += qi.ms_h2d; sum.ms_sketch += qi.ms_sketch; sum.ms_lookup += qi.ms_lookup; sum.ms_seed_sort += qi.ms_seed_sort;
+        sum.ms_l1 += qi.ms_l1; sum.ms_l2 += qi.ms_l2; sum.ms_cgi += qi.ms_cgi; sum.ms_d2h += qi.ms_d2h; sum.ms_total += qi.ms_total;
+        sum.ms_l2_prep += qi.ms_l2_prep; sum.ms_l2_events += qi.ms_l2_events; sum.ms_l2_slide += qi.ms_l2_slide;
+    }
+    if (info) *info = sum;
+    return FA_OK;
+}
+
 int fa_debug_last_candidates(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n) { return debug_candidates(ix, rows, cap, n); }
 int fa_debug_last_mappings(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n) { return debug_mappings(ix, rows, cap, n); }
 int fa_debug_set_l1_seed_cap(fa_index *ix, int64_t cap)

@@ -232,3 +232,14 @@ class Index:
 
     def query_genome(self, seq, **kw):
         return self.query_draft((seq,), **kw)
+
+    def query_batch(self, queries):
+        """fa_query_batch: `queries` = list of contig lists -> (list of HIT_DT arrays, summed info dict)."""
+        flat = [c for q in queries for c in q]
+        keeps, arr = contig_array(flat)
+        counts = (C.c_int32 * max(len(queries), 1))(*[len(q) for q in queries])
+        offs = (C.c_uint64 * (len(queries) + 1))()
+        hits = np.zeros(max(len(self.names), 1) * max(len(queries), 1), HIT_DT)
+        info = QueryInfo()
+        check(lib().fa_query_batch(self.h, arr, counts, len(queries), hits.ctypes.data_as(C.c_void_p), len(hits), offs, C.byref(info)))
+        return [hits[offs[q]:offs[q + 1]].copy() for q in range(len(queries))], info.as_dict()

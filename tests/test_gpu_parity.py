@@ -236,3 +236,25 @@ def test_l2_early_stop_keeps_first_and_last_optimum():
         assert np.array_equal(out["mappings"], oinfo["mappings"])
         assert np.array_equal(hits, ohits)
         assert 0 < out["info"]["events_replayed"] < out["info"]["events"]
+
+
+def test_query_batch_equals_single_queries():
+    """fa_query_batch: CSR hit rows of many queries in one call == fa_query per query; counters add up."""
+    q, refs, _ = synth.one_to_many(515, 6, 80_000, lo=0.84, hi=0.99)
+    sk = capi.Sketch()
+    for i, r in enumerate(refs):
+        sk.add_genome(i, r)
+    ix = sk.index()
+    rng = np.random.default_rng(6)
+    queries = [[q], synth.fragment(rng, q, 4, min_end=500), [refs[3]], [q[:2000], b"ACGTACGT"], [], [synth.revcomp(refs[5])]]
+    singles, frags, cands = [], 0, 0
+    for qq in queries:
+        h, out = ix.query_draft(qq)
+        singles.append(h)
+        frags += out["info"]["fragments"]; cands += out["info"]["candidates"]
+    batch, info = ix.query_batch(queries)
+    assert len(batch) == len(queries)
+    for a, b in zip(batch, singles):
+        assert np.array_equal(a, b)
+    assert info["fragments"] == frags and info["candidates"] == cands and info["short_contigs"] == 1
+    assert ix.query_batch([])[0] == []

@@ -162,3 +162,27 @@ def test_query_warnings_and_views(pf):
     assert k2 == key and p2 == pos
     dev = pf.DeviceSequence.from_host(g)
     assert mapper.query_genome(dev) == mapper.query_genome(g)
+
+
+def test_query_many_equals_single_queries(pf):
+    """`Mapper.query_many` / `fa_query_batch`: one call, results identical to query_genome / query_draft
+    item by item (genomes, drafts, a device-resident sequence, a query without hits, an empty batch)."""
+    import synth
+    q, refs, _ = synth.one_to_many(99, 5, 90_000, lo=0.85, hi=0.99)
+    sketch = pf.Sketch()
+    for i, r in enumerate(refs):
+        sketch.add_genome(i, r)
+    mapper = sketch.index()
+    rng = np.random.default_rng(5)
+    unrelated = synth.to_bytes(synth.random_codes(rng, 30_000))
+    draft = synth.fragment(rng, q, 5, min_end=500)
+    queries = [q, draft, unrelated, pf.DeviceSequence.from_host(refs[2]), tuple(draft[:2]), refs[4].decode()]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        single = [mapper.query_draft(x) if isinstance(x, (list, tuple)) else mapper.query_genome(x) for x in queries]
+        many = mapper.query_many(queries)
+    assert many == single and single[2] == [] and len(single[0]) == 5
+    assert mapper.last_query_info["queries"] == len(queries)
+    assert mapper.query_many([]) == []
+    with pytest.raises(ValueError):
+        mapper.query_many(queries, threads=-1)
