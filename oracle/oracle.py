@@ -69,9 +69,10 @@ def available():
 
 
 def make_params(k=16, fragment_length=3000, minimum_fraction=0.2, p_value=1e-3, percentage_identity=80.0,
-                reference_size=5_000_000, window=None):
-    p = Params(k, 0, fragment_length, 4, minimum_fraction, percentage_identity, p_value, reference_size)
-    return p, window
+                reference_size=5_000_000, window=None, protein=False):
+    # protein: alphabet 20 and window 1 (pyx:548-550)
+    p = Params(k, 0, fragment_length, 20 if protein else 4, minimum_fraction, percentage_identity, p_value, reference_size)
+    return p, (1 if protein and window is None else window)
 
 
 def _as_buf(seq):
@@ -151,11 +152,18 @@ class Oracle:
     def hash(self, kmer):
         return self._f("hash")(kmer, len(kmer))
 
-    def minimizers(self, seq, k=16, w=24, seq_id=0):
+    def minimizers(self, seq, k=16, w=24, seq_id=0, protein=False):
         keep, ptr, unit, n = _as_buf(seq)
         cap = max(n, 1)
         h = np.empty(cap, np.uint32); s = np.empty(cap, np.int32); wp = np.empty(cap, np.int32)
-        m = self._f("minimizers")(ptr, unit, n, k, w, seq_id, h.ctypes.data, s.ctypes.data, wp.ctypes.data, cap)
+        if protein:         # (C port only)
+            fn = self._f("minimizers_alpha")
+            fn.restype = C.c_int64
+            fn.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int32, C.c_int,
+                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+            m = fn(ptr, unit, n, k, w, seq_id, 20, h.ctypes.data, s.ctypes.data, wp.ctypes.data, cap)
+        else:
+            m = self._f("minimizers")(ptr, unit, n, k, w, seq_id, h.ctypes.data, s.ctypes.data, wp.ctypes.data, cap)
         return h[:m].copy(), s[:m].copy(), wp[:m].copy()
 
     # ---- sketch / query -------------------------------------------------
@@ -168,8 +176,7 @@ class OracleSketch:
 
     def __init__(self, orc, **kw):
         self.o = orc
-        window = kw.pop("window", None)
-        self.params, _ = make_params(**kw)
+        self.params, window = make_params(**kw)
         self.params.window = window if window is not None else orc._f("recommended_window")(C.byref(self.params))
         self.h = orc._f("sketch_new")(C.byref(self.params))
         self.names = []

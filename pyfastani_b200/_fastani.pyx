@@ -374,19 +374,21 @@ cdef class Sketch(_Parameterized):
                 f"Using k-mer size greater than 16 ({k!r}), accuracy will be degraded.",
                 UserWarning,
             )
-        if protein:
-            raise NotImplementedError("protein mode is not implemented on the GPU path")
-
         self._param.k = k
         self._param.frag_len = fragment_length
         self._param.min_fraction = minimum_fraction
         self._param.p_value = p_value
         self._param.pct_identity = percentage_identity
         self._param.ref_size = reference_size
-        self._param.alphabet = 4
-        self._param.window = 0
-        _check(fa_recommended_window(&self._param, &w))
-        self._param.window = w
+        if protein:
+            # alphabet 20, forward strand only, window 1 (pyx:548-550)
+            self._param.alphabet = 20
+            self._param.window = 1
+        else:
+            self._param.alphabet = 4
+            self._param.window = 0
+            _check(fa_recommended_window(&self._param, &w))
+            self._param.window = w
         self._device = device
 
         self._lock = threading.Lock()

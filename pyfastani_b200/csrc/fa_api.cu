@@ -59,7 +59,8 @@ int check_params(const fa_params *p)
     if (p->min_fraction < 0 || p->min_fraction > 1) { set_error("minimum_fraction must be between 0 and 1"); return FA_ERR_INVALID; }
     if (!(p->p_value > 0)) { set_error("p_value must be positive"); return FA_ERR_INVALID; }
     if (p->pct_identity < 0 || p->pct_identity > 100) { set_error("percentage_identity must be between 0 and 100"); return FA_ERR_INVALID; }
-    if (p->alphabet != 4) { set_error("only the nucleotide alphabet (4) is implemented on the device path"); return FA_ERR_UNSUPPORTED; }
+    // 4 = nucleotides; anything else is the reference's protein mode (pyx:548-550, 650-668): forward strand only
+    if (p->alphabet < 2) { set_error("alphabet size must be at least 2, got %d", p->alphabet); return FA_ERR_INVALID; }
     if (p->window < 0) { set_error("window must be >= 0"); return FA_ERR_INVALID; }
     return FA_OK;
 }
@@ -132,7 +133,7 @@ int sketch_add_batch(fa_sketch *s, const fa_contig *contigs, int32_t n_contigs, 
     FA_TRY(s->sc.counters.reserve(4)); FA_TRY(s->sc.seq_first.reserve(n_seqs)); FA_TRY(s->sc.drops.reserve(n_seqs));
     FA_TRY(s->ref.reserve(s->n + worst + 1, true, st));
     FA_CUDA(cudaMemcpyAsync(s->sc.seqs.p, s->h_seqs.data(), (size_t)n_seqs * sizeof(SeqDesc), cudaMemcpyHostToDevice, st));
-    FA_TRY(launch_sketch(st, s->sc, n_seqs, (int)tiles, P.k, P.window, s->ref.p, nullptr, s->n, &launches));
+    FA_TRY(launch_sketch(st, s->sc, n_seqs, (int)tiles, P.k, P.window, P.alphabet != 4, s->ref.p, nullptr, s->n, &launches));
     FA_TRY(launch_quirk_find(st, s->sc, n_seqs, s->ref.p + s->n, &launches));
     unsigned long long h_ct[4];
     FA_CUDA(cudaMemcpyAsync(h_ct, s->sc.counters.p, sizeof h_ct, cudaMemcpyDeviceToHost, st));
@@ -197,8 +198,8 @@ int fa_sketch_create(const fa_params *p, int32_t device, fa_sketch **out)
     fa_sketch *s = new (std::nothrow) fa_sketch();
     if (!s) return FA_ERR_NOMEM;
     s->prm = *p;
-    if (s->prm.window == 0)
-        s->prm.window = recommended_window(p->p_value, p->k, p->alphabet, p->pct_identity, p->frag_len, p->ref_size);
+    if (s->prm.window == 0)      // protein mode (alphabet != 4) maps with window 1, pyx:548-550
+        s->prm.window = p->alphabet == 4 ? recommended_window(p->p_value, p->k, p->alphabet, p->pct_identity, p->frag_len, p->ref_size) : 1;
     s->device = device;
     e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); delete s; return FA_ERR_CUDA; }

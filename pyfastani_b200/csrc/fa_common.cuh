@@ -104,7 +104,7 @@ constexpr int SK_TILE = SK_THREADS * SK_PER_THREAD;
 // Launch the sketch kernel over `n_tiles` tiles of the batch; minimizers are appended in
 // (sequence, position) order to out_ref[out_base ...] (reference mode: RefMini) or to
 // out_hash[...] (query mode: hash only).  counters[1] receives the total emitted.
-int launch_sketch(cudaStream_t st, const SketchScratch &sc, int n_seqs, int n_tiles, int k, int w,
+int launch_sketch(cudaStream_t st, const SketchScratch &sc, int n_seqs, int n_tiles, int k, int w, int fwd_only,
                   RefMini *out_ref, uint32_t *out_hash, uint64_t out_base, int *launches);
 
 // The reference's `wpos == 0` comparison quirk (pyx:219-222) suppresses some

@@ -1376,7 +1376,7 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
         qi.h2d_bytes += (uint64_t)F * sizeof(SeqDesc);
         FA_CUDA(cudaMemsetAsync(ws.counters.p, 0, CT_N * sizeof(unsigned long long), st));
         FA_CUDA(cudaEventRecord(ws.ev[1], st));
-        FA_TRY(launch_sketch(st, ws.sk, F, n_tiles, k, w, nullptr, ws.qhash.p, 0, &launches));
+        FA_TRY(launch_sketch(st, ws.sk, F, n_tiles, k, w, P.alphabet != 4, nullptr, ws.qhash.p, 0, &launches));
         {
             int p2 = 1; while (p2 < cmw) p2 <<= 1;
             int sort_cap = std::min(p2, 32768);

@@ -105,7 +105,7 @@ __device__ __forceinline__ unsigned long long ld_status(const unsigned long long
 template <bool K16>
 __global__ void __launch_bounds__(SK_THREADS)
 sketch_kernel(const uint8_t *__restrict__ bytes, const SeqDesc *__restrict__ seqs, int n_seqs, int n_tiles,
-              int k, int w, int nb_cap, int nk_cap,
+              int k, int w, int fwd_only, int nb_cap, int nk_cap,
               unsigned long long *status, unsigned long long *counters, uint64_t *seq_first,
               RefMini *out_ref, uint32_t *out_hash, uint64_t out_base)
 {
@@ -197,19 +197,20 @@ sketch_kernel(const uint8_t *__restrict__ bytes, const SeqDesc *__restrict__ seq
         uint32_t vword = 0;
         int vbase = x0 & ~31;
         for (int x = x0; x < x1; x++) {
-            uint32_t hf, hb;
+            uint32_t hf, hb = 0xFFFFFFFFu;
             if (K16) {
                 hf = murmur16(f1, f2);
-                hb = murmur16(r1, r2);
+                if (!fwd_only) hb = murmur16(r1, r2);
                 uint64_t nf = sf[x + 16], nc = sc[x + 16];    // (one byte past the tile on the last step: staged padding)
                 f1 = (f1 >> 8) | (f2 << 56); f2 = (f2 >> 8) | (nf << 56);
                 r2 = (r2 << 8) | (r1 >> 56); r1 = (r1 << 8) | nc;
             } else {
                 hf = murmur_any(sf, x, 1, k);
-                hb = murmur_any(sc, x + k - 1, -1, k);
+                if (!fwd_only) hb = murmur_any(sc, x + k - 1, -1, k);
             }
             unsigned long long key = KEY_INF;
-            if (hf != hb) {                                    // symmetric k-mers are skipped, pyx:202
+            // symmetric k-mers are skipped, pyx:202; proteins hash the forward strand only and skip nothing, pyx:290
+            if (hf != hb || fwd_only) {
                 key = ((unsigned long long)min(hf, hb) << 32) | (0xFFFFFFFFu - (uint32_t)x);
                 if ((x & ~31) != vbase) { if (vword) atomicOr(&vbits[vbase >> 5], vword); vword = 0; vbase = x & ~31; }
                 vword |= 1u << (x & 31);
@@ -394,7 +395,7 @@ static int init_tables()
     return FA_OK;
 }
 
-int launch_sketch(cudaStream_t st, const SketchScratch &sc, int n_seqs, int n_tiles, int k, int w,
+int launch_sketch(cudaStream_t st, const SketchScratch &sc, int n_seqs, int n_tiles, int k, int w, int fwd_only,
                   RefMini *out_ref, uint32_t *out_hash, uint64_t out_base, int *launches)
 {
     FA_TRY(init_tables());
@@ -408,7 +409,7 @@ int launch_sketch(cudaStream_t st, const SketchScratch &sc, int n_seqs, int n_ti
     FA_CUDA(cudaMemsetAsync(sc.seq_first.p, 0xFF, (size_t)n_seqs * sizeof(uint64_t), st));
     auto kern = (k == 16) ? sketch_kernel<true> : sketch_kernel<false>;
     if (smem > 48 * 1024) FA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<n_tiles, SK_THREADS, smem, st>>>(sc.bytes.p, sc.seqs.p, n_seqs, n_tiles, k, w, nb_cap, nk_cap,
+    kern<<<n_tiles, SK_THREADS, smem, st>>>(sc.bytes.p, sc.seqs.p, n_seqs, n_tiles, k, w, fwd_only, nb_cap, nk_cap,
                                             sc.tile_status.p, sc.counters.p, sc.seq_first.p, out_ref, out_hash, out_base);
     FA_CUDA(cudaGetLastError());
     if (launches) *launches += 1;

@@ -65,8 +65,9 @@ def check(rc):
 
 
 def make_params(k=16, fragment_length=3000, minimum_fraction=0.2, p_value=1e-3, percentage_identity=80.0,
-                reference_size=5_000_000, window=0):
-    return Params(k, window, fragment_length, 4, minimum_fraction, percentage_identity, p_value, reference_size)
+                reference_size=5_000_000, window=0, protein=False):
+    # protein: alphabet 20; window 0 lets the library choose (1 in protein mode, pyx:548-550)
+    return Params(k, window, fragment_length, 20 if protein else 4, minimum_fraction, percentage_identity, p_value, reference_size)
 
 
 def as_buf(seq):

@@ -115,3 +115,53 @@ def query_cases():
                            ("rep2", [synth.to_bytes(synth.mutate_codes(rng, rep, 0.93))])],
                   "queries": [[repb], [synth.to_bytes(unit) * 3], [repb[1000:]]]})
     return cases
+
+
+# ---- protein mode (reference: pyx:225-309, 548-550, test_ani.py:96-115) ------------------
+AA = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+
+
+def _rand_aa(rng, n):
+    return AA[rng.integers(0, 20, size=n)].tobytes()
+
+
+def _mutate_aa(rng, seq, identity):
+    a = np.frombuffer(seq, dtype=np.uint8).copy()
+    hit = rng.random(a.size) < (1.0 - identity)
+    a[hit] = AA[rng.integers(0, 20, size=int(hit.sum()))]
+    return a.tobytes()
+
+
+def protein_minimizer_cases():
+    rng = np.random.default_rng(2020)
+    cases = []
+
+    def add(name, contigs, **params):
+        cases.append({"name": name, "contigs": contigs, "params": dict(protein=True, **params)})
+
+    p1 = _rand_aa(rng, 5000)
+    add("prot_default", [p1], fragment_length=100)
+    add("prot_k5", [p1[:3000]], k=5, fragment_length=100)
+    add("prot_lower_mixed", [p1[:2500].lower(), p1[2500:4133]], fragment_length=100)       # blocks of 2048, 16-byte chunks + tails
+    add("prot_str", [p1[:2100].decode(), p1[:700].decode().lower()], fragment_length=100)
+    add("prot_ucs2", [p1[:1500].decode() + "Δ" + p1[1500:2300].decode()], fragment_length=100)
+    add("prot_x_runs", [p1[:300] + b"X" * 40 + p1[300:600] + b"*" + p1[600:900], b"M" * 64, b"MK" * 40], fragment_length=100)
+    add("prot_short", [p1[:15], p1[:16], p1[:17], b""], fragment_length=100)
+    add("prot_non_letters", [p1[:100] + b"-.*12" + p1[100:2050] + b"[]{}|" + p1[2050:2063]], fragment_length=100)
+    return cases
+
+
+def protein_query_cases():
+    rng = np.random.default_rng(2021)
+    fam = [_rand_aa(rng, int(n)) for n in rng.integers(150, 1200, size=40)]
+    close = [_mutate_aa(rng, p, 0.93) for p in fam]
+    far = [_mutate_aa(rng, p, 0.80) for p in fam]
+    other = [_rand_aa(rng, int(n)) for n in rng.integers(150, 1200, size=40)]
+    shuffled = [close[i] for i in rng.permutation(len(close))]
+    cases = [{"name": "prot_families", "params": dict(protein=True, fragment_length=100),
+              "refs": [("fam", fam), ("close", shuffled), ("far", far), ("other", other)],
+              "queries": [fam, close, other, fam[:5], [fam[0][:99]]]},
+             {"name": "prot_k7_frag60", "params": dict(protein=True, fragment_length=60, k=7, percentage_identity=70.0),
+              "refs": [("fam", fam[:20]), ("far", far[:20])],
+              "queries": [close[:20], far[5:15]]}]
+    return cases

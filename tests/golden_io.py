@@ -23,9 +23,15 @@ def config1_golden():
 
 
 def genome(name):
-    """Contigs of 'ecoli' / 'shigella' (vendor/FastANI/data in the reference), as bytes."""
+    """Contigs of 'ecoli' / 'shigella' (vendor/FastANI/data in the reference) or the proteins of 'BGC000142x'
+    (src/pyfastani/tests/data), as bytes."""
     with gzip.open(os.path.join(GOLD, "data", name + ".seq.gz"), "rb") as f:
         return f.read().split(b"\n")[:-1]
+
+
+def protein_golden():
+    """(manifest dict, npz arrays) of protein mode: minimizer cases, query cases, the reference's BGC test."""
+    return json.load(open(os.path.join(GOLD, "protein.json"))), np.load(os.path.join(GOLD, "protein.npz"))
 
 
 def f32(hexstr):

@@ -258,3 +258,54 @@ def test_query_batch_equals_single_queries():
         assert np.array_equal(a, b)
     assert info["fragments"] == frags and info["candidates"] == cands and info["short_contigs"] == 1
     assert ix.query_batch([])[0] == []
+
+
+# ---- protein mode (pyx:225-309, 548-550) ----------------------------------------
+@pytest.mark.parametrize("idx", range(len(cases.protein_minimizer_cases())))
+def test_protein_minimizers_match_pyfastani(idx):
+    case = cases.protein_minimizer_cases()[idx]
+    gold, arr = golden_io.protein_golden()
+    man = gold["minimizers"][idx]
+    sk = capi.Sketch(**case["params"])
+    sk.add_draft("g", case["contigs"])
+    gh, gs, gw = sk.minimizers()
+    assert len(gh) == man["n"]
+    assert np.array_equal(gh, arr["h%d" % idx]) and np.array_equal(gs, arr["s%d" % idx]) and np.array_equal(gw, arr["w%d" % idx])
+    assert sk.warnings == man["warnings"]
+
+
+@pytest.mark.parametrize("idx", range(len(cases.protein_query_cases())))
+def test_protein_queries_match_pyfastani_and_oracle(idx):
+    case = cases.protein_query_cases()[idx]
+    gold = golden_io.protein_golden()[0]["queries"][idx]
+    sk, osk = capi.Sketch(**case["params"]), _port().sketch(**case["params"])
+    for rname, contigs in case["refs"]:
+        sk.add_draft(rname, contigs)
+        osk.add_draft(rname, contigs)
+    ix = sk.index()
+    osk.index()
+    assert ix.counts()[0] == gold["minimizers"] and ix.counts()[1] == gold["unique"]
+    for q, res in zip(case["queries"], gold["results"]):
+        hits, out = ix.query_draft(q, dump=True)
+        ohits, oinfo = osk.query_draft(q, dump=True)
+        assert np.array_equal(out["candidates"], oinfo["candidates"])
+        assert np.array_equal(out["mappings"], oinfo["mappings"])
+        assert np.array_equal(hits, ohits)
+        assert [[ix.names[h["ref_genome"]], int(h["matches"]), int(h["fragments"])] for h in hits] == [[r[0], r[2], r[3]] for r in res["hits"]]
+        assert [h["identity"] for h in hits] == [golden_io.f32(r[1]) for r in res["hits"]]
+        assert out["short_contigs"] == res["warnings"]
+
+
+def test_protein_bgc_known_answer():
+    """The reference's own protein test (test_ani.py:96-115): 130 / 176 under both names."""
+    gold = golden_io.protein_golden()[0]["bgc"]
+    bgc = {n: golden_io.genome(n) for n in ("BGC0001425", "BGC0001427", "BGC0001428")}
+    sk = capi.Sketch(protein=True, fragment_length=100)
+    sk.add_draft("BGC0001425", bgc["BGC0001425"])
+    sk.add_draft("BGC0001427", bgc["BGC0001425"])
+    ix = sk.index()
+    assert ix.counts()[0] == gold["minimizers"] and ix.counts()[1] == gold["unique"]
+    hits, _ = ix.query_draft(bgc["BGC0001428"])
+    assert [(ix.names[h["ref_genome"]], int(h["matches"]), int(h["fragments"])) for h in hits] == \
+           [("BGC0001425", 130, 176), ("BGC0001427", 130, 176)]
+    assert [h["identity"] for h in hits] == [golden_io.f32(r[1]) for r in gold["as_in_test_ani"]]

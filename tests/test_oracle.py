@@ -144,3 +144,53 @@ class TestAgainstReferenceHeaders:
         assert np.array_equal(a[2], b[2]) and len(a[2]) > 100
         assert np.array_equal(a[3], b[3])
         assert a[4]["seeds"] == b[4]["seeds"]
+
+
+# ---- protein mode (pyx:225-309, 548-550) -------------------------------------------------------
+@pytest.mark.parametrize("idx", range(len(cases.protein_minimizer_cases())))
+def test_protein_minimizers_match_pyfastani(idx):
+    case = cases.protein_minimizer_cases()[idx]
+    gold, arr = golden_io.protein_golden()
+    man = gold["minimizers"][idx]
+    assert man["name"] == case["name"] and man["window"] == 1
+    sk = _contig_minimizers(PORT, case["contigs"], case["params"])
+    assert sk.params.window == 1 and sk.params.alphabet == 20
+    gh, gs, gw = sk.minimizers()
+    assert len(gh) == man["n"]
+    assert np.array_equal(gh, arr["h%d" % idx]) and np.array_equal(gs, arr["s%d" % idx]) and np.array_equal(gw, arr["w%d" % idx])
+    assert sk.warnings == man["warnings"]
+
+
+@pytest.mark.parametrize("idx", range(len(cases.protein_query_cases())))
+def test_protein_queries_match_pyfastani(idx):
+    case = cases.protein_query_cases()[idx]
+    gold = golden_io.protein_golden()[0]["queries"][idx]
+    sk = PORT.sketch(**case["params"])
+    for rname, contigs in case["refs"]:
+        sk.add_draft(rname, contigs)
+    sk.index()
+    assert len(sk.minimizers()[0]) == gold["minimizers"] and sk.unique() == gold["unique"]
+    for q, res in zip(case["queries"], gold["results"]):
+        hits, info = sk.query_draft(q)
+        _check_hits(hits, sk.names, res["hits"])
+        assert info["short_contigs"] == res["warnings"]
+
+
+def test_protein_bgc_known_answer():
+    """The reference's own protein test (test_ani.py:96-115): 130 / 176 for both names."""
+    gold = golden_io.protein_golden()[0]["bgc"]
+    bgc = {n: golden_io.genome(n) for n in ("BGC0001425", "BGC0001427", "BGC0001428")}
+    sk = PORT.sketch(protein=True, fragment_length=100)
+    sk.add_draft("BGC0001425", bgc["BGC0001425"])
+    sk.add_draft("BGC0001427", bgc["BGC0001425"])
+    sk.index()
+    assert len(sk.minimizers()[0]) == gold["minimizers"] and sk.unique() == gold["unique"]
+    hits, _ = sk.query_draft(bgc["BGC0001428"])
+    _check_hits(hits, sk.names, gold["as_in_test_ani"])
+    assert [(int(h["matches"]), int(h["fragments"])) for h in hits] == [(130, 176), (130, 176)]
+    sk2 = PORT.sketch(protein=True, fragment_length=100)
+    sk2.add_draft("BGC0001425", bgc["BGC0001425"])
+    sk2.add_draft("BGC0001427", bgc["BGC0001427"])
+    sk2.index()
+    _check_hits(sk2.query_draft(bgc["BGC0001428"])[0], sk2.names, gold["distinct_refs"])
+    _check_hits(sk2.query_draft(bgc["BGC0001427"])[0], sk2.names, gold["self"])

@@ -186,3 +186,19 @@ def test_query_many_equals_single_queries(pf):
     assert mapper.query_many([]) == []
     with pytest.raises(ValueError):
         mapper.query_many(queries, threads=-1)
+
+
+def test_protein_mode(pf):                                   # test_ani.py:96-115
+    """Sketch(protein=True): alphabet 20, window 1; the reference's MIBiG cluster test and pickling."""
+    gold = golden_io.protein_golden()[0]["bgc"]
+    bgc = {n: [c.decode() for c in golden_io.genome(n)] for n in ("BGC0001425", "BGC0001427", "BGC0001428")}
+    sketch = pf.Sketch(protein=True, fragment_length=100)
+    assert sketch.protein and sketch.window_size == 1
+    sketch.add_draft("BGC0001425", bgc["BGC0001425"])
+    sketch.add_draft("BGC0001427", bgc["BGC0001425"])
+    mapper = pickle.loads(pickle.dumps(sketch)).index()
+    assert mapper.protein and mapper.window_size == 1
+    hits = mapper.query_draft(bgc["BGC0001428"])
+    assert len(hits) == 2
+    assert [(h.name, h.matches, h.fragments) for h in hits] == [("BGC0001425", 130, 176), ("BGC0001427", 130, 176)]
+    assert [np.float32(h.identity) for h in hits] == [golden_io.f32(r[1]) for r in gold["as_in_test_ani"]]
