@@ -309,3 +309,34 @@ def test_protein_bgc_known_answer():
     assert [(ix.names[h["ref_genome"]], int(h["matches"]), int(h["fragments"])) for h in hits] == \
            [("BGC0001425", 130, 176), ("BGC0001427", 130, 176)]
     assert [h["identity"] for h in hits] == [golden_io.f32(r[1]) for r in gold["as_in_test_ani"]]
+
+
+def test_draft_all_vs_all_clusters():
+    """BASELINE configs 3 / 4 in the small: two 'species' (85 % apart) of five 'strains' each (95-99.9 %),
+    every genome cut into 40 contigs, half of them reverse-complemented, order permuted; all ten as
+    references (add_draft) and as queries (query_draft, one fa_query_batch call).  Candidates,
+    mappings and hits of every query against the oracle; the batch equals the single queries."""
+    rng = np.random.default_rng(303)
+    root = synth.random_codes(rng, 180_000)
+    species = [root, synth.mutate_codes(rng, root, 0.85)]
+    drafts = []
+    for sp in species:
+        for ident in (0.999, 0.99, 0.98, 0.965, 0.95):
+            g = synth.to_bytes(synth.mutate_codes(rng, sp, ident))
+            drafts.append(synth.fragment(rng, g, 40, min_end=300))
+    sk, osk = capi.Sketch(), _port().sketch()
+    for i, d in enumerate(drafts):
+        sk.add_draft(i, d)
+        osk.add_draft(i, d)
+    ix = sk.index()
+    osk.index()
+    batch, _ = ix.query_batch(drafts)
+    for i, d in enumerate(drafts):
+        hits, out = ix.query_draft(d, dump=True)
+        ohits, oinfo = osk.query_draft(d, dump=True)
+        assert np.array_equal(out["candidates"], oinfo["candidates"])
+        assert np.array_equal(out["mappings"], oinfo["mappings"])
+        assert np.array_equal(hits, ohits) and np.array_equal(batch[i], ohits)
+        assert len(hits) == 10 and hits[0]["ref_genome"] == i and hits[0]["identity"] > 99.9
+        same = {int(h["ref_genome"]) // 5 for h in hits[:5]}
+        assert same == {i // 5}                              # the own species ranks first
