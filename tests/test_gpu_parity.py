@@ -340,3 +340,36 @@ def test_draft_all_vs_all_clusters():
         assert len(hits) == 10 and hits[0]["ref_genome"] == i and hits[0]["identity"] > 99.9
         same = {int(h["ref_genome"]) // 5 for h in hits[:5]}
         assert same == {i // 5}                              # the own species ranks first
+
+
+def test_many_to_many_tree_vs_reference():
+    """BASELINE config 4 in the small: 24 genomes of 0.4-0.8 Mbp on a two-level tree (80-100 % ANI inside a clade, unrelated across clades),
+    a third of them as drafts, all-vs-all = 576 genome pairs in one fa_query_batch call.  Every hit
+    row (reference id, matches, fragments, identity bits, order) against the CPU reference
+    (the compiled reference when present, else the C port)."""
+    from oracle.oracle import available
+    rng = np.random.default_rng(44)
+    genomes = []
+    for clade in range(4):
+        anc = synth.random_codes(rng, int(rng.integers(400_000, 800_000)))
+        for sp in range(2):
+            spc = synth.mutate_codes(rng, anc, float(rng.uniform(0.91, 0.97)))
+            for strain in range(3):
+                g = synth.to_bytes(synth.mutate_codes(rng, spc, float(rng.uniform(0.95, 0.999))))
+                genomes.append(synth.fragment(rng, g, int(rng.integers(20, 60)), min_end=200) if len(genomes) % 3 == 0 else [g])
+    kind = "reference" if "reference" in available() else "port"
+    sk, osk = capi.Sketch(), Oracle(kind).sketch()
+    for i, g in enumerate(genomes):
+        sk.add_draft(i, g)
+        osk.add_draft(i, g)
+    ix = sk.index()
+    osk.index()
+    batch, info = ix.query_batch(genomes)
+    kw = {"threads": 0} if kind == "reference" else {}
+    pairs = 0
+    for i, g in enumerate(genomes):
+        ohits, _ = osk.query_draft(g, **kw)
+        assert np.array_equal(batch[i], ohits), i
+        assert ohits[0]["ref_genome"] == i
+        pairs += len(ohits)
+    assert pairs >= 24 * 5 and info["l2_fallback"] == 0
