@@ -68,6 +68,39 @@ __global__ void make_hw_kernel(const RefMini *ref, uint64_t n, uint2 *hw)
 // computeL1CandidateRegions (computeMap.hpp:325-330: same seqId, wpos distance < fragment length)
 // becomes one unsigned subtraction of two 4-byte gathers (fa_map.cu l1_fused_kernel).  Sums wrap
 // mod 2^32; differences of elements fewer than frag_len indices apart never do.
+// Order of the slide events, independent of the query.  L2 slides a window of cmw = fragLen - (w - 1) - (k - 1)
+// positions over a region of one contig (computeMap.hpp:415-488, MIIteratorL2.hpp:54-96): element j enters the
+// window at time wpos[j] - (cmw - 1) and leaves when the begin reaches element j + 1, at time wpos[j + 1].  Merging
+// the two event streams by time only asks, per element, how many elements of the contig lie cmw - 1 behind / ahead:
+//   lag(j)  = j - A(j),  A(j) = first index with wpos > wpos[j] - (cmw - 1): the elements at or before A(j) have
+//             left the window when j enters (their deletes precede the insert of j)
+//   lead(j) = B(j) - j,  B(j) = first index with wpos >= wpos[j + 1] + (cmw - 1): the elements before B(j) have
+//             entered when j leaves; twin(j): element B(j) enters at exactly that time (same group, after the delete)
+// packed as lag (15 bits, saturating) | twin << 15 | lead << 16 (saturating).  Saturated values only occur in
+// windows of more than 32 767 minimizers, which the event path of L2 (<= 1024 per region) never takes.
+__global__ void slide_order_kernel(const RefMini *ref, const uint32_t *contig_off, uint64_t n, int cmw1, uint32_t *ll)
+{
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const RefMini e = ref[j];
+    const uint32_t c0 = contig_off[e.z], c1 = contig_off[e.z + 1];
+    const int pos = (int)e.y;
+    // A(j): positions grow strictly inside a contig, so the answer is at most cmw1 elements back
+    uint32_t lo = (uint64_t)cmw1 < j - c0 ? (uint32_t)j - (uint32_t)cmw1 : c0, hi = (uint32_t)j;       // answer in [lo, j]
+    const int ta = pos - cmw1;
+    while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if ((int)ref[mid].y <= ta) lo = mid + 1; else hi = mid; }
+    const uint32_t lag = min((uint32_t)j - lo, 32767u);
+    uint32_t lead = 0, twin = 0;
+    if (j + 1 < c1) {
+        const int tb = (int)ref[j + 1].y + cmw1;
+        uint32_t l = (uint32_t)j + 1, h = (uint64_t)cmw1 + 1 < c1 - (j + 1) ? (uint32_t)j + 2 + (uint32_t)cmw1 : c1;   // answer in [j + 1, h]
+        while (l < h) { const uint32_t mid = l + ((h - l) >> 1); if ((int)ref[mid].y < tb) l = mid + 1; else h = mid; }
+        lead = min(l - (uint32_t)j, 65535u);
+        twin = (l < c1 && (int)ref[l].y == tb) ? 1u : 0u;
+    }
+    ll[j] = lag | (twin << 15) | (lead << 16);
+}
+
 __global__ void gpos_delta_kernel(const RefMini *ref, uint64_t n, uint32_t frag_len, uint32_t *gpos)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -226,6 +259,15 @@ int build_index(fa_index *ix, int *launches)
     make_hw_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(ix->ref.p, n, ix->hw.p);
     FA_CUDA(cudaGetLastError());
     if (launches) *launches += 1;
+
+    {
+        const int cmw1 = ix->prm.frag_len - (ix->prm.window - 1) - (ix->prm.k - 1) - 1;
+        FA_TRY(ix->ll.reserve(n + 8));
+        FA_CUDA(cudaMemsetAsync(ix->ll.p + n, 0, 8 * sizeof(uint32_t), st));
+        slide_order_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(ix->ref.p, ix->contig_off.p, n, cmw1 < 0 ? 0 : cmw1, ix->ll.p);
+        FA_CUDA(cudaGetLastError());
+        if (launches) *launches += 1;
+    }
 
     FA_TRY(ix->gpos.reserve(n));
     gpos_delta_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(ix->ref.p, n, (uint32_t)ix->prm.frag_len, ix->gpos.p);

@@ -610,12 +610,12 @@ constexpr uint32_t EV_MATCH = 4;      // the hash is in the query sketch: toggle
 constexpr uint32_t EV_ONLY = 8;       // the hash is not in the sketch: counts in bucket idx (neither bit: no state change)
 constexpr uint32_t EV_DEL = 16;       // delete (window begin advances) / insert
 constexpr uint32_t EV_GRP = 32;       // last event of its time group: evaluate the window after it
-constexpr uint32_t EV_DUP = 0x8000;   // (events kernel only) a same-hash neighbour exists: resolve against the window
 constexpr uint32_t EV_AOFF = 0x7F03;
 constexpr int EV_MAX_S = 508;         // largest sketch the 16-bit events address
 constexpr int EV_RMAX = 1024;         // most reference minimizers of a candidate region on the event path
 constexpr int EVK_THREADS = 128;
 constexpr int EV_UNROLL = 8;          // independent loads per lane in the classification loop
+constexpr int EV_WARP_BYTES = (2 * EV_RMAX + 16) * 2;   // per-warp staging of one event list
 
 __host__ __device__ inline uint32_t ev_aoff(int idx) { return ((uint32_t)(idx & ~3) << 6) | (uint32_t)(idx & 3); }
 
@@ -626,7 +626,7 @@ __host__ __device__ inline uint32_t ev_aoff(int idx) { return ((uint32_t)(idx & 
 struct Prep {
     uint32_t beg, last;         // first reference minimizer of the region; the slide stops when the window end reaches `last`
     int32_t  seq;               // refSeqId
-    uint32_t n_del;             // delete events before the slide stops (insert events: last - 1 - beg)
+    uint32_t n_del;             // delete events before the slide stops (insert events: last - 1 - beg) | elements of the first window << 16
 };
 
 __global__ void __launch_bounds__(256)
@@ -663,8 +663,11 @@ l2_prep_kernel(const Cand *cands, const uint32_t *cand_base, int n_frags, const 
             const int t_stop = (int)(hw[last - 1].y & 0x7FFFFFFFu) - cmw + 1;
             const uint32_t dstop = lb_near(hw, beg + 1, last, t_stop, (long long)last - 1 - (long long)cmw * dens_num / dens_den);
             pp.n_del = dstop - 1 - beg;
-            const bool fast = last - beg <= (uint32_t)EV_RMAX && qs[cd.frag] <= EV_MAX_S;
-            if (fast) cnt = ((unsigned long long)(last - 1 - beg) + pp.n_del + 7ull) & ~7ull;      // padded to whole 16-byte chunks
+            const bool fast = last - beg <= (uint32_t)EV_RMAX && qs[cd.frag] <= EV_MAX_S && cmw >= 2;
+            if (fast) {
+                cnt = ((unsigned long long)(last - 1 - beg) + pp.n_del + 7ull) & ~7ull;             // padded to whole 16-byte chunks
+                pp.n_del |= (end0 - beg) << 16;
+            }
             else { mp.ref_start = L2_REDO; redo++; }
         }
         prep[c] = pp;
@@ -707,14 +710,17 @@ struct SlideJob {
 // One CTA per work item (<= L2_ITEM candidates of one fragment): the fragment's sketch and the
 // classification table are staged once, then each warp takes candidates one by one.
 //   classification: slot table (above) + a few compares against the staged sketch
-//   merge: delete m (time wpos[beg + m + 1]) and insert m (time max(wpos[beg + m] - cmw + 1, first
-//          window position)) are two sorted sequences; every lane finds its split on the merge path
-//          and emits a contiguous run of whole 16-byte chunks, deletes first inside a time group
-//          (MIIteratorL2.hpp:74-96)
+//   placement: the order of the inserts and deletes of a slide does not depend on the query, only on
+//          the minimizer positions, so the index carries per element how many elements lie one window
+//          behind / ahead (fa_index.cu slide_order_kernel).  Insert i follows the deletes of the
+//          elements that left the window before it (i - lag), delete i the inserts of those that
+//          entered before it (i + lead), deletes first inside a time group (MIIteratorL2.hpp:74-96):
+//          every element is classified and both of its events go straight to their place in a staged
+//          list -- no merge, no position array; the list leaves in whole 16-byte chunks.
 struct EvCtx {
-    const uint32_t *s_q; const uint16_t *s_tab; int *w_pos; uint16_t *w_cls;
-    const RefMini *ref; const uint2 *hw; uint16_t *ev; SlideJob *jobs; uint16_t *room;
-    int s, cmw1, tab_p, maxn;
+    const uint32_t *s_q; const uint16_t *s_tab; uint16_t *w_ev;
+    const RefMini *ref; const uint2 *hw; const uint32_t *ll; uint16_t *ev; SlideJob *jobs; uint16_t *room;
+    int s, tab_p, maxn;
 };
 
 // MAXN > 0: every table slot holds at most MAXN sketch hashes; MAXN == 0: bisect inside the slot.
@@ -722,108 +728,85 @@ template <int MAXN>
 __device__ __forceinline__ void ev_candidate(const EvCtx &X, uint32_t c, const Prep &pp, unsigned long long off,
                                              unsigned long long off1, int lane)
 {
-    const uint32_t *s_q = X.s_q; const uint16_t *s_tab = X.s_tab; int *w_pos = X.w_pos; uint16_t *w_cls = X.w_cls;
-    const RefMini *ref = X.ref; const uint2 *hw = X.hw; uint16_t *ev = X.ev; SlideJob *jobs = X.jobs;
-    const int s = X.s, cmw1 = X.cmw1, tab_p = X.tab_p;
-            const uint32_t n_pad = (uint32_t)(off1 - off);
-            const int R = (int)(pp.last - pp.beg), nI = R - 1, nD = (int)pp.n_del;
-            const int N = n_pad ? nI + nD : 0;
-            if (lane == 0) jobs[c] = SlideJob{off, (uint32_t)N, s};
-            if (N) {
-                // 1. load + classify the region, EV_UNROLL independent loads per lane in flight
-                int n_mi = 0;                                      // elements that are in the sketch
-                for (int i0 = 0; i0 < R; i0 += 32 * EV_UNROLL) {
-                    uint2 xs[EV_UNROLL];
+    const uint32_t *s_q = X.s_q; const uint16_t *s_tab = X.s_tab; uint16_t *w_ev = X.w_ev;
+    const RefMini *ref = X.ref; const uint2 *hw = X.hw; const uint32_t *ll = X.ll; uint16_t *ev = X.ev; SlideJob *jobs = X.jobs;
+    const int s = X.s, tab_p = X.tab_p;
+    const uint32_t n_pad = (uint32_t)(off1 - off);
+    const int R = (int)(pp.last - pp.beg), nI = R - 1, nD = (int)(pp.n_del & 0xFFFFu), y0 = (int)(pp.n_del >> 16);
+    const int N = n_pad ? nI + nD : 0;
+    if (lane == 0) jobs[c] = SlideJob{off, (uint32_t)N, s};
+    if (!N) return;
+    int n_mi = 0;                                      // elements that are in the sketch
+    __syncwarp();                                      // (the copy-out of the previous list is done)
+    for (int i0 = 0; i0 < R; i0 += 32 * EV_UNROLL) {
+        uint2 xs[EV_UNROLL];
+        uint32_t ls[EV_UNROLL];
 #pragma unroll
-                    for (int u = 0; u < EV_UNROLL; u++) {
-                        const int i = i0 + u * 32 + lane;
-                        xs[u] = i < R ? __ldg(hw + pp.beg + i) : make_uint2(0u, 0u);
-                    }
+        for (int u = 0; u < EV_UNROLL; u++) {
+            const int i = i0 + u * 32 + lane;
+            xs[u] = i < R ? __ldg(hw + pp.beg + i) : make_uint2(0u, 0u);
+            ls[u] = i < R ? __ldg(ll + pp.beg + i) : 0u;
+        }
 #pragma unroll
-                    for (int u = 0; u < EV_UNROLL; u++) {
-                        const int i = i0 + u * 32 + lane;
-                        if (i < R) {
-                            const uint32_t h = xs[u].x;
-                            const uint32_t slot = l2_slot(h, tab_p);
-                            int l = (int)s_tab[slot], match;
-                            if (MAXN > 0) {
-                                int lt = 0, eq = 0;
+        for (int u = 0; u < EV_UNROLL; u++) {
+            const int i = i0 + u * 32 + lane;
+            if (i < R) {
+                const uint32_t h = xs[u].x;
+                const uint32_t slot = l2_slot(h, tab_p);
+                int l = (int)s_tab[slot], match;
+                if (MAXN > 0) {
+                    int lt = 0, eq = 0;
 #pragma unroll
-                                for (int q = 0; q < MAXN; q++) { const uint32_t qv = s_q[l + q]; lt += qv < h ? 1 : 0; eq |= qv == h ? 1 : 0; }
-                                l += lt;
-                                match = l < s ? eq : 0;
-                            } else {
-                                int r = (int)s_tab[slot + 1];
-                                while (l < r) { const int mid = (l + r) >> 1; if (s_q[mid] < h) l = mid + 1; else r = mid; }
-                                match = (l < s && s_q[l] == h) ? 1 : 0;
-                            }
-                            w_pos[i] = (int)(xs[u].y & 0x7FFFFFFFu);
-                            w_cls[i] = (uint16_t)(ev_aoff(l + match) | (match ? EV_MATCH : EV_ONLY) | ((xs[u].y >> 31) ? EV_DUP : 0u));
-                            n_mi += match;
-                        }
-                    }
+                    for (int q = 0; q < MAXN; q++) { const uint32_t qv = s_q[l + q]; lt += qv < h ? 1 : 0; eq |= qv == h ? 1 : 0; }
+                    l += lt;
+                    match = l < s ? eq : 0;
+                } else {
+                    int r = (int)s_tab[slot + 1];
+                    while (l < r) { const int mid = (l + r) >> 1; if (s_q[mid] < h) l = mid + 1; else r = mid; }
+                    match = (l < s && s_q[l] == h) ? 1 : 0;
                 }
-                __syncwarp();
-                // (an upper bound of the inserts that set a match bit -- same-hash copies and the last element are counted,
-                // too -- is all the early stop of the slide needs)
-                n_mi = __reduce_add_sync(0xFFFFFFFFu, n_mi);
-                if (lane == 0) X.room[c] = (uint16_t)n_mi;
-                // 2. merge path: lane -> events [t_lo, t_hi), whole chunks of eight
-                const int pos0 = w_pos[0];
-                const int per = (((N + 31) >> 5) + 7) & ~7;
-                const int t_lo = min(N, lane * per), t_hi = min((int)n_pad, lane * per + per);
-                int x;                                             // deletes among the first t_lo events
-                {
-                    int lo = max(0, t_lo - nI), hi = min(t_lo, nD);
-                    while (lo < hi) {
-                        const int mid = (lo + hi) >> 1;
-                        if (w_pos[mid + 1] <= max(w_pos[t_lo - mid - 1] - cmw1, pos0)) lo = mid + 1; else hi = mid;
-                    }
-                    x = lo;
+                n_mi += match;
+                const uint32_t code = ev_aoff(l + match) | (match ? EV_MATCH : EV_ONLY);
+                const bool dup = (xs[u].y >> 31) != 0u;                    // a same-hash neighbour exists (rare)
+                const uint32_t dd = dup ? ref[pp.beg + (uint32_t)i].w : 0u;
+                // insert i: after the deletes of the region's elements that left before it entered
+                const int x = min(max(i - (int)(ls[u] & 0x7FFFu) - 1, 0), nD);
+                if (i < nI) {
+                    const uint32_t dp = dd & 0xFFFFu;
+                    const bool skip = dp && i - (int)dp >= x;              // already present (REV)
+                    // one evaluation after the whole first window (elements before y0), then after every insert:
+                    // insert times are distinct
+                    w_ev[i + x] = (uint16_t)((skip ? 0u : code) | (i >= y0 - 1 ? EV_GRP : 0u));
                 }
-                int y = t_lo - x;
-                int kdx = x < nD ? w_pos[x + 1] : INT32_MAX;
-                int kiy = y < nI ? max(w_pos[y] - cmw1, pos0) : INT32_MAX;
-                uint4 *dst = reinterpret_cast<uint4 *>(ev + off) + (lane * per >> 3);
-                for (int t0 = lane * per; t0 < t_hi; t0 += 8) {
-                    uint32_t pk[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const bool live = t0 + u < N;                  // (the tail of the last chunk is padding: no-ops)
-                        const bool del = kdx <= kiy;                   // delete first inside a group
-                        const int key = min(kdx, kiy);
-                        const int m = del ? x : y;
-                        uint32_t code = live ? w_cls[m] : 0u;
-                        if (code & EV_DUP) {                           // a same-hash neighbour exists (rare)
-                            const uint32_t j = pp.beg + (uint32_t)m, b = pp.beg + (uint32_t)x, e = pp.beg + (uint32_t)y;
-                            const uint32_t d = ref[j].w;
-                            bool skip;
-                            if (del) { const uint32_t dn = d >> 16; skip = dn && j + dn < e; }              // a later copy stays (NOOP)
-                            else { const uint32_t dp = d & 0xFFFFu; skip = dp && j >= dp && j - dp >= b; }   // already present (REV)
-                            code &= skip ? ~(EV_DUP | EV_MATCH | EV_ONLY | EV_AOFF) : ~EV_DUP;
-                        }
-                        code |= (live && del) ? EV_DEL : 0u;
-                        x += (live && del) ? 1 : 0;
-                        y += (live && !del) ? 1 : 0;
-                        const int lim = del ? nD : nI, cur = del ? x : y;
-                        const int val = w_pos[min(del ? x + 1 : y, R - 1)];
-                        int nk = del ? val : max(val - cmw1, pos0);
-                        nk = cur < lim ? nk : INT32_MAX;
-                        kdx = (live && del) ? nk : kdx;
-                        kiy = (live && !del) ? nk : kiy;
-                        code |= (live && min(kdx, kiy) != key) ? EV_GRP : 0u;      // (both exhausted: the unreached final group)
-                        pk[u >> 1] |= code << (16 * (u & 1));
-                    }
-                    *dst++ = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                // delete i: after the inserts of the elements that entered before it leaves
+                if (i < nD) {
+                    const int lead = (int)(ls[u] >> 16);
+                    const int y = min(i + lead, nI);
+                    const bool twin = ((ls[u] >> 15) & 1u) && i + lead < nI;   // an insert of the same time follows: same group
+                    const uint32_t dn = dd >> 16;
+                    const bool skip = dn && i + (int)dn < y;               // a later copy stays (NOOP)
+                    w_ev[i + y] = (uint16_t)((skip ? 0u : code) | EV_DEL | (twin ? 0u : EV_GRP));
                 }
-                __syncwarp();
             }
+        }
+    }
+    // (an upper bound of the inserts that set a match bit -- same-hash copies and the last element are counted,
+    // too -- is all the early stop of the slide needs)
+    n_mi = __reduce_add_sync(0xFFFFFFFFu, n_mi);
+    if (lane == 0) X.room[c] = (uint16_t)n_mi;
+    if (lane < 8) w_ev[N + lane] = (uint16_t)0;        // the tail of the last chunk is padding: no-ops
+    __syncwarp();
+    {
+        const uint4 *srcv = reinterpret_cast<const uint4 *>(w_ev);
+        uint4 *dst = reinterpret_cast<uint4 *>(ev + off);
+        for (int t = lane; t < (int)(n_pad >> 3); t += 32) dst[t] = srcv[t];
+    }
 }
 
 __global__ void __launch_bounds__(EVK_THREADS)
 l2_events_kernel(const Prep *prep, const unsigned long long *ev_off, const uint32_t *cand_base, const uint32_t *work_base,
                  int n_frags, const uint32_t *qhash, const uint64_t *seq_first, const int32_t *qs,
-                 const RefMini *ref, const uint2 *hw, int cmw, int tab_p, uint16_t *ev, SlideJob *jobs, uint16_t *room,
+                 const RefMini *ref, const uint2 *hw, const uint32_t *ll, int tab_p, uint16_t *ev, SlideJob *jobs, uint16_t *room,
                  unsigned long long *counters, int q_cap)
 {
     extern __shared__ __align__(16) uint8_t ev_smem[];
@@ -833,11 +816,8 @@ l2_events_kernel(const Prep *prep, const unsigned long long *ev_off, const uint3
     __shared__ uint32_t s_item, s_next;
     __shared__ int s_maxn, s_cached_f;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    constexpr int WARP_BYTES = EV_RMAX * 4 + EV_RMAX * 2;
-    int *w_pos = reinterpret_cast<int *>(s_warp + wid * WARP_BYTES);              // wpos of the region's elements
-    uint16_t *w_cls = reinterpret_cast<uint16_t *>(w_pos + EV_RMAX);              // their event codes
+    uint16_t *w_ev = reinterpret_cast<uint16_t *>(s_warp + wid * EV_WARP_BYTES);  // the event list of the warp's candidate
     const uint32_t n_work = work_base[n_frags];
-    const int cmw1 = cmw - 1;
     if (tid == 0) s_cached_f = -1;
 
     for (;;) {
@@ -872,8 +852,8 @@ l2_events_kernel(const Prep *prep, const unsigned long long *ev_off, const uint3
         __syncthreads();
         const int maxn = s_maxn;
         EvCtx X;
-        X.s_q = s_q; X.s_tab = s_tab; X.w_pos = w_pos; X.w_cls = w_cls; X.ref = ref; X.hw = hw; X.ev = ev; X.jobs = jobs; X.room = room;
-        X.s = s; X.cmw1 = cmw1; X.tab_p = tab_p; X.maxn = maxn;
+        X.s_q = s_q; X.s_tab = s_tab; X.w_ev = w_ev; X.ref = ref; X.hw = hw; X.ll = ll; X.ev = ev; X.jobs = jobs; X.room = room;
+        X.s = s; X.tab_p = tab_p; X.maxn = maxn;
 
         // candidates are handed out one ahead, so the next descriptor is in flight while this one is processed
         uint32_t c = c_lo + (uint32_t)wid;
@@ -1506,14 +1486,14 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
                 if (n_ev > 0) {
                     {
                         const size_t smem = (size_t)q_cap * 4 + (size_t)(L2_TAB + 2) * 2 + 12 +
-                                            (size_t)(EVK_THREADS / 32) * (EV_RMAX * 4 + EV_RMAX * 2);
+                                            (size_t)(EVK_THREADS / 32) * EV_WARP_BYTES;
                         FA_CUDA(cudaFuncSetAttribute(l2_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                         int per_sm = 1;
                         FA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l2_events_kernel, EVK_THREADS, smem));
                         const uint32_t grid = std::min<uint32_t>(W, (uint32_t)dev_sms * (uint32_t)std::max(per_sm, 1));
                         l2_events_kernel<<<grid, EVK_THREADS, smem, st>>>(
                             reinterpret_cast<const Prep *>(ws.prep.p), reinterpret_cast<const unsigned long long *>(ws.ev_off.p),
-                            ws.frag_cands.p, ws.work_base.p, F, ws.qhash.p, ws.sk.seq_first.p, ws.qs.p, ix->ref.p, ix->hw.p, cmw,
+                            ws.frag_cands.p, ws.work_base.p, F, ws.qhash.p, ws.sk.seq_first.p, ws.qs.p, ix->ref.p, ix->hw.p, ix->ll.p,
                             l2_tab_shift(w), ws.events.p, reinterpret_cast<SlideJob *>(ws.jobs.p), ws.room.p, ws.counters.p, q_cap);
                         FA_CUDA(cudaGetLastError()); launches++;
                     }
