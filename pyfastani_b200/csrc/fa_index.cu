@@ -76,9 +76,10 @@ __global__ void make_hw_kernel(const RefMini *ref, uint64_t n, uint2 *hw)
 //             left the window when j enters (their deletes precede the insert of j)
 //   lead(j) = B(j) - j,  B(j) = first index with wpos >= wpos[j + 1] + (cmw - 1): the elements before B(j) have
 //             entered when j leaves; twin(j): element B(j) enters at exactly that time (same group, after the delete)
-// packed as lag (15 bits, saturating) | twin << 15 | lead << 16 (saturating).  Saturated values only occur in
-// windows of more than 32 767 minimizers, which the event path of L2 (<= 1024 per region) never takes.
-__global__ void slide_order_kernel(const RefMini *ref, const uint32_t *contig_off, uint64_t n, int cmw1, uint32_t *ll)
+// packed as lag (15 bits, saturating) | twin << 15 | lead << 16 (15 bits, saturating) | has-duplicate-nearby << 31
+// and stored next to the hash.  Saturated values only occur in windows of more than 32 767 minimizers, which the
+// event path of L2 (<= 1024 per region) never takes.
+__global__ void slide_order_kernel(const RefMini *ref, const uint32_t *contig_off, uint64_t n, int cmw1, uint2 *hl)
 {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
@@ -95,10 +96,10 @@ __global__ void slide_order_kernel(const RefMini *ref, const uint32_t *contig_of
         const int tb = (int)ref[j + 1].y + cmw1;
         uint32_t l = (uint32_t)j + 1, h = (uint64_t)cmw1 + 1 < c1 - (j + 1) ? (uint32_t)j + 2 + (uint32_t)cmw1 : c1;   // answer in [j + 1, h]
         while (l < h) { const uint32_t mid = l + ((h - l) >> 1); if ((int)ref[mid].y < tb) l = mid + 1; else h = mid; }
-        lead = min(l - (uint32_t)j, 65535u);
+        lead = min(l - (uint32_t)j, 32767u);
         twin = (l < c1 && (int)ref[l].y == tb) ? 1u : 0u;
     }
-    ll[j] = lag | (twin << 15) | (lead << 16);
+    hl[j] = make_uint2(e.x, lag | (twin << 15) | (lead << 16) | (e.w ? 0x80000000u : 0u));
 }
 
 __global__ void gpos_delta_kernel(const RefMini *ref, uint64_t n, uint32_t frag_len, uint32_t *gpos)
@@ -262,9 +263,9 @@ int build_index(fa_index *ix, int *launches)
 
     {
         const int cmw1 = ix->prm.frag_len - (ix->prm.window - 1) - (ix->prm.k - 1) - 1;
-        FA_TRY(ix->ll.reserve(n + 8));
-        FA_CUDA(cudaMemsetAsync(ix->ll.p + n, 0, 8 * sizeof(uint32_t), st));
-        slide_order_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(ix->ref.p, ix->contig_off.p, n, cmw1 < 0 ? 0 : cmw1, ix->ll.p);
+        FA_TRY(ix->hl.reserve(n + 8));
+        FA_CUDA(cudaMemsetAsync(ix->hl.p + n, 0, 8 * sizeof(uint2), st));
+        slide_order_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(ix->ref.p, ix->contig_off.p, n, cmw1 < 0 ? 0 : cmw1, ix->hl.p);
         FA_CUDA(cudaGetLastError());
         if (launches) *launches += 1;
     }

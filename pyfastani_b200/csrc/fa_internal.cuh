@@ -81,7 +81,7 @@ struct fa_index {
     // (minimizerPosLookupIndex, winSketch.hpp:83-84) as CSR over sorted unique hashes
     fa::DevBuf<fa::RefMini> ref;
     fa::DevBuf<uint2> hw;                        // (hash, wpos | has-duplicate-nearby << 31): the 8-byte stream L2 reads
-    fa::DevBuf<uint32_t> ll;                     // per minimizer: where its insert / delete falls in the slide of any region (fa_index.cu slide_order_kernel)
+    fa::DevBuf<uint2> hl;                        // (hash, slide order word): the 8-byte stream the L2 events kernel reads (fa_index.cu slide_order_kernel)
     fa::DevBuf<uint32_t> gpos;                   // running coordinate for the L1 proximity test (fa_index.cu gpos_delta_kernel)
     uint64_t n = 0, n_unique = 0;
     fa::DevBuf<uint32_t> pos_idx;                // ref indices grouped by hash, insertion order inside a group

@@ -719,7 +719,7 @@ struct SlideJob {
 //          list -- no merge, no position array; the list leaves in whole 16-byte chunks.
 struct EvCtx {
     const uint32_t *s_q; const uint16_t *s_tab; uint16_t *w_ev;
-    const RefMini *ref; const uint2 *hw; const uint32_t *ll; uint16_t *ev; SlideJob *jobs; uint16_t *room;
+    const RefMini *ref; const uint2 *hl; uint16_t *ev; SlideJob *jobs; uint16_t *room;
     int s, tab_p, maxn;
 };
 
@@ -729,7 +729,7 @@ __device__ __forceinline__ void ev_candidate(const EvCtx &X, uint32_t c, const P
                                              unsigned long long off1, int lane)
 {
     const uint32_t *s_q = X.s_q; const uint16_t *s_tab = X.s_tab; uint16_t *w_ev = X.w_ev;
-    const RefMini *ref = X.ref; const uint2 *hw = X.hw; const uint32_t *ll = X.ll; uint16_t *ev = X.ev; SlideJob *jobs = X.jobs;
+    const RefMini *ref = X.ref; const uint2 *hl = X.hl; uint16_t *ev = X.ev; SlideJob *jobs = X.jobs;
     const int s = X.s, tab_p = X.tab_p;
     const uint32_t n_pad = (uint32_t)(off1 - off);
     const int R = (int)(pp.last - pp.beg), nI = R - 1, nD = (int)(pp.n_del & 0xFFFFu), y0 = (int)(pp.n_del >> 16);
@@ -739,13 +739,11 @@ __device__ __forceinline__ void ev_candidate(const EvCtx &X, uint32_t c, const P
     int n_mi = 0;                                      // elements that are in the sketch
     __syncwarp();                                      // (the copy-out of the previous list is done)
     for (int i0 = 0; i0 < R; i0 += 32 * EV_UNROLL) {
-        uint2 xs[EV_UNROLL];
-        uint32_t ls[EV_UNROLL];
+        uint2 xs[EV_UNROLL];                           // (hash, order word)
 #pragma unroll
         for (int u = 0; u < EV_UNROLL; u++) {
             const int i = i0 + u * 32 + lane;
-            xs[u] = i < R ? __ldg(hw + pp.beg + i) : make_uint2(0u, 0u);
-            ls[u] = i < R ? __ldg(ll + pp.beg + i) : 0u;
+            xs[u] = i < R ? __ldg(hl + pp.beg + i) : make_uint2(0u, 0u);
         }
 #pragma unroll
         for (int u = 0; u < EV_UNROLL; u++) {
@@ -767,10 +765,11 @@ __device__ __forceinline__ void ev_candidate(const EvCtx &X, uint32_t c, const P
                 }
                 n_mi += match;
                 const uint32_t code = ev_aoff(l + match) | (match ? EV_MATCH : EV_ONLY);
-                const bool dup = (xs[u].y >> 31) != 0u;                    // a same-hash neighbour exists (rare)
-                const uint32_t dd = dup ? ref[pp.beg + (uint32_t)i].w : 0u;
+                const uint32_t ow = xs[u].y;
+                uint32_t dd = 0u;
+                if (__builtin_expect((ow >> 31) != 0u, 0)) dd = ref[pp.beg + (uint32_t)i].w;   // a same-hash neighbour exists (rare)
                 // insert i: after the deletes of the region's elements that left before it entered
-                const int x = min(max(i - (int)(ls[u] & 0x7FFFu) - 1, 0), nD);
+                const int x = min(max(i - (int)(ow & 0x7FFFu) - 1, 0), nD);
                 if (i < nI) {
                     const uint32_t dp = dd & 0xFFFFu;
                     const bool skip = dp && i - (int)dp >= x;              // already present (REV)
@@ -780,9 +779,9 @@ __device__ __forceinline__ void ev_candidate(const EvCtx &X, uint32_t c, const P
                 }
                 // delete i: after the inserts of the elements that entered before it leaves
                 if (i < nD) {
-                    const int lead = (int)(ls[u] >> 16);
+                    const int lead = (int)((ow >> 16) & 0x7FFFu);
                     const int y = min(i + lead, nI);
-                    const bool twin = ((ls[u] >> 15) & 1u) && i + lead < nI;   // an insert of the same time follows: same group
+                    const bool twin = ((ow >> 15) & 1u) && i + lead < nI;      // an insert of the same time follows: same group
                     const uint32_t dn = dd >> 16;
                     const bool skip = dn && i + (int)dn < y;               // a later copy stays (NOOP)
                     w_ev[i + y] = (uint16_t)((skip ? 0u : code) | EV_DEL | (twin ? 0u : EV_GRP));
@@ -806,7 +805,7 @@ __device__ __forceinline__ void ev_candidate(const EvCtx &X, uint32_t c, const P
 __global__ void __launch_bounds__(EVK_THREADS)
 l2_events_kernel(const Prep *prep, const unsigned long long *ev_off, const uint32_t *cand_base, const uint32_t *work_base,
                  int n_frags, const uint32_t *qhash, const uint64_t *seq_first, const int32_t *qs,
-                 const RefMini *ref, const uint2 *hw, const uint32_t *ll, int tab_p, uint16_t *ev, SlideJob *jobs, uint16_t *room,
+                 const RefMini *ref, const uint2 *hl, int tab_p, uint16_t *ev, SlideJob *jobs, uint16_t *room,
                  unsigned long long *counters, int q_cap)
 {
     extern __shared__ __align__(16) uint8_t ev_smem[];
@@ -852,7 +851,7 @@ l2_events_kernel(const Prep *prep, const unsigned long long *ev_off, const uint3
         __syncthreads();
         const int maxn = s_maxn;
         EvCtx X;
-        X.s_q = s_q; X.s_tab = s_tab; X.w_ev = w_ev; X.ref = ref; X.hw = hw; X.ll = ll; X.ev = ev; X.jobs = jobs; X.room = room;
+        X.s_q = s_q; X.s_tab = s_tab; X.w_ev = w_ev; X.ref = ref; X.hl = hl; X.ev = ev; X.jobs = jobs; X.room = room;
         X.s = s; X.tab_p = tab_p; X.maxn = maxn;
 
         // candidates are handed out one ahead, so the next descriptor is in flight while this one is processed
@@ -1493,7 +1492,7 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
                         const uint32_t grid = std::min<uint32_t>(W, (uint32_t)dev_sms * (uint32_t)std::max(per_sm, 1));
                         l2_events_kernel<<<grid, EVK_THREADS, smem, st>>>(
                             reinterpret_cast<const Prep *>(ws.prep.p), reinterpret_cast<const unsigned long long *>(ws.ev_off.p),
-                            ws.frag_cands.p, ws.work_base.p, F, ws.qhash.p, ws.sk.seq_first.p, ws.qs.p, ix->ref.p, ix->hw.p, ix->ll.p,
+                            ws.frag_cands.p, ws.work_base.p, F, ws.qhash.p, ws.sk.seq_first.p, ws.qs.p, ix->ref.p, ix->hl.p,
                             l2_tab_shift(w), ws.events.p, reinterpret_cast<SlideJob *>(ws.jobs.p), ws.room.p, ws.counters.p, q_cap);
                         FA_CUDA(cudaGetLastError()); launches++;
                     }
