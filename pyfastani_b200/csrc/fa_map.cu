@@ -34,9 +34,8 @@ enum { ERR_SORT_CAP = 1, ERR_S_MAX = 2 };
 constexpr int L2_THREADS = 64;          // lanes per L2 CTA: each lane slides one candidate at a time
 constexpr int L2_ITEM = 128;            // candidates of one fragment per work item (lanes pull them one by one)
 constexpr int L2_FB_STATE = 32 * 1024;  // u16 state of the exact fallback kernel
-constexpr int L2_TAB_BITS = 11;         // classification table over the top bits of the hash
+constexpr int L2_TAB_BITS = 12;         // classification table over the top bits of the hash
 constexpr int L2_TAB = 1 << L2_TAB_BITS;
-static_assert(L2_TAB_BITS == 11, "l2_slot() is written for 2048 slots");
 constexpr int L2_QPAD = 8;              // sentinel entries behind the staged query sketch
 constexpr int32_t L2_REDO = INT32_MIN;  // Mapping.ref_start marker: redo this candidate in the fallback kernel
 
@@ -631,7 +630,7 @@ struct Prep {
 
 __global__ void __launch_bounds__(256)
 l2_prep_kernel(const Cand *cands, const uint32_t *cand_base, int n_frags, const int32_t *qs, const RefMini *ref, const uint2 *hw,
-               const uint32_t *contig_off, int frag_len, int cmw, int dens_num, int dens_den, Prep *prep,
+               const uint2 *hl, const uint32_t *contig_off, int frag_len, int cmw, int dens_num, int dens_den, Prep *prep,
                unsigned long long *ev_cnt, Mapping *maps, unsigned long long *counters)
 {
     const uint32_t n = cand_base[n_frags];
@@ -647,7 +646,12 @@ l2_prep_kernel(const Cand *cands, const uint32_t *cand_base, int n_frags, const 
         const int back = (int)rh.y - cd.start;                                  // wpos[hint] >= start
         const uint32_t beg = lb_near(hw, c0, cd.hint, cd.start, (long long)cd.hint - (long long)back * dens_num / dens_den);
         const int wpos_beg = (int)(hw[beg].y & 0x7FFFFFFFu);
-        const uint32_t end0 = lb_near(hw, beg, c1, wpos_beg + cmw, (long long)beg + (long long)cmw * dens_num / dens_den);
+        // first index with wpos >= wpos[beg] + cmw: the index knows it for the element before beg (fa_index.cu
+        // slide_order_kernel: first index at or past wpos[j + 1] + cmw - 1, and whether it sits exactly there)
+        uint32_t end0;
+        const uint32_t ow_b = (beg > c0 && cmw >= 2) ? hl[beg - 1].y : 0xFFFFFFFFu;
+        if (((ow_b >> 16) & 0x7FFFu) != 0x7FFFu) end0 = min(beg - 1 + ((ow_b >> 16) & 0x7FFFu) + ((ow_b >> 15) & 1u), c1);
+        else end0 = lb_near(hw, beg, c1, wpos_beg + cmw, (long long)beg + (long long)cmw * dens_num / dens_den);
         const int target = cd.end + frag_len;
         uint32_t last = end0;
         if (end0 < c1) {
@@ -661,7 +665,14 @@ l2_prep_kernel(const Cand *cands, const uint32_t *cand_base, int n_frags, const 
         if (end0 < last) {
             // the slide stops before the insert of element last - 1; deletes at or after that time are not reached
             const int t_stop = (int)(hw[last - 1].y & 0x7FFFFFFFu) - cmw + 1;
-            const uint32_t dstop = lb_near(hw, beg + 1, last, t_stop, (long long)last - 1 - (long long)cmw * dens_num / dens_den);
+            // first index in [beg + 1, last) with wpos >= t_stop: the index knows the first one past t_stop
+            uint32_t dstop;
+            const uint32_t ow_l = hl[last - 1].y;
+            if ((ow_l & 0x7FFFu) != 0x7FFFu && cmw >= 2) {
+                const uint32_t a = last - 1 - (ow_l & 0x7FFFu);                     // first index of the contig with wpos > t_stop
+                dstop = (a > c0 && (int)(hw[a - 1].y & 0x7FFFFFFFu) == t_stop) ? a - 1 : a;
+                dstop = min(max(dstop, beg + 1), last);
+            } else dstop = lb_near(hw, beg + 1, last, t_stop, (long long)last - 1 - (long long)cmw * dens_num / dens_den);
             pp.n_del = dstop - 1 - beg;
             const bool fast = last - beg <= (uint32_t)EV_RMAX && qs[cd.frag] <= EV_MAX_S && cmw >= 2;
             if (fast) {
@@ -685,18 +696,19 @@ l2_prep_kernel(const Cand *cands, const uint32_t *cand_base, int n_frags, const 
 // Minimizer hashes are window minima, so they crowd towards zero (density ~ (1 - u)^(2w - 1)): a
 // table over the plain top bits would put most of a sketch into a few slots.  The slot function is
 // piecewise linear instead: the hash range is cut into equal pieces of 2^p (about the half-life of
-// that density) and piece k gets 1024 >> k slots, which spreads a sketch about evenly.  Monotone.
+// that density) and piece k gets L2_TAB / 2 >> k slots, which spreads a sketch about evenly.  Monotone.
+// (4096 slots for ~240 hashes: nine sketches in ten have at most two hashes in any slot.)
 __host__ __device__ inline int l2_tab_shift(int w)
 {
     const double half = 4294967296.0 * 0.6931471805599453 / (2.0 * (w < 1 ? 1 : w));
-    int p = 10;
+    int p = L2_TAB_BITS - 1;
     while (p < 30 && (double)(1u << p) < half) p++;
     return p;
 }
 __device__ __forceinline__ uint32_t l2_slot(uint32_t h, int p)
 {
-    const uint32_t k = min(h >> p, 11u);
-    return 2048u - (2048u >> k) + ((h & ((1u << p) - 1u)) >> (p - 10 + k));
+    const uint32_t k = min(h >> p, (uint32_t)L2_TAB_BITS);
+    return (uint32_t)L2_TAB - ((uint32_t)L2_TAB >> k) + ((h & ((1u << p) - 1u)) >> (p - (L2_TAB_BITS - 1) + k));
 }
 
 // Per candidate descriptor for the slide kernel.
@@ -1470,7 +1482,7 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
                 // ---- L2 -----------------------------------------------------------------------
                 FA_TRY(ws.prep.reserve(C)); FA_TRY(ws.ev_off.reserve(C + 1)); FA_TRY(ws.jobs.reserve(C)); FA_TRY(ws.room.reserve(C));
                 l2_prep_kernel<<<std::min<uint32_t>((uint32_t)((C + 256) / 256), (uint32_t)dev_sms * 8u), 256, 0, st>>>(
-                    ws.cands.p, ws.frag_cands.p, F, ws.qs.p, ix->ref.p, ix->hw.p, ix->contig_off.p, L, cmw, 2, w + 1,
+                    ws.cands.p, ws.frag_cands.p, F, ws.qs.p, ix->ref.p, ix->hw.p, ix->hl.p, ix->contig_off.p, L, cmw, 2, w + 1,
                     reinterpret_cast<Prep *>(ws.prep.p), reinterpret_cast<unsigned long long *>(ws.ev_off.p), ws.maps.p, ws.counters.p);
                 FA_CUDA(cudaGetLastError()); launches++;
                 FA_TRY(excl_scan<uint64_t>(st, ws.cub_tmp, ws.ev_off.p, ws.ev_off.p, (int64_t)C + 1, &launches));
