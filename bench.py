@@ -336,6 +336,7 @@ def run_b200(a):
         # L2 = prep (index searches) + events (classify + merge: reads the (hash, wpos) stream once, writes
         # 2-byte events) + slide (replays the events up to its early stop, writes 16-byte results)
         "ms_l2_prep": 56.0 * inf["candidates"],
+        # events: the (hash, order word) stream once (8 B / element), 2-byte events out
         "ms_l2_events": 8.0 * inf["scanned"] + 2.0 * inf["events"] + (4.0 * s_mean + 16.0) * inf["candidates"],
         "ms_l2_slide": 2.0 * inf["events_replayed"] + 34.0 * inf["candidates"],
         "ms_cgi": 16.0 * inf["candidates"],
@@ -382,7 +383,7 @@ def run_b200(a):
                    "parallelism": ("reference genomes sharded over the GPUs (%s per rank), same query on every GPU, NCCL all-gather "
                                    "of the hit rows inside the step" % [offsets[r + 1] - offsets[r] for r in range(world)]) if by_refs
                                   else "replicated index, one query stream per GPU",
-                   "l2_policy": "inputs larger than L2: the index is %.1f GB, every step streams it" % (n_min * 28 / 1e9)},
+                   "l2_policy": "inputs larger than L2: the index is %.1f GB, every step streams it" % (n_min * 42 / 1e9)},
         "fragments_per_s": jobs * frags / (ms_per_step * 1e-3),
         "clocks": clocks,
         "e2e": {"value": jobs * pairs * a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d // a.steps,
