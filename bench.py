@@ -35,6 +35,25 @@ METRIC, UNIT = "genome_pairs_per_s", "genome-pairs/s"
 FRAG = 3000
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout: whatever libraries print there (the NCCL version banner, ...)
+    goes to stderr instead; emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -188,7 +207,7 @@ def run_reference(a):
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "fragments_per_s": cb["fragments_per_s"],
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -400,13 +419,14 @@ def run_b200(a):
         "index_build": {"sketch_s": t_sketch, "index_s": t_index, "minimizers": n_min,
                         "sketch_mbp_per_s": a.refs * a.length / 1e6 / t_sketch},
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
     args = parse()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
