@@ -373,3 +373,25 @@ def test_many_to_many_tree_vs_reference():
         assert ohits[0]["ref_genome"] == i
         pairs += len(ohits)
     assert pairs >= 24 * 5 and info["l2_fallback"] == 0
+
+
+@pytest.mark.parametrize("params", [dict(fragment_length=40), dict(fragment_length=30, k=12), dict(fragment_length=24, k=16),
+                                    dict(fragment_length=64, k=20, percentage_identity=70.0)])
+def test_tiny_fragments_vs_oracle(params):
+    """Very short fragments: the L2 window (fragment_length - (w - 1) - (k - 1) positions) shrinks to a few
+    positions, down to the sizes where the event path of L2 hands over to the exact kernel.  Against the oracle."""
+    rng = np.random.default_rng(9)
+    base = synth.random_codes(rng, 6_000)
+    refs = [synth.to_bytes(base), synth.to_bytes(synth.mutate_codes(rng, base, 0.97)), synth.to_bytes(synth.random_codes(rng, 5_000))]
+    query = synth.to_bytes(synth.mutate_codes(rng, base, 0.99))[500:4_500]
+    sk, osk = capi.Sketch(**params), _port().sketch(**params)
+    for i, r in enumerate(refs):
+        sk.add_genome(i, r)
+        osk.add_genome(i, r)
+    ix = sk.index()
+    osk.index()
+    hits, out = ix.query_genome(query, dump=True)
+    ohits, oinfo = osk.query_genome(query, dump=True)
+    assert np.array_equal(out["candidates"], oinfo["candidates"])
+    assert np.array_equal(out["mappings"], oinfo["mappings"])
+    assert np.array_equal(hits, ohits)
