@@ -1266,22 +1266,35 @@ int stage_sequences(cudaStream_t st, SketchScratch &sc, PinBuf &stage, const std
     bool any_host = false;
     for (const Upload &u : ups) any_host |= !u.on_device && u.len > 0;
     if (any_host) {
+        // The staged bytes leave in pieces of about 1 MiB, so the copy engine works on one piece while the host
+        // fills the next (uploads lie at increasing offsets of the staging buffer; a piece may span several).
         FA_TRY(stage.reserve(total + 64));
+        const uint64_t piece = 1ull << 20;
+        uint64_t sent = 0;                                   // stage.p[0 .. sent) is on its way
+        auto flush = [&](uint64_t upto) -> int {
+            if (upto > sent) FA_CUDA(cudaMemcpyAsync(sc.bytes.p + sent, stage.p + sent, upto - sent, cudaMemcpyHostToDevice, st));
+            sent = std::max(sent, upto);
+            return FA_OK;
+        };
         for (const Upload &u : ups) {
             if (u.on_device || u.len <= 0) continue;
-            uint8_t *dst = stage.p + u.off;
-            if (u.unit == 1) memcpy(dst, u.ptr, (size_t)u.len);
-            else {
-                // pyx:147-148: (char)toupper(code point); glibc's toupper leaves values outside
-                // [-128, 255] unchanged
-                for (int64_t i = 0; i < u.len; i++) {
-                    uint32_t cp = u.unit == 2 ? ((const uint16_t *)u.ptr)[i] : ((const uint32_t *)u.ptr)[i];
-                    if (cp >= 'a' && cp <= 'z') cp -= 32;
-                    dst[i] = (uint8_t)cp;
+            for (int64_t o = 0; o < u.len; o += (int64_t)piece) {
+                const int64_t n = std::min<int64_t>((int64_t)piece, u.len - o);
+                uint8_t *dst = stage.p + u.off + o;
+                if (u.unit == 1) memcpy(dst, (const uint8_t *)u.ptr + o, (size_t)n);
+                else {
+                    // pyx:147-148: (char)toupper(code point); glibc's toupper leaves values outside
+                    // [-128, 255] unchanged
+                    for (int64_t i = 0; i < n; i++) {
+                        uint32_t cp = u.unit == 2 ? ((const uint16_t *)u.ptr)[o + i] : ((const uint32_t *)u.ptr)[o + i];
+                        if (cp >= 'a' && cp <= 'z') cp -= 32;
+                        dst[i] = (uint8_t)cp;
+                    }
                 }
+                if (u.off + (uint64_t)(o + n) - sent >= piece) FA_TRY(flush(u.off + (uint64_t)(o + n)));
             }
         }
-        FA_CUDA(cudaMemcpyAsync(sc.bytes.p, stage.p, total, cudaMemcpyHostToDevice, st));
+        FA_TRY(flush(total));
         if (h2d_bytes) *h2d_bytes += total;
     }
     for (const Upload &u : ups)
