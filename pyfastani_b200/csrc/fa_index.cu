@@ -79,7 +79,12 @@ __global__ void make_hw_kernel(const RefMini *ref, uint64_t n, uint2 *hw)
 // packed as lag (15 bits, saturating) | twin << 15 | lead << 16 (15 bits, saturating) | has-duplicate-nearby << 31
 // and stored next to the hash.  Saturated values only occur in windows of more than 32 767 minimizers, which the
 // event path of L2 (<= 1024 per region) never takes.
-__global__ void slide_order_kernel(const RefMini *ref, const uint32_t *contig_off, uint64_t n, int cmw1, uint2 *hl)
+// The same with a whole fragment length L for the L1 regions: fb[j] = (j - P(j)) | (Q(j) - j) << 16 with P(j) the
+// first index with wpos >= wpos[j] - (L - 1) (where a region that seed j opens begins) and Q(j) the first index
+// with wpos >= wpos[j] + L (where a region that seed j closes ends).  At most L minimizers lie in L positions and
+// L <= 32767, so both fit 16 bits.
+__global__ void slide_order_kernel(const RefMini *ref, const uint32_t *contig_off, uint64_t n, int cmw1, int frag_len, uint2 *hl,
+                                   uint32_t *fb)
 {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
@@ -100,6 +105,17 @@ __global__ void slide_order_kernel(const RefMini *ref, const uint32_t *contig_of
         twin = (l < c1 && (int)ref[l].y == tb) ? 1u : 0u;
     }
     hl[j] = make_uint2(e.x, lag | (twin << 15) | (lead << 16) | (e.w ? 0x80000000u : 0u));
+    {
+        const uint32_t Lm1 = (uint32_t)(frag_len - 1);
+        uint32_t l = (uint64_t)Lm1 < j - c0 ? (uint32_t)j - Lm1 : c0, h = (uint32_t)j;                       // P(j) in [l, j]
+        const int tp = pos - (int)Lm1;
+        while (l < h) { const uint32_t mid = l + ((h - l) >> 1); if ((int)ref[mid].y < tp) l = mid + 1; else h = mid; }
+        const uint32_t back = (uint32_t)j - l;
+        uint32_t l2 = (uint32_t)j + 1, h2 = (uint64_t)frag_len < c1 - j ? (uint32_t)j + (uint32_t)frag_len : c1;   // Q(j) in [j + 1, h2]
+        const int tq = pos + frag_len;
+        while (l2 < h2) { const uint32_t mid = l2 + ((h2 - l2) >> 1); if ((int)ref[mid].y < tq) l2 = mid + 1; else h2 = mid; }
+        fb[j] = min(back, 65535u) | (min(l2 - (uint32_t)j, 65535u) << 16);
+    }
 }
 
 __global__ void gpos_delta_kernel(const RefMini *ref, uint64_t n, uint32_t frag_len, uint32_t *gpos)
@@ -263,9 +279,10 @@ int build_index(fa_index *ix, int *launches)
 
     {
         const int cmw1 = ix->prm.frag_len - (ix->prm.window - 1) - (ix->prm.k - 1) - 1;
-        FA_TRY(ix->hl.reserve(n + 8));
+        FA_TRY(ix->hl.reserve(n + 8)); FA_TRY(ix->fb.reserve(n + 8));
         FA_CUDA(cudaMemsetAsync(ix->hl.p + n, 0, 8 * sizeof(uint2), st));
-        slide_order_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(ix->ref.p, ix->contig_off.p, n, cmw1 < 0 ? 0 : cmw1, ix->hl.p);
+        slide_order_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(ix->ref.p, ix->contig_off.p, n, cmw1 < 0 ? 0 : cmw1,
+                                                                              ix->prm.frag_len, ix->hl.p, ix->fb.p);
         FA_CUDA(cudaGetLastError());
         if (launches) *launches += 1;
     }

@@ -8,11 +8,14 @@
 namespace fa {
 
 // L1 candidate region (L1_candidateLocus_t, FA/map/include/computeMap.hpp:40-49) in device form.
+// The range is kept by the two seeds that define it, as indices of reference minimizers:
+// rangeStartPos = max(0, wpos[hint] - fragLen + 1), rangeEndPos = wpos[tail] (computeMap.hpp:325-347) -- L2 turns
+// them into index ranges with the per-minimizer offsets of fa_index.cu (slide_order_kernel), without a search.
 struct Cand {
     int32_t  frag;     // query fragment (querySeqId)
-    uint32_t hint;     // index of a reference minimizer inside the region (the seed that opened it)
-    int32_t  start;    // rangeStartPos
-    int32_t  end;      // rangeEndPos
+    uint32_t hint;     // last seed of the pair that opened the region
+    uint32_t tail;     // first seed of the last pair merged into it
+    uint32_t spare;
 };
 
 // L2 result per candidate slot (L2_mapLocus_t + the MappingResult fields computeCGI reads,
@@ -81,6 +84,7 @@ struct fa_index {
     // (minimizerPosLookupIndex, winSketch.hpp:83-84) as CSR over sorted unique hashes
     fa::DevBuf<fa::RefMini> ref;
     fa::DevBuf<uint2> hw;                        // (hash, wpos | has-duplicate-nearby << 31): the 8-byte stream L2 reads
+    fa::DevBuf<uint32_t> fb;                     // per minimizer: elements one fragment length behind (low 16 bits) / ahead (high 16 bits)
     fa::DevBuf<uint2> hl;                        // (hash, slide order word): the 8-byte stream the L2 events kernel reads (fa_index.cu slide_order_kernel)
     fa::DevBuf<uint32_t> gpos;                   // running coordinate for the L1 proximity test (fa_index.cu gpos_delta_kernel)
     uint64_t n = 0, n_unique = 0;

@@ -198,10 +198,10 @@ candidates_kernel(const uint64_t *seeds, const uint64_t *seed_base, const int32_
         const uint64_t t = base + tid;
         bool valid = false;
         int seq = -1, start = 0, end = 0;
-        uint32_t ja = 0;
+        uint32_t ja = 0, jb = 0;
         if (t + (uint64_t)(m - 1) < e) {
             ja = (uint32_t)(seeds[t] & idx_mask);
-            const uint32_t jb = (uint32_t)(seeds[t + m - 1] & idx_mask);
+            jb = (uint32_t)(seeds[t + m - 1] & idx_mask);
             const RefMini ra = ref[ja], rb = ref[jb];
             if (ra.z == rb.z && (int)(rb.y - ra.y) < frag_len) {
                 valid = true; seq = (int)ra.z; end = (int)ra.y;
@@ -228,9 +228,9 @@ candidates_kernel(const uint64_t *seeds, const uint64_t *seed_base, const int32_
         uint32_t tot, off = block_excl_scan<256>(head ? 1u : 0u, s_warp, &tot);
         if (FILL) {
             const uint32_t slot = out0 + heads_before + off;            // heads: their own slot
-            if (head) cands[slot] = Cand{f, ja, start, end};
+            if (head) cands[slot] = Cand{f, jb, ja, 0u};
             __syncthreads();
-            if (valid && !head) atomicMax(&cands[slot - 1].end, end);     // members: the open region
+            if (valid && !head) atomicMax(&cands[slot - 1].tail, ja);     // members: the open region (indices grow with positions)
         }
         heads_before += tot;
         __syncthreads();
@@ -516,10 +516,9 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
             if (head[u]) {
                 const int e = u * L1_THREADS + tid;
                 const uint32_t slot = heads_before + s_hpre[e >> 5] + __popc(s_head[e >> 5] & ((1u << lane) - 1u));
-                const int wb = (int)(__ldg(&hw[jb[u]].y) & 0x7FFFFFFFu);
                 Cand *o = out + slot;
-                o->frag = f; o->hint = ja[u]; o->start = max(0, wb - frag_len + 1);
-                if (pv[u]) out[slot - 1].end = (int)(__ldg(&hw[pj[u]].y) & 0x7FFFFFFFu);
+                o->frag = f; o->hint = jb[u]; o->spare = 0u;       // (tail: written by whoever closes the region, never here)
+                if (pv[u]) out[slot - 1].tail = pj[u];
             }
         }
         heads_before += s_hpre[L1_TILE / 32];
@@ -532,7 +531,7 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
         __syncthreads();
     }
     if (tid == 0) {
-        if (heads_before) out[heads_before - 1].end = (int)(hw[s_cj].y & 0x7FFFFFFFu);
+        if (heads_before) out[heads_before - 1].tail = s_cj;
         frag_cands[f] = heads_before;
     }
 }
@@ -630,7 +629,7 @@ struct Prep {
 
 __global__ void __launch_bounds__(256)
 l2_prep_kernel(const Cand *cands, const uint32_t *cand_base, int n_frags, const int32_t *qs, const RefMini *ref, const uint2 *hw,
-               const uint2 *hl, const uint32_t *contig_off, int frag_len, int cmw, int dens_num, int dens_den, Prep *prep,
+               const uint2 *hl, const uint32_t *fb, const uint32_t *contig_off, int frag_len, int cmw, int dens_num, int dens_den, Prep *prep,
                unsigned long long *ev_cnt, Mapping *maps, unsigned long long *counters)
 {
     const uint32_t n = cand_base[n_frags];
@@ -639,12 +638,12 @@ l2_prep_kernel(const Cand *cands, const uint32_t *cand_base, int n_frags, const 
     for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c <= n; c += gridDim.x * blockDim.x) {
         if (c == n) { ev_cnt[c] = 0; break; }
         const Cand cd = cands[c];
-        const RefMini rh = ref[cd.hint];
-        const int seq = (int)rh.z;
+        // the region [max(0, wpos[hint] - L + 1), wpos[tail]] as an index range: the first element at or past its start
+        // and the first one at or past wpos[tail] + L (computeMap.hpp:421-433), both known to the index
+        const uint32_t fb_h = fb[cd.hint], fb_t = fb[cd.tail];
+        const int seq = (int)ref[cd.hint].z;
         const uint32_t c0 = contig_off[seq], c1 = contig_off[seq + 1];
-        // expected index distance of a position distance: 2 / (w + 1) minimizers per base
-        const int back = (int)rh.y - cd.start;                                  // wpos[hint] >= start
-        const uint32_t beg = lb_near(hw, c0, cd.hint, cd.start, (long long)cd.hint - (long long)back * dens_num / dens_den);
+        const uint32_t beg = cd.hint - (fb_h & 0xFFFFu);
         const int wpos_beg = (int)(hw[beg].y & 0x7FFFFFFFu);
         // first index with wpos >= wpos[beg] + cmw: the index knows it for the element before beg (fa_index.cu
         // slide_order_kernel: first index at or past wpos[j + 1] + cmw - 1, and whether it sits exactly there)
@@ -652,12 +651,7 @@ l2_prep_kernel(const Cand *cands, const uint32_t *cand_base, int n_frags, const 
         const uint32_t ow_b = (beg > c0 && cmw >= 2) ? hl[beg - 1].y : 0xFFFFFFFFu;
         if (((ow_b >> 16) & 0x7FFFu) != 0x7FFFu) end0 = min(beg - 1 + ((ow_b >> 16) & 0x7FFFu) + ((ow_b >> 15) & 1u), c1);
         else end0 = lb_near(hw, beg, c1, wpos_beg + cmw, (long long)beg + (long long)cmw * dens_num / dens_den);
-        const int target = cd.end + frag_len;
-        uint32_t last = end0;
-        if (end0 < c1) {
-            const int d = target - (int)(hw[end0].y & 0x7FFFFFFFu);
-            if (d > 0) last = lb_near(hw, end0, c1, target, (long long)end0 + (long long)d * dens_num / dens_den);
-        }
+        const uint32_t last = max(end0, cd.tail + (fb_t >> 16));
         scanned += max(end0, last) - beg;
         Prep pp{beg, last, seq, 0u};
         unsigned long long cnt = 0;
@@ -1495,7 +1489,7 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
                 // ---- L2 -----------------------------------------------------------------------
                 FA_TRY(ws.prep.reserve(C)); FA_TRY(ws.ev_off.reserve(C + 1)); FA_TRY(ws.jobs.reserve(C)); FA_TRY(ws.room.reserve(C));
                 l2_prep_kernel<<<std::min<uint32_t>((uint32_t)((C + 256) / 256), (uint32_t)dev_sms * 8u), 256, 0, st>>>(
-                    ws.cands.p, ws.frag_cands.p, F, ws.qs.p, ix->ref.p, ix->hw.p, ix->hl.p, ix->contig_off.p, L, cmw, 2, w + 1,
+                    ws.cands.p, ws.frag_cands.p, F, ws.qs.p, ix->ref.p, ix->hw.p, ix->hl.p, ix->fb.p, ix->contig_off.p, L, cmw, 2, w + 1,
                     reinterpret_cast<Prep *>(ws.prep.p), reinterpret_cast<unsigned long long *>(ws.ev_off.p), ws.maps.p, ws.counters.p);
                 FA_CUDA(cudaGetLastError()); launches++;
                 FA_TRY(excl_scan<uint64_t>(st, ws.cub_tmp, ws.ev_off.p, ws.ev_off.p, (int64_t)C + 1, &launches));
@@ -1620,11 +1614,13 @@ int debug_candidates(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n)
     if (!m) return FA_OK;
     std::vector<Cand> h(m);
     FA_CUDA(cudaMemcpy(h.data(), ws.cands.p, m * sizeof(Cand), cudaMemcpyDeviceToHost));
-    std::vector<uint32_t> hints(m);
-    std::vector<RefMini> e(1);
-    for (uint64_t i = 0; i < m; i++) {
-        FA_CUDA(cudaMemcpy(e.data(), ix->ref.p + h[i].hint, sizeof(RefMini), cudaMemcpyDeviceToHost));
-        rows[4 * i] = h[i].frag; rows[4 * i + 1] = (int32_t)e[0].z; rows[4 * i + 2] = h[i].start; rows[4 * i + 3] = h[i].end;
+    std::vector<RefMini> e(2);
+    for (uint64_t i = 0; i < m; i++) {      // (test hook: two small copies per candidate)
+        FA_CUDA(cudaMemcpy(&e[0], ix->ref.p + h[i].hint, sizeof(RefMini), cudaMemcpyDeviceToHost));
+        FA_CUDA(cudaMemcpy(&e[1], ix->ref.p + h[i].tail, sizeof(RefMini), cudaMemcpyDeviceToHost));
+        rows[4 * i] = h[i].frag; rows[4 * i + 1] = (int32_t)e[0].z;
+        rows[4 * i + 2] = std::max(0, (int32_t)e[0].y - ix->prm.frag_len + 1);      // rangeStartPos, computeMap.hpp:332
+        rows[4 * i + 3] = (int32_t)e[1].y;                                          // rangeEndPos
     }
     return FA_OK;
 }
