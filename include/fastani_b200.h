@@ -88,7 +88,7 @@ typedef struct fa_query_info {
     uint64_t events;           /* insert/delete events replayed by the L2 slide kernel */
     float    ms_l2_prep, ms_l2_events, ms_l2_slide;   /* the three kernels inside ms_l2 */
     uint32_t l1_sorted_fragments;                     /* fragments whose seeds took the device-wide radix sort instead of the on-chip L1 */
-    uint32_t reserved0;
+    uint32_t l1_small_fragments;                      /* of the on-chip ones: fragments mapped by the small shape of the L1 kernel (256 threads, several CTAs per SM) */
     uint64_t events_replayed;  /* events the slide kernel went through before its early stop (<= events) */
 } fa_query_info;
 
@@ -168,6 +168,9 @@ FA_API int fa_debug_last_mappings(fa_index *ix, int32_t *rows, uint64_t cap, uin
 /* Test hook: cap on the seeds per fragment the on-chip L1 kernel accepts (fragments above it take the
  * device-wide radix-sort path); -1 restores the default (whatever fits in shared memory). */
 FA_API int fa_debug_set_l1_seed_cap(fa_index *ix, int64_t cap);
+/* Test hook: cap on the seeds per fragment the small shape of the on-chip L1 kernel accepts (0 = every on-chip
+ * fragment takes the large shape); -1 restores the default (what leaves room for four CTAs per SM). */
+FA_API int fa_debug_set_l1_small_cap(fa_index *ix, int64_t cap);
 /* Device buffers for callers that want inputs resident in HBM before the timed region
  * (fa_contig.on_device). */
 FA_API int fa_device_alloc(int32_t device, uint64_t bytes, void **dptr);

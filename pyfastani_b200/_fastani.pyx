@@ -74,7 +74,7 @@ cdef extern from "fastani_b200.h" nogil:
         float ms_l2_events
         float ms_l2_slide
         uint32_t l1_sorted_fragments
-        uint32_t reserved0
+        uint32_t l1_small_fragments
         uint64_t events_replayed
     ctypedef struct fa_sketch
     ctypedef struct fa_index
@@ -664,7 +664,7 @@ cdef class Mapper(_Parameterized):
                 "ms_cgi": info.ms_cgi, "ms_d2h": info.ms_d2h, "ms_total": info.ms_total,
                 "h2d_bytes": info.h2d_bytes, "d2h_bytes": info.d2h_bytes, "l2_fallback": info.l2_fallback, "events": info.events,
                 "ms_l2_prep": info.ms_l2_prep, "ms_l2_events": info.ms_l2_events, "ms_l2_slide": info.ms_l2_slide,
-                "l1_sorted_fragments": info.l1_sorted_fragments, "events_replayed": info.events_replayed,
+                "l1_sorted_fragments": info.l1_sorted_fragments, "l1_small_fragments": info.l1_small_fragments, "events_replayed": info.events_replayed,
             }
         finally:
             free(out)

@@ -3,6 +3,7 @@
 #include <cstring>
 #include <algorithm>
 #include <new>
+#include <thread>
 
 #include "fa_internal.cuh"
 
@@ -128,7 +129,7 @@ int sketch_add_batch(fa_sketch *s, const fa_contig *contigs, int32_t n_contigs, 
     if (tiles > 0x7FFFFF00ll) { set_error("batch too large"); return FA_ERR_UNSUPPORTED; }
     cudaStream_t st = s->st;
     int launches = 0;
-    FA_TRY(stage_sequences(st, s->sc, s->stage, ups, off, nullptr));
+    FA_TRY(stage_sequences(st, s->sc.bytes, s->stage, ups, off, nullptr));
     FA_TRY(s->sc.seqs.reserve(n_seqs)); FA_TRY(s->sc.tile_status.reserve((size_t)tiles));
     FA_TRY(s->sc.counters.reserve(4)); FA_TRY(s->sc.seq_first.reserve(n_seqs)); FA_TRY(s->sc.drops.reserve(n_seqs));
     FA_TRY(s->ref.reserve(s->n + worst + 1, true, st));
@@ -333,6 +334,7 @@ void fa_index_free(fa_index *ix)
     cudaSetDevice(ix->device);
     ix->ref.release(); ix->hw.release(); ix->hl.release(); ix->fb.release(); ix->gpos.release(); ix->pos_idx.release(); ix->ukeys.release(); ix->uoff.release(); ix->dir.release();
     ix->contig_off.release(); ix->genome_of_seq.release(); ix->bin_base.release(); ix->genome_cell.release();
+    ix->pre[0].release(); ix->pre[1].release();
     ix->d_min_hits.release(); ix->d_min_shared.release(); ix->d_id_off.release(); ix->d_identity.release();
     Workspace &w = ix->ws;
     free_sketch_scratch(w.sk); w.stage.release(); w.qhash.release(); w.qs.release(); w.hit_start.release(); w.hit_cnt.release();
@@ -418,18 +420,26 @@ int fa_index_occurrence_threshold(const fa_index *ix, int32_t *out)
     return FA_OK;
 }
 
-int fa_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *out, uint64_t cap, uint64_t *n_out,
-             fa_query_info *info)
+static int query_checked(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *out, uint64_t cap, uint64_t *n_out,
+                         fa_query_info *info, Prefetch *pf)
 {
     if (!ix || n_contigs < 0 || (n_contigs > 0 && !contigs) || !n_out) { set_error("bad arguments"); return FA_ERR_INVALID; }
     for (int32_t c = 0; c < n_contigs; c++)
         if (contigs[c].len < 0 || (contigs[c].len > 0 && !contigs[c].data)) { set_error("contig %d: bad buffer", c); return FA_ERR_INVALID; }
-    return run_query(ix, contigs, n_contigs, out, cap, n_out, info);
+    return run_query(ix, contigs, n_contigs, out, cap, n_out, info, pf);
+}
+
+int fa_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *out, uint64_t cap, uint64_t *n_out,
+             fa_query_info *info)
+{
+    return query_checked(ix, contigs, n_contigs, out, cap, n_out, info, nullptr);
 }
 
 // Many queries in one call (no host language between them): query q owns contigs
 // [sum(contigs_per_query[:q]), +contigs_per_query[q]); its hits are out[hit_offsets[q] .. hit_offsets[q + 1]).
-// Counters and stage times of `info` are summed over the queries.
+// Counters and stage times of `info` are summed over the queries.  While query q is mapped, a helper thread stages the
+// bytes of query q + 1 (its own pinned buffer, copy stream and device buffer, fa_map.cu prefetch_query), so host copy
+// and H2D of the next query overlap the kernels of the current one.
 int fa_query_batch(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_per_query, int32_t n_queries,
                    fa_hit *out, uint64_t cap, uint64_t *hit_offsets, fa_query_info *info)
 {
@@ -439,12 +449,24 @@ int fa_query_batch(fa_index *ix, const fa_contig *contigs, const int32_t *contig
     uint64_t used = 0;
     int64_t first = 0;
     hit_offsets[0] = 0;
+    for (int32_t q = 0; q < n_queries; q++)
+        if (contigs_per_query[q] < 0) { set_error("query %d: negative contig count", q); return FA_ERR_INVALID; }
+    std::unique_lock<std::mutex> pre_lock(ix->pre_mtx, std::try_to_lock);      // a second concurrent batch maps without staging ahead
+    const bool ahead = pre_lock.owns_lock() && n_queries > 1 && contigs;
     for (int32_t q = 0; q < n_queries; q++) {
         const int32_t nc = contigs_per_query[q];
-        if (nc < 0) { set_error("query %d: negative contig count", q); return FA_ERR_INVALID; }
         fa_query_info qi;
         uint64_t n = 0;
-        const int rc = fa_query(ix, nc ? contigs + first : nullptr, nc, out ? out + used : nullptr, cap - used, &n, &qi);
+        std::thread helper;
+        if (ahead && q + 1 < n_queries && contigs_per_query[q + 1] > 0) {
+            const fa_contig *nx = contigs + first + nc;
+            const int32_t nx_n = contigs_per_query[q + 1];
+            Prefetch *slot = &ix->pre[(q + 1) & 1];
+            helper = std::thread([ix, slot, nx, nx_n]() { if (prefetch_query(ix, *slot, nx, nx_n) != FA_OK) slot->valid = false; });
+        }
+        const int rc = query_checked(ix, nc ? contigs + first : nullptr, nc, out ? out + used : nullptr, cap - used, &n, &qi,
+                                     ahead ? &ix->pre[q & 1] : nullptr);
+        if (helper.joinable()) helper.join();
         if (rc != FA_OK) return rc;
         if (n > cap - used) { set_error("query %d: %llu hits do not fit the output (capacity %llu)", q, (unsigned long long)n, (unsigned long long)cap); return FA_ERR_INVALID; }
         used += n;
@@ -454,7 +476,7 @@ int fa_query_batch(fa_index *ix, const fa_contig *contigs, const int32_t *contig
         sum.scanned += qi.scanned; sum.mappings += qi.mappings; sum.short_contigs += qi.short_contigs;
         sum.kernel_launches += qi.kernel_launches; sum.h2d_bytes += qi.h2d_bytes; sum.d2h_bytes += qi.d2h_bytes;
         sum.l2_fallback += qi.l2_fallback; sum.events += qi.events; sum.events_replayed += qi.events_replayed;
-        sum.l1_sorted_fragments += qi.l1_sorted_fragments;
+        sum.l1_sorted_fragments += qi.l1_sorted_fragments; sum.l1_small_fragments += qi.l1_small_fragments;
         sum.ms_h2d += qi.ms_h2d; sum.ms_sketch += qi.ms_sketch; sum.ms_lookup += qi.ms_lookup; sum.ms_seed_sort += qi.ms_seed_sort;
         sum.ms_l1 += qi.ms_l1; sum.ms_l2 += qi.ms_l2; sum.ms_cgi += qi.ms_cgi; sum.ms_d2h += qi.ms_d2h; sum.ms_total += qi.ms_total;
         sum.ms_l2_prep += qi.ms_l2_prep; sum.ms_l2_events += qi.ms_l2_events; sum.ms_l2_slide += qi.ms_l2_slide;
@@ -470,6 +492,14 @@ int fa_debug_set_l1_seed_cap(fa_index *ix, int64_t cap)
     if (!ix) { set_error("index is NULL"); return FA_ERR_INVALID; }
     std::lock_guard<std::mutex> guard(ix->mtx);
     ix->l1_seed_cap = cap < 0 ? -1 : (long long)cap;
+    return FA_OK;
+}
+
+int fa_debug_set_l1_small_cap(fa_index *ix, int64_t cap)
+{
+    if (!ix) { set_error("index is NULL"); return FA_ERR_INVALID; }
+    std::lock_guard<std::mutex> guard(ix->mtx);
+    ix->l1_small_cap = cap < 0 ? -1 : (long long)cap;
     return FA_OK;
 }
 

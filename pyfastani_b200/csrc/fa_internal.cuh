@@ -59,6 +59,22 @@ struct Workspace {
     uint64_t last_cands = 0, last_frags = 0;
 };
 
+// One host or device buffer to place at `off` in the batch byte buffer.
+struct Upload { const void *ptr; int32_t unit; int32_t on_device; int64_t len; uint64_t off; };
+// The bytes of one query staged ahead of its turn (fa_query_batch): while query q is mapped, a helper thread copies
+// query q + 1 through its own pinned buffer and copy stream into `bytes`; run_query then swaps `bytes` with the
+// workspace's batch buffer and waits for `done` on its stream instead of staging.
+struct Prefetch {
+    DevBuf<uint8_t> bytes;
+    PinBuf stage;
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+    const fa_contig *contigs = nullptr;
+    int32_t n_contigs = 0;
+    uint64_t total = 0, h2d_bytes = 0;
+    bool valid = false;
+    void release();
+};
 }  // namespace fa
 
 struct fa_sketch {
@@ -106,19 +122,23 @@ struct fa_index {
     fa::DevBuf<int32_t>  d_min_hits, d_min_shared;
     fa::DevBuf<uint32_t> d_id_off;
     fa::DevBuf<float>    d_identity;
+    long long l1_small_cap = -1;                 // test hook: most seeds per fragment for the small shape of the on-chip L1 (-1 = default)
     long long l1_seed_cap = -1;                  // test hook: most seeds per fragment for the on-chip L1 (-1 = what fits)
     std::mutex mtx;                              // serialises queries on the single workspace
     fa::Workspace ws;
+    std::mutex pre_mtx;                          // one fa_query_batch at a time stages ahead (others map without)
+    fa::Prefetch pre[2];
 };
 
 namespace fa {
 int build_index(fa_index *ix, int *launches);
+// the uploads of a query (whole fragments of every contig that is long enough, pyx:1059-1105) and their layout
+void plan_uploads(const fa_params &P, const fa_contig *contigs, int32_t n_contigs, std::vector<Upload> &ups, uint64_t *total);
+int prefetch_query(fa_index *ix, Prefetch &pf, const fa_contig *contigs, int32_t n_contigs);
 int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *out, uint64_t cap, uint64_t *n_out,
-              fa_query_info *info);
-// One host or device buffer to place at `off` in the batch byte buffer.
-struct Upload { const void *ptr; int32_t unit; int32_t on_device; int64_t len; uint64_t off; };
+              fa_query_info *info, Prefetch *pf = nullptr);
 // shared by the sketch and query paths: narrow/copy the uploads into the batch byte buffer
-int stage_sequences(cudaStream_t st, SketchScratch &sc, PinBuf &stage, const std::vector<Upload> &ups, uint64_t total,
+int stage_sequences(cudaStream_t st, DevBuf<uint8_t> &bytes, PinBuf &stage, const std::vector<Upload> &ups, uint64_t total,
                     uint64_t *h2d_bytes);
 int debug_candidates(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n);
 int debug_mappings(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n);

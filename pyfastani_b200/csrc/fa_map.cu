@@ -262,17 +262,20 @@ candidates_kernel(const uint64_t *seeds, const uint64_t *seed_base, const int32_
 // Seeds never touch HBM; the only traffic is pos_idx (twice, the second time from L2) and the
 // gathers of gpos / hw.  Fragments whose hits do not fit the CTA's shared memory take the
 // radix-sort path.
-constexpr int L1_THREADS = 1024;
+// Two shapes of the same kernel: 1024 threads and tiles of 4096 hits for fragments with tens of thousands of hits
+// (one CTA per SM, its shared memory holds the hits), 256 threads and tiles of 1024 for fragments with a few
+// thousand (many-to-many workloads: several CTAs per SM hide each other's barriers and gathers).
+constexpr int L1L_THREADS = 1024, L1L_TILE = 4096;     // the large shape
+constexpr int L1S_THREADS = 256, L1S_TILE = 1024;      // the small shape
+constexpr size_t L1S_SMEM = 54 * 1024;                 // its shared memory per CTA: four CTAs per SM
 constexpr int L1_SHIFT = 16;
-constexpr int L1_TILE = 4096;                 // sorted hits per phase-D tile
-constexpr int L1_PER = L1_TILE / L1_THREADS;
-constexpr int L1_EXTRA = 1024;                // look-ahead of the pair test: minHits - 1 <= L1_EXTRA
 constexpr int L1_BM = 32;                     // bitmap words per warp in phase C (+ as many prefix words)
-constexpr int L1_STAGE = L1_TILE + L1_EXTRA;
+// look-ahead of the pair test: minHits - 1 <= THREADS; staged hits per tile = TILE + THREADS (also holds the s position lists)
+__host__ __device__ constexpr int l1_stage(int threads, int tile) { return tile + threads; }
 
-__host__ __device__ inline size_t l1_fixed_smem(uint32_t n_chunks)
+__host__ __device__ inline size_t l1_fixed_smem(uint32_t n_chunks, int stage)
 {
-    return (size_t)((n_chunks + 1 + 3) & ~3u) * 4 + (size_t)L1_STAGE * 8;
+    return (size_t)((n_chunks + 1 + 3) & ~3u) * 4 + (size_t)stage * 8;
 }
 
 // in-place sort of k[0, n) by one warp
@@ -347,12 +350,15 @@ __device__ __forceinline__ void l1_sort_bucket(uint16_t *k, int n, uint32_t *bm,
     }
 }
 
-__global__ void __launch_bounds__(L1_THREADS, 1)
+template <int L1_THREADS, int L1_TILE>
+__global__ void __launch_bounds__(L1_THREADS, 1024 / L1_THREADS)
 l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hit_start, const uint32_t *hit_cnt,
                 const uint64_t *seed_base, const uint32_t *pos_idx, const uint32_t *gpos, const uint2 *hw,
-                const int32_t *min_hits, int frag_len, uint32_t n_chunks, uint32_t seed_cap, uint32_t key_cap,
+                const int32_t *min_hits, int frag_len, uint32_t n_chunks, uint32_t seed_lo, uint32_t seed_cap, uint32_t key_cap,
                 Cand *tmp, uint32_t *frag_cands)
 {
+    constexpr int L1_PER = L1_TILE / L1_THREADS;
+    constexpr int L1_STAGE = l1_stage(L1_THREADS, L1_TILE);
     extern __shared__ __align__(16) uint8_t l1_smem[];
     uint32_t *hist = reinterpret_cast<uint32_t *>(l1_smem);                 // [n_chunks]: counts -> cursors -> bucket ends
     uint32_t *s_j = hist + ((n_chunks + 1 + 3) & ~3u);                       // phase D: reference index per staged hit
@@ -370,6 +376,7 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
     const uint64_t sb = seed_base[f];
     const uint64_t nf64 = seed_base[f + 1] - sb;
     if (nf64 > (uint64_t)seed_cap) return;                                   // the radix-sort path takes this fragment
+    if (nf64 < (uint64_t)seed_lo) return;                                    // the other shape of this kernel does
     const int s = qs[f];
     if (s <= 0 || nf64 == 0) { if (tid == 0) frag_cands[f] = 0; return; }
     const uint32_t n = (uint32_t)nf64;
@@ -1251,54 +1258,115 @@ inline int bits_for(uint64_t n) { int b = 1; while (b < 63 && (1ull << b) < n) b
 
 }  // namespace
 
-// Narrow / copy the uploads into the pinned staging buffer (host sources), then one H2D for the
-// whole batch and one D2D per device-resident source.
-int stage_sequences(cudaStream_t st, SketchScratch &sc, PinBuf &stage, const std::vector<Upload> &ups, uint64_t total,
+// Narrow / copy the uploads into the pinned staging buffer (host sources), then H2D copies and one D2D per
+// device-resident source.  The staged bytes leave in pieces of about 1 MiB, so the copy engine works on one piece
+// while the host fills the next.  (Helper threads sharing the host copy of a lone 5 MB query were tried: spawning them
+// costs more than the 0.3 ms they save.)
+int stage_sequences(cudaStream_t st, DevBuf<uint8_t> &bytes, PinBuf &stage, const std::vector<Upload> &ups, uint64_t total,
                     uint64_t *h2d_bytes)
 {
-    FA_TRY(sc.bytes.reserve(total + 64));
-    bool any_host = false;
-    for (const Upload &u : ups) any_host |= !u.on_device && u.len > 0;
-    if (any_host) {
-        // The staged bytes leave in pieces of about 1 MiB, so the copy engine works on one piece while the host
-        // fills the next (uploads lie at increasing offsets of the staging buffer; a piece may span several).
+    FA_TRY(bytes.reserve(total + 64));
+    struct Piece { const Upload *u; int64_t o, n; };
+    std::vector<Piece> pieces;
+    const int64_t piece = 1ll << 20;
+    uint64_t host_bytes = 0;
+    for (const Upload &u : ups) {
+        if (u.on_device || u.len <= 0) continue;
+        host_bytes += (uint64_t)u.len;
+        for (int64_t o = 0; o < u.len; o += piece) pieces.push_back(Piece{&u, o, std::min<int64_t>(piece, u.len - o)});
+    }
+    if (!pieces.empty()) {
         FA_TRY(stage.reserve(total + 64));
-        const uint64_t piece = 1ull << 20;
-        uint64_t sent = 0;                                   // stage.p[0 .. sent) is on its way
+        uint8_t *const sp = stage.p;
+        auto fill = [sp](const Piece &pc) {
+            const Upload &u = *pc.u;
+            uint8_t *dst = sp + u.off + pc.o;
+            if (u.unit == 1) memcpy(dst, (const uint8_t *)u.ptr + pc.o, (size_t)pc.n);
+            else {
+                // pyx:147-148: (char)toupper(code point); glibc's toupper leaves values outside
+                // [-128, 255] unchanged
+                for (int64_t i = 0; i < pc.n; i++) {
+                    uint32_t cp = u.unit == 2 ? ((const uint16_t *)u.ptr)[pc.o + i] : ((const uint32_t *)u.ptr)[pc.o + i];
+                    if (cp >= 'a' && cp <= 'z') cp -= 32;
+                    dst[i] = (uint8_t)cp;
+                }
+            }
+        };
+        uint64_t sent = 0;                                   // stage.p[0 .. sent) is on its way (uploads lie at increasing offsets)
         auto flush = [&](uint64_t upto) -> int {
-            if (upto > sent) FA_CUDA(cudaMemcpyAsync(sc.bytes.p + sent, stage.p + sent, upto - sent, cudaMemcpyHostToDevice, st));
+            if (upto > sent) FA_CUDA(cudaMemcpyAsync(bytes.p + sent, sp + sent, upto - sent, cudaMemcpyHostToDevice, st));
             sent = std::max(sent, upto);
             return FA_OK;
         };
-        for (const Upload &u : ups) {
-            if (u.on_device || u.len <= 0) continue;
-            for (int64_t o = 0; o < u.len; o += (int64_t)piece) {
-                const int64_t n = std::min<int64_t>((int64_t)piece, u.len - o);
-                uint8_t *dst = stage.p + u.off + o;
-                if (u.unit == 1) memcpy(dst, (const uint8_t *)u.ptr + o, (size_t)n);
-                else {
-                    // pyx:147-148: (char)toupper(code point); glibc's toupper leaves values outside
-                    // [-128, 255] unchanged
-                    for (int64_t i = 0; i < n; i++) {
-                        uint32_t cp = u.unit == 2 ? ((const uint16_t *)u.ptr)[o + i] : ((const uint32_t *)u.ptr)[o + i];
-                        if (cp >= 'a' && cp <= 'z') cp -= 32;
-                        dst[i] = (uint8_t)cp;
-                    }
-                }
-                if (u.off + (uint64_t)(o + n) - sent >= piece) FA_TRY(flush(u.off + (uint64_t)(o + n)));
-            }
+        for (const Piece &pc : pieces) {
+            fill(pc);
+            const uint64_t end = pc.u->off + (uint64_t)(pc.o + pc.n);
+            if (end - sent >= (uint64_t)piece) FA_TRY(flush(end));
         }
         FA_TRY(flush(total));
         if (h2d_bytes) *h2d_bytes += total;
     }
     for (const Upload &u : ups)
         if (u.on_device && u.len > 0)
-            FA_CUDA(cudaMemcpyAsync(sc.bytes.p + u.off, u.ptr, (size_t)u.len, cudaMemcpyDeviceToDevice, st));
+            FA_CUDA(cudaMemcpyAsync(bytes.p + u.off, u.ptr, (size_t)u.len, cudaMemcpyDeviceToDevice, st));
+    return FA_OK;
+}
+
+// Whole fragments of every contig that is long enough (pyx:1059-1105), at 16-byte aligned offsets of the batch buffer.
+void plan_uploads(const fa_params &P, const fa_contig *contigs, int32_t n_contigs, std::vector<Upload> &ups, uint64_t *total)
+{
+    const int L = P.frag_len;
+    const int lim = std::min(std::min(P.window, P.k), L);
+    uint64_t off = 0;
+    ups.clear();
+    for (int32_t c = 0; c < n_contigs; c++) {
+        const int64_t slen = contigs[c].len;
+        if (slen < lim) continue;
+        const int64_t nfrag = slen / L;
+        if (nfrag > 0) {
+            ups.push_back(Upload{contigs[c].data, contigs[c].unit_bytes, contigs[c].on_device, nfrag * L, off});
+            off += ((uint64_t)(nfrag * L) + 15) & ~15ull;
+        }
+    }
+    *total = off;
+}
+
+void Prefetch::release()
+{
+    bytes.release(); stage.release();
+    if (done) cudaEventDestroy(done);
+    if (st) cudaStreamDestroy(st);
+    done = nullptr; st = nullptr; valid = false;
+}
+
+// Stage the bytes of a query that is still waiting for its turn (called from a helper thread of fa_query_batch).
+// Anything unusual -- bad arguments, nothing to upload -- leaves the slot invalid and run_query stages as usual.
+int prefetch_query(fa_index *ix, Prefetch &pf, const fa_contig *contigs, int32_t n_contigs)
+{
+    pf.valid = false;
+    if (ix->prm.frag_len <= 0 || ix->prm.frag_len > 32767) return FA_OK;
+    for (int32_t c = 0; c < n_contigs; c++) {
+        if (contigs[c].len < 0 || (contigs[c].len > 0 && !contigs[c].data)) return FA_OK;
+        if (contigs[c].unit_bytes != 1 && contigs[c].unit_bytes != 2 && contigs[c].unit_bytes != 4) return FA_OK;
+        if (contigs[c].on_device && contigs[c].unit_bytes != 1) return FA_OK;
+    }
+    FA_CUDA(cudaSetDevice(ix->device));
+    if (!pf.st) FA_CUDA(cudaStreamCreateWithFlags(&pf.st, cudaStreamNonBlocking));
+    if (!pf.done) FA_CUDA(cudaEventCreateWithFlags(&pf.done, cudaEventDisableTiming));
+    std::vector<Upload> ups;
+    uint64_t total = 0;
+    plan_uploads(ix->prm, contigs, n_contigs, ups, &total);
+    if (!total) return FA_OK;
+    pf.h2d_bytes = 0;
+    FA_TRY(stage_sequences(pf.st, pf.bytes, pf.stage, ups, total, &pf.h2d_bytes));
+    FA_CUDA(cudaEventRecord(pf.done, pf.st));
+    pf.contigs = contigs; pf.n_contigs = n_contigs; pf.total = total;
+    pf.valid = true;
     return FA_OK;
 }
 
 int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *out, uint64_t cap, uint64_t *n_out,
-              fa_query_info *info)
+              fa_query_info *info, Prefetch *pf)
 {
     std::lock_guard<std::mutex> guard(ix->mtx);
     FA_CUDA(cudaSetDevice(ix->device));
@@ -1355,7 +1423,15 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
     FA_CUDA(cudaEventRecord(ws.ev[0], st));
     if (F > 0 && tiles_per_frag > 0 && ix->n > 0 && G > 0) {
         // ---- upload + sketch the fragments ---------------------------------------------------
-        FA_TRY(stage_sequences(st, ws.sk, ws.stage, ups, off, &qi.h2d_bytes));
+        if (pf && pf->valid && pf->contigs == contigs && pf->n_contigs == n_contigs && pf->total == off) {
+            // staged ahead by fa_query_batch: take its buffer (it gets ours, idle since the previous query returned)
+            std::swap(ws.sk.bytes.p, pf->bytes.p); std::swap(ws.sk.bytes.cap, pf->bytes.cap);
+            FA_CUDA(cudaStreamWaitEvent(st, pf->done, 0));
+            qi.h2d_bytes += pf->h2d_bytes;
+            pf->valid = false;
+        } else {
+            FA_TRY(stage_sequences(st, ws.sk.bytes, ws.stage, ups, off, &qi.h2d_bytes));
+        }
         const int n_tiles = F * tiles_per_frag;
         const int cmw = L - (w - 1) - (k - 1);                                // minimizer windows per fragment
         const uint64_t emit_cap = (uint64_t)F * (uint64_t)std::max(cmw, 1);
@@ -1411,23 +1487,37 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
             cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ix->device);
             // ---- which fragments fit the on-chip L1 (l1_fused_kernel), which take the radix sort ----
             const uint32_t n_chunks = (uint32_t)((ix->n + (1ull << L1_SHIFT) - 1) >> L1_SHIFT);
+            auto *const l1_large = l1_fused_kernel<L1L_THREADS, L1L_TILE>;
+            auto *const l1_small = l1_fused_kernel<L1S_THREADS, L1S_TILE>;
             cudaFuncAttributes l1_attr;
-            FA_CUDA(cudaFuncGetAttributes(&l1_attr, l1_fused_kernel));
-            const size_t l1_fixed = l1_fixed_smem(n_chunks), l1_room = (size_t)smem_optin - l1_attr.sharedSizeBytes;
+            FA_CUDA(cudaFuncGetAttributes(&l1_attr, l1_large));
+            const size_t l1_fixed = l1_fixed_smem(n_chunks, l1_stage(L1L_THREADS, L1L_TILE)), l1_room = (size_t)smem_optin - l1_attr.sharedSizeBytes;
             uint64_t seed_cap = 0;
-            if (l1_fixed + 256 < l1_room && ix->max_min_hits - 1 <= L1_EXTRA) seed_cap = ((l1_room - l1_fixed - 128) * 16 / 33) & ~31ull;   // 2 + 1/16 bytes per hit
+            if (l1_fixed + 256 < l1_room && ix->max_min_hits - 1 <= L1L_THREADS) seed_cap = ((l1_room - l1_fixed - 128) * 16 / 33) & ~31ull;   // 2 + 1/16 bytes per hit
             if (ix->l1_seed_cap >= 0) seed_cap = std::min<uint64_t>(seed_cap, (uint64_t)ix->l1_seed_cap);
             seed_cap = std::min<uint64_t>(seed_cap, 0x7FFFFFFFull);
-            uint64_t max_fast = 0, S_slow = 0;
-            uint32_t n_slow = 0;
+            // the small shape takes the fragments whose hits leave room for four CTAs per SM (and whose sketch and
+            // minHits fit its staging area); it is not used when hardly any fragment qualifies
+            const size_t l1s_fixed = l1_fixed_smem(n_chunks, l1_stage(L1S_THREADS, L1S_TILE));
+            uint64_t small_cap = 0;
+            if (l1s_fixed + 1024 < L1S_SMEM && ix->max_min_hits - 1 <= L1S_THREADS && max_s <= l1_stage(L1S_THREADS, L1S_TILE))
+                small_cap = std::min<uint64_t>(seed_cap, ((L1S_SMEM - l1s_fixed - 128) * 16 / 33) & ~31ull);
+            if (ix->l1_small_cap >= 0) small_cap = std::min<uint64_t>(small_cap, (uint64_t)ix->l1_small_cap);
+            uint64_t max_fast = 0, max_small = 0, S_slow = 0;
+            uint32_t n_slow = 0, n_small = 0;
             uint64_t *h_fb = h_fs + F + 1;
             h_fb[0] = 0;
             for (int f = 0; f < F; f++) {
                 const uint64_t nf = h_fs[f + 1] - h_fs[f];
                 const bool slow = nf > seed_cap;
-                if (slow) { n_slow++; S_slow += nf; } else max_fast = std::max(max_fast, nf);
+                if (slow) { n_slow++; S_slow += nf; }
+                else if (small_cap && nf <= small_cap) { n_small++; max_small = std::max(max_small, nf); }
+                else max_fast = std::max(max_fast, nf);
                 h_fb[f + 1] = h_fb[f] + (slow ? nf : 0);
             }
+            if (n_small * 8u < (uint32_t)F) { max_fast = std::max(max_fast, max_small); n_small = 0; small_cap = 0; max_small = 0; }
+            const uint32_t n_large = (uint32_t)F - n_slow - n_small;
+            qi.l1_small_fragments = n_small;
             qi.l1_sorted_fragments = n_slow;
             const int shift = bits_for(ix->n), fbits = bits_for((uint64_t)F);
             const uint64_t idx_mask = (1ull << shift) - 1;
@@ -1450,13 +1540,25 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
             // ---- L1 candidates -------------------------------------------------------------------
             if (n_slow < (uint32_t)F) {
                 FA_TRY(ws.cand_tmp.reserve(S));
-                const uint64_t key_cap = (max_fast + 31) & ~31ull;
-                const size_t smem = l1_fixed + 2 * key_cap + 2 * (key_cap / 32 + 8);
-                FA_CUDA(cudaFuncSetAttribute(l1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                l1_fused_kernel<<<F, L1_THREADS, smem, st>>>(ws.sk.seq_first.p, ws.qs.p, ws.hit_start.p, ws.hit_cnt.p, ws.frag_seeds.p,
-                                                             ix->pos_idx.p, ix->gpos.p, ix->hw.p, ix->d_min_hits.p, L, n_chunks,
-                                                             (uint32_t)seed_cap, (uint32_t)key_cap, ws.cand_tmp.p, ws.frag_cands.p);
-                FA_CUDA(cudaGetLastError()); launches++;
+                if (n_small) {          // fragments with [0, small_cap] hits
+                    const uint64_t key_cap = (max_small + 31) & ~31ull;
+                    const size_t smem = l1s_fixed + 2 * key_cap + 2 * (key_cap / 32 + 8);
+                    FA_CUDA(cudaFuncSetAttribute(l1_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    l1_small<<<F, L1S_THREADS, smem, st>>>(ws.sk.seq_first.p, ws.qs.p, ws.hit_start.p, ws.hit_cnt.p, ws.frag_seeds.p,
+                                                           ix->pos_idx.p, ix->gpos.p, ix->hw.p, ix->d_min_hits.p, L, n_chunks,
+                                                           0u, (uint32_t)small_cap, (uint32_t)key_cap, ws.cand_tmp.p, ws.frag_cands.p);
+                    FA_CUDA(cudaGetLastError()); launches++;
+                }
+                if (n_large) {          // fragments with (small_cap, seed_cap] hits (all of them when the small shape is off)
+                    const uint64_t key_cap = (max_fast + 31) & ~31ull;
+                    const size_t smem = l1_fixed + 2 * key_cap + 2 * (key_cap / 32 + 8);
+                    FA_CUDA(cudaFuncSetAttribute(l1_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    l1_large<<<F, L1L_THREADS, smem, st>>>(ws.sk.seq_first.p, ws.qs.p, ws.hit_start.p, ws.hit_cnt.p, ws.frag_seeds.p,
+                                                           ix->pos_idx.p, ix->gpos.p, ix->hw.p, ix->d_min_hits.p, L, n_chunks,
+                                                           n_small ? (uint32_t)small_cap + 1u : 0u, (uint32_t)seed_cap, (uint32_t)key_cap,
+                                                           ws.cand_tmp.p, ws.frag_cands.p);
+                    FA_CUDA(cudaGetLastError()); launches++;
+                }
             }
             if (n_slow) {
                 candidates_kernel<false><<<F, 256, 0, st>>>(ws.seeds_b.p, ws.fb_seeds.p, ws.qs.p, ix->d_min_hits.p, ix->ref.p,

@@ -31,7 +31,7 @@ class QueryInfo(C.Structure):
                                             "ms_cgi", "ms_d2h", "ms_total")]
                 + [("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("l2_fallback", C.c_uint64), ("events", C.c_uint64)]
                 + [(n, C.c_float) for n in ("ms_l2_prep", "ms_l2_events", "ms_l2_slide")]
-                + [("l1_sorted_fragments", C.c_uint32), ("reserved0", C.c_uint32), ("events_replayed", C.c_uint64)])
+                + [("l1_sorted_fragments", C.c_uint32), ("l1_small_fragments", C.c_uint32), ("events_replayed", C.c_uint64)])
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -211,6 +211,10 @@ class Index:
     def set_l1_seed_cap(self, cap):
         """Test hook: fragments with more seeds than `cap` take the radix-sort L1 path (-1 = default)."""
         check(lib().fa_debug_set_l1_seed_cap(self.h, C.c_int64(cap)))
+
+    def set_l1_small_cap(self, cap):
+        """Test hook: on-chip fragments with more seeds than `cap` take the large shape of the L1 kernel (-1 = default)."""
+        check(lib().fa_debug_set_l1_small_cap(self.h, C.c_int64(cap)))
 
     def query_draft(self, contigs, dump=False):
         contigs = list(contigs)

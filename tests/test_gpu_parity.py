@@ -46,7 +46,7 @@ def _check_hits(hits, names, rows):
         assert h["identity"] == golden_io.f32(ident), (float(h["identity"]).hex(), ident)
 
 
-@pytest.mark.parametrize("l1", ["chip", "sort", "mixed"])
+@pytest.mark.parametrize("l1", ["chip", "chip-large", "shapes", "sort", "mixed"])
 @pytest.mark.parametrize("name", [c["name"] for c in cases.query_cases()])
 def test_queries_match_pyfastani_and_oracle(name, l1):
     """`l1` selects the L1 path: all fragments through the on-chip kernel (the default), all through
@@ -69,10 +69,14 @@ def test_queries_match_pyfastani_and_oracle(name, l1):
     for q, res in zip(case["queries"], gold["results"]):
         ohits, oinfo = osk.query_draft(q, dump=True)
         st = oinfo["stats"]
-        ix.set_l1_seed_cap({"chip": -1, "sort": 0, "mixed": st["seeds"] // max(st["fragments"], 1) - 1}[l1])
+        mean = st["seeds"] // max(st["fragments"], 1)
+        ix.set_l1_seed_cap({"sort": 0, "mixed": mean - 1}.get(l1, -1))
+        ix.set_l1_small_cap({"chip-large": 0, "shapes": mean}.get(l1, -1))
         hits, out = ix.query_draft(q, dump=True)
-        if l1 == "chip":
+        if l1 in ("chip", "chip-large", "shapes"):
             assert out["info"]["l1_sorted_fragments"] == 0
+            if l1 == "chip-large":
+                assert out["info"]["l1_small_fragments"] == 0
         elif st["seeds"]:
             assert out["info"]["l1_sorted_fragments"] > 0
         # L1 candidate regions, bit-exact
@@ -88,7 +92,7 @@ def test_queries_match_pyfastani_and_oracle(name, l1):
         assert info["kernel_launches"] > 0 or st["fragments"] == 0
 
 
-@pytest.mark.parametrize("l1", ["chip", "sort", "mixed"])
+@pytest.mark.parametrize("l1", ["chip", "chip-large", "shapes", "sort", "mixed"])
 def test_l1_many_references(l1):
     """120 related references: every fragment has several thousand seed hits (more than one 4096-hit
     tile of the on-chip L1 kernel) spread over nine 2^16-minimizer chunks of the index, plus a
@@ -106,9 +110,17 @@ def test_l1_many_references(l1):
         ohits, oinfo = osk.query_draft(query, dump=True)
         st = oinfo["stats"]
         assert st["seeds"] // st["fragments"] > 4096
-        ix.set_l1_seed_cap({"chip": -1, "sort": 0, "mixed": st["seeds"] // st["fragments"] - 1}[l1])
+        mean = st["seeds"] // st["fragments"]
+        ix.set_l1_seed_cap({"sort": 0, "mixed": mean - 1}.get(l1, -1))
+        ix.set_l1_small_cap({"chip-large": 0, "shapes": mean}.get(l1, -1))
         hits, out = ix.query_draft(query, dump=True)
-        assert (out["info"]["l1_sorted_fragments"] == 0) == (l1 == "chip")
+        assert (out["info"]["l1_sorted_fragments"] == 0) == (l1 in ("chip", "chip-large", "shapes"))
+        if l1 == "chip":          # several 1024-hit tiles per fragment in the small shape
+            assert out["info"]["l1_small_fragments"] == st["fragments"]
+        if l1 == "chip-large":
+            assert out["info"]["l1_small_fragments"] == 0
+        if l1 == "shapes":
+            assert 0 < out["info"]["l1_small_fragments"] < st["fragments"]
         assert np.array_equal(out["candidates"], oinfo["candidates"])
         assert np.array_equal(out["mappings"], oinfo["mappings"])
         assert np.array_equal(hits, ohits)
