@@ -253,6 +253,7 @@ def run_b200(a):
     from pyfastani_b200 import sharding
     offsets = sharding.reference_shards([a.length] * a.refs, world) if by_refs else [0, a.refs]
     my_refs = range(offsets[rank], offsets[rank + 1]) if by_refs else range(a.refs)
+    shard_cap = max(offsets[r + 1] - offsets[r] for r in range(len(offsets) - 1))      # most hit rows one rank can hold
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     for i in my_refs:
@@ -285,7 +286,7 @@ def run_b200(a):
         if not by_refs:
             return hs
         rows = sharding.hits_to_rows(hs, name_to_local)
-        return sharding.merge_hits(sharding.gather_hits([rows], device=dev)[0], offsets)
+        return sharding.merge_hits(sharding.gather_hits([rows], device=dev, cap=shard_cap)[0], offsets)
 
     for _ in range(max(a.warmup, 1)):
         hits = map_query(q_dev)
@@ -402,7 +403,7 @@ def run_b200(a):
                    "parallelism": ("reference genomes sharded over the GPUs (%s per rank), same query on every GPU, NCCL all-gather "
                                    "of the hit rows inside the step" % [offsets[r + 1] - offsets[r] for r in range(world)]) if by_refs
                                   else "replicated index, one query stream per GPU",
-                   "l2_policy": "inputs larger than L2: the index is %.1f GB, every step streams it" % (n_min * 42 / 1e9)},
+                   "l2_policy": "inputs larger than L2: the index is %.1f GB, every step streams it" % (n_min * 50 / 1e9)},
         "fragments_per_s": jobs * frags / (ms_per_step * 1e-3),
         "clocks": clocks,
         "e2e": {"value": jobs * pairs * a.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d // a.steps,

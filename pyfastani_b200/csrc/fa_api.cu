@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <new>
 #include <thread>
+#include <vector>
 
 #include "fa_internal.cuh"
 
@@ -420,6 +421,18 @@ int fa_index_occurrence_threshold(const fa_index *ix, int32_t *out)
     return FA_OK;
 }
 
+static void add_info(fa_query_info &sum, const fa_query_info &qi)
+{
+    sum.fragments += qi.fragments; sum.sketch_sum += qi.sketch_sum; sum.seeds += qi.seeds; sum.candidates += qi.candidates;
+    sum.scanned += qi.scanned; sum.mappings += qi.mappings; sum.short_contigs += qi.short_contigs;
+    sum.kernel_launches += qi.kernel_launches; sum.h2d_bytes += qi.h2d_bytes; sum.d2h_bytes += qi.d2h_bytes;
+    sum.l2_fallback += qi.l2_fallback; sum.events += qi.events; sum.events_replayed += qi.events_replayed;
+    sum.l1_sorted_fragments += qi.l1_sorted_fragments; sum.l1_small_fragments += qi.l1_small_fragments;
+    sum.ms_h2d += qi.ms_h2d; sum.ms_sketch += qi.ms_sketch; sum.ms_lookup += qi.ms_lookup; sum.ms_seed_sort += qi.ms_seed_sort;
+    sum.ms_l1 += qi.ms_l1; sum.ms_l2 += qi.ms_l2; sum.ms_cgi += qi.ms_cgi; sum.ms_d2h += qi.ms_d2h; sum.ms_total += qi.ms_total;
+    sum.ms_l2_prep += qi.ms_l2_prep; sum.ms_l2_events += qi.ms_l2_events; sum.ms_l2_slide += qi.ms_l2_slide;
+}
+
 static int query_checked(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *out, uint64_t cap, uint64_t *n_out,
                          fa_query_info *info, Prefetch *pf)
 {
@@ -437,49 +450,103 @@ int fa_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *
 
 // Many queries in one call (no host language between them): query q owns contigs
 // [sum(contigs_per_query[:q]), +contigs_per_query[q]); its hits are out[hit_offsets[q] .. hit_offsets[q + 1]).
-// Counters and stage times of `info` are summed over the queries.  While query q is mapped, a helper thread stages the
-// bytes of query q + 1 (its own pinned buffer, copy stream and device buffer, fa_map.cu prefetch_query), so host copy
-// and H2D of the next query overlap the kernels of the current one.
+// Counters and stage times of `info` are summed over the passes.
+//  * Light queries share a pass of the pipeline (run_queries, fa_map.cu): a many-to-many query has a few thousand
+//    candidates, far too few to fill the GPU's lanes in the L2 slide, and its twenty kernel launches and four host
+//    syncs cost as much as its kernels.  The first pass takes one query; afterwards the seeds and events per fragment
+//    seen so far size the next pass (at most 32 queries / 48 k fragments / the budgets below), so a heavy query --
+//    config 2: 86 M seeds, 1.8 G events -- still runs alone.
+//  * While a pass is mapped, a helper thread stages the bytes of the next one (its own pinned buffer, copy stream and
+//    device buffer, fa_map.cu prefetch_query), so host copy and H2D overlap the kernels.
 int fa_query_batch(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_per_query, int32_t n_queries,
                    fa_hit *out, uint64_t cap, uint64_t *hit_offsets, fa_query_info *info)
 {
     if (!ix || n_queries < 0 || !hit_offsets || (n_queries > 0 && !contigs_per_query)) { set_error("bad arguments"); return FA_ERR_INVALID; }
     fa_query_info sum;
     memset(&sum, 0, sizeof sum);
-    uint64_t used = 0;
-    int64_t first = 0;
     hit_offsets[0] = 0;
-    for (int32_t q = 0; q < n_queries; q++)
-        if (contigs_per_query[q] < 0) { set_error("query %d: negative contig count", q); return FA_ERR_INVALID; }
-    std::unique_lock<std::mutex> pre_lock(ix->pre_mtx, std::try_to_lock);      // a second concurrent batch maps without staging ahead
-    const bool ahead = pre_lock.owns_lock() && n_queries > 1 && contigs;
+    int64_t n_contigs = 0;
     for (int32_t q = 0; q < n_queries; q++) {
-        const int32_t nc = contigs_per_query[q];
-        fa_query_info qi;
-        uint64_t n = 0;
-        std::thread helper;
-        if (ahead && q + 1 < n_queries && contigs_per_query[q + 1] > 0) {
-            const fa_contig *nx = contigs + first + nc;
-            const int32_t nx_n = contigs_per_query[q + 1];
-            Prefetch *slot = &ix->pre[(q + 1) & 1];
-            helper = std::thread([ix, slot, nx, nx_n]() { if (prefetch_query(ix, *slot, nx, nx_n) != FA_OK) slot->valid = false; });
+        if (contigs_per_query[q] < 0) { set_error("query %d: negative contig count", q); return FA_ERR_INVALID; }
+        n_contigs += contigs_per_query[q];
+    }
+    if (n_contigs > 0 && !contigs) { set_error("bad arguments"); return FA_ERR_INVALID; }
+    for (int64_t c = 0; c < n_contigs; c++)
+        if (contigs[c].len < 0 || (contigs[c].len > 0 && !contigs[c].data)) { set_error("contig %lld: bad buffer", (long long)c); return FA_ERR_INVALID; }
+    const int L = std::max(ix->prm.frag_len, 1);
+    std::vector<int64_t> first(n_queries + 1, 0);
+    std::vector<uint64_t> frags(n_queries, 0);
+    for (int32_t q = 0; q < n_queries; q++) {
+        first[q + 1] = first[q] + contigs_per_query[q];
+        for (int64_t c = first[q]; c < first[q + 1]; c++) frags[q] += (uint64_t)(contigs[c].len / L);
+    }
+    std::unique_lock<std::mutex> pre_lock(ix->pre_mtx, std::try_to_lock);      // a second concurrent batch maps without staging ahead
+    const bool ahead = pre_lock.owns_lock() && n_queries > 1;
+    if (pre_lock.owns_lock()) ix->pre[0].valid = ix->pre[1].valid = false;       // nothing staged by an earlier call is ours
+
+    constexpr uint64_t PASS_QUERIES = 32, PASS_FRAGS = 48 * 1024, PASS_SEEDS = 96ull << 20, PASS_EVENTS = 256ull << 20;
+    double seeds_per_frag = -1.0, events_per_frag = -1.0;      // largest seen so far in this call (-1: nothing seen)
+    auto pass_end = [&](int32_t q0) {
+        int32_t q1 = q0 + 1;
+        if (seeds_per_frag < 0) return q1;
+        uint64_t f = frags[q0];
+        while (q1 < n_queries && (uint64_t)(q1 - q0) < PASS_QUERIES) {
+            const uint64_t nf = f + frags[q1];
+            if (nf > PASS_FRAGS || (double)nf * seeds_per_frag * 1.5 > (double)PASS_SEEDS ||
+                (double)nf * events_per_frag * 1.5 > (double)PASS_EVENTS) break;
+            f = nf; q1++;
         }
-        const int rc = query_checked(ix, nc ? contigs + first : nullptr, nc, out ? out + used : nullptr, cap - used, &n, &qi,
-                                     ahead ? &ix->pre[q & 1] : nullptr);
+        return q1;
+    };
+
+    uint64_t used = 0;
+    std::vector<uint64_t> offs(PASS_QUERIES + 1);
+    int slot = 0;
+    int32_t q0 = 0, q1 = n_queries ? pass_end(0) : 0;
+    while (q0 < n_queries) {
+        const int32_t nq = q1 - q0;
+        fa_query_info qi;
+        // plan the pass after this one with what is known now, and stage it while this one runs
+        const int32_t q2 = q1 < n_queries ? pass_end(q1) : q1;
+        std::thread helper;
+        if (ahead && q1 < n_queries && first[q2] > first[q1]) {
+            const fa_contig *nx = contigs + first[q1];
+            const int32_t nx_n = (int32_t)(first[q2] - first[q1]);
+            Prefetch *pfs = &ix->pre[slot ^ 1];
+            helper = std::thread([ix, pfs, nx, nx_n]() { if (prefetch_query(ix, *pfs, nx, nx_n) != FA_OK) pfs->valid = false; });
+        }
+        int rc = run_queries(ix, contigs ? contigs + first[q0] : nullptr, contigs_per_query + q0, nq, out ? out + used : nullptr,
+                             cap - used, offs.data(), &qi, ahead ? &ix->pre[slot] : nullptr);
         if (helper.joinable()) helper.join();
+        if (rc == FA_ERR_NOMEM && nq > 1) {
+            // the pass was sized from lighter queries: map its queries one by one
+            cudaGetLastError();
+            memset(&qi, 0, sizeof qi);
+            uint64_t u2 = 0;
+            offs[0] = 0;
+            rc = FA_OK;
+            for (int32_t q = q0; q < q1 && rc == FA_OK; q++) {
+                fa_query_info one;
+                uint64_t o2[2];
+                const uint64_t room = cap - used > u2 ? cap - used - u2 : 0;
+                rc = run_queries(ix, contigs + first[q], contigs_per_query + q, 1, out && room ? out + used + u2 : nullptr, room, o2, &one, nullptr);
+                u2 += o2[1];
+                offs[q - q0 + 1] = u2;
+                add_info(qi, one);
+            }
+        }
         if (rc != FA_OK) return rc;
-        if (n > cap - used) { set_error("query %d: %llu hits do not fit the output (capacity %llu)", q, (unsigned long long)n, (unsigned long long)cap); return FA_ERR_INVALID; }
-        used += n;
-        first += nc;
-        hit_offsets[q + 1] = used;
-        sum.fragments += qi.fragments; sum.sketch_sum += qi.sketch_sum; sum.seeds += qi.seeds; sum.candidates += qi.candidates;
-        sum.scanned += qi.scanned; sum.mappings += qi.mappings; sum.short_contigs += qi.short_contigs;
-        sum.kernel_launches += qi.kernel_launches; sum.h2d_bytes += qi.h2d_bytes; sum.d2h_bytes += qi.d2h_bytes;
-        sum.l2_fallback += qi.l2_fallback; sum.events += qi.events; sum.events_replayed += qi.events_replayed;
-        sum.l1_sorted_fragments += qi.l1_sorted_fragments; sum.l1_small_fragments += qi.l1_small_fragments;
-        sum.ms_h2d += qi.ms_h2d; sum.ms_sketch += qi.ms_sketch; sum.ms_lookup += qi.ms_lookup; sum.ms_seed_sort += qi.ms_seed_sort;
-        sum.ms_l1 += qi.ms_l1; sum.ms_l2 += qi.ms_l2; sum.ms_cgi += qi.ms_cgi; sum.ms_d2h += qi.ms_d2h; sum.ms_total += qi.ms_total;
-        sum.ms_l2_prep += qi.ms_l2_prep; sum.ms_l2_events += qi.ms_l2_events; sum.ms_l2_slide += qi.ms_l2_slide;
+        if (offs[nq] > cap - used) { set_error("queries %d..%d: %llu hits do not fit the output (capacity %llu)", q0, q1 - 1, (unsigned long long)(used + offs[nq]), (unsigned long long)cap); return FA_ERR_INVALID; }
+        for (int32_t q = 0; q < nq; q++) hit_offsets[q0 + q + 1] = used + offs[q + 1];
+        used += offs[nq];
+        add_info(sum, qi);
+        if (qi.fragments) {
+            seeds_per_frag = std::max(seeds_per_frag, (double)qi.seeds / (double)qi.fragments);
+            events_per_frag = std::max(events_per_frag, (double)qi.events / (double)qi.fragments);
+        }
+        // the staged pass was planned before this one's counters were known: keep it as planned
+        q0 = q1; q1 = q2; slot ^= 1;
+        if (q0 < n_queries && q1 == q0) q1 = pass_end(q0);
     }
     if (info) *info = sum;
     return FA_OK;

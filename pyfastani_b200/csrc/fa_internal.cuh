@@ -31,6 +31,8 @@ struct Workspace {
     SketchScratch sk;
     PinBuf stage;                       // pinned host staging for query bytes
     std::vector<SeqDesc> h_seqs;
+    std::vector<int32_t> h_fragq;       // several queries in one pass: the query of every fragment
+    DevBuf<int32_t>  frag_q;
     DevBuf<uint32_t> qhash;             // per-fragment minimizer hashes -> sorted unique sketches in place
     DevBuf<int32_t>  qs;                // per-fragment sketch size s
     DevBuf<uint32_t> hit_start, hit_cnt;   // per query hash: bucket in pos_idx
@@ -137,6 +139,8 @@ void plan_uploads(const fa_params &P, const fa_contig *contigs, int32_t n_contig
 int prefetch_query(fa_index *ix, Prefetch &pf, const fa_contig *contigs, int32_t n_contigs);
 int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *out, uint64_t cap, uint64_t *n_out,
               fa_query_info *info, Prefetch *pf = nullptr);
+int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_per_query, int32_t n_queries, fa_hit *out,
+                uint64_t cap, uint64_t *hit_offsets, fa_query_info *info, Prefetch *pf = nullptr);
 // shared by the sketch and query paths: narrow/copy the uploads into the batch byte buffer
 int stage_sequences(cudaStream_t st, DevBuf<uint8_t> &bytes, PinBuf &stage, const std::vector<Upload> &ups, uint64_t total,
                     uint64_t *h2d_bytes);

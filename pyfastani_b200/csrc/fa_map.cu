@@ -1190,7 +1190,7 @@ l2_fallback_kernel(const Prep *prep, const uint32_t *cand_base, const uint32_t *
 // pattern (identities are positive floats, so the unsigned order is the float order).
 __global__ void cgi_best_kernel(const Cand *cands, const Mapping *maps, const uint32_t *cand_base, int n_frags,
                                 const int32_t *genome_of_seq, const uint32_t *bin_base, int bin_w, uint32_t *cells,
-                                unsigned long long *counters)
+                                const int32_t *frag_q, uint32_t n_cells, unsigned long long *counters)
 {
     const uint32_t n = cand_base[n_frags];
     unsigned int passed = 0;
@@ -1212,7 +1212,9 @@ __global__ void cgi_best_kernel(const Cand *cands, const Mapping *maps, const ui
                 best = q; have = true;
             }
         }
-        if (have) atomicMax(&cells[bin_base[best.seq] + (uint32_t)(best.ref_start / bin_w)], __float_as_uint(best.identity));
+        // (several queries in one pass: every query has its own cell table)
+        if (have) atomicMax(&cells[(frag_q ? (uint32_t)frag_q[f] * n_cells : 0u) + bin_base[best.seq] + (uint32_t)(best.ref_start / bin_w)],
+                            __float_as_uint(best.identity));
     }
     passed = __reduce_add_sync(0xFFFFFFFFu, passed);
     if ((threadIdx.x & 31) == 0 && passed) atomicAdd(&counters[CT_MAPPINGS], (unsigned long long)passed);
@@ -1221,24 +1223,46 @@ __global__ void cgi_best_kernel(const Cand *cands, const Mapping *maps, const ui
 // Per genome (:268-294): float32 sum of the surviving identities in (refSeqId, bin) order, count,
 // mean.  One warp per genome; the adds are sequential on purpose.  Cells are
 // cleared on the way so the table is ready for the next query.
-__global__ void cgi_sum_kernel(uint32_t *cells, const uint32_t *genome_cell, int n_genomes, int32_t *g_count, float *g_identity)
+__global__ void cgi_sum_kernel(uint32_t *cells, const uint32_t *genome_cell, int n_genomes, int n_queries, uint32_t n_cells,
+                               int32_t *g_count, float *g_identity)
 {
-    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (g >= n_genomes) return;
-    const uint32_t b = genome_cell[g], e = genome_cell[g + 1];
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;    // (query, genome) pair
+    if (g >= n_genomes * n_queries) return;
+    const uint32_t qb = (uint32_t)(g / n_genomes) * n_cells;
+    const uint32_t b = qb + genome_cell[g % n_genomes], e = qb + genome_cell[g % n_genomes + 1];
+    // The float32 sum runs over the non-empty cells in (contig, bin) order (computeCoreIdentity.hpp:264-294), one add
+    // after the other.  Empty cells hold +0.0f and x + 0.0f == x bit for bit (identities are positive), so lane 0 adds
+    // every cell of a 128-cell batch straight from shared memory -- a chain of plain FADDs, no shuffles or bit scans --
+    // while the loads of the next batch are in flight.
+    __shared__ __align__(16) float s_v[8][128];
+    float *sv = s_v[(threadIdx.x >> 5) & 7];
     float sum = 0.0f;
     int cnt = 0;
-    for (uint32_t base = b; base < e; base += 32) {
-        const uint32_t i = base + lane;
-        uint32_t v = i < e ? cells[i] : 0u;
-        if (v) cells[i] = 0u;
-        unsigned nz = __ballot_sync(0xFFFFFFFFu, v != 0u);
-        while (nz) {
-            const int l = __ffs(nz) - 1;
-            nz &= nz - 1;
-            sum += __uint_as_float(__shfl_sync(0xFFFFFFFFu, v, l));
-            cnt++;
+    uint32_t v[4], nx[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) { const uint32_t i = b + u * 32 + lane; nx[u] = i < e ? cells[i] : 0u; }
+    for (uint32_t base = b; base < e; base += 128) {
+        int in_batch = 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            v[u] = nx[u];
+            const uint32_t i = base + u * 32 + lane;
+            if (v[u]) cells[i] = 0u;
+            const uint32_t j = i + 128;
+            nx[u] = j < e ? cells[j] : 0u;
+            in_batch += __popc(__ballot_sync(0xFFFFFFFFu, v[u] != 0u));
+            sv[u * 32 + lane] = __uint_as_float(v[u]);
         }
+        cnt += in_batch;
+        __syncwarp();
+        if (lane == 0 && in_batch) {
+#pragma unroll 8
+            for (int j = 0; j < 128; j += 4) {
+                const float4 x = *reinterpret_cast<const float4 *>(sv + j);
+                sum += x.x; sum += x.y; sum += x.z; sum += x.w;
+            }
+        }
+        __syncwarp();
     }
     if (lane == 0) { g_count[g] = cnt; g_identity[g] = cnt ? sum / (float)cnt : 0.0f; }
 }
@@ -1269,10 +1293,8 @@ int stage_sequences(cudaStream_t st, DevBuf<uint8_t> &bytes, PinBuf &stage, cons
     struct Piece { const Upload *u; int64_t o, n; };
     std::vector<Piece> pieces;
     const int64_t piece = 1ll << 20;
-    uint64_t host_bytes = 0;
     for (const Upload &u : ups) {
         if (u.on_device || u.len <= 0) continue;
-        host_bytes += (uint64_t)u.len;
         for (int64_t o = 0; o < u.len; o += piece) pieces.push_back(Piece{&u, o, std::min<int64_t>(piece, u.len - o)});
     }
     if (!pieces.empty()) {
@@ -1368,6 +1390,19 @@ int prefetch_query(fa_index *ix, Prefetch &pf, const fa_contig *contigs, int32_t
 int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *out, uint64_t cap, uint64_t *n_out,
               fa_query_info *info, Prefetch *pf)
 {
+    uint64_t offs[2] = {0, 0};
+    const int rc = run_queries(ix, contigs, &n_contigs, 1, out, cap, offs, info, pf);
+    *n_out = offs[1];
+    return rc;
+}
+
+// One pass of the pipeline over the fragments of `n_queries` queries (query q owns the next contigs_per_query[q]
+// contigs).  Sketch, lookup, L1 and L2 see one flat list of fragments; only the core-genome step knows the queries:
+// every query has its own (contig, bin) cell table and per-genome sums.  hit_offsets[q + 1] - hit_offsets[q] hits of
+// query q are written at out + hit_offsets[q] (all counted, only those below `cap` stored).
+int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_per_query, int32_t n_queries, fa_hit *out,
+                uint64_t cap, uint64_t *hit_offsets, fa_query_info *info, Prefetch *pf)
+{
     std::lock_guard<std::mutex> guard(ix->mtx);
     FA_CUDA(cudaSetDevice(ix->device));
     cudaStream_t st = ix->st;
@@ -1381,36 +1416,43 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
         ws.ev_ready = true;
     }
     ws.last_cands = 0; ws.last_frags = 0;
-    *n_out = 0;
+    const uint32_t B = (uint32_t)std::max(n_queries, 0);
+    for (uint32_t q = 0; q <= B; q++) hit_offsets[q] = 0;
 
     // ---- fragments (pyx:1059-1105) -----------------------------------------------------------
     const int L = P.frag_len, k = P.k, w = P.window;
     const int lim = std::min(std::min(w, k), L);
     std::vector<Upload> ups;
-    ws.h_seqs.clear();
-    uint64_t total_len = 0, total_frags = 0, off = 0;
+    ws.h_seqs.clear(); ws.h_fragq.clear();
+    std::vector<uint64_t> q_len(B, 0), q_frags(B, 0);
+    uint64_t total_frags = 0, off = 0;
+    int32_t n_contigs = 0;
     const int nk = L - k + 1;
     const int tiles_per_frag = nk > 0 ? (nk + SK_TILE - 1) / SK_TILE : 0;
-    for (int32_t c = 0; c < n_contigs; c++) {
-        const int64_t slen = contigs[c].len;
-        if (slen < lim) { qi.short_contigs++; continue; }                  // pyx:1062-1070
-        if (contigs[c].unit_bytes != 1 && contigs[c].unit_bytes != 2 && contigs[c].unit_bytes != 4) {
-            set_error("unit_bytes must be 1, 2 or 4"); return FA_ERR_INVALID;
-        }
-        if (contigs[c].on_device && contigs[c].unit_bytes != 1) { set_error("device-resident contigs must be bytes"); return FA_ERR_INVALID; }
-        const int64_t nfrag = slen / L;                                      // pyx:1097
-        if (nfrag > 0) {
-            ups.push_back(Upload{contigs[c].data, contigs[c].unit_bytes, contigs[c].on_device, nfrag * L, off});
-            for (int64_t i = 0; i < nfrag; i++) {
-                SeqDesc d;
-                d.off = off + (uint64_t)i * L; d.len = L; d.id = (int32_t)(total_frags + i);
-                d.raw = contigs[c].unit_bytes != 1; d.tile0 = (int32_t)((total_frags + i) * tiles_per_frag);
-                ws.h_seqs.push_back(d);
+    for (uint32_t q = 0; q < B; q++) {
+        for (int32_t c = n_contigs; c < n_contigs + contigs_per_query[q]; c++) {
+            const int64_t slen = contigs[c].len;
+            if (slen < lim) { qi.short_contigs++; continue; }                  // pyx:1062-1070
+            if (contigs[c].unit_bytes != 1 && contigs[c].unit_bytes != 2 && contigs[c].unit_bytes != 4) {
+                set_error("unit_bytes must be 1, 2 or 4"); return FA_ERR_INVALID;
             }
-            off += ((uint64_t)(nfrag * L) + 15) & ~15ull;
+            if (contigs[c].on_device && contigs[c].unit_bytes != 1) { set_error("device-resident contigs must be bytes"); return FA_ERR_INVALID; }
+            const int64_t nfrag = slen / L;                                      // pyx:1097
+            if (nfrag > 0) {
+                ups.push_back(Upload{contigs[c].data, contigs[c].unit_bytes, contigs[c].on_device, nfrag * L, off});
+                for (int64_t i = 0; i < nfrag; i++) {
+                    SeqDesc d;
+                    d.off = off + (uint64_t)i * L; d.len = L; d.id = (int32_t)(total_frags + i);
+                    d.raw = contigs[c].unit_bytes != 1; d.tile0 = (int32_t)((total_frags + i) * tiles_per_frag);
+                    ws.h_seqs.push_back(d);
+                }
+                if (B > 1) ws.h_fragq.insert(ws.h_fragq.end(), (size_t)nfrag, (int32_t)q);
+                off += ((uint64_t)(nfrag * L) + 15) & ~15ull;
+            }
+            total_frags += (uint64_t)nfrag; q_frags[q] += (uint64_t)nfrag;       // pyx:1104
+            q_len[q] += (uint64_t)slen;                                          // pyx:1105
         }
-        total_frags += (uint64_t)nfrag;                                      // pyx:1104
-        total_len += (uint64_t)slen;                                         // pyx:1105
+        n_contigs += contigs_per_query[q];
     }
     const int F = (int)total_frags;
     const uint32_t G = (uint32_t)ix->seqs_by_genome.size();
@@ -1441,11 +1483,18 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
         FA_TRY(ws.qs.reserve(F)); FA_TRY(ws.frag_seeds.reserve((size_t)F + 1));
         FA_TRY(ws.frag_cands.reserve((size_t)F + 1)); FA_TRY(ws.work_base.reserve((size_t)F + 1));
         FA_TRY(ws.counters.reserve(CT_N));
-        if (ws.cells.cap < (ix->n_cells ? ix->n_cells : 1)) {
-            FA_TRY(ws.cells.reserve(ix->n_cells ? ix->n_cells : 1));
+        const uint64_t n_cells = ix->n_cells ? ix->n_cells : 1;
+        if ((uint64_t)B * n_cells > 0xFFFFFFFFull) { set_error("too many queries in one pass"); return FA_ERR_UNSUPPORTED; }
+        if (ws.cells.cap < (size_t)B * n_cells) {
+            FA_TRY(ws.cells.reserve((size_t)B * n_cells));
             FA_CUDA(cudaMemsetAsync(ws.cells.p, 0, ws.cells.cap * sizeof(uint32_t), st));   // kept clean by cgi_sum_kernel afterwards
         }
-        FA_TRY(ws.g_count.reserve(G)); FA_TRY(ws.g_identity.reserve(G));
+        FA_TRY(ws.g_count.reserve((size_t)B * G)); FA_TRY(ws.g_identity.reserve((size_t)B * G));
+        if (B > 1) {
+            FA_TRY(ws.frag_q.reserve(F));
+            FA_CUDA(cudaMemcpyAsync(ws.frag_q.p, ws.h_fragq.data(), (size_t)F * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            qi.h2d_bytes += (uint64_t)F * sizeof(int32_t);
+        }
         FA_CUDA(cudaMemcpyAsync(ws.sk.seqs.p, ws.h_seqs.data(), (size_t)F * sizeof(SeqDesc), cudaMemcpyHostToDevice, st));
         qi.h2d_bytes += (uint64_t)F * sizeof(SeqDesc);
         FA_CUDA(cudaMemsetAsync(ws.counters.p, 0, CT_N * sizeof(unsigned long long), st));
@@ -1466,7 +1515,7 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
                                          ix->uoff.p, ws.hit_start.p, ws.hit_cnt.p, ws.frag_seeds.p);
         FA_CUDA(cudaGetLastError()); launches++;
         FA_TRY(excl_scan<uint64_t>(st, ws.cub_tmp, ws.frag_seeds.p, ws.frag_seeds.p, (int64_t)F + 1, &launches));
-        FA_TRY(ws.hres.reserve(128 + (size_t)G * 8));
+        FA_TRY(ws.hres.reserve(128 + (size_t)B * G * 8));
         FA_TRY(ws.hfs.reserve(((size_t)F + 1) * 16));
         unsigned long long *h_ct = reinterpret_cast<unsigned long long *>(ws.hres.p);
         uint64_t *h_fs = reinterpret_cast<uint64_t *>(ws.hfs.p);              // per-fragment seed prefix (F + 1), then the slow-path prefix
@@ -1646,7 +1695,8 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
                 FA_CUDA(cudaEventRecord(ws.ev[6], st));
                 // ---- CGI ----------------------------------------------------------------------
                 cgi_best_kernel<<<std::min<uint32_t>((uint32_t)((C + 255) / 256), 148u * 8u), 256, 0, st>>>(
-                    ws.cands.p, ws.maps.p, ws.frag_cands.p, F, ix->genome_of_seq.p, ix->bin_base.p, L - 20, ws.cells.p, ws.counters.p);
+                    ws.cands.p, ws.maps.p, ws.frag_cands.p, F, ix->genome_of_seq.p, ix->bin_base.p, L - 20, ws.cells.p,
+                    B > 1 ? ws.frag_q.p : nullptr, (uint32_t)n_cells, ws.counters.p);
                 FA_CUDA(cudaGetLastError()); launches++;
             } else {
                 FA_CUDA(cudaEventRecord(ws.ev[5], st));
@@ -1655,21 +1705,22 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
         } else {
             for (int i = 4; i <= 6; i++) FA_CUDA(cudaEventRecord(ws.ev[i], st));
         }
-        cgi_sum_kernel<<<(G * 32 + 255) / 256, 256, 0, st>>>(ws.cells.p, ix->genome_cell.p, (int)G, ws.g_count.p, ws.g_identity.p);
+        cgi_sum_kernel<<<(B * G * 32 + 255) / 256, 256, 0, st>>>(ws.cells.p, ix->genome_cell.p, (int)G, (int)B, (uint32_t)n_cells,
+                                                                 ws.g_count.p, ws.g_identity.p);
         FA_CUDA(cudaGetLastError()); launches++;
         FA_CUDA(cudaEventRecord(ws.ev[7], st));
         // ---- results back ----------------------------------------------------------------------
         int32_t *h_c = reinterpret_cast<int32_t *>(ws.hres.p + 128);
-        float *h_i = reinterpret_cast<float *>(ws.hres.p + 128 + (size_t)G * 4);
-        FA_CUDA(cudaMemcpyAsync(h_c, ws.g_count.p, (size_t)G * 4, cudaMemcpyDeviceToHost, st));
-        FA_CUDA(cudaMemcpyAsync(h_i, ws.g_identity.p, (size_t)G * 4, cudaMemcpyDeviceToHost, st));
+        float *h_i = reinterpret_cast<float *>(ws.hres.p + 128 + (size_t)B * G * 4);
+        FA_CUDA(cudaMemcpyAsync(h_c, ws.g_count.p, (size_t)B * G * 4, cudaMemcpyDeviceToHost, st));
+        FA_CUDA(cudaMemcpyAsync(h_i, ws.g_identity.p, (size_t)B * G * 4, cudaMemcpyDeviceToHost, st));
         FA_CUDA(cudaMemcpyAsync(h_ct, ws.counters.p, CT_N * 8, cudaMemcpyDeviceToHost, st));
         FA_CUDA(cudaEventRecord(ws.ev[8], st));
         FA_CUDA(cudaStreamSynchronize(st));                                   // sync 3: results
-        qi.d2h_bytes = (uint64_t)G * 8 + CT_N * 8 * 2 + 16;
+        qi.d2h_bytes = (uint64_t)B * G * 8 + CT_N * 8 * 2 + 16;
         qi.candidates = C; qi.scanned = h_ct[CT_SCANNED]; qi.mappings = h_ct[CT_MAPPINGS]; qi.l2_fallback = h_ct[CT_REDO];
         qi.events_replayed = h_ct[CT_REPLAYED];
-        h_count.assign(h_c, h_c + G); h_ident.assign(h_i, h_i + G);
+        h_count.assign(h_c, h_c + (size_t)B * G); h_ident.assign(h_i, h_i + (size_t)B * G);
         ws.last_cands = C; ws.last_frags = (uint64_t)F;
         float ms;
         cudaEventElapsedTime(&ms, ws.ev[0], ws.ev[1]); qi.ms_h2d = ms;
@@ -1688,19 +1739,27 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
         cudaEventElapsedTime(&ms, ws.ev[0], ws.ev[8]); qi.ms_total = ms;
     }
 
-    // ---- hit filter + sort (pyx:1121-1135) ------------------------------------------------------
+    // ---- hit filter + sort (pyx:1121-1135), query by query ----------------------------------------
+    uint64_t used = 0;
     std::vector<fa_hit> hits;
-    for (uint32_t g = 0; g < (uint32_t)h_count.size(); g++) {
-        if (h_count[g] <= 0) continue;
-        const uint64_t ref_len = ix->genome_len[g];
-        const uint64_t min_length = std::min(total_len, ref_len);
-        const uint64_t shared_length = (uint64_t)h_count[g] * (uint64_t)L;
-        if ((float)shared_length >= (float)min_length * P.min_fraction)
-            hits.push_back(fa_hit{(int32_t)g, h_count[g], (int32_t)total_frags, h_ident[g]});
+    for (uint32_t q = 0; q < B; q++) {
+        hits.clear();
+        if (!h_count.empty())
+            for (uint32_t g = 0; g < G; g++) {
+                const int32_t cnt = h_count[(size_t)q * G + g];
+                if (cnt <= 0) continue;
+                const uint64_t ref_len = ix->genome_len[g];
+                const uint64_t min_length = std::min(q_len[q], ref_len);
+                const uint64_t shared_length = (uint64_t)cnt * (uint64_t)L;
+                if ((float)shared_length >= (float)min_length * P.min_fraction)
+                    hits.push_back(fa_hit{(int32_t)g, cnt, (int32_t)q_frags[q], h_ident[(size_t)q * G + g]});
+            }
+        std::stable_sort(hits.begin(), hits.end(), [](const fa_hit &a, const fa_hit &b) { return a.identity > b.identity; });
+        for (size_t i = 0; i < hits.size(); i++)
+            if (out && used + i < cap) out[used + i] = hits[i];
+        used += hits.size();
+        hit_offsets[q + 1] = used;
     }
-    std::stable_sort(hits.begin(), hits.end(), [](const fa_hit &a, const fa_hit &b) { return a.identity > b.identity; });
-    *n_out = hits.size();
-    for (size_t i = 0; i < hits.size() && i < cap; i++) out[i] = hits[i];
     qi.kernel_launches = launches;
     if (info) *info = qi;
     return FA_OK;

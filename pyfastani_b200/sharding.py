@@ -88,13 +88,18 @@ def merge_hits(rows_per_rank, offsets):
     return allrows[order]
 
 
-def gather_hits(rows_per_query, group=None, device=None):
+def gather_hits(rows_per_query, group=None, device=None, cap=None):
     """All-gather the hit rows of a list of queries.
 
     `rows_per_query`: list (same length on every rank) of HIT_DT arrays with LOCAL genome ids.
-    Returns `out[q][r]` = rows of query q from rank r.  Two collectives for the whole list: the
-    per-query counts, then one padded payload of 16-byte rows -- a few KB per query, latency-bound
-    on NVLink, nothing to fuse with the mapping kernels.
+    Returns `out[q][r]` = rows of query q from rank r.
+
+    `cap`: an upper bound, known on every rank, of the rows one rank can hold for the whole list
+    (queries x genomes of the largest shard).  With it the exchange is ONE collective of a fixed-width
+    block per rank -- the per-query counts followed by the 16-byte rows -- and one device-to-host copy;
+    without it (or when the block would pass 4 MiB) two collectives: the counts, then a payload padded
+    to the largest total.  A few KB per query either way: latency-bound on NVLink, nothing to fuse with
+    the mapping kernels.
     """
     import torch
     import torch.distributed as dist
@@ -102,18 +107,39 @@ def gather_hits(rows_per_query, group=None, device=None):
     world = dist.get_world_size(group)
     nq = len(rows_per_query)
     dev = device if device is not None else torch.device("cpu")
+    mine = np.concatenate([np.asarray(r, dtype=HIT_DT) for r in rows_per_query]) if nq else np.zeros(0, dtype=HIT_DT)
+    out = [[None] * world for _ in range(nq)]
+
+    if cap is not None and len(mine) > cap:
+        raise ValueError("gather_hits: %d rows on this rank exceed cap=%d (cap must bound every rank)" % (len(mine), cap))
+    if cap is not None and (nq + 4 * cap) * 4 <= (4 << 20):         # (the same decision on every rank)
+        width = nq + 4 * int(cap)
+        block = np.zeros(width, dtype=np.int32)
+        block[:nq] = [len(r) for r in rows_per_query]
+        block[nq:nq + 4 * len(mine)] = mine.view(np.int32)
+        send = torch.from_numpy(block).to(dev)
+        recv = torch.empty(world * width, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(recv, send, group=group)
+        host = recv.cpu().numpy().reshape(world, width)
+        for r in range(world):
+            cnt = host[r, :nq]
+            rows = host[r, nq:nq + 4 * int(cnt.sum())].copy().view(HIT_DT)
+            pos = 0
+            for q in range(nq):
+                out[q][r] = rows[pos:pos + int(cnt[q])]
+                pos += int(cnt[q])
+        return out
+
     counts = torch.tensor([len(r) for r in rows_per_query], dtype=torch.int64, device=dev)
     all_counts = [torch.zeros_like(counts) for _ in range(world)]
     dist.all_gather(all_counts, counts, group=group)
     totals = [int(c.sum().item()) for c in all_counts]
     width = max(max(totals), 1)
     flat = np.zeros(width, dtype=HIT_DT)
-    mine = np.concatenate([np.asarray(r, dtype=HIT_DT) for r in rows_per_query]) if nq else np.zeros(0, dtype=HIT_DT)
     flat[:len(mine)] = mine
     payload = torch.from_numpy(flat.view(np.int32).reshape(width, 4).copy()).to(dev)
     all_payload = [torch.zeros_like(payload) for _ in range(world)]
     dist.all_gather(all_payload, payload, group=group)
-    out = [[None] * world for _ in range(nq)]
     for r in range(world):
         rows = all_payload[r].cpu().numpy().reshape(-1).view(HIT_DT)
         cnt = all_counts[r].cpu().numpy()
@@ -133,5 +159,6 @@ def query_reference_sharded(mapper, queries, offsets, group=None, device=None, d
     for q in queries:
         hits = mapper.query_draft(q) if drafts else mapper.query_genome(q)
         local.append(hits_to_rows(hits, name_to_id))
-    gathered = gather_hits(local, group=group, device=device)
+    shard = max(int(offsets[r + 1]) - int(offsets[r]) for r in range(len(offsets) - 1))
+    gathered = gather_hits(local, group=group, device=device, cap=len(local) * shard)
     return [merge_hits(per_rank, offsets) for per_rank in gathered]

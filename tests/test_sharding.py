@@ -80,8 +80,14 @@ def _gloo_worker(rank, world, port, out_dir):
             rows["fragments"] = 100 + q
             rows["identity"] = np.sort(rng.uniform(80, 100, n).astype(np.float32))[::-1]
             local.append(rows)
-        gathered = sharding.gather_hits(local)
+        gathered = sharding.gather_hits(local)                       # two collectives: counts, padded payload
         merged = [sharding.merge_hits(per_rank, [0, 3, 4]) for per_rank in gathered]
+        with pytest.raises(ValueError):
+            sharding.gather_hits(local, cap=-1)                      # a bound below the rows held: refused before any collective
+        one = sharding.gather_hits(local, cap=3 * 3)                 # one fixed-width collective (3 queries x 3 genomes)
+        for q in range(3):
+            for r in range(world):
+                assert np.array_equal(one[q][r], gathered[q][r]), (q, r)
         np.savez(os.path.join(out_dir, "rank%d.npz" % rank), *merged, **{"local%d" % q: local[q] for q in range(3)})
     finally:
         dist.destroy_process_group()
