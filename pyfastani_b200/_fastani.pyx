@@ -734,6 +734,11 @@ cdef class Mapper(_Parameterized):
                 "fragments": info.fragments, "seeds": info.seeds, "candidates": info.candidates, "mappings": info.mappings,
                 "kernel_launches": info.kernel_launches, "ms_total": info.ms_total, "h2d_bytes": info.h2d_bytes,
                 "d2h_bytes": info.d2h_bytes, "events": info.events, "events_replayed": info.events_replayed, "queries": nq,
+                "ms_h2d": info.ms_h2d, "ms_sketch": info.ms_sketch, "ms_lookup": info.ms_lookup,
+                "ms_seed_sort": info.ms_seed_sort, "ms_l1": info.ms_l1, "ms_l2": info.ms_l2, "ms_cgi": info.ms_cgi,
+                "ms_d2h": info.ms_d2h, "ms_l2_prep": info.ms_l2_prep, "ms_l2_events": info.ms_l2_events,
+                "ms_l2_slide": info.ms_l2_slide, "l1_small_fragments": info.l1_small_fragments,
+                "l1_sorted_fragments": info.l1_sorted_fragments,
             }
         finally:
             free(counts)

@@ -143,7 +143,7 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
                 uint64_t cap, uint64_t *hit_offsets, fa_query_info *info, Prefetch *pf = nullptr);
 // shared by the sketch and query paths: narrow/copy the uploads into the batch byte buffer
 int stage_sequences(cudaStream_t st, DevBuf<uint8_t> &bytes, PinBuf &stage, const std::vector<Upload> &ups, uint64_t total,
-                    uint64_t *h2d_bytes);
+                    uint64_t *h2d_bytes, int workers = 0);
 int debug_candidates(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n);
 int debug_mappings(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n);
 }

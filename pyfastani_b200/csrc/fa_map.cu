@@ -19,7 +19,10 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <memory>
+#include <thread>
 
 #include "fa_internal.cuh"
 
@@ -1278,18 +1281,47 @@ int excl_scan(cudaStream_t st, DevBuf<uint8_t> &tmp, const T *in, T *out, int64_
     return FA_OK;
 }
 
+// Device-resident contigs of a draft (hundreds per query) into the batch buffer with ONE launch instead of one
+// cudaMemcpyAsync each: thread t owns the 16 bytes at 16 t; uploads start at ascending 16-byte aligned offsets.
+struct DevCopy { const uint8_t *src; uint64_t off; int64_t len; };
+__global__ void gather_contigs_kernel(const DevCopy *tab, int n, uint8_t *dst, uint64_t n_chunks)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_chunks) return;
+    const uint64_t c = t * 16;
+    int lo = 0, hi = n - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (tab[mid].off <= c) lo = mid; else hi = mid - 1; }
+    const DevCopy d = tab[lo];
+    if (c < d.off) return;
+    const int64_t rel = (int64_t)(c - d.off);
+    if (rel >= d.len) return;                                // padding between two uploads
+    const uint8_t *sp = d.src + rel;
+    if (d.len - rel >= 16 && ((uintptr_t)sp & 15) == 0) *reinterpret_cast<uint4 *>(dst + c) = *reinterpret_cast<const uint4 *>(sp);
+    else {
+        const int m = (int)min((int64_t)16, d.len - rel);
+        for (int i = 0; i < m; i++) dst[c + i] = sp[i];
+    }
+}
+
 inline int bits_for(uint64_t n) { int b = 1; while (b < 63 && (1ull << b) < n) b++; return b; }
 
 }  // namespace
 
 // Narrow / copy the uploads into the pinned staging buffer (host sources), then H2D copies and one D2D per
 // device-resident source.  The staged bytes leave in pieces of about 1 MiB, so the copy engine works on one piece
-// while the host fills the next.  (Helper threads sharing the host copy of a lone 5 MB query were tried: spawning them
-// costs more than the 0.3 ms they save.)
+// while the host fills the next.  `workers` > 0: that many helper threads fill the pieces and this thread only issues
+// the copies, in order, as pieces complete -- used when a whole pass of fa_query_batch (tens of MB) is staged ahead;
+// for a lone 5 MB query spawning the threads costs more than the 0.3 ms they save.
 int stage_sequences(cudaStream_t st, DevBuf<uint8_t> &bytes, PinBuf &stage, const std::vector<Upload> &ups, uint64_t total,
-                    uint64_t *h2d_bytes)
+                    uint64_t *h2d_bytes, int workers)
 {
-    FA_TRY(bytes.reserve(total + 64));
+    // device-resident sources: more than a few go through one gather launch, its table behind the bytes
+    std::vector<DevCopy> dcopy;
+    for (const Upload &u : ups)
+        if (u.on_device && u.len > 0) dcopy.push_back(DevCopy{(const uint8_t *)u.ptr, u.off, u.len});
+    const bool gather = dcopy.size() > 4;
+    const uint64_t tab_off = (total + 64 + 15) & ~15ull, tab_bytes = gather ? dcopy.size() * sizeof(DevCopy) : 0;
+    FA_TRY(bytes.reserve(tab_off + tab_bytes));
     struct Piece { const Upload *u; int64_t o, n; };
     std::vector<Piece> pieces;
     const int64_t piece = 1ll << 20;
@@ -1297,8 +1329,8 @@ int stage_sequences(cudaStream_t st, DevBuf<uint8_t> &bytes, PinBuf &stage, cons
         if (u.on_device || u.len <= 0) continue;
         for (int64_t o = 0; o < u.len; o += piece) pieces.push_back(Piece{&u, o, std::min<int64_t>(piece, u.len - o)});
     }
+    if (!pieces.empty() || gather) FA_TRY(stage.reserve(tab_off + tab_bytes));
     if (!pieces.empty()) {
-        FA_TRY(stage.reserve(total + 64));
         uint8_t *const sp = stage.p;
         auto fill = [sp](const Piece &pc) {
             const Upload &u = *pc.u;
@@ -1320,17 +1352,47 @@ int stage_sequences(cudaStream_t st, DevBuf<uint8_t> &bytes, PinBuf &stage, cons
             sent = std::max(sent, upto);
             return FA_OK;
         };
-        for (const Piece &pc : pieces) {
-            fill(pc);
-            const uint64_t end = pc.u->off + (uint64_t)(pc.o + pc.n);
-            if (end - sent >= (uint64_t)piece) FA_TRY(flush(end));
+        const size_t np = pieces.size();
+        const int nw = np >= 16 ? std::min<int>(workers, 8) : 0;
+        std::vector<std::thread> pool;
+        std::unique_ptr<std::atomic<int>[]> ready;
+        std::atomic<size_t> next{0};
+        if (nw > 0) {
+            ready.reset(new std::atomic<int>[np]);
+            for (size_t i = 0; i < np; i++) ready[i].store(0, std::memory_order_relaxed);
+            for (int t = 0; t < nw; t++)
+                pool.emplace_back([&]() {
+                    for (;;) {
+                        const size_t i = next.fetch_add(1, std::memory_order_relaxed);
+                        if (i >= np) break;
+                        fill(pieces[i]);
+                        ready[i].store(1, std::memory_order_release);
+                    }
+                });
         }
+        int rc = FA_OK;
+        for (size_t i = 0; i < np; i++) {
+            if (nw > 0) { while (!ready[i].load(std::memory_order_acquire)) std::this_thread::yield(); }
+            else fill(pieces[i]);
+            const uint64_t end = pieces[i].u->off + (uint64_t)(pieces[i].o + pieces[i].n);
+            if (rc == FA_OK && end - sent >= (uint64_t)piece) rc = flush(end);       // (keep draining the workers after an error)
+        }
+        for (auto &t : pool) t.join();
+        FA_TRY(rc);
         FA_TRY(flush(total));
         if (h2d_bytes) *h2d_bytes += total;
     }
-    for (const Upload &u : ups)
-        if (u.on_device && u.len > 0)
-            FA_CUDA(cudaMemcpyAsync(bytes.p + u.off, u.ptr, (size_t)u.len, cudaMemcpyDeviceToDevice, st));
+    if (gather) {
+        memcpy(stage.p + tab_off, dcopy.data(), (size_t)tab_bytes);
+        FA_CUDA(cudaMemcpyAsync(bytes.p + tab_off, stage.p + tab_off, (size_t)tab_bytes, cudaMemcpyHostToDevice, st));
+        const uint64_t n_chunks = (total + 15) / 16;
+        gather_contigs_kernel<<<(unsigned int)((n_chunks + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const DevCopy *>(bytes.p + tab_off), (int)dcopy.size(), bytes.p, n_chunks);
+        FA_CUDA(cudaGetLastError());
+    } else {
+        for (const DevCopy &d : dcopy)
+            FA_CUDA(cudaMemcpyAsync(bytes.p + d.off, d.src, (size_t)d.len, cudaMemcpyDeviceToDevice, st));
+    }
     return FA_OK;
 }
 
@@ -1380,7 +1442,7 @@ int prefetch_query(fa_index *ix, Prefetch &pf, const fa_contig *contigs, int32_t
     plan_uploads(ix->prm, contigs, n_contigs, ups, &total);
     if (!total) return FA_OK;
     pf.h2d_bytes = 0;
-    FA_TRY(stage_sequences(pf.st, pf.bytes, pf.stage, ups, total, &pf.h2d_bytes));
+    FA_TRY(stage_sequences(pf.st, pf.bytes, pf.stage, ups, total, &pf.h2d_bytes, 3));
     FA_CUDA(cudaEventRecord(pf.done, pf.st));
     pf.contigs = contigs; pf.n_contigs = n_contigs; pf.total = total;
     pf.valid = true;

@@ -155,10 +155,11 @@ def query_reference_sharded(mapper, queries, offsets, group=None, device=None, d
     global hit rows per query.  `mapper.names` must be the LOCAL genome ids 0..n_local-1 (or any
     names whose position in `mapper.names` is the local id)."""
     name_to_id = {n: i for i, n in enumerate(mapper.names)}
-    local = []
-    for q in queries:
-        hits = mapper.query_draft(q) if drafts else mapper.query_genome(q)
-        local.append(hits_to_rows(hits, name_to_id))
+    # one call for the whole list: light queries share passes of the pipeline and the next pass is staged while the
+    # current one is mapped (fa_query_batch)
+    queries = list(queries)
+    items = [list(q) for q in queries] if drafts else queries
+    local = [hits_to_rows(hits, name_to_id) for hits in mapper.query_many(items)]
     shard = max(int(offsets[r + 1]) - int(offsets[r]) for r in range(len(offsets) - 1))
     gathered = gather_hits(local, group=group, device=device, cap=len(local) * shard)
     return [merge_hits(per_rank, offsets) for per_rank in gathered]

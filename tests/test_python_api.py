@@ -188,6 +188,29 @@ def test_query_many_equals_single_queries(pf):
         mapper.query_many(queries, threads=-1)
 
 
+def test_device_resident_drafts(pf):
+    """Drafts whose contigs already live in HBM (`DeviceSequence`): more than a handful go through one gather launch
+    instead of one copy each -- odd lengths, a contig shorter than a fragment, a host contig in between -- as
+    references (`add_draft`) and as queries (`query_draft`, `query_many`); results equal the host-bytes path."""
+    import synth
+    q, refs, _ = synth.one_to_many(123, 4, 150_000, lo=0.86, hi=0.99)
+    rng = np.random.default_rng(8)
+    drafts = [synth.fragment(rng, r, 11, min_end=300) for r in refs]
+    qd = synth.fragment(rng, q, 13, min_end=300) + [b"ACGTTGCA" * 20]
+    host, devs = pf.Sketch(), pf.Sketch()
+    for i, d in enumerate(drafts):
+        host.add_draft(i, d)
+        devs.add_draft(i, [pf.DeviceSequence.from_host(c) if j != 3 else c for j, c in enumerate(d)])
+    assert devs.minimizers.__getstate__() == host.minimizers.__getstate__()
+    mh, md = host.index(), devs.index()
+    qdev = [pf.DeviceSequence.from_host(c) if j != 5 else c for j, c in enumerate(qd)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = mh.query_draft(qd)
+        assert md.query_draft(qdev) == want and len(want) == 4
+        assert md.query_many([qdev, qd, qdev[:6], qdev]) == [want, want, mh.query_draft(qd[:6]), want]
+
+
 def test_protein_mode(pf):                                   # test_ani.py:96-115
     """Sketch(protein=True): alphabet 20, window 1; the reference's MIBiG cluster test and pickling."""
     gold = golden_io.protein_golden()[0]["bgc"]

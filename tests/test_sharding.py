@@ -137,3 +137,30 @@ def test_reference_sharding_equals_single_index():
         got = sharding.merge_hits(per_rank, off)
         assert np.array_equal(got, want)
     assert len(want) == 9
+
+
+@pytest.mark.gpu
+def test_query_reference_sharded_world1(tmp_path):
+    """`query_reference_sharded` end to end on one rank (a gloo group of one): the list of queries goes through one
+    `query_many` call, the rows through the one-collective gather, and come back as the rows of plain queries."""
+    import torch.distributed as dist
+    import pyfastani_b200 as pf
+    import synth
+
+    query, refs, _ = synth.one_to_many(78, 7, 90_000, lo=0.85, hi=0.99)
+    sk = pf.Sketch()
+    for i, r in enumerate(refs):
+        sk.add_genome(i, r)
+    mapper = sk.index()
+    queries = [query, refs[2], synth.revcomp(refs[5]), b"ACGT" * 10]
+    ident = {i: i for i in range(len(refs))}
+    want = [sharding.hits_to_rows(mapper.query_genome(q), ident) for q in queries]
+    dist.init_process_group("gloo", init_method="file://" + str(tmp_path / "rdv"), rank=0, world_size=1)
+    try:
+        got = sharding.query_reference_sharded(mapper, queries, [0, len(refs)])
+    finally:
+        dist.destroy_process_group()
+    assert len(got) == len(queries)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    assert len(want[0]) == 7 and len(want[3]) == 0
