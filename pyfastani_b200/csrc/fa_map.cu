@@ -390,15 +390,44 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
     if (tid == 0) { s_blk = 0u; s_cvalid = 0; s_cj = 0u; s_cg = 0u; }
     __syncthreads();
 
+    // The small shape serves fragments whose position lists hold a handful of entries each (a hash occurs once per
+    // related genome): a warp per list would leave most lanes idle and walk ~30 lists one DRAM round trip after the
+    // other.  There the hits are numbered through all lists instead -- s_lcnt becomes the exclusive prefix of the
+    // list lengths -- and thread t fetches hit t, t + THREADS, ...: every load of a phase is in flight at once.
+    constexpr bool FLAT = L1_THREADS <= 256;
+    auto flat_hit = [&](uint32_t t) -> uint32_t {             // the reference index of hit t
+        int lo = 0, hi = s - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_lcnt[mid] <= t) lo = mid; else hi = mid - 1; }
+        return __ldg(pos_idx + s_lst[lo] + (t - s_lcnt[lo]));
+    };
+    if (FLAT) {
+        const int per = (s + L1_THREADS - 1) / L1_THREADS;
+        const int i0 = min(tid * per, s), i1 = min(i0 + per, s);
+        uint32_t sum = 0;
+        for (int i = i0; i < i1; i++) sum += s_lcnt[i];
+        uint32_t tot, x = block_excl_scan<L1_THREADS>(sum, s_warp, &tot);
+        for (int i = i0; i < i1; i++) { const uint32_t v = s_lcnt[i]; s_lcnt[i] = x; x += v; }
+        __syncthreads();
+    }
     // ---- A: histogram over chunks ------------------------------------------------------------
-    for (int q = wid; q < s; q += L1_THREADS / 32) {
-        const uint32_t st = s_lst[q], c = s_lcnt[q];
-        for (uint32_t t0 = 0; t0 < c; t0 += 128) {
+    if (FLAT) {
+        for (uint32_t t0 = tid; t0 < n; t0 += 4 * L1_THREADS) {
             uint32_t v[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) { const uint32_t t = t0 + u * 32 + lane; v[u] = t < c ? __ldg(pos_idx + st + t) : 0xFFFFFFFFu; }
+            for (int u = 0; u < 4; u++) { const uint32_t t = t0 + u * L1_THREADS; v[u] = t < n ? flat_hit(t) : 0xFFFFFFFFu; }
 #pragma unroll
             for (int u = 0; u < 4; u++) if (v[u] != 0xFFFFFFFFu) atomicAdd(&hist[v[u] >> L1_SHIFT], 1u);
+        }
+    } else {
+        for (int q = wid; q < s; q += L1_THREADS / 32) {
+            const uint32_t st = s_lst[q], c = s_lcnt[q];
+            for (uint32_t t0 = 0; t0 < c; t0 += 128) {
+                uint32_t v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) { const uint32_t t = t0 + u * 32 + lane; v[u] = t < c ? __ldg(pos_idx + st + t) : 0xFFFFFFFFu; }
+#pragma unroll
+                for (int u = 0; u < 4; u++) if (v[u] != 0xFFFFFFFFu) atomicAdd(&hist[v[u] >> L1_SHIFT], 1u);
+            }
         }
     }
     __syncthreads();
@@ -413,15 +442,26 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
     }
     __syncthreads();
     // ---- B: scatter the low 16 bits into chunk order; afterwards hist[c] = end of bucket c -------
-    for (int q = wid; q < s; q += L1_THREADS / 32) {
-        const uint32_t st = s_lst[q], c = s_lcnt[q];
-        for (uint32_t t0 = 0; t0 < c; t0 += 128) {
+    if (FLAT) {
+        for (uint32_t t0 = tid; t0 < n; t0 += 4 * L1_THREADS) {
             uint32_t v[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) { const uint32_t t = t0 + u * 32 + lane; v[u] = t < c ? __ldg(pos_idx + st + t) : 0xFFFFFFFFu; }
+            for (int u = 0; u < 4; u++) { const uint32_t t = t0 + u * L1_THREADS; v[u] = t < n ? flat_hit(t) : 0xFFFFFFFFu; }
 #pragma unroll
             for (int u = 0; u < 4; u++)
                 if (v[u] != 0xFFFFFFFFu) { const uint32_t slot = atomicAdd(&hist[v[u] >> L1_SHIFT], 1u); keys[slot] = (uint16_t)v[u]; }
+        }
+    } else {
+        for (int q = wid; q < s; q += L1_THREADS / 32) {
+            const uint32_t st = s_lst[q], c = s_lcnt[q];
+            for (uint32_t t0 = 0; t0 < c; t0 += 128) {
+                uint32_t v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) { const uint32_t t = t0 + u * 32 + lane; v[u] = t < c ? __ldg(pos_idx + st + t) : 0xFFFFFFFFu; }
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (v[u] != 0xFFFFFFFFu) { const uint32_t slot = atomicAdd(&hist[v[u] >> L1_SHIFT], 1u); keys[slot] = (uint16_t)v[u]; }
+            }
         }
     }
     __syncthreads();

@@ -67,10 +67,15 @@ def reference_shards(genome_lengths, world_size):
 
 
 def hits_to_rows(hits, name_to_id):
-    """Hit objects of one query -> HIT_DT rows with local genome ids."""
-    rows = np.zeros(len(hits), dtype=HIT_DT)
-    for i, h in enumerate(hits):
-        rows[i] = (name_to_id[h.name], h.matches, h.fragments, h.identity)
+    """Hit objects of one query -> HIT_DT rows with local genome ids (column by column: a structured
+    assignment per hit costs 2 us, which is a millisecond per query against a 500-genome shard)."""
+    n = len(hits)
+    rows = np.zeros(n, dtype=HIT_DT)
+    if n:
+        rows["ref_genome"] = np.fromiter((name_to_id[h.name] for h in hits), dtype=np.int32, count=n)
+        rows["matches"] = np.fromiter((h.matches for h in hits), dtype=np.int32, count=n)
+        rows["fragments"] = np.fromiter((h.fragments for h in hits), dtype=np.int32, count=n)
+        rows["identity"] = np.fromiter((h.identity for h in hits), dtype=np.float32, count=n)
     return rows
 
 
