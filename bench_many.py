@@ -117,8 +117,10 @@ def main():
     if a.profile:
         torch.cuda.synchronize(dev)
         torch.cuda.profiler.start()
-        for q in dq[4:4 + a.profile]:
-            one(q)
+        if a.profile == 1:
+            one(dq[4])
+        else:               # one query_many call: a pass of one query, then shared passes
+            mapper.query_many([q if a.drafts else q[0] for q in dq[4:4 + a.profile]])
         torch.cuda.synchronize(dev)
         torch.cuda.profiler.stop()
         return

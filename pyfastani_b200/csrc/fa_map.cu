@@ -372,7 +372,7 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
     uint16_t *blk_chunk = keys + key_cap;                                    // chunk holding sorted hit 32 * q
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_valid[L1_TILE / 32], s_head[L1_TILE / 32], s_hpre[L1_TILE / 32 + 1];
-    __shared__ uint32_t s_blk, s_cj, s_cg;
+    __shared__ uint32_t s_blk, s_nlist, s_cj, s_cg;
     __shared__ int s_cvalid;
 
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -387,7 +387,7 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
 
     for (uint32_t i = tid; i <= n_chunks; i += L1_THREADS) hist[i] = 0u;
     for (int q = tid; q < s; q += L1_THREADS) { s_lst[q] = hit_start[qb + q]; s_lcnt[q] = hit_cnt[qb + q]; }
-    if (tid == 0) { s_blk = 0u; s_cvalid = 0; s_cj = 0u; s_cg = 0u; }
+    if (tid == 0) { s_blk = 0u; s_nlist = 0u; s_cvalid = 0; s_cj = 0u; s_cg = 0u; }
     __syncthreads();
 
     // The small shape serves fragments whose position lists hold a handful of entries each (a hash occurs once per
@@ -465,21 +465,47 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
         }
     }
     __syncthreads();
-    // ---- C: sort the buckets (warps take blocks of 32 chunks) ----------------------------------
-    for (;;) {
-        uint32_t blk = 0;
-        if (lane == 0) blk = atomicAdd(&s_blk, 1u);
-        blk = __shfl_sync(0xFFFFFFFFu, blk, 0);
-        const uint32_t c = blk * 32u + (uint32_t)lane;
-        if (blk * 32u >= n_chunks) break;
-        uint32_t b0 = 0, sz = 0;
-        if (c < n_chunks) { b0 = c ? hist[c - 1] : 0u; sz = hist[c] - b0; }
-        for (uint32_t t0 = (b0 + 31u) & ~31u; t0 < b0 + sz; t0 += 32u) blk_chunk[t0 >> 5] = (uint16_t)c;
-        unsigned todo = __ballot_sync(0xFFFFFFFFu, sz >= 2u);
-        while (todo) {
-            const int l = __ffs(todo) - 1;
-            todo &= todo - 1u;
-            l1_sort_bucket(keys + __shfl_sync(0xFFFFFFFFu, b0, l), (int)__shfl_sync(0xFFFFFFFFu, sz, l), s_bm + wid * (2 * L1_BM), lane);
+    // ---- C: sort the buckets ------------------------------------------------------------------------
+    if (FLAT) {
+        // The hits of a many-to-many fragment sit in a few dozen chunks next to each other (the genomes of its genus):
+        // blocks of 32 chunks would hand all of them to two or three warps.  The buckets that need sorting are listed
+        // first (s_g is free since phase B) and the warps take them one by one.
+        uint32_t *list = s_g;
+        for (uint32_t c = tid; c < n_chunks; c += L1_THREADS) {
+            const uint32_t b0 = c ? hist[c - 1] : 0u, sz = hist[c] - b0;
+            for (uint32_t t0 = (b0 + 31u) & ~31u; t0 < b0 + sz; t0 += 32u) blk_chunk[t0 >> 5] = (uint16_t)c;
+            if (sz >= 2u) { const uint32_t i = atomicAdd(&s_nlist, 1u); if (i < (uint32_t)L1_STAGE) list[i] = c; }
+        }
+        __syncthreads();
+        const uint32_t n_list = s_nlist;
+        if (n_list <= (uint32_t)L1_STAGE) {
+            for (;;) {
+                uint32_t i = 0;
+                if (lane == 0) i = atomicAdd(&s_blk, 1u);
+                i = __shfl_sync(0xFFFFFFFFu, i, 0);
+                if (i >= n_list) break;
+                const uint32_t c = list[i];
+                const uint32_t b0 = c ? hist[c - 1] : 0u;
+                l1_sort_bucket(keys + b0, (int)(hist[c] - b0), s_bm + wid * (2 * L1_BM), lane);
+            }
+        }
+    }
+    if (!FLAT || s_nlist > (uint32_t)L1_STAGE) {            // (the list overflowed: blocks of 32 chunks, as in the large shape)
+        for (;;) {
+            uint32_t blk = 0;
+            if (lane == 0) blk = atomicAdd(&s_blk, 1u);
+            blk = __shfl_sync(0xFFFFFFFFu, blk, 0);
+            const uint32_t c = blk * 32u + (uint32_t)lane;
+            if (blk * 32u >= n_chunks) break;
+            uint32_t b0 = 0, sz = 0;
+            if (c < n_chunks) { b0 = c ? hist[c - 1] : 0u; sz = hist[c] - b0; }
+            for (uint32_t t0 = (b0 + 31u) & ~31u; t0 < b0 + sz; t0 += 32u) blk_chunk[t0 >> 5] = (uint16_t)c;
+            unsigned todo = __ballot_sync(0xFFFFFFFFu, sz >= 2u);
+            while (todo) {
+                const int l = __ffs(todo) - 1;
+                todo &= todo - 1u;
+                l1_sort_bucket(keys + __shfl_sync(0xFFFFFFFFu, b0, l), (int)__shfl_sync(0xFFFFFFFFu, sz, l), s_bm + wid * (2 * L1_BM), lane);
+            }
         }
     }
     __syncthreads();
