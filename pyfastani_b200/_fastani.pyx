@@ -649,12 +649,7 @@ cdef class Mapper(_Parameterized):
                     UserWarning,
                 )
             for i in range(min(n_out, cap)):
-                hits.append(Hit(
-                    name=self._names[out[i].ref_genome],
-                    identity=out[i].identity,
-                    matches=out[i].matches,
-                    fragments=out[i].fragments,
-                ))
+                hits.append(_make_hit(self._names[out[i].ref_genome], out[i].identity, out[i].matches, out[i].fragments))
             self.last_query_info = {
                 "fragments": info.fragments, "sketch_sum": info.sketch_sum, "seeds": info.seeds,
                 "candidates": info.candidates, "scanned": info.scanned, "mappings": info.mappings,
@@ -723,12 +718,7 @@ cdef class Mapper(_Parameterized):
             for q in range(nq):
                 hits = []
                 for i in range(offs[q], offs[q + 1]):
-                    hits.append(Hit(
-                        name=self._names[out[i].ref_genome],
-                        identity=out[i].identity,
-                        matches=out[i].matches,
-                        fragments=out[i].fragments,
-                    ))
+                    hits.append(_make_hit(self._names[out[i].ref_genome], out[i].identity, out[i].matches, out[i].fragments))
                 result.append(hits)
             self.last_query_info = {
                 "fragments": info.fragments, "seeds": info.seeds, "candidates": info.candidates, "mappings": info.mappings,
@@ -996,3 +986,14 @@ cdef class MinimizerIndex:
     def items(self):
         for key in self._keys():
             yield key, self[key]
+
+
+cdef inline Hit _make_hit(object name, float identity, int matches, int fragments):
+    """A `Hit` without the keyword-argument call of `Hit.__init__` (a query against a thousand genomes builds a
+    thousand of them inside the timed path)."""
+    cdef Hit h = Hit.__new__(Hit)
+    h.name = name
+    h.identity = identity
+    h.matches = matches
+    h.fragments = fragments
+    return h
