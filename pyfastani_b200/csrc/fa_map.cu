@@ -270,7 +270,9 @@ candidates_kernel(const uint64_t *seeds, const uint64_t *seed_base, const int32_
 // thousand (many-to-many workloads: several CTAs per SM hide each other's barriers and gathers).
 constexpr int L1L_THREADS = 1024, L1L_TILE = 4096;     // the large shape
 constexpr int L1S_THREADS = 256, L1S_TILE = 1024;      // the small shape
-constexpr size_t L1S_SMEM = 54 * 1024;                 // its shared memory per CTA: four CTAs per SM
+// its shared memory per CTA: four CTAs per SM; three or two when the chunk histogram of a large index (4 B per 2^16
+// reference minimizers: 46 KB for 2 000 genomes) leaves no room for the hits otherwise
+constexpr size_t L1S_SMEM[3] = {54 * 1024, 72 * 1024, 110 * 1024};
 constexpr int L1_SHIFT = 16;
 constexpr int L1_BM = 32;                     // bitmap words per warp in phase C (+ as many prefix words)
 // look-ahead of the pair test: minHits - 1 <= THREADS; staged hits per tile = TILE + THREADS (also holds the s position lists)
@@ -1677,8 +1679,10 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
             // minHits fit its staging area); it is not used when hardly any fragment qualifies
             const size_t l1s_fixed = l1_fixed_smem(n_chunks, l1_stage(L1S_THREADS, L1S_TILE));
             uint64_t small_cap = 0;
-            if (l1s_fixed + 1024 < L1S_SMEM && ix->max_min_hits - 1 <= L1S_THREADS && max_s <= l1_stage(L1S_THREADS, L1S_TILE))
-                small_cap = std::min<uint64_t>(seed_cap, ((L1S_SMEM - l1s_fixed - 128) * 16 / 33) & ~31ull);
+            size_t l1s_smem = 0;
+            for (size_t b : L1S_SMEM) if (!l1s_smem && l1s_fixed + 8 * 1024 <= b) l1s_smem = b;
+            if (l1s_smem && ix->max_min_hits - 1 <= L1S_THREADS && max_s <= l1_stage(L1S_THREADS, L1S_TILE))
+                small_cap = std::min<uint64_t>(seed_cap, ((l1s_smem - l1s_fixed - 128) * 16 / 33) & ~31ull);
             if (ix->l1_small_cap >= 0) small_cap = std::min<uint64_t>(small_cap, (uint64_t)ix->l1_small_cap);
             uint64_t max_fast = 0, max_small = 0, S_slow = 0;
             uint32_t n_slow = 0, n_small = 0;
