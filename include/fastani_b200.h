@@ -90,6 +90,7 @@ typedef struct fa_query_info {
     uint32_t l1_sorted_fragments;                     /* fragments whose seeds took the device-wide radix sort instead of the on-chip L1 */
     uint32_t l1_small_fragments;                      /* of the on-chip ones: fragments mapped by the small shape of the L1 kernel (256 threads, several CTAs per SM) */
     uint64_t events_replayed;  /* events the slide kernel went through before its early stop (<= events) */
+    float    ms_batch;         /* ONE event pair around the whole call on the library's stream (fa_query: == ms_total) */
 } fa_query_info;
 
 typedef struct fa_sketch fa_sketch;   /* skch::Sketch under construction (pyx:465-470) */
@@ -106,6 +107,11 @@ FA_API int fa_recommended_window(const fa_params *p, int32_t *w_out);
  * filter of Map::doL2Mapping (computeMap.hpp:371-380); exported for the parity tests. */
 FA_API int fa_stat_minimum_hits(int32_t s, int32_t k, float pct_identity, int32_t *out);
 FA_API int fa_stat_l2(int32_t shared, int32_t s, int32_t k, float pct_identity, float *identity, int32_t *pass);
+/* The row the device kernels read for sketch size s (tabulated once per (k, identity), csrc/fa_stat.cpp): minHits of
+ * computeMap.hpp:312-313 and the smallest shared count that passes the filter of :380.  *irregular (optional) counts
+ * the rows of the table, built for sizes 1..s_max, where a bisection had to fall back to the reference's linear walk. */
+FA_API int fa_stat_table_row(int32_t s, int32_t s_max, int32_t k, float pct_identity, int32_t *min_hits, int32_t *min_shared,
+                      int32_t *irregular);
 
 /* -- Sketch (pyx:449-806) ---------------------------------------------------------------- */
 FA_API int fa_sketch_create(const fa_params *p, int32_t device, fa_sketch **out);            /* pyx:476 */
@@ -120,6 +126,13 @@ FA_API int fa_sketch_end_genome(fa_sketch *s, uint64_t *genome_len_out);
  * all contigs).  *n_short (optional) counts contigs that raise the warning. */
 FA_API int fa_sketch_add_genome(fa_sketch *s, const fa_contig *contigs, int32_t n_contigs,
                          uint64_t *genome_len_out, int32_t *n_short);
+/* Many genomes in one call (not in the reference API, which adds genome by genome from Python): genome g owns the next
+ * contigs_per_genome[g] entries of `contigs`.  Whole genomes are sketched about 256 MB of bases per launch sequence.
+ * genome_len_out (optional) has n_genomes entries. */
+FA_API int fa_sketch_add_genomes(fa_sketch *s, const fa_contig *contigs, const int32_t *contigs_per_genome, int32_t n_genomes,
+                          uint64_t *genome_len_out, int32_t *n_short);
+/* CUDA-event time of the device work of all add calls so far (staging copies + kernels) and the bases they saw. */
+FA_API int fa_sketch_build_stats(const fa_sketch *s, double *ms_sketch, uint64_t *bases);
 FA_API int fa_sketch_clear(fa_sketch *s);                                                    /* pyx:746-767 */
 FA_API int fa_sketch_counts(const fa_sketch *s, uint64_t *n_minimizers, uint64_t *n_contigs, uint64_t *n_genomes);
 /* Minimizers view, pyx:1222-1254: copy [first, first+n) of (hash, seqId, wpos). */
@@ -140,6 +153,8 @@ FA_API void fa_index_free(fa_index *ix);                                        
 FA_API int fa_index_counts(const fa_index *ix, uint64_t *n_minimizers, uint64_t *n_unique,
                     uint64_t *n_contigs, uint64_t *n_genomes);                        /* pyx:1222, 1454-1456 */
 FA_API int fa_index_params(const fa_index *ix, fa_params *out);
+/* CUDA-event time of fa_sketch_index's device work: the whole build / the radix sort of (hash, position) inside it. */
+FA_API int fa_index_build_stats(const fa_index *ix, float *ms_build, float *ms_sort);
 FA_API int fa_index_copy_minimizers(const fa_index *ix, uint64_t first, uint64_t n,
                              uint32_t *hash, int32_t *seq, int32_t *wpos);           /* pyx:1225-1254 */
 FA_API int fa_index_copy_meta(const fa_index *ix, int32_t *seqs_by_genome, uint64_t *genome_len);
@@ -160,6 +175,31 @@ FA_API int fa_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs,
  * do).  `info` (may be NULL) receives the counters and stage times summed over the queries. */
 FA_API int fa_query_batch(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_per_query, int32_t n_queries,
                    fa_hit *out, uint64_t cap, uint64_t *hit_offsets, fa_query_info *info);
+/* -- multi-GPU: reference-sharded mapping (BASELINE configs[4]) ----------------------------------------
+ * One process per GPU.  Whole reference genomes are dealt to the ranks in contiguous blocks (genome_offsets, world + 1
+ * entries: rank r indexes genomes [genome_offsets[r], genome_offsets[r + 1])), every rank maps every query against its
+ * shard and the final per-genome rows are exchanged with one small ncclAllGather (a second one only when a rank holds
+ * more than 2048 rows for the batch) -- what upstream FastANI does per thread (splitReferenceGenomes /
+ * correctRefGenomeIds, FA/cgi/include/computeCoreIdentity.hpp:454-484).  NCCL is bound at run time (libnccl.so.2). */
+typedef struct fa_comm fa_comm;
+enum { FA_COMM_ID_BYTES = 128 };
+/* ncclGetUniqueId on one rank; the 128 bytes reach the other ranks by whatever channel the host has (a socket, a file,
+ * MPI, torch.distributed), then every rank calls fa_comm_create (ncclCommInitRank; collective). */
+FA_API int fa_comm_unique_id(uint8_t *id);
+FA_API int fa_comm_create(const uint8_t *id, int32_t world, int32_t rank, int32_t device, fa_comm **out);
+FA_API void fa_comm_free(fa_comm *c);
+FA_API int fa_comm_info(const fa_comm *c, int32_t *world, int32_t *rank, int32_t *nccl_version, uint64_t *collectives,
+                 uint64_t *bytes_gathered);
+/* Collective.  This rank's rows of n_queries queries (rows[hit_offsets[q] .. hit_offsets[q + 1]), LOCAL genome ids, in
+ * the order fa_query returns them) -> on every rank the rows of all ranks with GLOBAL genome ids, per query in the order
+ * of pyx:1135 (identity descending, stable in ascending genome id): out[out_offsets[q] .. out_offsets[q + 1]). */
+FA_API int fa_gather_hits(fa_comm *c, const fa_hit *rows, const uint64_t *hit_offsets, int32_t n_queries,
+                   const int32_t *genome_offsets, fa_hit *out, uint64_t cap, uint64_t *out_offsets);
+/* Collective.  fa_query_batch against this rank's shard followed by fa_gather_hits: the whole reference-sharded step
+ * without the host language in between. */
+FA_API int fa_query_batch_sharded(fa_index *ix, fa_comm *comm, const fa_contig *contigs, const int32_t *contigs_per_query,
+                           int32_t n_queries, const int32_t *genome_offsets, fa_hit *out, uint64_t cap,
+                           uint64_t *hit_offsets, fa_query_info *info);
 /* Intermediates of the last fa_query on this index, for the bit-exact parity tests
  * (SURVEY.md 7.1 step 0): L1 candidates as (frag, seq, start, end) rows and L2 mappings as
  * (frag, seq, refStartPos, shared, sketch, identity-bits) rows of int32. */
@@ -171,12 +211,17 @@ FA_API int fa_debug_set_l1_seed_cap(fa_index *ix, int64_t cap);
 /* Test hook: cap on the seeds per fragment the small shape of the on-chip L1 kernel accepts (0 = every on-chip
  * fragment takes the large shape); -1 restores the default (what leaves room for four CTAs per SM). */
 FA_API int fa_debug_set_l1_small_cap(fa_index *ix, int64_t cap);
+/* Test hook: the small shape of the on-chip L1 kernel has three shared-memory sizes (four, three or two CTAs per SM; the
+ * larger ones serve indexes whose chunk histogram leaves no room otherwise, i.e. thousands of genomes); `shape` = 0, 1, 2
+ * is the smallest one it may pick, -1 restores the default. */
+FA_API int fa_debug_set_l1_small_shape(fa_index *ix, int32_t shape);
 /* Device buffers for callers that want inputs resident in HBM before the timed region
  * (fa_contig.on_device). */
 FA_API int fa_device_alloc(int32_t device, uint64_t bytes, void **dptr);
 FA_API int fa_device_upload(int32_t device, void *dptr, const void *src, uint64_t bytes);
 FA_API int fa_device_download(int32_t device, void *dst, const void *dptr, uint64_t bytes);
 FA_API int fa_device_free(int32_t device, void *dptr);
+FA_API int fa_device_mem_info(int32_t device, uint64_t *free_bytes, uint64_t *total_bytes);
 
 #ifdef __cplusplus
 }

@@ -199,6 +199,25 @@ class OracleSketch:
     def add_genome(self, name, seq):
         return self.add_draft(name, (seq,))
 
+    def add_genomes(self, names, seqs, threads=1):
+        """Many single-contig genomes; the compiled reference sketches them on `threads` threads (set-up of the CPU
+        baseline), the port one by one.  Same result as add_genome in a loop."""
+        if self.o.kind != "reference" or threads <= 1:
+            for n, s in zip(names, seqs):
+                self.add_genome(n, s)
+            return self
+        keeps, arr = [], (Contig * max(len(seqs), 1))()
+        for i, c in enumerate(seqs):
+            keep, ptr, unit, n = _as_buf(c)
+            keeps.append(keep)
+            arr[i] = Contig(ptr, unit, n)
+        fn = self.o._f("sketch_add_genomes")
+        fn.argtypes = [C.c_void_p, C.POINTER(Contig), C.c_int32, C.c_int]
+        fn.restype = None
+        fn(self.h, arr, len(seqs), threads)
+        self.names.extend(names)
+        return self
+
     def index(self):
         self.o._f("sketch_index")(self.h)
         return self

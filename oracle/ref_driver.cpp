@@ -143,6 +143,41 @@ int64_t ref_sketch_add_contig(ref_sketch *s, const void *data, int unit, int64_t
     s->counter++;
     return n;
 }
+// Set-up helper for the CPU baseline of bench.py: many single-contig genomes at once, each sketched by the reference's
+// addMinimizers into a private vector on its own thread, then appended in genome order -- the same minimizers, ids and
+// bookkeeping as calling ref_sketch_add_contig + ref_sketch_end_genome genome by genome.
+void ref_sketch_add_genomes(ref_sketch *s, const ref_contig *genomes, int32_t n_genomes, int threads)
+{
+    std::vector<std::vector<skch::MinimizerInfo>> parts(n_genomes);
+    std::atomic<int32_t> next(0);
+    const size_t base = s->counter;
+    auto work = [&]() {
+        for (;;) {
+            const int32_t g = next.fetch_add(1);
+            if (g >= n_genomes) break;
+            const int64_t slen = genomes[g].len;
+            if (slen >= s->param.windowSize && slen >= s->param.kmerSize) {
+                std::string buf; narrow(buf, genomes[g].data, genomes[g].unit_bytes, slen);
+                kseq_t ks; memset(&ks, 0, sizeof ks);
+                ks.seq.s = &buf[0]; ks.seq.l = slen;
+                skch::CommonFunc::addMinimizers(parts[g], &ks, s->param.kmerSize, s->param.windowSize,
+                                                s->param.alphabetSize, (skch::seqno_t)(base + g));
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < std::max(1, std::min(threads, (int)n_genomes)); t++) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    for (int32_t g = 0; g < n_genomes; g++) {
+        s->sk->minimizerIndex.insert(s->sk->minimizerIndex.end(), parts[g].begin(), parts[g].end());
+        std::vector<skch::MinimizerInfo>().swap(parts[g]);
+        s->cur_len = (uint64_t)(genomes[g].len / s->param.minReadLength) * s->param.minReadLength;
+        s->counter++;
+        s->lengths.push_back(s->cur_len); s->cur_len = 0;
+        s->sk->sequencesByFileInfo.push_back((skch::seqno_t)s->counter);
+    }
+}
 void ref_sketch_end_genome(ref_sketch *s)
 {   // pyx:686-690
     s->lengths.push_back(s->cur_len); s->cur_len = 0;

@@ -23,6 +23,7 @@ from cpython.unicode cimport (
 from libc.stdint cimport int32_t, int64_t, uint32_t, uint64_t, uintptr_t
 from libc.stdlib cimport malloc, free
 from libc.string cimport memset
+from cpython.bytes cimport PyBytes_FromStringAndSize
 
 import threading
 import warnings
@@ -76,8 +77,10 @@ cdef extern from "fastani_b200.h" nogil:
         uint32_t l1_sorted_fragments
         uint32_t l1_small_fragments
         uint64_t events_replayed
+        float ms_batch
     ctypedef struct fa_sketch
     ctypedef struct fa_index
+    ctypedef struct fa_comm
 
     const char* fa_last_error()
     int fa_device_count(int32_t* n)
@@ -85,6 +88,10 @@ cdef extern from "fastani_b200.h" nogil:
     int fa_sketch_create(const fa_params* p, int32_t device, fa_sketch** out)
     void fa_sketch_free(fa_sketch* s)
     int fa_sketch_add_genome(fa_sketch* s, const fa_contig* contigs, int32_t n, uint64_t* glen, int32_t* n_short)
+    int fa_sketch_add_genomes(fa_sketch* s, const fa_contig* contigs, const int32_t* contigs_per_genome, int32_t n_genomes,
+                              uint64_t* glen, int32_t* n_short)
+    int fa_sketch_build_stats(const fa_sketch* s, double* ms_sketch, uint64_t* bases)
+    int fa_index_build_stats(const fa_index* ix, float* ms_build, float* ms_sort)
     int fa_sketch_clear(fa_sketch* s)
     int fa_sketch_counts(const fa_sketch* s, uint64_t* n_min, uint64_t* n_contigs, uint64_t* n_genomes)
     int fa_sketch_copy_minimizers(const fa_sketch* s, uint64_t first, uint64_t n, uint32_t* h, int32_t* sq, int32_t* w)
@@ -103,6 +110,16 @@ cdef extern from "fastani_b200.h" nogil:
                  fa_query_info* info)
     int fa_query_batch(fa_index* ix, const fa_contig* contigs, const int32_t* contigs_per_query, int32_t n_queries,
                        fa_hit* out, uint64_t cap, uint64_t* hit_offsets, fa_query_info* info)
+    int fa_comm_unique_id(unsigned char* id)
+    int fa_comm_create(const unsigned char* id, int32_t world, int32_t rank, int32_t device, fa_comm** out)
+    void fa_comm_free(fa_comm* c)
+    int fa_comm_info(const fa_comm* c, int32_t* world, int32_t* rank, int32_t* nccl_version, uint64_t* collectives,
+                     uint64_t* bytes_gathered)
+    int fa_gather_hits(fa_comm* c, const fa_hit* rows, const uint64_t* hit_offsets, int32_t n_queries,
+                       const int32_t* genome_offsets, fa_hit* out, uint64_t cap, uint64_t* out_offsets)
+    int fa_query_batch_sharded(fa_index* ix, fa_comm* comm, const fa_contig* contigs, const int32_t* contigs_per_query,
+                               int32_t n_queries, const int32_t* genome_offsets, fa_hit* out, uint64_t cap,
+                               uint64_t* hit_offsets, fa_query_info* info)
     int fa_device_alloc(int32_t device, uint64_t nbytes, void** dptr)
     int fa_device_upload(int32_t device, void* dptr, const void* src, uint64_t nbytes)
     int fa_device_free(int32_t device, void* dptr)
@@ -140,6 +157,99 @@ def device_count():
     cdef int32_t n = 0
     _check(fa_device_count(&n))
     return n
+
+
+# --- multi-GPU ------------------------------------------------------------------
+
+HIT_FIELDS = [("ref_genome", "<i4"), ("matches", "<i4"), ("fragments", "<i4"), ("identity", "<f4")]
+
+
+cdef object _hit_rows(const fa_hit* rows, const uint64_t* offs, int32_t nq):
+    """`fa_hit` rows of nq queries -> a list of numpy structured arrays (slices of one array), no `Hit` objects."""
+    import numpy
+    cdef uint64_t total = offs[nq]
+    data = bytearray(PyBytes_FromStringAndSize(<const char*> rows, total * sizeof(fa_hit))) if total else bytearray()
+    allrows = numpy.frombuffer(data, dtype=numpy.dtype(HIT_FIELDS))
+    return [allrows[offs[q]:offs[q + 1]] for q in range(nq)]
+
+
+cdef class Communicator:
+    """One rank of a group of GPUs that map against shards of a reference set (not in the reference API; the analogue of
+    upstream FastANI's per-thread reference split, computeCoreIdentity.hpp:454-484).  Wraps an NCCL communicator owned
+    by the library: `unique_id()` on one rank, its 128 bytes handed to the others by the caller, then
+    `Communicator(id, world_size, rank, device)` on every rank (collective)."""
+    cdef fa_comm* _c
+    cdef readonly int world_size
+    cdef readonly int rank
+    cdef readonly int device
+
+    def __cinit__(self):
+        self._c = NULL
+
+    def __init__(self, bytes unique_id, int world_size, int rank, int device=0):
+        cdef const unsigned char* idp = unique_id
+        cdef int rc
+        if len(unique_id) != 128:
+            raise ValueError("unique_id must be the 128 bytes returned by Communicator.unique_id()")
+        with nogil:
+            rc = fa_comm_create(idp, world_size, rank, device, &self._c)
+        _check(rc)
+        self.world_size, self.rank, self.device = world_size, rank, device
+
+    def __dealloc__(self):
+        if self._c != NULL:
+            fa_comm_free(self._c)
+            self._c = NULL
+
+    @staticmethod
+    def unique_id():
+        cdef unsigned char buf[128]
+        _check(fa_comm_unique_id(buf))
+        return PyBytes_FromStringAndSize(<const char*> buf, 128)
+
+    @property
+    def info(self):
+        cdef int32_t w = 0, r = 0, v = 0
+        cdef uint64_t n = 0, b = 0
+        _check(fa_comm_info(self._c, &w, &r, &v, &n, &b))
+        return {"world_size": w, "rank": r, "nccl_version": v, "collectives": n, "bytes_gathered": b}
+
+    def gather_hits(self, object rows_per_query, object genome_offsets):
+        """Collective: this rank's rows (structured arrays with LOCAL genome ids, one per query) -> on every rank one
+        array per query with the rows of all ranks, GLOBAL ids, in the reference's order (`fa_gather_hits`)."""
+        import numpy
+        cdef list items = [numpy.ascontiguousarray(r, dtype=numpy.dtype(HIT_FIELDS)) for r in rows_per_query]
+        cdef int32_t nq = <int32_t> len(items)
+        cdef list offs_l = list(genome_offsets)
+        if len(offs_l) != self.world_size + 1:
+            raise ValueError("genome_offsets needs world_size + 1 entries")
+        cdef uint64_t cap = <uint64_t> max(nq, 1) * <uint64_t> max(int(offs_l[-1]) - int(offs_l[0]), 1)
+        cdef uint64_t* in_offs = <uint64_t*> malloc((nq + 1) * sizeof(uint64_t))
+        cdef uint64_t* out_offs = <uint64_t*> malloc((nq + 1) * sizeof(uint64_t))
+        cdef int32_t* goffs = <int32_t*> malloc((self.world_size + 1) * sizeof(int32_t))
+        cdef fa_hit* out = <fa_hit*> malloc(cap * sizeof(fa_hit))
+        cdef const unsigned char[::1] view
+        cdef const fa_hit* inp = NULL
+        cdef int rc
+        cdef int32_t q
+        try:
+            if in_offs == NULL or out_offs == NULL or goffs == NULL or out == NULL:
+                raise MemoryError()
+            flat = numpy.concatenate(items) if nq else numpy.zeros(0, dtype=numpy.dtype(HIT_FIELDS))
+            in_offs[0] = 0
+            for q in range(nq):
+                in_offs[q + 1] = in_offs[q] + <uint64_t> len(items[q])
+            for q in range(self.world_size + 1):
+                goffs[q] = offs_l[q]
+            if len(flat):
+                view = flat.view(numpy.uint8)
+                inp = <const fa_hit*> &view[0]
+            with nogil:
+                rc = fa_gather_hits(self._c, inp, in_offs, nq, goffs, out, cap, out_offs)
+            _check(rc)
+            return _hit_rows(out, out_offs, nq)
+        finally:
+            free(in_offs); free(out_offs); free(goffs); free(out)
 
 
 # --- input adaptation ---------------------------------------------------------
@@ -189,6 +299,10 @@ cdef class DeviceSequence:
         cdef DeviceSequence d = DeviceSequence.__new__(DeviceSequence)
         d.device = device
         d.length = length
+        if length < 0 or (length > 0 and pointer == 0):
+            raise ValueError("from_pointer: a null pointer or a negative length")
+        if device < 0 or device >= device_count():
+            raise ValueError(f"from_pointer: device {device} out of range")
         d._ptr = <void*> pointer
         d._owner = owner
         return d
@@ -208,7 +322,7 @@ cdef class _Contigs:
     def __dealloc__(self):
         free(self.arr)
 
-    cdef int fill(self, object contigs) except -1:
+    cdef int fill(self, object contigs, int device) except -1:
         cdef const unsigned char[::1] view
         cdef list items = list(contigs)
         cdef object contig
@@ -230,6 +344,9 @@ cdef class _Contigs:
                 self.keep.append(contig)
             elif isinstance(contig, DeviceSequence):
                 dev = contig
+                # the kernels dereference the pointer on the Sketch / Mapper's own device
+                if dev.device != device:
+                    raise ValueError(f"DeviceSequence lives on device {dev.device}, expected device {device}")
                 self.arr[i].data = dev._ptr
                 self.arr[i].len = dev.length
                 self.arr[i].unit_bytes = 1
@@ -452,7 +569,7 @@ cdef class Sketch(_Parameterized):
         cdef uint64_t glen = 0
         cdef int32_t  n_short = 0
         cdef int      rc
-        c.fill(contigs)
+        c.fill(contigs, self._device)
         with nogil:
             rc = fa_sketch_add_genome(self._sk, c.arr, c.n, &glen, &n_short)
         _check(rc)
@@ -482,6 +599,61 @@ cdef class Sketch(_Parameterized):
         with self._lock:
             self._add_draft(name, (sequence,))
         return self
+
+    def add_many(self, object names, object genomes):
+        """add_many(self, names, genomes)\n--
+
+        Add many reference genomes with one call into the library (`fa_sketch_add_genomes`; not in the
+        reference API, which adds genome by genome): ``genomes[i]`` is one sequence (a complete genome) or a
+        list / tuple of contigs (a draft), named ``names[i]``.  Same result as `add_genome` / `add_draft` in a
+        loop; whole genomes share launch sequences (about 256 MB of bases each)."""
+        cdef _Contigs c = _Contigs.__new__(_Contigs)
+        cdef list     name_l = list(names)
+        cdef list     items = list(genomes)
+        cdef list     flat = []
+        cdef int32_t  ng = <int32_t> len(items)
+        cdef int32_t  n_short = 0
+        cdef int32_t* counts
+        cdef int      rc
+        cdef int32_t  g
+        if len(name_l) != len(items):
+            raise ValueError("`names` and `genomes` differ in length")
+        counts = <int32_t*> malloc(max(ng, 1) * sizeof(int32_t))
+        if counts == NULL:
+            raise MemoryError()
+        try:
+            for g in range(ng):
+                if isinstance(items[g], (list, tuple)):
+                    counts[g] = <int32_t> len(items[g])
+                    flat.extend(items[g])
+                else:
+                    counts[g] = 1
+                    flat.append(items[g])
+            c.fill(flat, self._device)
+            with self._lock:
+                with nogil:
+                    rc = fa_sketch_add_genomes(self._sk, c.arr, counts, ng, NULL, &n_short)
+                _check(rc)
+                self._names.extend(name_l)
+        finally:
+            free(counts)
+        for _ in range(n_short):
+            warnings.warn(
+                (
+                    "Sketch received a short contig relative to parameters, "
+                    "minimizers will not be added."
+                ),
+                UserWarning,
+            )
+        return self
+
+    @property
+    def build_stats(self):
+        """`dict`: CUDA-event time of the device work of all `add_*` calls so far and the bases they saw."""
+        cdef double ms = 0
+        cdef uint64_t bases = 0
+        _check(fa_sketch_build_stats(self._sk, &ms, &bases))
+        return {"ms_sketch": ms, "bases": bases}
 
     cpdef Sketch clear(self):
         """clear(self)\n--
@@ -618,6 +790,13 @@ cdef class Mapper(_Parameterized):
         """`list`: The names of the indexed reference genomes (not in the reference API)."""
         return self._names[:]
 
+    @property
+    def build_stats(self):
+        """`dict`: CUDA-event time of the index build (`Sketch.index`): all of it / the radix sort inside it."""
+        cdef float ms_build = 0, ms_sort = 0
+        _check(fa_index_build_stats(self._ix, &ms_build, &ms_sort))
+        return {"ms_build": ms_build, "ms_sort": ms_sort}
+
     cdef list _query_draft(self, object contigs, int threads=0):
         cdef _Contigs      c = _Contigs.__new__(_Contigs)
         cdef uint64_t      cap = len(self._names)
@@ -632,7 +811,7 @@ cdef class Mapper(_Parameterized):
         # by GPU threads here, so only its validation is kept
         if threads < 0:
             raise ValueError(f"`threads` must be positive or null, got {threads!r}")
-        c.fill(contigs)
+        c.fill(contigs, self._device)
         out = <fa_hit*> malloc(max(cap, 1) * sizeof(fa_hit))
         if out == NULL:
             raise MemoryError()
@@ -660,36 +839,56 @@ cdef class Mapper(_Parameterized):
                 "h2d_bytes": info.h2d_bytes, "d2h_bytes": info.d2h_bytes, "l2_fallback": info.l2_fallback, "events": info.events,
                 "ms_l2_prep": info.ms_l2_prep, "ms_l2_events": info.ms_l2_events, "ms_l2_slide": info.ms_l2_slide,
                 "l1_sorted_fragments": info.l1_sorted_fragments, "l1_small_fragments": info.l1_small_fragments, "events_replayed": info.events_replayed,
+                "ms_batch": info.ms_batch, "queries": 1,
             }
         finally:
             free(out)
         return hits
 
-    cpdef list query_many(self, object queries, int threads=0):
-        """query_many(self, queries, threads=0)\n--
+    def query_many(self, object queries, int threads=0, bint rows=False, Communicator comm=None, object genome_offsets=None):
+        """query_many(self, queries, threads=0, rows=False, comm=None, genome_offsets=None)\n--
 
         Map many queries with one call into the library (`fa_query_batch`; not in the reference
         API, which loops over `query_draft` in Python).  Each item of `queries` is either one
         sequence (`str`, bytes-like, `DeviceSequence`: a complete genome) or a list / tuple of
         contigs (a draft).  Returns one list of `Hit` per query, each exactly what
-        `query_genome` / `query_draft` returns for that item.  Releases the GIL for the whole batch."""
+        `query_genome` / `query_draft` returns for that item.  Releases the GIL for the whole batch.
+
+        ``rows=True`` returns numpy structured arrays ``(ref_genome, matches, fragments, identity)`` instead of
+        `Hit` objects (``ref_genome`` = position in `names`).  With ``comm`` and ``genome_offsets`` (world + 1
+        entries) the call is collective: this `Mapper` holds the reference genomes
+        ``[genome_offsets[rank], genome_offsets[rank + 1])`` and every rank receives, per query, the rows of ALL
+        ranks with global genome ids in the reference's order (`fa_query_batch_sharded`; implies ``rows``)."""
         cdef _Contigs      c = _Contigs.__new__(_Contigs)
         cdef list          flat = []
         cdef list          items = list(queries)
         cdef int32_t       nq = <int32_t> len(items)
-        cdef uint64_t      cap = <uint64_t> max(len(self._names), 1) * <uint64_t> max(nq, 1)
+        cdef uint64_t      n_refs = <uint64_t> max(len(self._names), 1)
+        cdef uint64_t      cap
         cdef int32_t*      counts = NULL
+        cdef int32_t*      goffs = NULL
         cdef uint64_t*     offs = NULL
         cdef fa_hit*       out = NULL
+        cdef fa_comm*      cc = NULL
         cdef fa_query_info info
         cdef int           rc
         cdef list          result = []
         cdef list          hits
+        cdef list          offs_l
         cdef uint64_t      i
         cdef int32_t       q
 
         if threads < 0:
             raise ValueError(f"`threads` must be positive or null, got {threads!r}")
+        if comm is not None:
+            if genome_offsets is None:
+                raise ValueError("`genome_offsets` is required with `comm`")
+            offs_l = list(genome_offsets)
+            if len(offs_l) != comm.world_size + 1:
+                raise ValueError("genome_offsets needs world_size + 1 entries")
+            n_refs = <uint64_t> max(int(offs_l[-1]) - int(offs_l[0]), 1)
+            cc = comm._c
+        cap = n_refs * <uint64_t> max(nq, 1)
         counts = <int32_t*> malloc(max(nq, 1) * sizeof(int32_t))
         offs = <uint64_t*> malloc((nq + 1) * sizeof(uint64_t))
         out = <fa_hit*> malloc(cap * sizeof(fa_hit))
@@ -703,9 +902,18 @@ cdef class Mapper(_Parameterized):
                 else:
                     counts[q] = 1
                     flat.append(items[q])
-            c.fill(flat)
-            with nogil:
-                rc = fa_query_batch(self._ix, c.arr, counts, nq, out, cap, offs, &info)
+            c.fill(flat, self._device)
+            if cc != NULL:
+                goffs = <int32_t*> malloc((comm.world_size + 1) * sizeof(int32_t))
+                if goffs == NULL:
+                    raise MemoryError()
+                for q in range(comm.world_size + 1):
+                    goffs[q] = offs_l[q]
+                with nogil:
+                    rc = fa_query_batch_sharded(self._ix, cc, c.arr, counts, nq, goffs, out, cap, offs, &info)
+            else:
+                with nogil:
+                    rc = fa_query_batch(self._ix, c.arr, counts, nq, out, cap, offs, &info)
             _check(rc)
             for _ in range(info.short_contigs):
                 warnings.warn(
@@ -715,25 +923,30 @@ cdef class Mapper(_Parameterized):
                     ),
                     UserWarning,
                 )
-            for q in range(nq):
-                hits = []
-                for i in range(offs[q], offs[q + 1]):
-                    hits.append(_make_hit(self._names[out[i].ref_genome], out[i].identity, out[i].matches, out[i].fragments))
-                result.append(hits)
+            if rows or cc != NULL:
+                result = _hit_rows(out, offs, nq)
+            else:
+                for q in range(nq):
+                    hits = []
+                    for i in range(offs[q], offs[q + 1]):
+                        hits.append(_make_hit(self._names[out[i].ref_genome], out[i].identity, out[i].matches, out[i].fragments))
+                    result.append(hits)
             self.last_query_info = {
                 "fragments": info.fragments, "seeds": info.seeds, "candidates": info.candidates, "mappings": info.mappings,
+                "scanned": info.scanned, "sketch_sum": info.sketch_sum,
                 "kernel_launches": info.kernel_launches, "ms_total": info.ms_total, "h2d_bytes": info.h2d_bytes,
                 "d2h_bytes": info.d2h_bytes, "events": info.events, "events_replayed": info.events_replayed, "queries": nq,
                 "ms_h2d": info.ms_h2d, "ms_sketch": info.ms_sketch, "ms_lookup": info.ms_lookup,
                 "ms_seed_sort": info.ms_seed_sort, "ms_l1": info.ms_l1, "ms_l2": info.ms_l2, "ms_cgi": info.ms_cgi,
                 "ms_d2h": info.ms_d2h, "ms_l2_prep": info.ms_l2_prep, "ms_l2_events": info.ms_l2_events,
                 "ms_l2_slide": info.ms_l2_slide, "l1_small_fragments": info.l1_small_fragments,
-                "l1_sorted_fragments": info.l1_sorted_fragments,
+                "l1_sorted_fragments": info.l1_sorted_fragments, "l2_fallback": info.l2_fallback, "ms_batch": info.ms_batch,
             }
         finally:
             free(counts)
             free(offs)
             free(out)
+            free(goffs)
         return result
 
     cpdef list query_draft(self, object contigs, int threads=0):

@@ -73,7 +73,7 @@ int copy_minimizers(int device, cudaStream_t st, const RefMini *ref, uint64_t to
     if (first > total || n > total - first) { set_error("minimizer range out of bounds"); return FA_ERR_INVALID; }
     if (n == 0) return FA_OK;
     FA_CUDA(cudaSetDevice(device));
-    DevBuf<uint32_t> dh; DevBuf<int32_t> ds, dw;
+    TmpBuf<uint32_t> dh; TmpBuf<int32_t> ds, dw;
     int rc = dh.reserve(n);
     if (rc == FA_OK) rc = ds.reserve(n);
     if (rc == FA_OK) rc = dw.reserve(n);
@@ -86,12 +86,13 @@ int copy_minimizers(int device, cudaStream_t st, const RefMini *ref, uint64_t to
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { set_error("copy_minimizers: %s", cudaGetErrorString(e)); rc = FA_ERR_CUDA; }
     }
-    dh.release(); ds.release(); dw.release();
     return rc;
 }
 
 // Sketch one batch of contigs (each consumes a sequence id, pyx:683) and append the minimizers.
-int sketch_add_batch(fa_sketch *s, const fa_contig *contigs, int32_t n_contigs, int32_t *n_short, int64_t *n_added)
+// With `contigs_per_genome` the batch holds n_genomes whole genomes (pyx:686-690 after each: length and id bookkeeping).
+int sketch_add_batch(fa_sketch *s, const fa_contig *contigs, int32_t n_contigs, int32_t *n_short, int64_t *n_added,
+                     const int32_t *contigs_per_genome = nullptr, int32_t n_genomes = 0, uint64_t *genome_len_out = nullptr)
 {
     FA_CUDA(cudaSetDevice(s->device));
     const fa_params &P = s->prm;
@@ -100,6 +101,9 @@ int sketch_add_batch(fa_sketch *s, const fa_contig *contigs, int32_t n_contigs, 
     uint64_t off = 0, worst = 0;
     int64_t tiles = 0;
     int32_t shorts = 0;
+    // ids and lengths consumed by this batch: committed to the sketch only when the GPU work has succeeded, so a failed
+    // call (out of memory, CUDA error) leaves the sketch as it was
+    uint64_t counter = s->counter, cur_len = s->cur_len;
     for (int32_t c = 0; c < n_contigs; c++) {
         const fa_contig &ct = contigs[c];
         if (ct.len < 0 || (ct.len > 0 && !ct.data)) { set_error("contig %d: bad buffer", c); return FA_ERR_INVALID; }
@@ -107,9 +111,22 @@ int sketch_add_batch(fa_sketch *s, const fa_contig *contigs, int32_t n_contigs, 
         if (ct.on_device && ct.unit_bytes != 1) { set_error("device-resident contigs must be bytes"); return FA_ERR_INVALID; }
         if (ct.len > 0x7FFFFF00ll) { set_error("contigs longer than 2^31 bases are not supported"); return FA_ERR_UNSUPPORTED; }
     }
+    uint64_t bases = 0;
+    std::vector<uint64_t> g_len;            // per genome of the batch: its length and the ids consumed when it ends
+    std::vector<int32_t> g_end;
+    int32_t g = 0, g_left = n_genomes ? contigs_per_genome[0] : 0;
+    auto close_genomes = [&]() {            // (genomes without contigs close at once)
+        while (g < n_genomes && g_left == 0) {
+            g_len.push_back(cur_len); g_end.push_back((int32_t)counter); cur_len = 0;
+            g++;
+            g_left = g < n_genomes ? contigs_per_genome[g] : 0;
+        }
+    };
+    close_genomes();
     for (int32_t c = 0; c < n_contigs; c++) {
         const fa_contig &ct = contigs[c];
-        const int32_t id = (int32_t)s->counter;
+        const int32_t id = (int32_t)counter;
+        bases += (uint64_t)ct.len;
         if (ct.len >= P.window && ct.len >= P.k) {                                    // pyx:648
             const int nk = (int)ct.len - P.k + 1;
             SeqDesc d;
@@ -120,16 +137,29 @@ int sketch_add_batch(fa_sketch *s, const fa_contig *contigs, int32_t n_contigs, 
             tiles += (nk + SK_TILE - 1) / SK_TILE;
             if (nk >= P.window) worst += (uint64_t)(nk - P.window + 1);
         } else shorts++;                                                              // pyx:670-677
-        s->cur_len += (uint64_t)(ct.len / P.frag_len) * (uint64_t)P.frag_len;         // pyx:680
-        s->counter++;                                                                 // pyx:683
+        cur_len += (uint64_t)(ct.len / P.frag_len) * (uint64_t)P.frag_len;            // pyx:680
+        counter++;                                                                    // pyx:683
+        if (n_genomes) { g_left--; close_genomes(); }
     }
+    auto commit = [&]() {
+        s->counter = counter; s->cur_len = cur_len;
+        for (size_t i = 0; i < g_len.size(); i++) {
+            s->genome_len.push_back(g_len[i]); s->seqs_by_genome.push_back(g_end[i]);
+            if (genome_len_out) genome_len_out[i] = g_len[i];
+        }
+    };
     if (n_short) *n_short = shorts;
     if (n_added) *n_added = shorts == n_contigs && n_contigs == 1 ? -1 : 0;
     const int n_seqs = (int)s->h_seqs.size();
-    if (n_seqs == 0) return FA_OK;
+    if (n_seqs == 0) { commit(); return FA_OK; }
     if (tiles > 0x7FFFFF00ll) { set_error("batch too large"); return FA_ERR_UNSUPPORTED; }
     cudaStream_t st = s->st;
     int launches = 0;
+    if (!s->ev_ready) {
+        FA_CUDA(cudaEventCreate(&s->ev[0])); FA_CUDA(cudaEventCreate(&s->ev[1]));
+        s->ev_ready = true;
+    }
+    FA_CUDA(cudaEventRecord(s->ev[0], st));
     FA_TRY(stage_sequences(st, s->sc.bytes, s->stage, ups, off, nullptr));
     FA_TRY(s->sc.seqs.reserve(n_seqs)); FA_TRY(s->sc.tile_status.reserve((size_t)tiles));
     FA_TRY(s->sc.counters.reserve(4)); FA_TRY(s->sc.seq_first.reserve(n_seqs)); FA_TRY(s->sc.drops.reserve(n_seqs));
@@ -142,7 +172,13 @@ int sketch_add_batch(fa_sketch *s, const fa_contig *contigs, int32_t n_contigs, 
     FA_CUDA(cudaStreamSynchronize(st));
     uint64_t added = h_ct[1];
     if (h_ct[2] > 0) FA_TRY(quirk_compact(st, s->sc, (unsigned int)h_ct[2], s->ref.p + s->n, added, &added, &launches));
+    FA_CUDA(cudaEventRecord(s->ev[1], st));
+    FA_CUDA(cudaEventSynchronize(s->ev[1]));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]);
+    s->ms_sketch += ms; s->bases += bases;
     s->n += added;
+    commit();
     if (n_added) *n_added = (int64_t)added;
     return FA_OK;
 }
@@ -189,6 +225,16 @@ int fa_stat_l2(int32_t shared, int32_t s, int32_t k, float pid, float *identity,
     return FA_OK;
 }
 
+int fa_stat_table_row(int32_t s, int32_t s_max, int32_t k, float pid, int32_t *min_hits, int32_t *min_shared, int32_t *irregular)
+{
+    if (s < 1 || s > s_max || s_max > 4096 || k < 1) { set_error("bad arguments"); return FA_ERR_INVALID; }
+    const StatTable &t = stat_table(k, pid, s_max);
+    if (min_hits) *min_hits = t.min_hits[s];
+    if (min_shared) *min_shared = t.min_shared[s];
+    if (irregular) *irregular = t.irregular + t.irregular_l2;
+    return FA_OK;
+}
+
 int fa_sketch_create(const fa_params *p, int32_t device, fa_sketch **out)
 {
     FA_TRY(check_params(p));
@@ -214,6 +260,7 @@ void fa_sketch_free(fa_sketch *s)
     if (!s) return;
     cudaSetDevice(s->device);
     s->ref.release(); free_sketch_scratch(s->sc); s->stage.release();
+    if (s->ev_ready) { cudaEventDestroy(s->ev[0]); cudaEventDestroy(s->ev[1]); }
     if (s->st) cudaStreamDestroy(s->st);
     delete s;
 }
@@ -244,6 +291,50 @@ int fa_sketch_add_genome(fa_sketch *s, const fa_contig *contigs, int32_t n_conti
     if (!s || n_contigs < 0 || (n_contigs > 0 && !contigs)) { set_error("bad arguments"); return FA_ERR_INVALID; }
     FA_TRY(sketch_add_batch(s, contigs, n_contigs, n_short, nullptr));
     return fa_sketch_end_genome(s, genome_len_out);
+}
+
+int fa_sketch_add_genomes(fa_sketch *s, const fa_contig *contigs, const int32_t *contigs_per_genome, int32_t n_genomes,
+                          uint64_t *genome_len_out, int32_t *n_short)
+{
+    if (!s || n_genomes < 0 || (n_genomes > 0 && !contigs_per_genome)) { set_error("bad arguments"); return FA_ERR_INVALID; }
+    if (n_short) *n_short = 0;
+    // whole genomes per launch sequence, about 256 MB of bases at a time: one H2D stream, one sketch launch, one sync
+    constexpr int64_t BATCH_BYTES = 256ll << 20;
+    int64_t c0 = 0;
+    int32_t g0 = 0;
+    while (g0 < n_genomes) {
+        int32_t g1 = g0;
+        int64_t c1 = c0, bytes = 0;
+        while (g1 < n_genomes) {
+            if (contigs_per_genome[g1] < 0) { set_error("genome %d: negative contig count", g1); return FA_ERR_INVALID; }
+            int64_t gb = 0;
+            for (int64_t c = c1; c < c1 + contigs_per_genome[g1]; c++) gb += contigs[c].len > 0 ? contigs[c].len : 0;
+            if (g1 > g0 && (bytes + gb > BATCH_BYTES || c1 + contigs_per_genome[g1] - c0 > 0x3FFFFFFF)) break;
+            bytes += gb; c1 += contigs_per_genome[g1]; g1++;
+        }
+        int32_t shorts = 0;
+        FA_TRY(sketch_add_batch(s, contigs ? contigs + c0 : nullptr, (int32_t)(c1 - c0), &shorts, nullptr, contigs_per_genome + g0, g1 - g0,
+                                genome_len_out ? genome_len_out + g0 : nullptr));
+        if (n_short) *n_short += shorts;
+        c0 = c1; g0 = g1;
+    }
+    return FA_OK;
+}
+
+int fa_sketch_build_stats(const fa_sketch *s, double *ms_sketch, uint64_t *bases)
+{
+    if (!s) { set_error("sketch is NULL"); return FA_ERR_INVALID; }
+    if (ms_sketch) *ms_sketch = s->ms_sketch;
+    if (bases) *bases = s->bases;
+    return FA_OK;
+}
+
+int fa_index_build_stats(const fa_index *ix, float *ms_build, float *ms_sort)
+{
+    if (!ix) { set_error("index is NULL"); return FA_ERR_INVALID; }
+    if (ms_build) *ms_build = ix->ms_build;
+    if (ms_sort) *ms_sort = ix->ms_sort;
+    return FA_OK;
 }
 
 int fa_sketch_clear(fa_sketch *s)
@@ -289,7 +380,7 @@ int fa_sketch_restore(fa_sketch *s, const uint32_t *hash, const int32_t *seq, co
     s->counter = n_contigs;
     if (n == 0) return FA_OK;
     FA_TRY(s->ref.reserve(n + 1));
-    DevBuf<uint32_t> dh; DevBuf<int32_t> ds, dw;
+    TmpBuf<uint32_t> dh; TmpBuf<int32_t> ds, dw;
     FA_TRY(dh.reserve(n)); FA_TRY(ds.reserve(n)); FA_TRY(dw.reserve(n));
     FA_CUDA(cudaMemcpyAsync(dh.p, hash, n * 4, cudaMemcpyHostToDevice, s->st));
     FA_CUDA(cudaMemcpyAsync(ds.p, seq, n * 4, cudaMemcpyHostToDevice, s->st));
@@ -297,7 +388,6 @@ int fa_sketch_restore(fa_sketch *s, const uint32_t *hash, const int32_t *seq, co
     pack_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, s->st>>>(s->ref.p, n, dh.p, ds.p, dw.p);
     FA_CUDA(cudaGetLastError());
     FA_CUDA(cudaStreamSynchronize(s->st));
-    dh.release(); ds.release(); dw.release();
     s->n = n;
     return FA_OK;
 }
@@ -312,19 +402,26 @@ int fa_sketch_index(fa_sketch *s, fa_index **out)
     if (!ix) return FA_ERR_NOMEM;
     ix->prm = s->prm; ix->device = s->device;
     cudaError_t e = cudaStreamCreateWithFlags(&ix->st, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); delete ix; return FA_ERR_CUDA; }
-    // ownership of the minimizers moves to the index; the sketch stays usable but empty (pyx:795-804)
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+    if (e != cudaSuccess) { set_error("fa_sketch_index: %s", cudaGetErrorString(e)); fa_index_free(ix); return FA_ERR_CUDA; }
+    // The index is built on the sketch's minimizers in place; ownership moves to it only when the build has succeeded
+    // (pyx:795-804: the Mapper takes the Sketch_t, the Sketch gets a fresh one).  A failed build -- out of memory in the
+    // sort buffers, more than 2^32 minimizers, a CUDA error -- leaves the sketch as it was.
     ix->ref = s->ref; ix->n = s->n;
-    s->ref = DevBuf<RefMini>();
-    ix->seqs_by_genome.swap(s->seqs_by_genome);
-    ix->genome_len.swap(s->genome_len);
+    ix->seqs_by_genome = s->seqs_by_genome;
+    ix->genome_len = s->genome_len;
     ix->n_contigs = s->counter;
-    fa_sketch_clear(s);
-    FA_CUDA(cudaStreamSynchronize(s->st));
-    if (!ix->ref.p) { int rc = ix->ref.reserve(1); if (rc) { fa_index_free(ix); return rc; } }
+    int rc = FA_OK;
+    if (!ix->ref.p) { rc = ix->ref.reserve(1); if (rc == FA_OK) s->ref = ix->ref; }
     int launches = 0;
-    int rc = build_index(ix, &launches);
-    if (rc != FA_OK) { fa_index_free(ix); return rc; }
+    if (rc == FA_OK) rc = build_index(ix, &launches);
+    if (rc != FA_OK) {
+        ix->ref = DevBuf<RefMini>();          // still the sketch's
+        fa_index_free(ix);
+        return rc;
+    }
+    s->ref = DevBuf<RefMini>();
+    fa_sketch_clear(s);
     *out = ix;
     return FA_OK;
 }
@@ -337,12 +434,7 @@ void fa_index_free(fa_index *ix)
     ix->contig_off.release(); ix->genome_of_seq.release(); ix->bin_base.release(); ix->genome_cell.release();
     ix->pre[0].release(); ix->pre[1].release();
     ix->d_min_hits.release(); ix->d_min_shared.release(); ix->d_id_off.release(); ix->d_identity.release();
-    Workspace &w = ix->ws;
-    free_sketch_scratch(w.sk); w.stage.release(); w.qhash.release(); w.qs.release(); w.hit_start.release(); w.hit_cnt.release();
-    w.frag_seeds.release(); w.seeds_a.release(); w.seeds_b.release(); w.fb_seeds.release(); w.cand_tmp.release(); w.hfs.release(); w.cub_tmp.release(); w.frag_cands.release();
-    w.work_base.release(); w.cands.release(); w.maps.release(); w.cells.release(); w.g_identity.release(); w.g_count.release();
-    w.counters.release(); w.hres.release();
-    if (w.ev_ready) for (auto &e : w.ev) cudaEventDestroy(e);
+    ix->ws.release();
     if (ix->st) cudaStreamDestroy(ix->st);
     delete ix;
 }
@@ -394,22 +486,21 @@ int fa_index_lookup(const fa_index *ix, uint32_t hash, int32_t *seq, int32_t *wp
     *n = 0;
     if (ix->n_unique == 0) return FA_OK;
     FA_CUDA(cudaSetDevice(ix->device));
-    uint32_t *d_out = nullptr, h_out[2] = {0, 0};
-    FA_CUDA(cudaMalloc((void **)&d_out, 8));
-    lookup_one_kernel<<<1, 1, 0, ix->st>>>(ix->ukeys.p, ix->uoff.p, (uint32_t)ix->n_unique, hash, d_out);
-    FA_CUDA(cudaMemcpyAsync(h_out, d_out, 8, cudaMemcpyDeviceToHost, ix->st));
+    uint32_t h_out[2] = {0, 0};
+    TmpBuf<uint32_t> d_out;
+    FA_TRY(d_out.reserve(2));
+    lookup_one_kernel<<<1, 1, 0, ix->st>>>(ix->ukeys.p, ix->uoff.p, (uint32_t)ix->n_unique, hash, d_out.p);
+    FA_CUDA(cudaMemcpyAsync(h_out, d_out.p, 8, cudaMemcpyDeviceToHost, ix->st));
     FA_CUDA(cudaStreamSynchronize(ix->st));
-    cudaFree(d_out);
     *n = h_out[1];
     uint32_t m = (uint32_t)std::min<uint64_t>(cap, h_out[1]);
     if (m && seq && wpos) {
-        DevBuf<int32_t> ds, dw;
+        TmpBuf<int32_t> ds, dw;
         FA_TRY(ds.reserve(m)); FA_TRY(dw.reserve(m));
         gather_kernel<<<(m + 127) / 128, 128, 0, ix->st>>>(ix->ref.p, ix->pos_idx.p, h_out[0], m, ds.p, dw.p);
         FA_CUDA(cudaMemcpyAsync(seq, ds.p, m * 4, cudaMemcpyDeviceToHost, ix->st));
         FA_CUDA(cudaMemcpyAsync(wpos, dw.p, m * 4, cudaMemcpyDeviceToHost, ix->st));
         FA_CUDA(cudaStreamSynchronize(ix->st));
-        ds.release(); dw.release();
     }
     return FA_OK;
 }
@@ -431,6 +522,7 @@ static void add_info(fa_query_info &sum, const fa_query_info &qi)
     sum.ms_h2d += qi.ms_h2d; sum.ms_sketch += qi.ms_sketch; sum.ms_lookup += qi.ms_lookup; sum.ms_seed_sort += qi.ms_seed_sort;
     sum.ms_l1 += qi.ms_l1; sum.ms_l2 += qi.ms_l2; sum.ms_cgi += qi.ms_cgi; sum.ms_d2h += qi.ms_d2h; sum.ms_total += qi.ms_total;
     sum.ms_l2_prep += qi.ms_l2_prep; sum.ms_l2_events += qi.ms_l2_events; sum.ms_l2_slide += qi.ms_l2_slide;
+    sum.ms_batch += qi.ms_batch;
 }
 
 static int query_checked(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *out, uint64_t cap, uint64_t *n_out,
@@ -480,6 +572,15 @@ int fa_query_batch(fa_index *ix, const fa_contig *contigs, const int32_t *contig
         first[q + 1] = first[q] + contigs_per_query[q];
         for (int64_t c = first[q]; c < first[q + 1]; c++) frags[q] += (uint64_t)(contigs[c].len / L);
     }
+    // one event pair around the whole call on the library's stream: the device-side time of the batch, gaps between
+    // the passes included (the per-stage timers of `info` only cover the passes themselves)
+    struct Pair {
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~Pair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    } outer;
+    FA_CUDA(cudaSetDevice(ix->device));
+    FA_CUDA(cudaEventCreate(&outer.a)); FA_CUDA(cudaEventCreate(&outer.b));
+    FA_CUDA(cudaEventRecord(outer.a, ix->st));
     std::unique_lock<std::mutex> pre_lock(ix->pre_mtx, std::try_to_lock);      // a second concurrent batch maps without staging ahead
     const bool ahead = pre_lock.owns_lock() && n_queries > 1;
     if (pre_lock.owns_lock()) ix->pre[0].valid = ix->pre[1].valid = false;       // nothing staged by an earlier call is ours
@@ -548,6 +649,10 @@ int fa_query_batch(fa_index *ix, const fa_contig *contigs, const int32_t *contig
         q0 = q1; q1 = q2; slot ^= 1;
         if (q0 < n_queries && q1 == q0) q1 = pass_end(q0);
     }
+    FA_CUDA(cudaEventRecord(outer.b, ix->st));
+    FA_CUDA(cudaEventSynchronize(outer.b));
+    sum.ms_batch = 0;
+    cudaEventElapsedTime(&sum.ms_batch, outer.a, outer.b);
     if (info) *info = sum;
     return FA_OK;
 }
@@ -567,6 +672,14 @@ int fa_debug_set_l1_small_cap(fa_index *ix, int64_t cap)
     if (!ix) { set_error("index is NULL"); return FA_ERR_INVALID; }
     std::lock_guard<std::mutex> guard(ix->mtx);
     ix->l1_small_cap = cap < 0 ? -1 : (long long)cap;
+    return FA_OK;
+}
+
+int fa_debug_set_l1_small_shape(fa_index *ix, int32_t shape)
+{
+    if (!ix || shape > 2) { set_error("bad arguments"); return FA_ERR_INVALID; }
+    std::lock_guard<std::mutex> guard(ix->mtx);
+    ix->l1_small_shape = shape < 0 ? -1 : shape;
     return FA_OK;
 }
 
@@ -593,6 +706,15 @@ int fa_device_free(int32_t device, void *dptr)
 {
     FA_CUDA(cudaSetDevice(device));
     FA_CUDA(cudaFree(dptr));
+    return FA_OK;
+}
+int fa_device_mem_info(int32_t device, uint64_t *free_bytes, uint64_t *total_bytes)
+{
+    size_t f = 0, t = 0;
+    FA_CUDA(cudaSetDevice(device));
+    FA_CUDA(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
     return FA_OK;
 }
 

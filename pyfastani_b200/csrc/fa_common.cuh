@@ -60,6 +60,16 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// A DevBuf that frees itself: for temporaries of one call (DevBuf itself is a plain handle that is moved between owners).
+template <typename T>
+struct TmpBuf : DevBuf<T> {
+    TmpBuf() = default;
+    TmpBuf(const TmpBuf &) = delete;
+    TmpBuf &operator=(const TmpBuf &) = delete;
+    ~TmpBuf() { this->release(); }
+    DevBuf<T> take() { DevBuf<T> d = *this; this->p = nullptr; this->cap = 0; return d; }   // hand the memory to a long-lived owner
+};
+
 // Pinned host staging buffer.
 struct PinBuf {
     uint8_t *p = nullptr;

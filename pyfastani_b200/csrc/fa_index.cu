@@ -172,6 +172,12 @@ int build_index(fa_index *ix, int *launches)
     const uint32_t n_contigs = (uint32_t)ix->n_contigs;
     const uint32_t n_genomes = (uint32_t)ix->seqs_by_genome.size();
     if (n >= 0xFFFFFFF0ull) { set_error("index of %llu minimizers exceeds the 32-bit position index", (unsigned long long)n); return FA_ERR_UNSUPPORTED; }
+    struct Ev {                                  // build timers: whole build, and the radix sort inside it
+        cudaEvent_t e[4] = {};
+        ~Ev() { for (auto &x : e) if (x) cudaEventDestroy(x); }
+    } ev;
+    for (auto &x : ev.e) FA_CUDA(cudaEventCreate(&x));
+    FA_CUDA(cudaEventRecord(ev.e[0], st));
 
     // ---- host-side tables: contig -> genome, (contig, bin) cells ---------------------------
     std::vector<int32_t> genome_of(n_contigs ? n_contigs : 1, 0);
@@ -186,7 +192,7 @@ int build_index(fa_index *ix, int *launches)
     std::vector<int32_t> first_contig(n_genomes + 1, 0);
     for (uint32_t g = 0; g < n_genomes; g++) first_contig[g + 1] = std::min<int32_t>(ix->seqs_by_genome[g], (int32_t)n_contigs);
     first_contig[n_genomes] = (int32_t)n_contigs;
-    DevBuf<int32_t> d_first;
+    TmpBuf<int32_t> d_first;
     FA_TRY(d_first.reserve(first_contig.size()));
     FA_TRY(ix->genome_of_seq.reserve(genome_of.size()));
     FA_TRY(ix->bin_base.reserve((size_t)n_contigs + 1));
@@ -201,6 +207,11 @@ int build_index(fa_index *ix, int *launches)
         int s_max = cmw < 1 ? 1 : cmw;
         if (s_max > 4096) s_max = 4096;       // larger sketches are reported as unsupported at query time
         const StatTable &t = stat_table(ix->prm.k, ix->prm.pct_identity, s_max);
+        if (t.irregular_l2) {
+            set_error("the identity filter is not monotone in the shared-sketch count for k=%d, identity=%g (%d sketch sizes): "
+                      "not supported on the device path", ix->prm.k, (double)ix->prm.pct_identity, t.irregular_l2);
+            return FA_ERR_UNSUPPORTED;
+        }
         ix->s_max = s_max;
         ix->max_min_hits = 1;
         for (int32_t v : t.min_hits) ix->max_min_hits = std::max(ix->max_min_hits, (int)v);
@@ -224,7 +235,7 @@ int build_index(fa_index *ix, int *launches)
     }
     {
         const int bin_w = ix->prm.frag_len - 20;                                   // computeCoreIdentity.hpp:191
-        DevBuf<uint8_t> tmp0;
+        TmpBuf<uint8_t> tmp0;
         contig_bins_kernel<<<(n_contigs + 1 + 255) / 256, 256, 0, st>>>(ix->ref.p, ix->contig_off.p, n_contigs, bin_w, ix->bin_base.p);
         FA_CUDA(cudaGetLastError());
         size_t sb = 0;
@@ -252,18 +263,20 @@ int build_index(fa_index *ix, int *launches)
     }
 
     // ---- sort (hash, index) ------------------------------------------------------------------
-    DevBuf<uint32_t> keys_a, keys_b, vals_a;
+    TmpBuf<uint32_t> keys_a, keys_b, vals_a;
     FA_TRY(keys_a.reserve(n)); FA_TRY(keys_b.reserve(n)); FA_TRY(vals_a.reserve(n));
     FA_TRY(ix->pos_idx.reserve(n));
     extract_keys_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(ix->ref.p, n, keys_a.p, vals_a.p);
     FA_CUDA(cudaGetLastError());
     if (launches) *launches += 1;
     size_t tmp_bytes = 0;
+    FA_CUDA(cudaEventRecord(ev.e[2], st));
     FA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a.p, keys_b.p, vals_a.p, ix->pos_idx.p, (int64_t)n, 0, 32, st));
-    DevBuf<uint8_t> tmp;
+    TmpBuf<uint8_t> tmp;
     FA_TRY(tmp.reserve(tmp_bytes + 16));
     FA_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_a.p, keys_b.p, vals_a.p, ix->pos_idx.p, (int64_t)n, 0, 32, st));
     if (launches) *launches += 5;
+    FA_CUDA(cudaEventRecord(ev.e[3], st));
     vals_a.release();
 
     // duplicate distances for the L2 sliding window
@@ -299,8 +312,8 @@ int build_index(fa_index *ix, int *launches)
     if (launches) *launches += 3;
 
     // ---- CSR over unique hashes --------------------------------------------------------------
-    DevBuf<uint32_t> run_len;
-    DevBuf<uint64_t> d_nruns;
+    TmpBuf<uint32_t> run_len;
+    TmpBuf<uint64_t> d_nruns;
     FA_TRY(run_len.reserve(n)); FA_TRY(d_nruns.reserve(1));
     FA_TRY(ix->ukeys.reserve(n));             // trimmed below
     size_t rle_bytes = 0;
@@ -322,12 +335,12 @@ int build_index(fa_index *ix, int *launches)
     const uint32_t n32 = (uint32_t)n;
     FA_CUDA(cudaMemcpyAsync(ix->uoff.p + n_unique, &n32, 4, cudaMemcpyHostToDevice, st));
     {   // trim ukeys to n_unique (the sort buffers above are the transient peak)
-        DevBuf<uint32_t> trimmed;
+        TmpBuf<uint32_t> trimmed;
         FA_TRY(trimmed.reserve(n_unique ? n_unique : 1));
         FA_CUDA(cudaMemcpyAsync(trimmed.p, ix->ukeys.p, n_unique * 4, cudaMemcpyDeviceToDevice, st));
         FA_CUDA(cudaStreamSynchronize(st));
         ix->ukeys.release();
-        ix->ukeys = trimmed;
+        ix->ukeys = trimmed.take();
     }
 
     // ---- directory ---------------------------------------------------------------------------
@@ -338,7 +351,10 @@ int build_index(fa_index *ix, int *launches)
     directory_kernel<<<((1u << bits) + 1 + 255) / 256, 256, 0, st>>>(ix->ukeys.p, (uint32_t)n_unique, bits, ix->dir.p);
     FA_CUDA(cudaGetLastError());
     if (launches) *launches += 1;
+    FA_CUDA(cudaEventRecord(ev.e[1], st));
     FA_CUDA(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&ix->ms_build, ev.e[0], ev.e[1]);
+    cudaEventElapsedTime(&ix->ms_sort, ev.e[2], ev.e[3]);
     run_len.release(); d_nruns.release(); tmp.release();
     return FA_OK;
 }

@@ -59,6 +59,18 @@ struct Workspace {
     cudaEvent_t ev[12] = {};
     bool ev_ready = false;
     uint64_t last_cands = 0, last_frags = 0;
+    // every buffer above, in one place: a member added to the struct is released here or nowhere
+    void release()
+    {
+        sk.bytes.release(); sk.seqs.release(); sk.tile_status.release(); sk.counters.release(); sk.seq_first.release(); sk.drops.release();
+        stage.release(); frag_q.release(); qhash.release(); qs.release(); hit_start.release(); hit_cnt.release();
+        frag_seeds.release(); seeds_a.release(); seeds_b.release(); fb_seeds.release(); cand_tmp.release(); hfs.release();
+        cub_tmp.release(); frag_cands.release(); work_base.release(); cands.release(); maps.release(); prep.release();
+        ev_off.release(); jobs.release(); room.release(); events.release(); cells.release(); g_identity.release();
+        g_count.release(); counters.release(); hres.release();
+        if (ev_ready) for (auto &e : ev) cudaEventDestroy(e);
+        ev_ready = false;
+    }
 };
 
 // One host or device buffer to place at `off` in the batch byte buffer.
@@ -92,6 +104,10 @@ struct fa_sketch {
     fa::SketchScratch sc;
     fa::PinBuf stage;
     std::vector<fa::SeqDesc> h_seqs;
+    cudaEvent_t ev[2] = {};                      // around the device work of every add call
+    bool ev_ready = false;
+    double ms_sketch = 0;                        // staging + sketch kernels, summed over the add calls (CUDA events)
+    uint64_t bases = 0;                          // bases seen by those calls
 };
 
 struct fa_index {
@@ -124,7 +140,9 @@ struct fa_index {
     fa::DevBuf<int32_t>  d_min_hits, d_min_shared;
     fa::DevBuf<uint32_t> d_id_off;
     fa::DevBuf<float>    d_identity;
+    float ms_build = 0, ms_sort = 0;             // build_index on its stream (CUDA events): everything / the radix sort of (hash, index)
     long long l1_small_cap = -1;                 // test hook: most seeds per fragment for the small shape of the on-chip L1 (-1 = default)
+    int l1_small_shape = -1;                     // test hook: smallest entry of L1S_SMEM the small shape may use (-1 = 0: the first that fits)
     long long l1_seed_cap = -1;                  // test hook: most seeds per fragment for the on-chip L1 (-1 = what fits)
     std::mutex mtx;                              // serialises queries on the single workspace
     fa::Workspace ws;

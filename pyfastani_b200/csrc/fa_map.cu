@@ -1680,7 +1680,8 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
             const size_t l1s_fixed = l1_fixed_smem(n_chunks, l1_stage(L1S_THREADS, L1S_TILE));
             uint64_t small_cap = 0;
             size_t l1s_smem = 0;
-            for (size_t b : L1S_SMEM) if (!l1s_smem && l1s_fixed + 8 * 1024 <= b) l1s_smem = b;
+            for (int i = std::max(ix->l1_small_shape, 0); i < 3; i++)
+                if (!l1s_smem && l1s_fixed + 8 * 1024 <= L1S_SMEM[i]) l1s_smem = L1S_SMEM[i];
             if (l1s_smem && ix->max_min_hits - 1 <= L1S_THREADS && max_s <= l1_stage(L1S_THREADS, L1S_TILE))
                 small_cap = std::min<uint64_t>(seed_cap, ((l1s_smem - l1s_fixed - 128) * 16 / 33) & ~31ull);
             if (ix->l1_small_cap >= 0) small_cap = std::min<uint64_t>(small_cap, (uint64_t)ix->l1_small_cap);
@@ -1868,7 +1869,7 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
         }
         cudaEventElapsedTime(&ms, ws.ev[6], ws.ev[7]); qi.ms_cgi = ms;
         cudaEventElapsedTime(&ms, ws.ev[7], ws.ev[8]); qi.ms_d2h = ms;
-        cudaEventElapsedTime(&ms, ws.ev[0], ws.ev[8]); qi.ms_total = ms;
+        cudaEventElapsedTime(&ms, ws.ev[0], ws.ev[8]); qi.ms_total = ms; qi.ms_batch = ms;
     }
 
     // ---- hit filter + sort (pyx:1121-1135), query by query ----------------------------------------

@@ -3,6 +3,7 @@
 // everything is double except where the reference stores into a float.
 #include "fa_stat.h"
 
+#include <algorithm>
 #include <cmath>
 #include <map>
 #include <mutex>
@@ -172,8 +173,10 @@ const StatTable &stat_table(int k, float pid, int s_max)
     for (int s = 1; s <= s_max; s++) t.id_off[s + 1] = t.id_off[s] + (uint32_t)(s + 1);
     t.identity.assign(t.id_off[s_max + 1], 0.0f);
     for (int s = 1; s <= s_max; s++) {
-        // estimateMinimumHitsRelaxed walks down from m0 while the bound passes; with the
-        // bound monotone in x that is a bisection for the smallest passing x in [0, m0].
+        // estimateMinimumHitsRelaxed walks down from m0 while the bound passes (map_stats.hpp:152-165).  The bound is
+        // monotone in x (the binomial quantile is monotone in its success probability), so the first failure of that walk
+        // is found by bisection -- and the neighbourhood of the answer is then checked against the walk's own rule, so a
+        // float-rounding wobble cannot change a result silently: the row falls back to the reference's linear walk.
         int m0 = minimum_hits(s, k, pid), mh = m0;
         if (m0 > s) m0 = mh = s + 1;       // jaccard cut-off above 1 cannot happen for pid in [0,100]
         if (m0 <= s && upper_bound_passes(m0, s, k, pid)) {
@@ -183,6 +186,9 @@ const StatTable &stat_table(int k, float pid, int s_max)
                 if (upper_bound_passes(mid, s, k, pid)) b = mid; else a = mid + 1;
             }
             mh = a;
+            bool regular = mh == 0 || !upper_bound_passes(mh - 1, s, k, pid);
+            for (int x = mh; x <= std::min(m0, mh + 4) && regular; x++) regular = upper_bound_passes(x, s, k, pid);
+            if (!regular) { mh = minimum_hits_relaxed(s, k, pid); t.irregular++; }
         }
         t.min_hits[s] = mh < 1 ? 1 : mh;
         float *row = &t.identity[t.id_off[s]];
@@ -190,13 +196,24 @@ const StatTable &stat_table(int k, float pid, int s_max)
             float mash = j2md((float)(1.0 * x / s), k);
             row[x] = 100 * (1 - mash);
         }
-        // The CI upper bound is non-decreasing in x (the binomial quantile is monotone in
-        // its success probability), so the filter of computeMap.hpp:380 is x >= min_shared[s].
-        // (checked exhaustively against the reference in tests/test_stat.py); bisect.
+        // The filter of computeMap.hpp:380 is evaluated per candidate, x by x.  Its CI upper bound is non-decreasing in x,
+        // so it is x >= min_shared[s]; the threshold is bisected and its neighbourhood checked (tests/test_abi.py checks
+        // whole rows against fa_stat_l2).  A row that is not a clean step is scanned in full: the threshold becomes the
+        // smallest x from which everything passes, and passing values below it are counted in `irregular` -- the index
+        // build refuses such parameters instead of mapping with a filter that differs from the reference's.
         int lo = 0, hi = s + 1;
         while (lo < hi) {
             int mid = (lo + hi) / 2;
             if (l2_pass(mid, s, k, pid, nullptr)) hi = mid; else lo = mid + 1;
+        }
+        bool step = true;
+        for (int x = std::max(0, lo - 4); x < lo && step; x++) step = !l2_pass(x, s, k, pid, nullptr);
+        for (int x = lo; x <= std::min(s, lo + 4) && step; x++) step = l2_pass(x, s, k, pid, nullptr);
+        if (!step) {
+            int thr = s + 1;
+            for (int x = s; x >= 0 && l2_pass(x, s, k, pid, nullptr); x--) thr = x;
+            for (int x = 0; x < thr; x++) if (l2_pass(x, s, k, pid, nullptr)) { t.irregular_l2++; break; }
+            lo = thr;
         }
         t.min_shared[s] = lo;
     }

@@ -27,6 +27,8 @@ struct StatTable {
     std::vector<int32_t>  min_shared;   // smallest x whose CI upper bound passes; s+1 if none
     std::vector<uint32_t> id_off;       // s_max + 2 entries
     std::vector<float>    identity;     // nucIdentity(x, s), computeMap.hpp:376
+    int irregular = 0;                  // rows whose minHits bisection disagreed with the reference's walk (the walk's value is stored)
+    int irregular_l2 = 0;               // rows whose L2 filter is not a step in x: no single threshold reproduces the reference
 };
 // Cached per (k, pid, s_max); thread-safe.
 const StatTable &stat_table(int k, float pid, int s_max);

@@ -12,14 +12,21 @@ Two ways to shard, both result-preserving:
   (computeCoreIdentity.hpp:218-250) and the min-fraction filter uses that genome's own length
   (pyx:1124-1126), so every rank produces FINAL hit rows for its genomes -- upstream FastANI does
   the same per thread (splitReferenceGenomes / correctRefGenomeIds, computeCoreIdentity.hpp:
-  454-484).  `gather_hits` moves the per-query rows (16 bytes each) to every rank with two small
-  collectives (counts, then payload) and `merge_hits` restores the reference's ordering: identity
-  descending, stable in ascending global genome id (pyx:1135).
+  454-484).  The exchange lives in the library (`fa_gather_hits` / `fa_query_batch_sharded`,
+  csrc/fa_comm.cu): the per-query rows (16 bytes each) of all ranks travel in one small
+  ncclAllGather over NVLink and are merged into the reference's ordering, identity descending,
+  stable in ascending global genome id (pyx:1135).  `merge_hits` is the same merge in numpy, kept
+  as the specification the tests compare the library against.
 
-The collectives go through ``torch.distributed`` (NCCL over NVLink on the GPU box, gloo in the CPU
-tests); torch is imported lazily and is plumbing only.
+No torch here: the NCCL communicator belongs to the library (`Communicator`), and `connect` hands
+its 128-byte id from rank 0 to the other ranks over a plain TCP socket (MASTER_ADDR / MASTER_PORT
+of the launcher, port + 1) -- or pass an `exchange` callable to use a channel you already have.
 """
 import heapq
+import os
+import socket
+import struct
+import time
 
 import numpy as np
 
@@ -93,78 +100,60 @@ def merge_hits(rows_per_rank, offsets):
     return allrows[order]
 
 
-def gather_hits(rows_per_query, group=None, device=None, cap=None):
-    """All-gather the hit rows of a list of queries.
+def connect(world_size=None, rank=None, device=None, exchange=None, timeout=120.0):
+    """Create this rank's `Communicator` (collective over all ranks).
 
-    `rows_per_query`: list (same length on every rank) of HIT_DT arrays with LOCAL genome ids.
-    Returns `out[q][r]` = rows of query q from rank r.
-
-    `cap`: an upper bound, known on every rank, of the rows one rank can hold for the whole list
-    (queries x genomes of the largest shard).  With it the exchange is ONE collective of a fixed-width
-    block per rank -- the per-query counts followed by the 16-byte rows -- and one device-to-host copy;
-    without it (or when the block would pass 4 MiB) two collectives: the counts, then a payload padded
-    to the largest total.  A few KB per query either way: latency-bound on NVLink, nothing to fuse with
-    the mapping kernels.
-    """
-    import torch
-    import torch.distributed as dist
-
-    world = dist.get_world_size(group)
-    nq = len(rows_per_query)
-    dev = device if device is not None else torch.device("cpu")
-    mine = np.concatenate([np.asarray(r, dtype=HIT_DT) for r in rows_per_query]) if nq else np.zeros(0, dtype=HIT_DT)
-    out = [[None] * world for _ in range(nq)]
-
-    if cap is not None and len(mine) > cap:
-        raise ValueError("gather_hits: %d rows on this rank exceed cap=%d (cap must bound every rank)" % (len(mine), cap))
-    if cap is not None and (nq + 4 * cap) * 4 <= (4 << 20):         # (the same decision on every rank)
-        width = nq + 4 * int(cap)
-        block = np.zeros(width, dtype=np.int32)
-        block[:nq] = [len(r) for r in rows_per_query]
-        block[nq:nq + 4 * len(mine)] = mine.view(np.int32)
-        send = torch.from_numpy(block).to(dev)
-        recv = torch.empty(world * width, dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(recv, send, group=group)
-        host = recv.cpu().numpy().reshape(world, width)
-        for r in range(world):
-            cnt = host[r, :nq]
-            rows = host[r, nq:nq + 4 * int(cnt.sum())].copy().view(HIT_DT)
-            pos = 0
-            for q in range(nq):
-                out[q][r] = rows[pos:pos + int(cnt[q])]
-                pos += int(cnt[q])
-        return out
-
-    counts = torch.tensor([len(r) for r in rows_per_query], dtype=torch.int64, device=dev)
-    all_counts = [torch.zeros_like(counts) for _ in range(world)]
-    dist.all_gather(all_counts, counts, group=group)
-    totals = [int(c.sum().item()) for c in all_counts]
-    width = max(max(totals), 1)
-    flat = np.zeros(width, dtype=HIT_DT)
-    flat[:len(mine)] = mine
-    payload = torch.from_numpy(flat.view(np.int32).reshape(width, 4).copy()).to(dev)
-    all_payload = [torch.zeros_like(payload) for _ in range(world)]
-    dist.all_gather(all_payload, payload, group=group)
-    for r in range(world):
-        rows = all_payload[r].cpu().numpy().reshape(-1).view(HIT_DT)
-        cnt = all_counts[r].cpu().numpy()
-        pos = 0
-        for q in range(nq):
-            out[q][r] = rows[pos:pos + int(cnt[q])].copy()
-            pos += int(cnt[q])
-    return out
+    `world_size`, `rank`, `device` default to the launcher's WORLD_SIZE / RANK / LOCAL_RANK.  Rank 0
+    draws the NCCL unique id; `exchange(id_or_None) -> id` broadcasts it (rank 0 passes the id, the
+    others None) -- by default a one-shot TCP hand-out on MASTER_ADDR:(MASTER_PORT + 1)
+    (FA_COMM_PORT overrides the port)."""
+    from ._fastani import Communicator
+    world_size = int(os.environ.get("WORLD_SIZE", "1")) if world_size is None else int(world_size)
+    rank = int(os.environ.get("RANK", "0")) if rank is None else int(rank)
+    device = int(os.environ.get("LOCAL_RANK", str(rank))) if device is None else int(device)
+    uid = Communicator.unique_id() if rank == 0 else None
+    if world_size > 1:
+        uid = (exchange or _tcp_broadcast(world_size, rank, timeout))(uid)
+    return Communicator(uid, world_size, rank, device)
 
 
-def query_reference_sharded(mapper, queries, offsets, group=None, device=None, drafts=False):
+def _tcp_broadcast(world_size, rank, timeout):
+    addr = os.environ.get("MASTER_ADDR", "127.0.0.1")
+    port = int(os.environ.get("FA_COMM_PORT", str(int(os.environ.get("MASTER_PORT", "29500")) + 1)))
+
+    def exchange(uid):
+        if rank == 0:
+            with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as srv:
+                srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+                srv.bind((addr, port))
+                srv.listen(world_size)
+                srv.settimeout(timeout)
+                for _ in range(world_size - 1):
+                    conn, _peer = srv.accept()
+                    with conn:
+                        conn.sendall(struct.pack("<I", len(uid)) + uid)
+            return uid
+        deadline = time.monotonic() + timeout
+        while True:
+            try:
+                with socket.create_connection((addr, port), timeout=5.0) as conn:
+                    buf = b""
+                    while len(buf) < 4 or len(buf) < 4 + struct.unpack("<I", buf[:4])[0]:
+                        chunk = conn.recv(4096)
+                        if not chunk:
+                            raise ConnectionError("rank 0 closed the connection early")
+                        buf += chunk
+                    return buf[4:4 + struct.unpack("<I", buf[:4])[0]]
+            except (ConnectionRefusedError, ConnectionError, socket.timeout, OSError):
+                if time.monotonic() > deadline:
+                    raise
+                time.sleep(0.05)
+
+    return exchange
+
+
+def query_reference_sharded(mapper, queries, offsets, comm):
     """Map every query against this rank's reference shard and return, on every rank, the merged
-    global hit rows per query.  `mapper.names` must be the LOCAL genome ids 0..n_local-1 (or any
-    names whose position in `mapper.names` is the local id)."""
-    name_to_id = {n: i for i, n in enumerate(mapper.names)}
-    # one call for the whole list: light queries share passes of the pipeline and the next pass is staged while the
-    # current one is mapped (fa_query_batch)
-    queries = list(queries)
-    items = [list(q) for q in queries] if drafts else queries
-    local = [hits_to_rows(hits, name_to_id) for hits in mapper.query_many(items)]
-    shard = max(int(offsets[r + 1]) - int(offsets[r]) for r in range(len(offsets) - 1))
-    gathered = gather_hits(local, group=group, device=device, cap=len(local) * shard)
-    return [merge_hits(per_rank, offsets) for per_rank in gathered]
+    global hit rows per query (numpy structured arrays, HIT_DT).  Collective; one library call:
+    no `Hit` objects, no host language between the mapping and the gather."""
+    return mapper.query_many(list(queries), rows=True, comm=comm, genome_offsets=[int(o) for o in offsets])

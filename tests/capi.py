@@ -31,7 +31,8 @@ class QueryInfo(C.Structure):
                                             "ms_cgi", "ms_d2h", "ms_total")]
                 + [("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("l2_fallback", C.c_uint64), ("events", C.c_uint64)]
                 + [(n, C.c_float) for n in ("ms_l2_prep", "ms_l2_events", "ms_l2_slide")]
-                + [("l1_sorted_fragments", C.c_uint32), ("l1_small_fragments", C.c_uint32), ("events_replayed", C.c_uint64)])
+                + [("l1_sorted_fragments", C.c_uint32), ("l1_small_fragments", C.c_uint32), ("events_replayed", C.c_uint64),
+                   ("ms_batch", C.c_float)])
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -95,6 +96,12 @@ def contig_array(contigs):
     return keeps, arr
 
 
+def mem_info(device=0):
+    f, t = C.c_uint64(), C.c_uint64()
+    check(lib().fa_device_mem_info(device, C.byref(f), C.byref(t)))
+    return f.value, t.value
+
+
 def recommended_window(**kw):
     p = make_params(**kw)
     w = C.c_int32()
@@ -146,6 +153,24 @@ class Sketch:
 
     def add_genome(self, name, seq):
         return self.add_draft(name, (seq,))
+
+    def add_many(self, names, genomes):
+        """fa_sketch_add_genomes: `genomes` = list of contig lists."""
+        flat = [c for g in genomes for c in g]
+        keeps, arr = contig_array(flat)
+        counts = (C.c_int32 * max(len(genomes), 1))(*[len(g) for g in genomes])
+        glen = (C.c_uint64 * max(len(genomes), 1))()
+        nshort = C.c_int32()
+        check(lib().fa_sketch_add_genomes(self.h, arr, counts, len(genomes), glen, C.byref(nshort)))
+        self.warnings += nshort.value
+        self.names.extend(names)
+        return list(glen)[:len(genomes)]
+
+    def meta(self):
+        n = self.counts()[2]
+        sbg = (C.c_int32 * max(n, 1))(); gl = (C.c_uint64 * max(n, 1))()
+        check(lib().fa_sketch_copy_meta(self.h, sbg, gl))
+        return list(sbg)[:n], list(gl)[:n]
 
     def counts(self):
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
@@ -215,6 +240,10 @@ class Index:
     def set_l1_small_cap(self, cap):
         """Test hook: on-chip fragments with more seeds than `cap` take the large shape of the L1 kernel (-1 = default)."""
         check(lib().fa_debug_set_l1_small_cap(self.h, C.c_int64(cap)))
+
+    def set_l1_small_shape(self, shape):
+        """Test hook: smallest of the three shared-memory sizes the small L1 shape may use (-1 = default)."""
+        check(lib().fa_debug_set_l1_small_shape(self.h, C.c_int32(shape)))
 
     def query_draft(self, contigs, dump=False):
         contigs = list(contigs)

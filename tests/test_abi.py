@@ -68,6 +68,22 @@ def test_filter_is_monotone_in_shared_count():
             assert [capi.stat_l2(x, s, k, pid)[0] for x in range(s + 1)] == flags
 
 
+def test_stat_table_rows_match_the_walk_down_functions():
+    """The device kernels read the TABLE (csrc/fa_stat.cpp stat_table: bisection + neighbourhood check), not the walk-down
+    functions the two tests above exercise: every row, for the default and two other parameter sets, must equal
+    max(1, estimateMinimumHitsRelaxed(s)) and the first shared count from which the filter of computeMap.hpp:380 passes."""
+    lib = capi.lib()
+    for k, pid, s_max, dense in ((16, 80.0, 2962, 320), (16, 95.0, 600, 200), (12, 90.0, 500, 200), (5, 70.0, 120, 120)):
+        for s in list(range(1, dense + 1)) + list(range(dense + 1, s_max + 1, 97)) + [s_max]:
+            mh, ms, irr = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+            capi.check(lib.fa_stat_table_row(s, s_max, k, ctypes.c_float(pid), ctypes.byref(mh), ctypes.byref(ms), ctypes.byref(irr)))
+            assert irr.value == 0
+            assert mh.value == max(1, capi.stat_minimum_hits(s, k, pid)), (s, k, pid)
+            xs = range(s + 1) if s <= 150 else sorted({x for x in (0, 1, ms.value - 2, ms.value - 1, ms.value, ms.value + 1, s // 2, s) if 0 <= x <= s})
+            for x in xs:
+                assert capi.stat_l2(x, s, k, pid)[0] == (x >= ms.value), (x, s, k, pid)
+
+
 def test_python_value_classes_and_errors():
     import pyfastani_b200 as pf
     assert pf.MAX_KMER_SIZE == 2048

@@ -1,6 +1,7 @@
-"""Host-side logic of the multi-GPU decomposition (pyfastani_b200/sharding.py): CPU tests with a
-world_size-2 gloo group, and one GPU test that reference sharding reproduces the single-index
-hits exactly."""
+"""The multi-GPU decomposition (pyfastani_b200/sharding.py, csrc/fa_comm.cu).  On CPU: the
+partitions, the merge specification, the product's own TCP rendezvous (three processes) and bench.py's
+torch.distributed plumbing on a world-size-2 gloo group.  On the GPU: reference sharding reproduces the single-index
+hits exactly, and the library's NCCL gather equals the numpy merge (two ranks when two GPUs are visible)."""
 import os
 import socket
 
@@ -62,42 +63,111 @@ def _free_port():
     return p
 
 
+def _fake_local_rows(rank):
+    """Three queries; rank r reports hits on its own (local) genomes only, ragged and empty cases."""
+    rng = np.random.default_rng(100 + rank)
+    local = []
+    for q in range(3):
+        n = [2, 0, 3][q] if rank == 0 else [1, 0, 0][q]
+        rows = np.zeros(n, dtype=HIT_DT)
+        rows["ref_genome"] = np.arange(n)
+        rows["matches"] = rng.integers(1, 100, n)
+        rows["fragments"] = 100 + q
+        rows["identity"] = np.sort(rng.uniform(80, 100, n).astype(np.float32))[::-1]
+        local.append(rows)
+    return local
+
+
+def _rendezvous_worker(rank, world, port, out_dir):
+    """The product's own rendezvous (no torch): rank 0 hands a 128-byte id to the others over TCP."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    uid = bytes(range(128)) if rank == 0 else None
+    got = sharding._tcp_broadcast(world, rank, 30.0)(uid)
+    open(os.path.join(out_dir, "id%d.bin" % rank), "wb").write(got)
+
+
+def test_tcp_rendezvous_world3(tmp_path):
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    port = _free_port()
+    procs = [ctx.Process(target=_rendezvous_worker, args=(r, 3, port, str(tmp_path))) for r in (2, 1, 0)]   # rank 0 last: the others retry
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for r in range(3):
+        assert open(tmp_path / ("id%d.bin" % r), "rb").read() == bytes(range(128))
+
+
 def _gloo_worker(rank, world, port, out_dir):
+    """World-size-2 gloo group on CPU: the N > 1 host logic of bench.py (its partition of the query list, the max over
+    ranks of the step time, the hit total) with torch.distributed as the plumbing, as on the GPU box."""
+    import torch
     import torch.distributed as dist
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        # three queries; rank r reports hits on its own (local) genomes only, ragged and empty cases
-        rng = np.random.default_rng(100 + rank)
-        local = []
-        for q in range(3):
-            n = [2, 0, 3][q] if rank == 0 else [1, 0, 0][q]
-            rows = np.zeros(n, dtype=HIT_DT)
-            rows["ref_genome"] = np.arange(n)
-            rows["matches"] = rng.integers(1, 100, n)
-            rows["fragments"] = 100 + q
-            rows["identity"] = np.sort(rng.uniform(80, 100, n).astype(np.float32))[::-1]
-            local.append(rows)
-        gathered = sharding.gather_hits(local)                       # two collectives: counts, padded payload
-        merged = [sharding.merge_hits(per_rank, [0, 3, 4]) for per_rank in gathered]
-        with pytest.raises(ValueError):
-            sharding.gather_hits(local, cap=-1)                      # a bound below the rows held: refused before any collective
-        one = sharding.gather_hits(local, cap=3 * 3)                 # one fixed-width collective (3 queries x 3 genomes)
-        for q in range(3):
-            for r in range(world):
-                assert np.array_equal(one[q][r], gathered[q][r]), (q, r)
-        np.savez(os.path.join(out_dir, "rank%d.npz" % rank), *merged, **{"local%d" % q: local[q] for q in range(3)})
+        import bench
+        counts = [1666, 1666, 1500, 900, 1666, 400, 1666, 1200, 1666]
+        mine = sharding.partition_queries(counts, world)[rank]
+        t = bench.max_over_ranks(dist, torch, torch.device("cpu"), 1.0 + rank, world)
+        n = bench.sum_over_ranks(dist, torch, torch.device("cpu"), len(mine), world)
+        # the unique id reaches every rank through the group as well (what bench.py hands to sharding.connect)
+        uid = bench.broadcast_bytes(dist, torch, torch.device("cpu"), bytes(range(128)) if rank == 0 else None, 128, world)
+        np.savez(os.path.join(out_dir, "rank%d.npz" % rank), mine=np.array(mine), t=t, n=n, uid=np.frombuffer(uid, np.uint8))
     finally:
         dist.destroy_process_group()
 
 
-def test_gather_hits_gloo_world2(tmp_path):
+def test_bench_plumbing_gloo_world2(tmp_path):
     import torch.multiprocessing as mp
 
     port = _free_port()
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a = np.load(tmp_path / "rank0.npz")
+    b = np.load(tmp_path / "rank1.npz")
+    assert sorted(a["mine"].tolist() + b["mine"].tolist()) == list(range(9))
+    assert float(a["t"]) == float(b["t"]) == 2.0 and int(a["n"]) == int(b["n"]) == 9
+    assert a["uid"].tobytes() == b["uid"].tobytes() == bytes(range(128))
+
+
+def _nccl_worker(rank, world, port, out_dir):
+    """One rank of the library's own exchange: fa_gather_hits over NCCL (no torch), against the numpy merge."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    comm = sharding.connect(world, rank, rank)
+    local = _fake_local_rows(rank)
+    merged = comm.gather_hits(local, [0, 3, 4])
+    # a batch with more rows than travel with the counts (2048): the second collective
+    big = np.zeros(3000 + 500 * rank, dtype=HIT_DT)
+    big["ref_genome"] = np.arange(len(big)) % 3000
+    big["identity"] = np.linspace(99, 80, len(big)).astype(np.float32)
+    merged_big = comm.gather_hits([big[:10], big[10:]], [0, 3000, 6500])
+    info = comm.info
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), *merged, big0=merged_big[0], big1=merged_big[1], mybig=big,
+             collectives=info["collectives"], **{"local%d" % q: local[q] for q in range(3)})
+
+
+@pytest.mark.gpu
+def test_gather_hits_nccl_world2(tmp_path):
+    import multiprocessing as mp
+    import pyfastani_b200 as pf
+
+    if pf.device_count() < 2:
+        pytest.skip("needs two GPUs (NCCL refuses two ranks on one device); run with gpurun --gpus 2")
+    ctx = mp.get_context("spawn")
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
     a = np.load(tmp_path / "rank0.npz")
     b = np.load(tmp_path / "rank1.npz")
     for q in range(3):
@@ -107,6 +177,10 @@ def test_gather_hits_gloo_world2(tmp_path):
         assert np.array_equal(ma, expect)
         assert len(ma) == [3, 0, 3][q]
         assert np.all(np.diff(ma["identity"]) <= 0)
+    for q, sl in enumerate((slice(0, 10), slice(10, None))):
+        expect = sharding.merge_hits([a["mybig"][sl], b["mybig"][sl]], [0, 3000, 6500])
+        assert np.array_equal(a["big%d" % q], expect) and np.array_equal(b["big%d" % q], expect)
+    assert int(a["collectives"]) == 3                                   # one for the small batch, two for the large one
 
 
 @pytest.mark.gpu
@@ -140,10 +214,9 @@ def test_reference_sharding_equals_single_index():
 
 
 @pytest.mark.gpu
-def test_query_reference_sharded_world1(tmp_path):
-    """`query_reference_sharded` end to end on one rank (a gloo group of one): the list of queries goes through one
-    `query_many` call, the rows through the one-collective gather, and come back as the rows of plain queries."""
-    import torch.distributed as dist
+def test_query_reference_sharded_world1():
+    """`query_reference_sharded` end to end on one rank (an NCCL communicator of one): the list of queries goes through
+    ONE library call -- fa_query_batch, the all-gather, the merge -- and comes back as the rows of plain queries."""
     import pyfastani_b200 as pf
     import synth
 
@@ -155,12 +228,12 @@ def test_query_reference_sharded_world1(tmp_path):
     queries = [query, refs[2], synth.revcomp(refs[5]), b"ACGT" * 10]
     ident = {i: i for i in range(len(refs))}
     want = [sharding.hits_to_rows(mapper.query_genome(q), ident) for q in queries]
-    dist.init_process_group("gloo", init_method="file://" + str(tmp_path / "rdv"), rank=0, world_size=1)
-    try:
-        got = sharding.query_reference_sharded(mapper, queries, [0, len(refs)])
-    finally:
-        dist.destroy_process_group()
+    comm = sharding.connect(1, 0, 0)
+    assert comm.info["nccl_version"] >= 21800
+    got = sharding.query_reference_sharded(mapper, queries, [0, len(refs)], comm)
+    rows = mapper.query_many(queries, rows=True)                    # the same rows without the communicator
     assert len(got) == len(queries)
-    for a, b in zip(got, want):
-        assert np.array_equal(a, b)
+    for a, b, c in zip(got, want, rows):
+        assert np.array_equal(a, b) and np.array_equal(c, b)
     assert len(want[0]) == 7 and len(want[3]) == 0
+    assert comm.info["collectives"] == 1
