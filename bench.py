@@ -178,6 +178,31 @@ def reference_on_host(a, base, index):
     return synth.to_bytes(synth.mutate_codes(rng, base, float(identities(a)[index])))
 
 
+KERNEL_NAMES = {"ms_sketch": "sketch_kernel", "ms_lookup": "lookup_kernel", "ms_seed_sort": "fill_seeds+DeviceRadixSort",
+                "ms_l1": "l1_fused_kernel", "ms_l2_prep": "l2_prep_kernel", "ms_l2_events": "l2_events_kernel",
+                "ms_l2_slide": "l2_slide_kernel", "ms_cgi": "cgi_best_kernel"}
+
+
+def stage_bytes(inf, bases):
+    """Algorithmic bytes per stage from the realised counters of `inf`
+    (Mapper.last_query_info, possibly summed over calls) and the query bases they cover."""
+    s_mean = inf["sketch_sum"] / max(inf["fragments"], 1)
+    return {
+        "ms_sketch": 1.96 * bases,
+        "ms_lookup": 36.0 * inf["sketch_sum"],
+        # L1 on chip (l1_fused_kernel): the position lists once (4 B / seed), one 4-byte gpos gather per seed, 16 B per
+        # candidate; ms_seed_sort is the device-wide sort of the fragments that do not fit on chip (none here)
+        "ms_seed_sort": 16.0 * inf["seeds"] * inf["l1_sorted_fragments"] / max(inf["fragments"], 1),
+        "ms_l1": 8.0 * inf["seeds"] + 16.0 * inf["candidates"],
+        # L2 = prep (index searches) + events (classify: reads the (hash, order word) stream once, writes 2-byte events
+        # and the start state) + slide (replays the events from the start window until both sides are pruned)
+        "ms_l2_prep": 56.0 * inf["candidates"],
+        "ms_l2_events": 8.0 * inf["scanned"] + 2.0 * inf["events"] + (4.0 * s_mean + 16.0) * inf["candidates"],
+        "ms_l2_slide": 2.0 * inf["events_replayed"] + (s_mean + 54.0) * inf["candidates"],
+        "ms_cgi": 16.0 * inf["candidates"],
+    }
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
 
@@ -478,28 +503,12 @@ def run_b200(a):
     # rank; a heavy query runs alone in its pass, so one launch = one query) ------------------------------------------
     peak, which = peaks()
     nq_rank = max(len(mine), 1)
-    s_mean = inf["sketch_sum"] / max(inf["fragments"], 1)
-    alg = {
-        "ms_sketch": 1.96 * a.length * nq_rank,
-        "ms_lookup": 36.0 * inf["sketch_sum"],
-        # L1 on chip (l1_fused_kernel): the position lists once (4 B / seed), one 4-byte gpos gather per seed, 16 B per
-        # candidate; ms_seed_sort is the device-wide sort of the fragments that do not fit on chip (none here)
-        "ms_seed_sort": 16.0 * inf["seeds"] * inf["l1_sorted_fragments"] / max(inf["fragments"], 1),
-        "ms_l1": 8.0 * inf["seeds"] + 16.0 * inf["candidates"],
-        # L2 = prep (index searches) + events (classify: reads the (hash, order word) stream once, writes 2-byte events
-        # and the start state) + slide (replays the events from the start window until both sides are pruned)
-        "ms_l2_prep": 56.0 * inf["candidates"],
-        "ms_l2_events": 8.0 * inf["scanned"] + 2.0 * inf["events"] + (4.0 * s_mean + 16.0) * inf["candidates"],
-        "ms_l2_slide": 2.0 * inf["events_replayed"] + (s_mean + 54.0) * inf["candidates"],
-        "ms_cgi": 16.0 * inf["candidates"],
-    }
+    alg = stage_bytes(inf, a.length * nq_rank)
     per_step = {k: v / a.steps for k, v in stage.items()}
     top = max(alg, key=lambda k: per_step.get(k, 0.0))
     top_ms = per_step[top]
     achieved = alg[top] / (top_ms * 1e-3) / 1e9 if top_ms > 0 else 0.0
-    kernel_names = {"ms_sketch": "sketch_kernel", "ms_lookup": "lookup_kernel", "ms_seed_sort": "fill_seeds+DeviceRadixSort",
-                    "ms_l1": "l1_fused_kernel", "ms_l2_prep": "l2_prep_kernel", "ms_l2_events": "l2_events_kernel",
-                    "ms_l2_slide": "l2_slide_kernel", "ms_cgi": "cgi_best_kernel"}
+    kernel_names = KERNEL_NAMES
     step_ms_rank = per_step.get("ms_batch", dev_ms / a.steps)
     roofline = {"bound": "hbm", "kernel": kernel_names[top], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": measured_traffic(kernel_names[top], a),
