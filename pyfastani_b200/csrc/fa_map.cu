@@ -686,12 +686,17 @@ constexpr uint32_t EV_MATCH = 4;      // the hash is in the query sketch: toggle
 constexpr uint32_t EV_ONLY = 8;       // the hash is not in the sketch: counts in bucket idx (neither bit: no state change)
 constexpr uint32_t EV_DEL = 16;       // delete (window begin advances) / insert
 constexpr uint32_t EV_GRP = 32;       // last event of its time group: evaluate the window after it
+constexpr uint32_t EV_GRPB = 64;      // the event BEFORE this one ends a time group: the backward replay evaluates after undoing this one
 constexpr uint32_t EV_AOFF = 0x7F03;
 constexpr int EV_MAX_S = 508;         // largest sketch the 16-bit events address
 constexpr int EV_RMAX = 1024;         // most reference minimizers of a candidate region on the event path
 constexpr int EVK_THREADS = 128;
 constexpr int EV_UNROLL = 8;          // independent loads per lane in the classification loop
-constexpr int EV_WARP_BYTES = (2 * EV_RMAX + 16) * 2;   // per-warp staging of one event list
+constexpr int EV_LIST_BYTES = (2 * EV_RMAX + 16) * 2;   // per-warp staging of one event list
+constexpr int EV_HIST_BYTES = 512;                      // per-warp byte state of the start window (EV_MAX_S + 4 buckets)
+constexpr int EV_WARP_BYTES = EV_LIST_BYTES + EV_HIST_BYTES;
+// 16-bit units of the state block that precedes a candidate's event list: one byte per bucket, padded to 16 bytes
+__host__ __device__ inline int ev_state_u16(int s) { return ((((s + 4) >> 2) * 4 + 15) & ~15) >> 1; }
 
 __host__ __device__ inline uint32_t ev_aoff(int idx) { return ((uint32_t)(idx & ~3) << 6) | (uint32_t)(idx & 3); }
 
@@ -708,7 +713,7 @@ struct Prep {
 __global__ void __launch_bounds__(256)
 l2_prep_kernel(const Cand *cands, const uint32_t *cand_base, int n_frags, const int32_t *qs, const RefMini *ref, const uint2 *hw,
                const uint2 *hl, const uint32_t *fb, const uint32_t *contig_off, int frag_len, int cmw, int dens_num, int dens_den, Prep *prep,
-               unsigned long long *ev_cnt, Mapping *maps, unsigned long long *counters)
+               uint32_t *mid, unsigned long long *ev_cnt, Mapping *maps, unsigned long long *counters)
 {
     const uint32_t n = cand_base[n_frags];
     unsigned long long scanned = 0;
@@ -748,7 +753,23 @@ l2_prep_kernel(const Cand *cands, const uint32_t *cand_base, int n_frags, const 
             pp.n_del = dstop - 1 - beg;
             const bool fast = last - beg <= (uint32_t)EV_RMAX && qs[cd.frag] <= EV_MAX_S && cmw >= 2;
             if (fast) {
-                cnt = ((unsigned long long)(last - 1 - beg) + pp.n_del + 7ull) & ~7ull;             // padded to whole 16-byte chunks
+                // The slide starts in the MIDDLE of the region -- at the window centred on the seeds that define it -- and
+                // runs to the right, then to the left (l2_slide_kernel).  d_m = begin index of that window relative to beg
+                // (= deletes before it), e_m = its end index (= inserts before it); the state after delete d_m - 1 (and the
+                // insert that shares its time, if any) is an evaluation point of the forward order.
+                const int nI = (int)(last - 1 - beg), nD = (int)pp.n_del, y0 = (int)(end0 - beg);
+                const int ctr = (int)(((long long)cd.hint + (long long)cd.tail) / 2 - (long long)beg);
+                const int dm = min(max(ctr - y0 / 2, 0), nD);
+                int em = y0;
+                if (dm > 0) {
+                    const uint32_t ow = hl[beg + (uint32_t)dm - 1u].y;
+                    const int lead = (int)((ow >> 16) & 0x7FFFu);
+                    em = min(dm - 1 + lead, nI);
+                    em += (((ow >> 15) & 1u) && dm - 1 + lead < nI) ? 1 : 0;
+                }
+                const int pad0 = (8 - ((dm + em - y0) & 7)) & 7;                // the start state sits on a 16-byte boundary
+                cnt = (unsigned long long)(ev_state_u16(qs[cd.frag]) + ((pad0 + nI + nD - y0 + 7) & ~7));   // (the first window is never replayed)
+                mid[c] = (uint32_t)dm | ((uint32_t)em << 16);
                 pp.n_del |= (end0 - beg) << 16;
             }
             else { mp.ref_start = L2_REDO; redo++; }
