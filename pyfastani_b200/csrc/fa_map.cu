@@ -686,12 +686,11 @@ constexpr uint32_t EV_MATCH = 4;      // the hash is in the query sketch: toggle
 constexpr uint32_t EV_ONLY = 8;       // the hash is not in the sketch: counts in bucket idx (neither bit: no state change)
 constexpr uint32_t EV_DEL = 16;       // delete (window begin advances) / insert
 constexpr uint32_t EV_GRP = 32;       // last event of its time group: evaluate the window after it
-constexpr uint32_t EV_GRPB = 64;      // the event BEFORE this one ends a time group: the backward replay evaluates after undoing this one
 constexpr uint32_t EV_AOFF = 0x7F03;
 constexpr int EV_MAX_S = 508;         // largest sketch the 16-bit events address
 constexpr int EV_RMAX = 1024;         // most reference minimizers of a candidate region on the event path
 constexpr int EVK_THREADS = 128;
-constexpr int EV_UNROLL = 8;          // independent loads per lane in the classification loop
+constexpr int EV_UNROLL = 4;          // elements per lane and trip of the classification loop (the loop body has to stay in the instruction cache)
 constexpr int EV_LIST_BYTES = (2 * EV_RMAX + 16) * 2;   // per-warp staging of one event list
 constexpr int EV_HIST_BYTES = 512;                      // per-warp byte state of the start window (EV_MAX_S + 4 buckets)
 constexpr int EV_WARP_BYTES = EV_LIST_BYTES + EV_HIST_BYTES;
@@ -804,11 +803,14 @@ __device__ __forceinline__ uint32_t l2_slot(uint32_t h, int p)
     return (uint32_t)L2_TAB - ((uint32_t)L2_TAB >> k) + ((h & ((1u << p) - 1u)) >> (p - (L2_TAB_BITS - 1) + k));
 }
 
-// Per candidate descriptor for the slide kernel.
+// Per candidate descriptor for the slide kernel (32 bytes).
 struct SlideJob {
-    unsigned long long ev_off;  // first event
-    uint32_t n_events;          // unpadded; 0 = nothing to slide
-    int32_t  s;                 // sketch size of the fragment
+    unsigned long long ev_off;  // the candidate's state block in the event buffer (16-bit units); its event list follows
+    uint32_t n_list;            // events of the list, leading padding included, PLUS ONE; 0 = nothing to slide (no window)
+    uint32_t k_mid;             // list position of the start state (a multiple of 8)
+    uint16_t s, d_m;            // sketch size; begin index of the start window relative to the region
+    uint16_t room_r, room_l;    // elements in the sketch at or right of the start window's begin / left of its end
+    uint16_t istar, sigma, shared, flags;   // pivot and shared count of the start window; flags bit 0: a bucket count overflowed
 };
 
 // ---- events --------------------------------------------------------------------------------
@@ -822,33 +824,112 @@ struct SlideJob {
 //          entered before it (i + lead), deletes first inside a time group (MIIteratorL2.hpp:74-96):
 //          every element is classified and both of its events go straight to their place in a staged
 //          list -- no merge, no position array; the list leaves in whole 16-byte chunks.
+//   start state: the slide starts at the window in the middle of the region (l2_prep_kernel) and replays the
+//          list from there in both directions, so the bucket bytes of that window are built here, in
+//          parallel (one shared-memory atomic per element of the window), together with its pivot and shared
+//          count (ev_pivot); they travel in front of the list.  The events of the first window are never
+//          replayed and are not written.
 struct EvCtx {
-    const uint32_t *s_q; const uint16_t *s_tab; uint16_t *w_ev;
-    const RefMini *ref; const uint2 *hl; uint16_t *ev; SlideJob *jobs; uint16_t *room;
+    const uint32_t *s_q; const uint16_t *s_tab; uint16_t *w_ev; uint32_t *w_hist;
+    const RefMini *ref; const uint2 *hl; uint16_t *ev; SlideJob *jobs;
     int s, tab_p, maxn;
 };
 
-// MAXN > 0: every table slot holds at most MAXN sketch hashes; MAXN == 0: bisect inside the slot.
-template <int MAXN>
-__device__ __forceinline__ void ev_candidate(const EvCtx &X, uint32_t c, const Prep &pp, unsigned long long off,
-                                             unsigned long long off1, int lane)
+// Pivot (istar, sigma) and shared count of the window whose bucket bytes (count << 1 | match bit) are in `hist`:
+// T(x) = x + sum of the counts of the buckets below x grows strictly with x; istar is the largest x with T(x) <= s,
+// sigma = s - T(istar) (<= the count of bucket istar), shared = match bits of the buckets 1..istar.  One warp, every
+// lane owns 16 buckets.
+__device__ __forceinline__ void ev_pivot(const uint32_t *hist, int s, int lane, int &istar, int &sigma, int &shared)
 {
-    const uint32_t *s_q = X.s_q; const uint16_t *s_tab = X.s_tab; uint16_t *w_ev = X.w_ev;
-    const RefMini *ref = X.ref; const uint2 *hl = X.hl; uint16_t *ev = X.ev; SlideJob *jobs = X.jobs;
+    constexpr unsigned full = 0xFFFFFFFFu;
+    const uint4 v = reinterpret_cast<const uint4 *>(hist)[lane];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    int csum = 0, msum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        csum += (int)__dp4a((w[j] >> 1) & 0x7F7F7F7Fu, 0x01010101u, 0u);
+        msum += __popc(w[j] & 0x01010101u);
+    }
+    int cpre = csum, mpre = msum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int a = __shfl_up_sync(full, cpre, o), b = __shfl_up_sync(full, mpre, o);
+        if (lane >= o) { cpre += a; mpre += b; }
+    }
+    cpre -= csum; mpre -= msum;
+    int t = 16 * lane + cpre, m = mpre;                         // T(16 lane), match bits below bucket 16 lane
+    const unsigned ok = __ballot_sync(full, t <= s);            // (lane 0: T(0) = 0)
+    const int src = 31 - __clz(ok);
+    int bi = 16 * lane, bt = t, bm = m;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const int byte = (int)((w[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+        if (t <= s) { bi = 16 * lane + j; bt = t; bm = m + (byte & 1); }
+        t += 1 + (byte >> 1); m += byte & 1;
+    }
+    istar = __shfl_sync(full, bi, src);
+    sigma = s - __shfl_sync(full, bt, src);
+    shared = __shfl_sync(full, bm, src);
+}
+
+// The tail of a candidate: pivot of the start window, state block and event list to global memory, descriptor.
+__device__ __forceinline__ void ev_finish(const EvCtx &X, uint32_t c, unsigned long long off, int n_list, int kmid_list, int dm,
+                                       int room_r, int room_l, int ovf, int lane)
+{
+    uint16_t *w_ev = X.w_ev;
+    const int s = X.s, sb = ev_state_u16(s);
+    if (lane < 8) w_ev[n_list + lane] = (uint16_t)0;        // the tail of the last chunk is padding: no-ops
+    __syncwarp();
+    int istar, sigma, shared;
+    ev_pivot(X.w_hist, s, lane, istar, sigma, shared);
+    if (lane == 0) {
+        SlideJob jb;
+        jb.ev_off = off; jb.n_list = (uint32_t)n_list + 1u; jb.k_mid = (uint32_t)kmid_list;
+        jb.s = (uint16_t)s; jb.d_m = (uint16_t)dm; jb.room_r = (uint16_t)room_r; jb.room_l = (uint16_t)room_l;
+        jb.istar = (uint16_t)istar; jb.sigma = (uint16_t)sigma; jb.shared = (uint16_t)shared; jb.flags = (uint16_t)(ovf ? 1 : 0);
+        const uint4 *src = reinterpret_cast<const uint4 *>(&jb);
+        uint4 *dst = reinterpret_cast<uint4 *>(X.jobs + c);
+        dst[0] = src[0]; dst[1] = src[1];
+    }
+    // state block: the bucket bytes, 16 per lane (the rest of the histogram is zero)
+    if (lane < (sb >> 3)) reinterpret_cast<uint4 *>(X.ev + off)[lane] = reinterpret_cast<const uint4 *>(X.w_hist)[lane];
+    // the list, in 16-byte chunks
+    {
+        const uint4 *srcv = reinterpret_cast<const uint4 *>(w_ev);
+        uint4 *dst = reinterpret_cast<uint4 *>(X.ev + off + sb);
+        const int n_chunks = (n_list + 7) >> 3;
+        for (int t = lane; t < n_chunks; t += 32) dst[t] = srcv[t];
+    }
+}
+
+// MAXN > 0: every table slot holds at most MAXN sketch hashes; MAXN == 0: bisect inside the slot.
+// The classification loop of one candidate (one warp): events into the staged list, the start window into the histogram.
+// Returns (packed) the elements in the sketch at or right of the start window's begin / left of its end, and whether a
+// bucket count of the start window overflowed.
+template <int MAXN>
+__device__ __forceinline__ uint32_t ev_candidate(const EvCtx &X, const Prep &pp, int dm, int em, int shift, int lane)
+{
+    const uint32_t *s_q = X.s_q; const uint16_t *s_tab = X.s_tab; uint16_t *w_ev = X.w_ev; uint32_t *w_hist = X.w_hist;
+    const RefMini *ref = X.ref; const uint2 *hl = X.hl;
     const int s = X.s, tab_p = X.tab_p;
-    const uint32_t n_pad = (uint32_t)(off1 - off);
     const int R = (int)(pp.last - pp.beg), nI = R - 1, nD = (int)(pp.n_del & 0xFFFFu), y0 = (int)(pp.n_del >> 16);
-    const int N = n_pad ? nI + nD : 0;
-    if (lane == 0) jobs[c] = SlideJob{off, (uint32_t)N, s};
-    if (!N) return;
-    int n_mi = 0;                                      // elements that are in the sketch
-    __syncwarp();                                      // (the copy-out of the previous list is done)
+    int n_r = 0, n_l = 0;                              // elements in the sketch right / left of the start window's edges
+    uint32_t ovf = 0;                                  // OR of the bucket words the adds found
+    // (hash, order word) of EV_UNROLL elements per lane and trip, the next trip's loads in flight while this one is classified
+    uint2 nx[EV_UNROLL];
+#pragma unroll
+    for (int u = 0; u < EV_UNROLL; u++) {
+        const int i = u * 32 + lane;
+        nx[u] = i < R ? __ldg(hl + pp.beg + i) : make_uint2(0u, 0u);
+    }
+#pragma unroll 1
     for (int i0 = 0; i0 < R; i0 += 32 * EV_UNROLL) {
-        uint2 xs[EV_UNROLL];                           // (hash, order word)
+        uint2 xs[EV_UNROLL];
 #pragma unroll
         for (int u = 0; u < EV_UNROLL; u++) {
-            const int i = i0 + u * 32 + lane;
-            xs[u] = i < R ? __ldg(hl + pp.beg + i) : make_uint2(0u, 0u);
+            xs[u] = nx[u];
+            const int i = i0 + (EV_UNROLL + u) * 32 + lane;
+            if (i < R) nx[u] = __ldg(hl + pp.beg + i);
         }
 #pragma unroll
         for (int u = 0; u < EV_UNROLL; u++) {
@@ -865,22 +946,28 @@ __device__ __forceinline__ void ev_candidate(const EvCtx &X, uint32_t c, const P
                     match = l < s ? eq : 0;
                 } else {
                     int r = (int)s_tab[slot + 1];
-                    while (l < r) { const int mid = (l + r) >> 1; if (s_q[mid] < h) l = mid + 1; else r = mid; }
+                    while (l < r) { const int mid2 = (l + r) >> 1; if (s_q[mid2] < h) l = mid2 + 1; else r = mid2; }
                     match = (l < s && s_q[l] == h) ? 1 : 0;
                 }
-                n_mi += match;
-                const uint32_t code = ev_aoff(l + match) | (match ? EV_MATCH : EV_ONLY);
+                n_r += (match && i >= dm) ? 1 : 0;
+                n_l += (match && i < em) ? 1 : 0;
+                const int idx = l + match;
+                const uint32_t code = ev_aoff(idx) | (match ? EV_MATCH : EV_ONLY);
                 const uint32_t ow = xs[u].y;
                 uint32_t dd = 0u;
                 if (__builtin_expect((ow >> 31) != 0u, 0)) dd = ref[pp.beg + (uint32_t)i].w;   // a same-hash neighbour exists (rare)
+                const uint32_t dp = dd & 0xFFFFu;
+                // start window [dm, em): one count per distinct hash
+                if (i >= dm && i < em && !(dp && i - (int)dp >= dm)) {
+                    // (a byte cannot wrap before an add has seen its top bit set: counts from 64 on go to the exact kernel)
+                    ovf |= atomicAdd(&w_hist[idx >> 2], (match ? 1u : 2u) << (8u * (uint32_t)(idx & 3)));
+                }
                 // insert i: after the deletes of the region's elements that left before it entered
-                const int x = min(max(i - (int)(ow & 0x7FFFu) - 1, 0), nD);
-                if (i < nI) {
-                    const uint32_t dp = dd & 0xFFFFu;
+                if (i >= y0 && i < nI) {
+                    const int x = min(max(i - (int)(ow & 0x7FFFu) - 1, 0), nD);
                     const bool skip = dp && i - (int)dp >= x;              // already present (REV)
-                    // one evaluation after the whole first window (elements before y0), then after every insert:
-                    // insert times are distinct
-                    w_ev[i + x] = (uint16_t)((skip ? 0u : code) | (i >= y0 - 1 ? EV_GRP : 0u));
+                    // insert times are distinct: every insert after the first window ends its time group
+                    w_ev[i + x + shift] = (uint16_t)((skip ? 0u : code) | EV_GRP);
                 }
                 // delete i: after the inserts of the elements that entered before it leaves
                 if (i < nD) {
@@ -889,28 +976,20 @@ __device__ __forceinline__ void ev_candidate(const EvCtx &X, uint32_t c, const P
                     const bool twin = ((ow >> 15) & 1u) && i + lead < nI;      // an insert of the same time follows: same group
                     const uint32_t dn = dd >> 16;
                     const bool skip = dn && i + (int)dn < y;               // a later copy stays (NOOP)
-                    w_ev[i + y] = (uint16_t)((skip ? 0u : code) | EV_DEL | (twin ? 0u : EV_GRP));
+                    w_ev[i + y + shift] = (uint16_t)((skip ? 0u : code) | EV_DEL | (twin ? 0u : EV_GRP));
                 }
             }
         }
     }
-    // (an upper bound of the inserts that set a match bit -- same-hash copies and the last element are counted,
-    // too -- is all the early stop of the slide needs)
-    n_mi = __reduce_add_sync(0xFFFFFFFFu, n_mi);
-    if (lane == 0) X.room[c] = (uint16_t)n_mi;
-    if (lane < 8) w_ev[N + lane] = (uint16_t)0;        // the tail of the last chunk is padding: no-ops
-    __syncwarp();
-    {
-        const uint4 *srcv = reinterpret_cast<const uint4 *>(w_ev);
-        uint4 *dst = reinterpret_cast<uint4 *>(ev + off);
-        for (int t = lane; t < (int)(n_pad >> 3); t += 32) dst[t] = srcv[t];
-    }
+    // (upper bounds of the inserts that set a match bit -- same-hash copies and the last element are counted, too --
+    // are all the early stops of the slide need)
+    return (uint32_t)n_r | ((uint32_t)n_l << 12) | ((ovf & 0x80808080u) ? 1u << 24 : 0u);     // (at most EV_RMAX = 1024 elements per lane sum)
 }
 
-__global__ void __launch_bounds__(EVK_THREADS)
-l2_events_kernel(const Prep *prep, const unsigned long long *ev_off, const uint32_t *cand_base, const uint32_t *work_base,
+__global__ void __launch_bounds__(EVK_THREADS, 8)
+l2_events_kernel(const Prep *prep, const uint32_t *mid, const unsigned long long *ev_off, const uint32_t *cand_base, const uint32_t *work_base,
                  int n_frags, const uint32_t *qhash, const uint64_t *seq_first, const int32_t *qs,
-                 const RefMini *ref, const uint2 *hl, int tab_p, uint16_t *ev, SlideJob *jobs, uint16_t *room,
+                 const RefMini *ref, const uint2 *hl, int tab_p, uint16_t *ev, SlideJob *jobs,
                  unsigned long long *counters, int q_cap)
 {
     extern __shared__ __align__(16) uint8_t ev_smem[];
@@ -921,6 +1000,7 @@ l2_events_kernel(const Prep *prep, const unsigned long long *ev_off, const uint3
     __shared__ int s_maxn, s_cached_f;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint16_t *w_ev = reinterpret_cast<uint16_t *>(s_warp + wid * EV_WARP_BYTES);  // the event list of the warp's candidate
+    uint32_t *w_hist = reinterpret_cast<uint32_t *>(s_warp + wid * EV_WARP_BYTES + EV_LIST_BYTES);   // bucket bytes of its start window
     const uint32_t n_work = work_base[n_frags];
     if (tid == 0) s_cached_f = -1;
 
@@ -931,7 +1011,7 @@ l2_events_kernel(const Prep *prep, const unsigned long long *ev_off, const uint3
         const uint32_t item = s_item;
         if (item >= n_work) break;
         int flo = 0, fhi = n_frags - 1;
-        while (flo < fhi) { int mid = (flo + fhi + 1) >> 1; if (work_base[mid] <= item) flo = mid; else fhi = mid - 1; }
+        while (flo < fhi) { int mid2 = (flo + fhi + 1) >> 1; if (work_base[mid2] <= item) flo = mid2; else fhi = mid2 - 1; }
         const int f = flo;
         const int s = qs[f];
         const uint32_t c_lo = cand_base[f] + (item - work_base[f]) * L2_ITEM;
@@ -956,29 +1036,46 @@ l2_events_kernel(const Prep *prep, const unsigned long long *ev_off, const uint3
         __syncthreads();
         const int maxn = s_maxn;
         EvCtx X;
-        X.s_q = s_q; X.s_tab = s_tab; X.w_ev = w_ev; X.ref = ref; X.hl = hl; X.ev = ev; X.jobs = jobs; X.room = room;
+        X.s_q = s_q; X.s_tab = s_tab; X.w_ev = w_ev; X.w_hist = w_hist; X.ref = ref; X.hl = hl; X.ev = ev; X.jobs = jobs;
         X.s = s; X.tab_p = tab_p; X.maxn = maxn;
 
         // candidates are handed out one ahead, so the next descriptor is in flight while this one is processed
         uint32_t c = c_lo + (uint32_t)wid;
         Prep pp{};
+        uint32_t md = 0;
         unsigned long long off = 0, off1 = 0;
-        if (c < c_hi) { pp = prep[c]; off = ev_off[c]; off1 = ev_off[c + 1]; }
+        if (c < c_hi) { pp = prep[c]; md = mid[c]; off = ev_off[c]; off1 = ev_off[c + 1]; }
         while (c < c_hi) {
             uint32_t c_nx = 0;
             if (lane == 0) c_nx = atomicAdd(&s_next, 1u);
             c_nx = __shfl_sync(0xFFFFFFFFu, c_nx, 0);
             Prep pp_nx{};
+            uint32_t md_nx = 0;
             unsigned long long off_nx = 0, off1_nx = 0;
-            if (c_nx < c_hi) { pp_nx = prep[c_nx]; off_nx = ev_off[c_nx]; off1_nx = ev_off[c_nx + 1]; }
+            if (c_nx < c_hi) { pp_nx = prep[c_nx]; md_nx = mid[c_nx]; off_nx = ev_off[c_nx]; off1_nx = ev_off[c_nx + 1]; }
 
-            switch (maxn <= 2 ? 2 : (maxn <= 4 ? 4 : (maxn <= L2_QPAD - 1 ? L2_QPAD - 1 : 0))) {
-            case 2: ev_candidate<2>(X, c, pp, off, off1, lane); break;
-            case 4: ev_candidate<4>(X, c, pp, off, off1, lane); break;
-            case L2_QPAD - 1: ev_candidate<L2_QPAD - 1>(X, c, pp, off, off1, lane); break;
-            default: ev_candidate<0>(X, c, pp, off, off1, lane); break;
+            if (off1 == off) {                              // nothing to slide (no window, or left to the exact kernel)
+                if (lane == 0) { uint4 *dst = reinterpret_cast<uint4 *>(jobs + c); dst[0] = make_uint4(0, 0, 0, 0); dst[1] = make_uint4(0, 0, 0, 0); }
+            } else {
+                const int nI = (int)(pp.last - pp.beg) - 1, nD = (int)(pp.n_del & 0xFFFFu), y0 = (int)(pp.n_del >> 16);
+                const int dm = (int)(md & 0xFFFFu), em = (int)(md >> 16);
+                const int pad0 = (8 - ((dm + em - y0) & 7)) & 7;
+                __syncwarp();                                  // (the copy-out of the previous list is done)
+                reinterpret_cast<uint4 *>(w_hist)[lane] = make_uint4(0, 0, 0, 0);
+                if (lane < pad0) w_ev[lane] = (uint16_t)0;
+                __syncwarp();
+                uint32_t r;
+                switch (maxn <= 2 ? 2 : (maxn <= 4 ? 4 : (maxn <= L2_QPAD - 1 ? L2_QPAD - 1 : 0))) {
+                case 2: r = ev_candidate<2>(X, pp, dm, em, pad0 - y0, lane); break;
+                case 4: r = ev_candidate<4>(X, pp, dm, em, pad0 - y0, lane); break;
+                case L2_QPAD - 1: r = ev_candidate<L2_QPAD - 1>(X, pp, dm, em, pad0 - y0, lane); break;
+                default: r = ev_candidate<0>(X, pp, dm, em, pad0 - y0, lane); break;
+                }
+                const int n_r = (int)__reduce_add_sync(0xFFFFFFFFu, r & 0xFFFu), n_l = (int)__reduce_add_sync(0xFFFFFFFFu, (r >> 12) & 0xFFFu);
+                const int ovf = __any_sync(0xFFFFFFFFu, (r >> 24) != 0u) ? 1 : 0;
+                ev_finish(X, c, off, pad0 + nI + nD - y0, dm + em - y0 + pad0, dm, n_r, n_l, ovf, lane);
             }
-            c = c_nx; pp = pp_nx; off = off_nx; off1 = off1_nx;
+            c = c_nx; pp = pp_nx; md = md_nx; off = off_nx; off1 = off1_nx;
         }
     }
 }
@@ -986,16 +1083,27 @@ l2_events_kernel(const Prep *prep, const unsigned long long *ev_off, const uint3
 // ---- slide ---------------------------------------------------------------------------------
 // One lane per candidate, eight events (one 16-byte chunk) per loop trip, the next chunk in
 // flight.  Every event is applied with selects only, so lanes do not diverge whatever mix of
-// inserts / deletes / matches they replay.  Lanes take candidates from one global counter: a lane
-// that finishes starts the next candidate at the next trip.  State is one byte per bucket (7-bit
-// count + match bit), four buckets per 32-bit word, words interleaved by lane so that every lane
-// owns a shared-memory bank.  A count that would pass 127 sends the candidate to the fallback.
+// inserts / deletes / matches they replay -- in either direction: the state is a function of the
+// window content, so an event is undone by applying its opposite.  A lane starts from the state of
+// the window in the middle of its region (built by the events kernel), replays the list to the
+// right until no later window can reach the best one, takes the start state again and replays the
+// list to the left until the same holds there.  State is one byte per bucket (7-bit count + match
+// bit), four buckets per 32-bit word, words interleaved by lane so that every lane owns a
+// shared-memory bank.  A count that would pass 127 sends the candidate to the fallback.
+//   Nothing a lane waits for is fetched by that lane alone while the other 31 idle:
+//   * candidates are claimed one ahead (one atomic per warp and trip), so the descriptor of the next
+//     candidate is in registers when the current one ends;
+//   * the start state (one 16-byte piece per lane of the warp, a single coalesced request) is put
+//     into the owner's column by the whole warp -- when a candidate starts and when it turns round;
+//   * the two position gathers of a finished candidate are consumed one trip after they were issued.
 struct SlideLane {
-    int sigma, shared, best, nb, first_nb, last_nb;
+    int sigma, shared, best, nb;
+    int pa, pb;                // begin index of the optimum: pa is set when it improves, pb also when it is equalled
+                               // (forward: first / last position of computeMap.hpp:467-481, backward: last / first)
     uint32_t a;                // cached state byte of bucket istar
     uint32_t ioff;             // ev_aoff(istar)
     uint32_t mx;               // largest state byte written (> 255: a bucket count overflowed)
-    int room;                  // match inserts of the list less the match deletes so far: no later window shares more
+    int room;                  // elements in the sketch still inside or ahead of the window: no later window shares more
 };
 
 // shared-memory bytes by 32-bit shared address (keeps the window base out of the per-event code)
@@ -1007,30 +1115,45 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
 }
 __device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v)); }
 
-// state byte of a bucket: count << 1 | match bit, so an event adds +-(EV_MATCH ? 1 : EV_ONLY ? 2 : 0)
-__device__ __forceinline__ void slide_event(SlideLane &L, uint32_t st, uint32_t ev)
+// window evaluation at the end of a time group (computeMap.hpp:467-481), by begin index
+__device__ __forceinline__ void slide_eval(SlideLane &L, bool grp)
 {
-    const uint32_t aoff = ev & EV_AOFF;
+    const bool gt = grp && L.shared > L.best, ge = grp && L.shared >= L.best;
+    L.best = gt ? L.shared : L.best;
+    L.pa = gt ? L.nb : L.pa;
+    L.pb = ge ? L.nb : L.pb;
+}
+
+// state byte of a bucket: count << 1 | match bit, so an event adds +-(EV_MATCH ? 1 : EV_ONLY ? 2 : 0).
+// The event sits in bits SH..SH+15 of w (two events per word; the flags are tested in place).  xdel2 = EV_DEL in both
+// halves undoes the events (backward replay: a delete puts its element back); gw = the word whose EV_GRP flag (same
+// half) asks for an evaluation after this event (forward: the event itself; backward: the one undone next, which ends
+// its time group with the state this event leaves); dir = +1 / -1, the way the begin index moves.
+template <int SH>
+__device__ __forceinline__ void slide_event(SlideLane &L, uint32_t st, uint32_t w, uint32_t xdel2, uint32_t gw, int dir)
+{
+    const uint32_t aoff = (w >> SH) & EV_AOFF;
     const uint32_t pa = st + aoff;
     const uint32_t v = lds_u8(pa);
-    const bool del = (ev & EV_DEL) != 0;
+    const bool del = ((w ^ xdel2) & (EV_DEL << SH)) != 0;                        // the element leaves the window
     const int sgn = del ? -1 : 1;
     const uint32_t noff = (L.ioff + (del ? 0xFDu : 0xFFFFFFFFu)) & ~0xFCu;       // bucket istar + 1 / istar - 1
     const uint32_t pn = lds_u8(st + noff);                                      // (slack rows on both sides)
-    const uint32_t v2 = v + (uint32_t)(sgn * (int)((ev >> 2) & 3u));
+    const uint32_t v2 = v + (uint32_t)(sgn * (int)((w >> (SH + 2)) & 3u));
     sts_u8(pa, v2);
     L.mx = max(L.mx, v2);
     const bool below = aoff < L.ioff, at_p = aoff == L.ioff;
     L.a = at_p ? v2 : L.a;
     const int cc = (int)(L.a >> 1);
-    const bool on = (ev & EV_ONLY) != 0;
+    const bool on = (w & (EV_ONLY << SH)) != 0;
     const bool in_ins = on && !del && below;
     const bool in_del = on && del && (below || (at_p && L.sigma > cc));
     const bool mv_dn = in_ins && L.sigma == 0;
     const bool mv_up = in_del && (at_p || L.sigma >= cc);
     const bool mv = mv_dn || mv_up;
-    L.shared += ((ev & EV_MATCH) != 0 && aoff <= L.ioff) ? sgn : 0;
-    L.room -= (ev & (EV_MATCH | EV_DEL)) == (EV_MATCH | EV_DEL) ? 1 : 0;
+    const bool mt = (w & (EV_MATCH << SH)) != 0;
+    L.shared += (mt && aoff <= L.ioff) ? sgn : 0;
+    L.room -= (mt && del) ? 1 : 0;
     const uint32_t a_nb = (aoff == noff) ? v2 : pn;                  // (only possible when moving down)
     const int dsh = mv_up ? (int)(a_nb & 1u) : (mv_dn ? -(int)(L.a & 1u) : 0);
     L.shared += dsh;
@@ -1038,99 +1161,216 @@ __device__ __forceinline__ void slide_event(SlideLane &L, uint32_t st, uint32_t 
     L.ioff = mv ? noff : L.ioff;
     const int sig_n = L.sigma + (in_del ? 1 : 0) - (in_ins ? 1 : 0);
     L.sigma = mv_dn ? (int)(L.a >> 1) : (mv_up ? 0 : sig_n);
-    // window evaluation at the end of a time group (computeMap.hpp:467-481), by begin index
-    L.nb += del ? 1 : 0;
-    const bool grp = (ev & EV_GRP) != 0;
-    const bool gt = grp && L.shared > L.best, ge = grp && L.shared >= L.best;
-    L.best = gt ? L.shared : L.best;
-    L.first_nb = gt ? L.nb : L.first_nb;
-    L.last_nb = ge ? L.nb : L.last_nb;
+    L.nb += (w & (EV_DEL << SH)) ? dir : 0;
+    slide_eval(L, (gw & (EV_GRP << SH)) != 0);
 }
 
+// 4 bytes global -> shared without a register in between (LDGSTS); n = 0 writes zeros
+__device__ __forceinline__ void cp_async_u32(uint32_t dst_sh, const void *src, int n)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_sh), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+constexpr int L2_BATCH = 32;            // candidates a warp claims with one atomic
+
 __global__ void __launch_bounds__(L2_THREADS)
-l2_slide_kernel(const SlideJob *jobs, const uint16_t *room, const Prep *prep, uint32_t n_cands, const uint2 *hw, const uint16_t *ev,
+l2_slide_kernel(const SlideJob *jobs, const Prep *prep, uint32_t n_cands, const uint2 *hw, const uint16_t *ev,
                 const int32_t *min_shared, const uint32_t *id_off, const float *id_tab,
-                Mapping *maps, unsigned long long *counters)
+                Mapping *maps, unsigned long long *counters, int rows_above)
 {
     extern __shared__ __align__(16) uint8_t l2_smem[];
     const int tid = threadIdx.x, lane = tid & 31;
     constexpr int pitch = L2_THREADS * 4;
     uint8_t *const st = l2_smem + pitch + tid * 4;                 // one row of slack below bucket 0
     const uint32_t st_sh = (uint32_t)__cvta_generic_to_shared(st);
+    const uint32_t st_warp_sh = st_sh - (uint32_t)lane * 4u;       // column of lane 0 of this warp
     constexpr unsigned wmask = 0xFFFFFFFFu;
+    const uint4 *jobv = reinterpret_cast<const uint4 *>(jobs);
+    const unsigned long long n_c = n_cands;
 
-    bool alive = true, have = false;
-    uint32_t c = 0, k = 0, n_pad = 0;
-    int s = 0;
+    // fills the columns of the lanes in `lm` with their start states: piece `lane` (16 bytes = four rows) of every
+    // block, zeros above the sketch (the slack rows); the copies land while the other lanes replay a chunk
+    auto issue_states = [&](unsigned lm, const uint16_t *blk, int s) {
+        while (lm) {
+            const int t = __ffs(lm) - 1;
+            lm &= lm - 1u;
+            const unsigned long long bp = __shfl_sync(wmask, (unsigned long long)blk, t);
+            const int nw = __shfl_sync(wmask, l2_words_for(s), t);
+            const int w0 = 4 * lane;
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(bp) + w0;
+            const uint32_t dst = st_warp_sh + (uint32_t)t * 4u + (uint32_t)w0 * (uint32_t)pitch;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (w0 + j < rows_above) cp_async_u32(dst + (uint32_t)(j * pitch), w0 + j < nw ? src + j : src - w0, w0 + j < nw ? 4 : 0);
+        }
+    };
+
+    bool have = false, wait = false, pend = false;
+    uint32_t c = 0, xdel = 0;
+    uint32_t pv0 = 0, sh0 = 0;                                     // pivot word and shared count of the start window
+    int s = 0, kc = 0, kmc = 0, n_chunks = 0, room_l = 0, d_m = 0, dir = 1;
+    int ms_s = 0;                                                  // min_shared[s]
+    uint32_t ido_s = 0, pp_beg = 0;                                // id_off[s]; first reference minimizer of the region
+    int pp_seq = 0;
+    // result of the candidate that ended last trip: three gathers in flight
+    uint32_t c_pend = 0, fpos = 0, lpos = 0;
+    int seq_pend = 0, sh_pend = 0;
+    float id_pend = 0.0f;
     unsigned long long replayed = 0;
+    const uint16_t *blk = nullptr;
     const uint4 *evp = nullptr;
     uint4 nxt = make_uint4(0, 0, 0, 0);
     SlideLane L{};
 
+    // ---- the warp's queue: a batch of L2_BATCH candidates in use, the next batch claimed (its base may still be in flight
+    // in lane 0); every lane holds the candidate after its current one with the descriptor in flight --------------------
+    unsigned long long q_cur = 0, q_end = 0, q_next_raw = 0;
+    if (lane == 0) {
+        q_cur = atomicAdd(&counters[CT_WORK], (unsigned long long)(2 * L2_BATCH));
+        q_next_raw = q_cur + L2_BATCH;
+    }
+    q_cur = __shfl_sync(wmask, q_cur, 0);
+    q_end = q_cur + L2_BATCH;
+    unsigned long long nc = q_cur + (unsigned long long)lane;     // (L2_BATCH == 32: the first batch is used up at once)
+    q_cur = q_end;
+    uint4 nj0 = make_uint4(0, 0, 0, 0), nj1 = make_uint4(0, 0, 0, 0);
+    if (nc < n_c) { nj0 = __ldg(jobv + 2 * nc); nj1 = __ldg(jobv + 2 * nc + 1); }
+    bool alive = true;
+
     for (;;) {
-        // ---- lanes without a candidate take the next ones of the global queue ------------------
+        bool fin = false, overflow = false;
+        // ---- start states issued last trip have landed -----------------------------------------------
+        cp_async_wait_all();
+        __syncwarp();
+        if (wait) {
+            L.ioff = ev_aoff((int)(pv0 & 0xFFFFu)); L.sigma = (int)(pv0 >> 16); L.shared = (int)sh0; L.nb = d_m;
+            L.a = lds_u8(st_sh + L.ioff);
+            wait = false;
+        }
+        // ---- the result of the candidate that ended last trip ------------------------------------------
+        if (pend) {
+            Mapping mp;
+            mp.seq = seq_pend;
+            mp.ref_start = ((int)(fpos & 0x7FFFFFFFu) + (int)(lpos & 0x7FFFFFFFu)) / 2;    // computeMap.hpp:492
+            mp.shared = sh_pend;
+            mp.identity = sh_pend >= 0 ? id_pend : 0.0f;
+            maps[c_pend] = mp;
+            pend = false;
+        }
+        // ---- lanes without a candidate start the one they hold and take the one after it from the warp's queue ----
         const unsigned need = __ballot_sync(wmask, !have && alive);
         if (need) {
-            const int leader = __ffs(need) - 1;
-            unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(&counters[CT_WORK], (unsigned long long)__popc(need));
-            base = __shfl_sync(wmask, base, leader);
+            const unsigned long long used = (unsigned long long)__popc(need);
+            unsigned long long idx = q_cur + (unsigned long long)__popc(need & ((1u << lane) - 1u));
+            q_cur += used;
+            if (q_cur > q_end) {                                     // (warp-uniform) into the next batch; claim the one after it
+                const unsigned long long q_next = __shfl_sync(wmask, q_next_raw, 0);
+                if (idx >= q_end) idx = q_next + (idx - q_end);
+                q_cur = q_next + (q_cur - q_end);
+                q_end = q_next + L2_BATCH;
+                if (lane == 0) q_next_raw = atomicAdd(&counters[CT_WORK], (unsigned long long)L2_BATCH);
+            }
             if (!have && alive) {
-                const unsigned long long cc64 = base + (unsigned long long)__popc(need & ((1u << lane) - 1u));
-                if (cc64 >= (unsigned long long)n_cands) alive = false;
+                if (nc >= n_c) alive = false;
                 else {
-                    c = (uint32_t)cc64;
-                    const SlideJob jb = jobs[c];
-                    if (jb.n_events) {                               // (else: nothing to slide, ask again next trip)
-                        s = jb.s;
-                        L.room = (int)room[c];
-                        const int nwords = l2_words_for(s);
-                        for (int wd = 0; wd < nwords; wd++) *reinterpret_cast<uint32_t *>(st + wd * pitch) = 0u;
-                        evp = reinterpret_cast<const uint4 *>(ev + jb.ev_off);
-                        n_pad = (jb.n_events + 7u) & ~7u;
-                        k = 0;
-                        nxt = __ldg(evp);
-                        L.ioff = ev_aoff(s); L.sigma = 0; L.shared = 0; L.a = 0; L.mx = 0;
-                        L.best = 0; L.nb = 0; L.first_nb = 0; L.last_nb = 0;
+                    c = (uint32_t)nc;
+                    const uint4 j0 = nj0, j1 = nj1;
+                    nc = idx;
+                    if (nc < n_c) { nj0 = __ldg(jobv + 2 * nc); nj1 = __ldg(jobv + 2 * nc + 1); }
+                    if (j0.z) {                                      // (else: nothing to slide, ask again next trip)
+                        s = (int)(j1.x & 0xFFFFu); d_m = (int)(j1.x >> 16);
+                        blk = ev + (((unsigned long long)j0.y << 32) | j0.x);
+                        evp = reinterpret_cast<const uint4 *>(blk + ev_state_u16(s));
+                        n_chunks = (int)((j0.z + 6u) >> 3);                  // (j0.z = events + 1)
+                        kmc = (int)(j0.w >> 3);
+                        pv0 = j1.z; sh0 = j1.w & 0xFFFFu;
+                        // the start window is an evaluation point (computeMap.hpp:467-481)
+                        L.best = (int)sh0; L.pa = d_m; L.pb = d_m; L.mx = 0;
+                        L.room = (int)(j1.y & 0xFFFFu); room_l = (int)(j1.y >> 16);
+                        xdel = 0; dir = 1; kc = kmc;
                         have = true;
+                        overflow = (j1.w >> 16) != 0u;
+                        if (overflow) fin = true;
+                        else if (kmc >= n_chunks) {                   // no window to the right of the start window
+                            if (kmc == 0 || room_l < L.best) fin = true;
+                            else { xdel = EV_DEL | (EV_DEL << 16); dir = -1; kc = kmc - 1; L.room = room_l; }
+                        }
+                        if (!fin) { nxt = __ldg(evp + kc); wait = true; }
+                        // what the end of the candidate needs (all in flight until then)
+                        const Prep pp = prep[c];
+                        pp_beg = pp.beg; pp_seq = pp.seq;
+                        ms_s = __ldg(min_shared + s); ido_s = __ldg(id_off + s);
                     }
                 }
             }
+            issue_states(__ballot_sync(wmask, wait), blk, s);
         }
         if (!__any_sync(wmask, alive)) break;
-        if (have) {
+        bool turn = false;
+        if (have && !fin && !wait) {
             const uint4 cur = nxt;
-            nxt = __ldg(evp + (k >> 3) + 1);                         // (one chunk of slack behind the last list)
-            slide_event(L, st_sh, cur.x & 0xFFFFu);
-            slide_event(L, st_sh, cur.x >> 16);
-            slide_event(L, st_sh, cur.y & 0xFFFFu);
-            slide_event(L, st_sh, cur.y >> 16);
-            slide_event(L, st_sh, cur.z & 0xFFFFu);
-            slide_event(L, st_sh, cur.z >> 16);
-            slide_event(L, st_sh, cur.w & 0xFFFFu);
-            slide_event(L, st_sh, cur.w >> 16);
-            k += 8;
-            const bool overflow = L.mx > 255u;                       // (checked once per chunk: the pivot strays at most eight buckets)
-            // early stop: the shared count of a window is at most its number of matches, and the windows still to
-            // come hold at most `room` of them -- below the best so far they change neither the optimum nor its
-            // first / last position (computeMap.hpp:467-481)
-            if (k >= n_pad || overflow || L.room < L.best) {
-                const Prep pp = prep[c];
-                Mapping mp;
-                mp.seq = pp.seq;
-                if (overflow) { mp.ref_start = L2_REDO; mp.shared = -1; mp.identity = 0.0f; atomicAdd(&counters[CT_REDO], 1ull); }
-                else {
-                    const int first_pos = (int)(hw[pp.beg + (uint32_t)L.first_nb].y & 0x7FFFFFFFu);
-                    const int last_pos = (int)(hw[pp.beg + (uint32_t)L.last_nb].y & 0x7FFFFFFFu);
-                    mp.ref_start = (first_pos + last_pos) / 2;                        // computeMap.hpp:492
-                    const bool pass = L.best >= min_shared[s];                          // computeMap.hpp:371-380 via the table
-                    mp.shared = pass ? L.best : -1 - L.best;
-                    mp.identity = pass ? id_tab[id_off[s] + L.best] : 0.0f;
-                }
-                maps[c] = mp;
-                replayed += k;
-                have = false;
+            nxt = __ldg(evp + kc + dir);                             // (a chunk of slack behind the last list; the state block in front)
+            // backward: the eight events of the chunk in reverse order.  The state in front of an event that ends a time group
+            // is an evaluation point: the flag of an event is looked at after the one undone before it -- for the first
+            // event of a chunk that is now, for the last one of the list (in front of it sits the first window) at the end.
+            const bool bw = xdel != 0u;
+            const uint32_t e0 = bw ? __byte_perm(cur.w, 0u, 0x1032) : cur.x, e1 = bw ? __byte_perm(cur.z, 0u, 0x1032) : cur.y;
+            const uint32_t e2 = bw ? __byte_perm(cur.y, 0u, 0x1032) : cur.z, e3 = bw ? __byte_perm(cur.x, 0u, 0x1032) : cur.w;
+            const uint32_t g0 = bw ? __funnelshift_r(e0, e1, 16) : e0, g1 = bw ? __funnelshift_r(e1, e2, 16) : e1;
+            const uint32_t g2 = bw ? __funnelshift_r(e2, e3, 16) : e2, g3 = bw ? e3 >> 16 : e3;
+            slide_eval(L, bw && (e0 & EV_GRP) != 0u);
+            slide_event<0>(L, st_sh, e0, xdel, g0, dir);
+            slide_event<16>(L, st_sh, e0, xdel, g0, dir);
+            slide_event<0>(L, st_sh, e1, xdel, g1, dir);
+            slide_event<16>(L, st_sh, e1, xdel, g1, dir);
+            slide_event<0>(L, st_sh, e2, xdel, g2, dir);
+            slide_event<16>(L, st_sh, e2, xdel, g2, dir);
+            slide_event<0>(L, st_sh, e3, xdel, g3, dir);
+            slide_event<16>(L, st_sh, e3, xdel, g3, dir);
+            replayed += 8;
+            overflow = L.mx > 255u;                                  // (checked once per chunk: the pivot strays at most eight buckets)
+            // early stops: the shared count of a window is at most its number of elements in the sketch, and the windows
+            // still to come on this side hold at most `room` of them -- below the best so far they change neither the
+            // optimum nor its first / last position (computeMap.hpp:467-481)
+            if (overflow) fin = true;
+            else if (!bw) {
+                if (kc + 1 >= n_chunks || L.room < L.best) {
+                    if (kmc == 0 || room_l < L.best) fin = true;
+                    else {                                           // turn round: the start state again, then to the left
+                        xdel = EV_DEL | (EV_DEL << 16); dir = -1; kc = kmc - 1; L.room = room_l;
+                        const int t = L.pa; L.pa = L.pb; L.pb = t;
+                        nxt = __ldg(evp + kc);
+                        turn = true;
+                    }
+                } else kc++;
+            } else {
+                if (kc == 0) { slide_eval(L, true); fin = true; }    // the first window
+                else if (L.room < L.best) fin = true;
+                else kc--;
             }
+        }
+        {
+            const unsigned tm = __ballot_sync(wmask, turn);
+            if (tm) { issue_states(tm, blk, s); wait = wait || turn; }
+        }
+        if (fin) {
+            if (overflow) {
+                Mapping mp;
+                mp.seq = pp_seq; mp.ref_start = L2_REDO; mp.shared = -1; mp.identity = 0.0f;
+                maps[c] = mp;
+                atomicAdd(&counters[CT_REDO], 1ull);
+            } else {
+                const bool bw = xdel != 0u;
+                const int first_nb = bw ? L.pb : L.pa, last_nb = bw ? L.pa : L.pb;
+                fpos = __ldg(&hw[pp_beg + (uint32_t)first_nb].y);
+                lpos = __ldg(&hw[pp_beg + (uint32_t)last_nb].y);
+                id_pend = __ldg(id_tab + ido_s + (uint32_t)L.best);
+                sh_pend = L.best >= ms_s ? L.best : -1 - L.best;      // computeMap.hpp:371-380 via the table
+                c_pend = c; seq_pend = pp_seq;
+                pend = true;
+            }
+            have = false; wait = false;
         }
     }
     for (int o = 16; o > 0; o >>= 1) replayed += __shfl_xor_sync(wmask, replayed, o);
@@ -1792,10 +2032,10 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
                 }
                 FA_CUDA(cudaEventRecord(ws.ev[5], st));
                 // ---- L2 -----------------------------------------------------------------------
-                FA_TRY(ws.prep.reserve(C)); FA_TRY(ws.ev_off.reserve(C + 1)); FA_TRY(ws.jobs.reserve(C)); FA_TRY(ws.room.reserve(C));
+                FA_TRY(ws.prep.reserve(C)); FA_TRY(ws.ev_off.reserve(C + 1)); FA_TRY(ws.jobs.reserve(2 * (size_t)C)); FA_TRY(ws.mid.reserve(C));
                 l2_prep_kernel<<<std::min<uint32_t>((uint32_t)((C + 256) / 256), (uint32_t)dev_sms * 8u), 256, 0, st>>>(
                     ws.cands.p, ws.frag_cands.p, F, ws.qs.p, ix->ref.p, ix->hw.p, ix->hl.p, ix->fb.p, ix->contig_off.p, L, cmw, 2, w + 1,
-                    reinterpret_cast<Prep *>(ws.prep.p), reinterpret_cast<unsigned long long *>(ws.ev_off.p), ws.maps.p, ws.counters.p);
+                    reinterpret_cast<Prep *>(ws.prep.p), ws.mid.p, reinterpret_cast<unsigned long long *>(ws.ev_off.p), ws.maps.p, ws.counters.p);
                 FA_CUDA(cudaGetLastError()); launches++;
                 FA_TRY(excl_scan<uint64_t>(st, ws.cub_tmp, ws.ev_off.p, ws.ev_off.p, (int64_t)C + 1, &launches));
                 FA_CUDA(cudaEventRecord(ws.ev[9], st));
@@ -1815,9 +2055,9 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
                         FA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, l2_events_kernel, EVK_THREADS, smem));
                         const uint32_t grid = std::min<uint32_t>(W, (uint32_t)dev_sms * (uint32_t)std::max(per_sm, 1));
                         l2_events_kernel<<<grid, EVK_THREADS, smem, st>>>(
-                            reinterpret_cast<const Prep *>(ws.prep.p), reinterpret_cast<const unsigned long long *>(ws.ev_off.p),
+                            reinterpret_cast<const Prep *>(ws.prep.p), ws.mid.p, reinterpret_cast<const unsigned long long *>(ws.ev_off.p),
                             ws.frag_cands.p, ws.work_base.p, F, ws.qhash.p, ws.sk.seq_first.p, ws.qs.p, ix->ref.p, ix->hl.p,
-                            l2_tab_shift(w), ws.events.p, reinterpret_cast<SlideJob *>(ws.jobs.p), ws.room.p, ws.counters.p, q_cap);
+                            l2_tab_shift(w), ws.events.p, reinterpret_cast<SlideJob *>(ws.jobs.p), ws.counters.p, q_cap);
                         FA_CUDA(cudaGetLastError()); launches++;
                     }
                     FA_CUDA(cudaEventRecord(ws.ev[10], st));
@@ -1831,8 +2071,8 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
                         const uint64_t want = (C + L2_THREADS - 1) / L2_THREADS;
                         const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)dev_sms * (uint64_t)std::max(per_sm, 1));
                         slide_fn<<<grid, L2_THREADS, smem, st>>>(
-                            reinterpret_cast<const SlideJob *>(ws.jobs.p), ws.room.p, reinterpret_cast<const Prep *>(ws.prep.p), (uint32_t)C, ix->hw.p,
-                            ws.events.p, ix->d_min_shared.p, ix->d_id_off.p, ix->d_identity.p, ws.maps.p, ws.counters.p);
+                            reinterpret_cast<const SlideJob *>(ws.jobs.p), reinterpret_cast<const Prep *>(ws.prep.p), (uint32_t)C, ix->hw.p,
+                            ws.events.p, ix->d_min_shared.p, ix->d_id_off.p, ix->d_identity.p, ws.maps.p, ws.counters.p, rows - 1);
                         FA_CUDA(cudaGetLastError()); launches++;
                     }
                 }

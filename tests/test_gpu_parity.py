@@ -250,6 +250,76 @@ def test_l2_early_stop_keeps_first_and_last_optimum():
         assert 0 < out["info"]["events_replayed"] < out["info"]["events"]
 
 
+def test_l2_both_directions_from_the_middle():
+    """The slide starts at the window in the middle of a candidate region and replays its events to the right, takes the
+    start state again and replays them to the left, each side until the sketch matches still to come cannot reach the
+    best window.  Regions built
+    so that the optimum -- or the first / last of several equal optima -- lies left of, right of and far from that start
+    window: graded copies in both orders, three tandem copies, partial copies at the region's edges, copies on the
+    reverse strand, and a reference made of many short random pieces of the query (the seeds' centre is anywhere)."""
+    rng = np.random.default_rng(777)
+    base = synth.random_codes(rng, 24_000)
+    q = synth.to_bytes(base)
+    filler = lambda n: synth.to_bytes(synth.random_codes(rng, n))
+    mut = lambda ident: synth.to_bytes(synth.mutate_codes(rng, base, ident))
+    pieces = b"".join(q[a:a + int(rng.integers(400, 2_500))] + filler(int(rng.integers(50, 900)))
+                      for a in rng.integers(0, 21_000, size=40))
+    refs = [
+        filler(4_000) + q + filler(300) + mut(0.95) + filler(300) + mut(0.90) + filler(4_000),      # best copy leftmost
+        filler(4_000) + mut(0.90) + filler(300) + mut(0.95) + filler(300) + q + filler(4_000),      # best copy rightmost
+        filler(2_000) + q + filler(500) + q + filler(500) + q + filler(2_000),                      # three equal optima
+        q[:7_000] + filler(6_000) + q[17_000:],                                                     # copies at both edges
+        filler(3_000) + synth.revcomp(mut(0.96)) + filler(200) + synth.revcomp(q) + filler(3_000),
+        filler(1_000) + mut(0.88)[2_000:20_000] + filler(2_800) + mut(0.99)[2_000:20_000] + filler(1_000),
+        pieces,
+    ]
+    sk, osk = capi.Sketch(), _port().sketch()
+    for i, r in enumerate(refs):
+        sk.add_genome(i, r)
+        osk.add_genome(i, r)
+    ix = sk.index()
+    osk.index()
+    for query in (q, synth.revcomp(q), q[777:23_000], mut(0.97)):
+        hits, out = ix.query_genome(query, dump=True)
+        ohits, oinfo = osk.query_genome(query, dump=True)
+        assert np.array_equal(out["candidates"], oinfo["candidates"])
+        assert np.array_equal(out["mappings"], oinfo["mappings"])
+        assert np.array_equal(hits, ohits)
+        # (the few regions of the `pieces` reference that span more than EV_RMAX = 1024 minimizers go to the exact kernel)
+        assert out["info"]["l2_fallback"] * 10 < len(out["candidates"]) and 0 < out["info"]["events_replayed"]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_l2_random_regions_against_the_oracle(seed):
+    """Fuzz of the event path: references stitched from random slices of mutated copies of the query (both strands,
+    random gaps), so candidate regions hold several loci of unequal quality in random order; every mapping field
+    against the oracle."""
+    rng = np.random.default_rng(9000 + seed)
+    base = synth.random_codes(rng, 18_000)
+    q = synth.to_bytes(base)
+    refs = []
+    for _ in range(6):
+        parts = []
+        for _ in range(int(rng.integers(3, 9))):
+            copy = synth.to_bytes(synth.mutate_codes(rng, base, float(rng.uniform(0.82, 1.0))))
+            a = int(rng.integers(0, 12_000))
+            piece = copy[a:a + int(rng.integers(1_500, 6_000))]
+            parts.append(synth.revcomp(piece) if rng.random() < 0.3 else piece)
+            parts.append(synth.to_bytes(synth.random_codes(rng, int(rng.integers(0, 3_000)))))
+        refs.append(b"".join(parts))
+    sk, osk = capi.Sketch(), _port().sketch()
+    for i, r in enumerate(refs):
+        sk.add_genome(i, r)
+        osk.add_genome(i, r)
+    ix = sk.index()
+    osk.index()
+    hits, out = ix.query_genome(q, dump=True)
+    ohits, oinfo = osk.query_genome(q, dump=True)
+    assert np.array_equal(out["candidates"], oinfo["candidates"])
+    assert np.array_equal(out["mappings"], oinfo["mappings"])
+    assert np.array_equal(hits, ohits)
+
+
 def test_query_batch_equals_single_queries():
     """fa_query_batch: CSR hit rows of many queries in one call == fa_query per query; counters add up."""
     q, refs, _ = synth.one_to_many(515, 6, 80_000, lo=0.84, hi=0.99)
