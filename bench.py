@@ -82,6 +82,8 @@ def parse(argv=None):
                     help="N > 1: 'queries' = replicated index, the query list partitioned over the GPUs (the default); "
                          "'references' = whole reference genomes split over the GPUs, every GPU maps every query against its shard, "
                          "hit rows all-gathered over NCCL inside the library and merged (SURVEY.md 8(e), BASELINE configs[4] layout)")
+    ap.add_argument("--profile-build", action="store_true",
+                    help="bracket Sketch.index() with cudaProfilerStart/Stop, print its timers and exit (launch list of the index build)")
     ap.add_argument("--profile", action="store_true",
                     help="bracket the device-timed steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     return ap.parse_args(argv)
@@ -416,9 +418,17 @@ def run_b200(a):
     t_sketch = time.perf_counter() - t0
     sk_stats = sketch.build_stats
     n_min = len(sketch.minimizers)
+    if a.profile_build:
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.start()
     t0 = time.perf_counter()
     mapper = sketch.index()
     t_index = time.perf_counter() - t0
+    if a.profile_build:
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        emit({"index_build": {"wall_index_s": t_index, "minimizers": n_min, "stats": mapper.build_stats}})
+        return
     ix_stats = mapper.build_stats
     del base_dev
     torch.cuda.empty_cache()

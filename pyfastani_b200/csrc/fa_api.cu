@@ -430,7 +430,7 @@ void fa_index_free(fa_index *ix)
 {
     if (!ix) return;
     cudaSetDevice(ix->device);
-    ix->ref.release(); ix->hw.release(); ix->hl.release(); ix->fb.release(); ix->gpos.release(); ix->pos_idx.release(); ix->ukeys.release(); ix->uoff.release(); ix->dir.release();
+    ix->ref.release(); ix->hw.release(); ix->hl.release(); ix->fb.release(); ix->gpos.release(); ix->irr.release(); ix->pos_idx.release(); ix->ukeys.release(); ix->uoff.release(); ix->dir.release();
     ix->contig_off.release(); ix->genome_of_seq.release(); ix->bin_base.release(); ix->genome_cell.release();
     ix->pre[0].release(); ix->pre[1].release();
     ix->d_min_hits.release(); ix->d_min_shared.release(); ix->d_id_off.release(); ix->d_identity.release();

@@ -43,8 +43,11 @@ struct DevBuf {
     int reserve(size_t n, bool keep = false, cudaStream_t st = 0)
     {
         if (n <= cap) return FA_OK;
-        size_t ncap = cap ? cap : 256;
-        while (ncap < n) ncap += ncap / 2 + 256;
+        size_t ncap = n;                       // a first allocation is exact (index arrays are gigabytes); a buffer that
+        if (cap) {                             // grows is a workspace: leave head-room
+            ncap = cap;
+            while (ncap < n) ncap += ncap / 2 + 256;
+        }
         T *np = nullptr;
         cudaError_t e = cudaMalloc((void **)&np, ncap * sizeof(T));
         if (e != cudaSuccess) { set_error("cudaMalloc(%zu bytes): %s", ncap * sizeof(T), cudaGetErrorString(e)); return FA_ERR_NOMEM; }

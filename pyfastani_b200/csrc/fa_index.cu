@@ -10,6 +10,8 @@
 // `pos_idx` grouped by hash with insertion order kept inside each group; run-length encoding
 // gives the CSR (ukeys, uoff); a directory over the top bits of the hash narrows each lookup
 // to a few keys.  The sort is cub::DeviceRadixSort (library code); the other kernels are ours.
+#include <chrono>
+#include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_run_length_encode.cuh>
 #include <cub/device/device_scan.cuh>
@@ -118,7 +120,7 @@ __global__ void slide_order_kernel(const RefMini *ref, const uint32_t *contig_of
     }
 }
 
-__global__ void gpos_delta_kernel(const RefMini *ref, uint64_t n, uint32_t frag_len, uint32_t *gpos)
+__global__ void gpos_delta_kernel(const RefMini *ref, uint64_t n, uint32_t frag_len, uint32_t window, uint32_t *gpos, uint32_t *irr)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -129,6 +131,15 @@ __global__ void gpos_delta_kernel(const RefMini *ref, uint64_t n, uint32_t frag_
         if (a.z == b.z) d = min(b.y - a.y, frag_len);          // (an unordered pair wraps to a huge value: frag_len)
     }
     gpos[i] = d;
+    // Winnowing leaves at most `window` positions between neighbouring minimizers, except across contig ends and runs
+    // of skipped k-mers.  Blocks of 1024 minimizers in which every step obeys that bound let the L1 kernel decide
+    // "closer than a fragment" from the index distance alone (fa_map.cu l1_near); the others are marked here.
+    // (A step into the first minimizer of a block also marks the block before it, so two minimizers less than 1024
+    // apart are covered by the marks of the blocks they sit in.)
+    const bool bad = d > window;
+    const unsigned any = __ballot_sync(__activemask(), bad);
+    if (bad && (any & ((1u << (threadIdx.x & 31)) - 1u)) == 0u) atomicOr(&irr[i >> 15], 1u << ((i >> 10) & 31u));
+    if (bad && (i & 1023u) == 0u && i > 0) atomicOr(&irr[(i - 1) >> 15], 1u << (((i - 1) >> 10) & 31u));
 }
 
 // contig_off[s] = first ref index with seqId >= s (contigs without minimizers get empty ranges)
@@ -178,6 +189,16 @@ int build_index(fa_index *ix, int *launches)
     } ev;
     for (auto &x : ev.e) FA_CUDA(cudaEventCreate(&x));
     FA_CUDA(cudaEventRecord(ev.e[0], st));
+    // FA_BUILD_TRACE=1: host-clock phase times on stderr (each mark drains the stream first)
+    const bool trace = getenv("FA_BUILD_TRACE") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what) {
+        if (!trace) return;
+        cudaStreamSynchronize(st);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[fa build] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
 
     // ---- host-side tables: contig -> genome, (contig, bin) cells ---------------------------
     std::vector<int32_t> genome_of(n_contigs ? n_contigs : 1, 0);
@@ -201,6 +222,7 @@ int build_index(fa_index *ix, int *launches)
     FA_CUDA(cudaMemcpyAsync(d_first.p, first_contig.data(), first_contig.size() * 4, cudaMemcpyHostToDevice, st));
     FA_CUDA(cudaStreamSynchronize(st));       // the host vectors go out of scope
 
+    mark("contig tables to the device");
     // ---- statistics tables -------------------------------------------------------------------
     {
         int cmw = ix->prm.frag_len - (ix->prm.window - 1) - (ix->prm.k - 1);     // windows per fragment
@@ -226,6 +248,7 @@ int build_index(fa_index *ix, int *launches)
         FA_CUDA(cudaStreamSynchronize(st));
     }
 
+    mark("statistics tables");
     FA_TRY(ix->contig_off.reserve((size_t)n_contigs + 1));
     {
         uint64_t m = n + 1;
@@ -262,46 +285,80 @@ int build_index(fa_index *ix, int *launches)
         return FA_OK;
     }
 
+    mark("contig offsets, bins, cells");
     // ---- sort (hash, index) ------------------------------------------------------------------
-    TmpBuf<uint32_t> keys_a, keys_b, vals_a;
-    FA_TRY(keys_a.reserve(n)); FA_TRY(keys_b.reserve(n)); FA_TRY(vals_a.reserve(n));
+    // Every array of 4 or 8 bytes per minimizer is a cudaMalloc of gigabytes, and those cost more than the kernels
+    // (config 2: 37 ms of kernels inside a 196 ms build).  So the transient arrays live in the index's own buffers
+    // until these are filled: the sort input in `hl`, the sorted keys and the run lengths in `hw`, the untrimmed
+    // unique keys in `gpos`.
     FA_TRY(ix->pos_idx.reserve(n));
-    extract_keys_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(ix->ref.p, n, keys_a.p, vals_a.p);
+    FA_TRY(ix->hw.reserve(n + 8));            // L2 reads whole 32-byte chunks and one chunk ahead
+    FA_TRY(ix->hl.reserve(n + 8)); FA_TRY(ix->fb.reserve(n + 8));
+    FA_TRY(ix->gpos.reserve(n));
+    mark("cudaMalloc of the index arrays");
+    uint32_t *keys_a = reinterpret_cast<uint32_t *>(ix->hl.p), *vals_a = keys_a + n;
+    uint32_t *keys_b = reinterpret_cast<uint32_t *>(ix->hw.p), *run_len = keys_b + n;
+    uint32_t *ukeys_all = ix->gpos.p;
+    extract_keys_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(ix->ref.p, n, keys_a, vals_a);
     FA_CUDA(cudaGetLastError());
     if (launches) *launches += 1;
     size_t tmp_bytes = 0;
     FA_CUDA(cudaEventRecord(ev.e[2], st));
-    FA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a.p, keys_b.p, vals_a.p, ix->pos_idx.p, (int64_t)n, 0, 32, st));
+    FA_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a, keys_b, vals_a, ix->pos_idx.p, (int64_t)n, 0, 32, st));
     TmpBuf<uint8_t> tmp;
     FA_TRY(tmp.reserve(tmp_bytes + 16));
-    FA_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_a.p, keys_b.p, vals_a.p, ix->pos_idx.p, (int64_t)n, 0, 32, st));
+    FA_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys_a, keys_b, vals_a, ix->pos_idx.p, (int64_t)n, 0, 32, st));
     if (launches) *launches += 5;
     FA_CUDA(cudaEventRecord(ev.e[3], st));
-    vals_a.release();
 
+    mark("extract + radix sort");
     // duplicate distances for the L2 sliding window
-    dup_delta_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(keys_b.p, ix->pos_idx.p, n, ix->ref.p);
+    dup_delta_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(keys_b, ix->pos_idx.p, n, ix->ref.p);
     FA_CUDA(cudaGetLastError());
     if (launches) *launches += 1;
 
-    FA_TRY(ix->hw.reserve(n + 8));            // L2 reads whole 32-byte chunks and one chunk ahead
+    // ---- CSR over unique hashes --------------------------------------------------------------
+    TmpBuf<uint64_t> d_nruns;
+    FA_TRY(d_nruns.reserve(1));
+    size_t rle_bytes = 0;
+    FA_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, rle_bytes, keys_b, ukeys_all, run_len, d_nruns.p, (int64_t)n, st));
+    FA_TRY(tmp.reserve(rle_bytes + 16));
+    FA_CUDA(cub::DeviceRunLengthEncode::Encode(tmp.p, rle_bytes, keys_b, ukeys_all, run_len, d_nruns.p, (int64_t)n, st));
+    if (launches) *launches += 2;
+    uint64_t n_unique = 0;
+    FA_CUDA(cudaMemcpyAsync(&n_unique, d_nruns.p, 8, cudaMemcpyDeviceToHost, st));
+    FA_CUDA(cudaStreamSynchronize(st));
+    ix->n_unique = n_unique;
+    mark("dup distances + run lengths");
+    FA_TRY(ix->uoff.reserve(n_unique + 1));
+    FA_TRY(ix->ukeys.reserve(n_unique ? n_unique : 1));
+    size_t scan_bytes = 0;
+    FA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, run_len, ix->uoff.p, (int64_t)n_unique, st));
+    FA_TRY(tmp.reserve(scan_bytes + 16));
+    FA_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, scan_bytes, run_len, ix->uoff.p, (int64_t)n_unique, st));
+    if (launches) *launches += 2;
+    const uint32_t n32 = (uint32_t)n;
+    FA_CUDA(cudaMemcpyAsync(ix->uoff.p + n_unique, &n32, 4, cudaMemcpyHostToDevice, st));
+    FA_CUDA(cudaMemcpyAsync(ix->ukeys.p, ukeys_all, n_unique * 4, cudaMemcpyDeviceToDevice, st));
+
+    mark("CSR offsets, unique keys");
+    // ---- the streams of the query path (over the transient arrays, which are done) -------------
     FA_CUDA(cudaMemsetAsync(ix->hw.p + n, 0, 8 * sizeof(uint2), st));
     make_hw_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(ix->ref.p, n, ix->hw.p);
     FA_CUDA(cudaGetLastError());
     if (launches) *launches += 1;
-
     {
         const int cmw1 = ix->prm.frag_len - (ix->prm.window - 1) - (ix->prm.k - 1) - 1;
-        FA_TRY(ix->hl.reserve(n + 8)); FA_TRY(ix->fb.reserve(n + 8));
         FA_CUDA(cudaMemsetAsync(ix->hl.p + n, 0, 8 * sizeof(uint2), st));
         slide_order_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(ix->ref.p, ix->contig_off.p, n, cmw1 < 0 ? 0 : cmw1,
                                                                               ix->prm.frag_len, ix->hl.p, ix->fb.p);
         FA_CUDA(cudaGetLastError());
         if (launches) *launches += 1;
     }
-
-    FA_TRY(ix->gpos.reserve(n));
-    gpos_delta_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(ix->ref.p, n, (uint32_t)ix->prm.frag_len, ix->gpos.p);
+    FA_TRY(ix->irr.reserve((size_t)(n >> 15) + 2));
+    FA_CUDA(cudaMemsetAsync(ix->irr.p, 0, ((size_t)(n >> 15) + 2) * 4, st));
+    gpos_delta_kernel<<<(unsigned int)((n + 255) / 256), 256, 0, st>>>(ix->ref.p, n, (uint32_t)ix->prm.frag_len, (uint32_t)ix->prm.window,
+                                                                         ix->gpos.p, ix->irr.p);
     FA_CUDA(cudaGetLastError());
     {
         size_t sb = 0;
@@ -311,38 +368,7 @@ int build_index(fa_index *ix, int *launches)
     }
     if (launches) *launches += 3;
 
-    // ---- CSR over unique hashes --------------------------------------------------------------
-    TmpBuf<uint32_t> run_len;
-    TmpBuf<uint64_t> d_nruns;
-    FA_TRY(run_len.reserve(n)); FA_TRY(d_nruns.reserve(1));
-    FA_TRY(ix->ukeys.reserve(n));             // trimmed below
-    size_t rle_bytes = 0;
-    FA_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, rle_bytes, keys_b.p, ix->ukeys.p, run_len.p, d_nruns.p, (int64_t)n, st));
-    FA_TRY(tmp.reserve(rle_bytes + 16));
-    FA_CUDA(cub::DeviceRunLengthEncode::Encode(tmp.p, rle_bytes, keys_b.p, ix->ukeys.p, run_len.p, d_nruns.p, (int64_t)n, st));
-    if (launches) *launches += 2;
-    uint64_t n_unique = 0;
-    FA_CUDA(cudaMemcpyAsync(&n_unique, d_nruns.p, 8, cudaMemcpyDeviceToHost, st));
-    FA_CUDA(cudaStreamSynchronize(st));
-    ix->n_unique = n_unique;
-    keys_a.release(); keys_b.release();
-    FA_TRY(ix->uoff.reserve(n_unique + 1));
-    size_t scan_bytes = 0;
-    FA_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, run_len.p, ix->uoff.p, (int64_t)n_unique, st));
-    FA_TRY(tmp.reserve(scan_bytes + 16));
-    FA_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, scan_bytes, run_len.p, ix->uoff.p, (int64_t)n_unique, st));
-    if (launches) *launches += 2;
-    const uint32_t n32 = (uint32_t)n;
-    FA_CUDA(cudaMemcpyAsync(ix->uoff.p + n_unique, &n32, 4, cudaMemcpyHostToDevice, st));
-    {   // trim ukeys to n_unique (the sort buffers above are the transient peak)
-        TmpBuf<uint32_t> trimmed;
-        FA_TRY(trimmed.reserve(n_unique ? n_unique : 1));
-        FA_CUDA(cudaMemcpyAsync(trimmed.p, ix->ukeys.p, n_unique * 4, cudaMemcpyDeviceToDevice, st));
-        FA_CUDA(cudaStreamSynchronize(st));
-        ix->ukeys.release();
-        ix->ukeys = trimmed.take();
-    }
-
+    mark("hw, slide order, gpos");
     // ---- directory ---------------------------------------------------------------------------
     int bits = 1;
     while (bits < 24 && (1ull << bits) < n_unique) bits++;      // about one key per directory slot, <= 64 MiB
@@ -355,7 +381,7 @@ int build_index(fa_index *ix, int *launches)
     FA_CUDA(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&ix->ms_build, ev.e[0], ev.e[1]);
     cudaEventElapsedTime(&ix->ms_sort, ev.e[2], ev.e[3]);
-    run_len.release(); d_nruns.release(); tmp.release();
+    d_nruns.release(); tmp.release();
     return FA_OK;
 }
 

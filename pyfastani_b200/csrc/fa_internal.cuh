@@ -121,6 +121,7 @@ struct fa_index {
     fa::DevBuf<uint32_t> fb;                     // per minimizer: elements one fragment length behind (low 16 bits) / ahead (high 16 bits)
     fa::DevBuf<uint2> hl;                        // (hash, slide order word): the 8-byte stream the L2 events kernel reads (fa_index.cu slide_order_kernel)
     fa::DevBuf<uint32_t> gpos;                   // running coordinate for the L1 proximity test (fa_index.cu gpos_delta_kernel)
+    fa::DevBuf<uint32_t> irr;                    // one bit per 1024 minimizers: some step of gpos inside is longer than the window
     uint64_t n = 0, n_unique = 0;
     fa::DevBuf<uint32_t> pos_idx;                // ref indices grouped by hash, insertion order inside a group
     fa::DevBuf<uint32_t> ukeys, uoff;            // unique hashes, group offsets (n_unique + 1)

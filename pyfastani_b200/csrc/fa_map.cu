@@ -358,9 +358,9 @@ __device__ __forceinline__ void l1_sort_bucket(uint16_t *k, int n, uint32_t *bm,
 template <int L1_THREADS, int L1_TILE>
 __global__ void __launch_bounds__(L1_THREADS, 1024 / L1_THREADS)
 l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hit_start, const uint32_t *hit_cnt,
-                const uint64_t *seed_base, const uint32_t *pos_idx, const uint32_t *gpos, const uint2 *hw,
-                const int32_t *min_hits, int frag_len, uint32_t n_chunks, uint32_t seed_lo, uint32_t seed_cap, uint32_t key_cap,
-                Cand *tmp, uint32_t *frag_cands)
+                const uint64_t *seed_base, const uint32_t *pos_idx, const uint32_t *gpos, const uint32_t *irr, const uint2 *hw,
+                const int32_t *min_hits, int frag_len, uint32_t d_near, uint32_t n_chunks, uint32_t seed_lo, uint32_t seed_cap,
+                uint32_t key_cap, Cand *tmp, uint32_t *frag_cands)
 {
     constexpr int L1_PER = L1_TILE / L1_THREADS;
     constexpr int L1_STAGE = l1_stage(L1_THREADS, L1_TILE);
@@ -374,7 +374,7 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
     uint16_t *blk_chunk = keys + key_cap;                                    // chunk holding sorted hit 32 * q
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_valid[L1_TILE / 32], s_head[L1_TILE / 32], s_hpre[L1_TILE / 32 + 1];
-    __shared__ uint32_t s_blk, s_nlist, s_cj, s_cg;
+    __shared__ uint32_t s_blk, s_nlist, s_cj, s_cf;
     __shared__ int s_cvalid;
 
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -389,7 +389,7 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
 
     for (uint32_t i = tid; i <= n_chunks; i += L1_THREADS) hist[i] = 0u;
     for (int q = tid; q < s; q += L1_THREADS) { s_lst[q] = hit_start[qb + q]; s_lcnt[q] = hit_cnt[qb + q]; }
-    if (tid == 0) { s_blk = 0u; s_nlist = 0u; s_cvalid = 0; s_cj = 0u; s_cg = 0u; }
+    if (tid == 0) { s_blk = 0u; s_nlist = 0u; s_cvalid = 0; s_cj = 0u; s_cf = 0u; }
     __syncthreads();
 
     // The small shape serves fragments whose position lists hold a handful of entries each (a hash occurs once per
@@ -515,12 +515,25 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
     // ---- D: candidate regions -------------------------------------------------------------------
     const int m = min_hits[s];
     const uint32_t L = (uint32_t)frag_len;
+    // "Reference minimizers a <= b lie closer than a fragment" (same contig, position distance < L; computeMap.hpp:325-330
+    // and :338-340) is gpos[b] - gpos[a] < L.  Almost every time the index distance decides it without touching gpos:
+    // positions grow by at least one per minimizer, so b - a >= L is far; and where every step is at most one window
+    // (all blocks of 1024 minimizers between a and b unmarked in `irr`), (b - a) * window < L is near.  The two gathers
+    // are left for what falls between (and for hits next to a contig end).
+    // The mark of its block is staged with every hit, so the tests themselves read shared memory only.
+    auto l1_near = [&](uint32_t a, uint32_t fa, uint32_t b2, uint32_t fb2) -> bool {
+        const uint32_t d = b2 - a;
+        if (d >= L) return false;
+        if (d <= d_near && (fa | fb2) == 0u) return true;                        // (d_near < 1024: at most two blocks)
+        return __ldg(gpos + b2) - __ldg(gpos + a) < L;
+    };
     Cand *out = tmp + sb;
     uint32_t heads_before = 0;
     for (uint32_t base = 0; base < n; base += L1_TILE) {
-        // D1: stage (reference index, gpos) of the tile and of the m - 1 hits behind it; all gathers of a thread in flight
+        // D1: stage the reference indices of the tile and of the m - 1 hits behind it, each with the marks of its blocks
+        // (a table of one bit per 1024 minimizers: it stays in L2, and all loads of a thread are in flight at once)
         {
-            uint32_t jv[L1_PER + 1], gv[L1_PER + 1];
+            uint32_t jv[L1_PER + 1], w0[L1_PER + 1];
 #pragma unroll
             for (int u = 0; u <= L1_PER; u++) {
                 const int e0 = u * L1_THREADS + wid * 32;
@@ -533,23 +546,23 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
                 }
             }
 #pragma unroll
-            for (int u = 0; u <= L1_PER; u++) gv[u] = jv[u] != 0xFFFFFFFFu ? __ldg(gpos + jv[u]) : 0u;
+            for (int u = 0; u <= L1_PER; u++) w0[u] = jv[u] != 0xFFFFFFFFu ? __ldg(irr + (jv[u] >> 15)) : 0u;
 #pragma unroll
             for (int u = 0; u <= L1_PER; u++)
-                if (jv[u] != 0xFFFFFFFFu) { const int e = u * L1_THREADS + tid; s_j[e] = jv[u]; s_g[e] = gv[u]; }
+                if (jv[u] != 0xFFFFFFFFu) { const int e = u * L1_THREADS + tid; s_j[e] = jv[u]; s_g[e] = (w0[u] >> ((jv[u] >> 10) & 31u)) & 1u; }
         }
         __syncthreads();
         // D2: valid pairs (computeMap.hpp:325-330) as a bitmap
-        uint32_t ja[L1_PER], jb[L1_PER], gb[L1_PER];
+        uint32_t jb[L1_PER];
         bool valid[L1_PER];
 #pragma unroll
         for (int u = 0; u < L1_PER; u++) {
             const int e = u * L1_THREADS + tid;
             const uint32_t t = base + (uint32_t)e;
-            valid[u] = false; ja[u] = 0; jb[u] = 0; gb[u] = 0;
+            valid[u] = false; jb[u] = 0;
             if (t + (uint32_t)(m - 1) < n) {
-                ja[u] = s_j[e]; jb[u] = s_j[e + m - 1]; gb[u] = s_g[e + m - 1];
-                valid[u] = (jb[u] - ja[u] < L) && (gb[u] - s_g[e] < L);
+                jb[u] = s_j[e + m - 1];
+                valid[u] = l1_near(s_j[e], s_g[e], jb[u], s_g[e + m - 1]);
             }
             const unsigned bal = __ballot_sync(0xFFFFFFFFu, valid[u]);
             if (lane == 0) s_valid[e >> 5] = bal;
@@ -566,10 +579,10 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
                 int w = e >> 5;
                 uint32_t x = s_valid[w] & ((1u << lane) - 1u);
                 while (x == 0u && w > 0) x = s_valid[--w];
-                uint32_t pg;
-                if (x) { const int p = w * 32 + 31 - __clz(x); pj[u] = s_j[p]; pg = s_g[p]; pv[u] = true; }
-                else { pj[u] = s_cj; pg = s_cg; pv[u] = s_cvalid != 0; }
-                head[u] = !pv[u] || (jb[u] - pj[u] >= L) || (gb[u] - pg >= L);
+                uint32_t pf;
+                if (x) { const int p = w * 32 + 31 - __clz(x); pj[u] = s_j[p]; pf = s_g[p]; pv[u] = true; }
+                else { pj[u] = s_cj; pf = s_cf; pv[u] = s_cvalid != 0; }
+                head[u] = !pv[u] || !l1_near(pj[u], pf, jb[u], s_g[e + m - 1]);
             }
             const unsigned bal = __ballot_sync(0xFFFFFFFFu, head[u]);
             if (lane == 0) s_head[e >> 5] = bal;
@@ -604,7 +617,7 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
         if (tid == 0) {
             int w = L1_TILE / 32 - 1;
             while (w >= 0 && s_valid[w] == 0u) w--;
-            if (w >= 0) { const int p = w * 32 + 31 - __clz(s_valid[w]); s_cj = s_j[p]; s_cg = s_g[p]; s_cvalid = 1; }
+            if (w >= 0) { const int p = w * 32 + 31 - __clz(s_valid[w]); s_cj = s_j[p]; s_cf = s_g[p]; s_cvalid = 1; }
         }
         __syncthreads();
     }
@@ -1812,6 +1825,7 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
 
     // ---- fragments (pyx:1059-1105) -----------------------------------------------------------
     const int L = P.frag_len, k = P.k, w = P.window;
+    const uint32_t d_near = std::min<uint32_t>((uint32_t)(std::max(L - 1, 0) / std::max(w, 1)), 1023u);   // l1_fused_kernel: index distance that is near for sure
     const int lim = std::min(std::min(w, k), L);
     std::vector<Upload> ups;
     ws.h_seqs.clear(); ws.h_fragq.clear();
@@ -1988,7 +2002,7 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
                     const size_t smem = l1s_fixed + 2 * key_cap + 2 * (key_cap / 32 + 8);
                     FA_CUDA(cudaFuncSetAttribute(l1_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     l1_small<<<F, L1S_THREADS, smem, st>>>(ws.sk.seq_first.p, ws.qs.p, ws.hit_start.p, ws.hit_cnt.p, ws.frag_seeds.p,
-                                                           ix->pos_idx.p, ix->gpos.p, ix->hw.p, ix->d_min_hits.p, L, n_chunks,
+                                                           ix->pos_idx.p, ix->gpos.p, ix->irr.p, ix->hw.p, ix->d_min_hits.p, L, d_near, n_chunks,
                                                            0u, (uint32_t)small_cap, (uint32_t)key_cap, ws.cand_tmp.p, ws.frag_cands.p);
                     FA_CUDA(cudaGetLastError()); launches++;
                 }
@@ -1997,7 +2011,7 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
                     const size_t smem = l1_fixed + 2 * key_cap + 2 * (key_cap / 32 + 8);
                     FA_CUDA(cudaFuncSetAttribute(l1_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     l1_large<<<F, L1L_THREADS, smem, st>>>(ws.sk.seq_first.p, ws.qs.p, ws.hit_start.p, ws.hit_cnt.p, ws.frag_seeds.p,
-                                                           ix->pos_idx.p, ix->gpos.p, ix->hw.p, ix->d_min_hits.p, L, n_chunks,
+                                                           ix->pos_idx.p, ix->gpos.p, ix->irr.p, ix->hw.p, ix->d_min_hits.p, L, d_near, n_chunks,
                                                            n_small ? (uint32_t)small_cap + 1u : 0u, (uint32_t)seed_cap, (uint32_t)key_cap,
                                                            ws.cand_tmp.p, ws.frag_cands.p);
                     FA_CUDA(cudaGetLastError()); launches++;
