@@ -92,7 +92,7 @@ def test_queries_match_pyfastani_and_oracle(name, l1):
         assert info["kernel_launches"] > 0 or st["fragments"] == 0
 
 
-@pytest.mark.parametrize("l1", ["chip", "chip-large", "shapes", "sort", "mixed"])
+@pytest.mark.parametrize("l1", ["chip", "chip-large", "shapes", "sort", "mixed", "small-72k", "small-110k"])
 def test_l1_many_references(l1):
     """120 related references: every fragment has several thousand seed hits (more than one 4096-hit
     tile of the on-chip L1 kernel) spread over nine 2^16-minimizer chunks of the index, plus a
@@ -113,9 +113,12 @@ def test_l1_many_references(l1):
         mean = st["seeds"] // st["fragments"]
         ix.set_l1_seed_cap({"sort": 0, "mixed": mean - 1}.get(l1, -1))
         ix.set_l1_small_cap({"chip-large": 0, "shapes": mean}.get(l1, -1))
+        # the small shape with three / two CTAs per SM (72 KB / 110 KB each): what an index of a few thousand genomes
+        # selects because its chunk histogram leaves no room for the hits in 54 KB
+        ix.set_l1_small_shape({"small-72k": 1, "small-110k": 2}.get(l1, -1))
         hits, out = ix.query_draft(query, dump=True)
-        assert (out["info"]["l1_sorted_fragments"] == 0) == (l1 in ("chip", "chip-large", "shapes"))
-        if l1 == "chip":          # several 1024-hit tiles per fragment in the small shape
+        assert (out["info"]["l1_sorted_fragments"] == 0) == (l1 not in ("sort", "mixed"))
+        if l1 in ("chip", "small-72k", "small-110k"):          # several 1024-hit tiles per fragment in the small shape
             assert out["info"]["l1_small_fragments"] == st["fragments"]
         if l1 == "chip-large":
             assert out["info"]["l1_small_fragments"] == 0
@@ -318,6 +321,129 @@ def test_l2_random_regions_against_the_oracle(seed):
     assert np.array_equal(out["candidates"], oinfo["candidates"])
     assert np.array_equal(out["mappings"], oinfo["mappings"])
     assert np.array_equal(hits, ohits)
+
+
+def test_l1_irregular_blocks_next_to_candidate_loci():
+    """The L1 kernel decides "closer than a fragment" from index distances wherever every step between neighbouring
+    minimizers is at most one window, and gathers positions only in blocks of 1024 minimizers the index marked
+    otherwise: contig ends and runs without minimizers (every k-mer of an (AT)n run is its own reverse complement and
+    is skipped).  Loci cut by such runs and by contig ends a few hundred bases apart, against the oracle."""
+    rng = np.random.default_rng(4242)
+    base = synth.random_codes(rng, 40_000)
+    q = synth.to_bytes(base)
+    mut = lambda ident: synth.to_bytes(synth.mutate_codes(rng, base, ident))
+    at = lambda n: b"AT" * n
+    filler = lambda n: synth.to_bytes(synth.random_codes(rng, n))
+    g1, g2, g3 = mut(0.97), mut(0.93), mut(0.99)
+    refs = [
+        [g1[:6_000] + at(400) + g1[6_000:9_000] + at(60) + g1[9_000:20_000] + at(1_700) + g1[20_000:]],
+        [g2[:7_500], g2[7_500:7_900], at(300) + g2[7_900:16_000] + at(300), g2[16_000:16_050], g2[16_050:]],
+        [filler(1_000) + g3[10_000:13_100] + at(1_450) + g3[13_100:30_000] + filler(500), at(2_000), g3[:10_000]],
+    ]
+    sk, osk = capi.Sketch(), _port().sketch()
+    for i, r in enumerate(refs):
+        sk.add_draft(i, r)
+        osk.add_draft(i, r)
+    ix = sk.index()
+    osk.index()
+    for query in ([q], [synth.revcomp(q)], [q[:11_000] + at(700) + q[11_000:]]):
+        for cap in (-1, 0):                                     # the small and the large shape of the kernel
+            ix.set_l1_small_cap(cap)
+            hits, out = ix.query_draft(query, dump=True)
+            ohits, oinfo = osk.query_draft(query, dump=True)
+            assert out["info"]["l1_sorted_fragments"] == 0
+            assert np.array_equal(out["candidates"], oinfo["candidates"])
+            assert np.array_equal(out["mappings"], oinfo["mappings"])
+            assert np.array_equal(hits, ohits)
+    ix.set_l1_small_cap(-1)
+
+
+def test_config2_shaped_drafts_vs_reference():
+    """BASELINE configs[2] at its own shape, few genomes: six fragmented assemblies of 2.0-2.6 Mbp in 200-320 contigs
+    (two species 88 % apart, strains at 96-99.7 %, half of the contigs reverse-complemented, order permuted; contig
+    ends down to 200 bp), all-vs-all through add_draft / query_draft and one fa_query_batch call: every hit row against
+    the CPU reference (the compiled reference when present, else the C port)."""
+    from oracle.oracle import Oracle, available
+    rng = np.random.default_rng(2024)
+    root = synth.random_codes(rng, 2_000_000)
+    species = [root, synth.mutate_codes(rng, root, 0.88)]
+    drafts = []
+    for sp in species:
+        for ident in (0.997, 0.98, 0.96):
+            codes = synth.mutate_codes(rng, sp, ident)
+            extra = synth.random_codes(rng, int(rng.integers(0, 600_000)))        # strain-specific DNA: 2.0-2.6 Mbp
+            g = synth.to_bytes(np.concatenate([codes, extra]))
+            drafts.append(synth.fragment(rng, g, int(rng.integers(200, 321)), min_end=200))
+    assert all(200 <= len(d) <= 320 and sum(map(len, d)) >= 2_000_000 for d in drafts)
+    kind = "reference" if "reference" in available() else "port"
+    sk, osk = capi.Sketch(), Oracle(kind).sketch()
+    for i, d in enumerate(drafts):
+        sk.add_draft(i, d)
+        osk.add_draft(i, d)
+    ix = sk.index()
+    osk.index()
+    batch, _ = ix.query_batch(drafts)
+    for i, d in enumerate(drafts):
+        ohits, _ = osk.query_draft(d, threads=8) if kind == "reference" else osk.query_draft(d)
+        hits = ix.query_draft(d)[0]
+        assert np.array_equal(hits, ohits) and np.array_equal(batch[i], ohits)
+        assert len(hits) == 6 and hits[0]["ref_genome"] == i
+
+
+def test_concurrent_queries_on_one_index():
+    """Mapper.query_* may be called from several threads at once (pyx:1158-1161: the reference maps under `nogil` with
+    its own state per call).  Here the calls of one index share a workspace and are serialised inside the library:
+    four threads, three rounds over six queries each, every result equal to the single-threaded one."""
+    import threading
+    q, refs, _ = synth.one_to_many(77, 12, 120_000, lo=0.85, hi=0.99)
+    rng = np.random.default_rng(5)
+    queries = [q, synth.revcomp(q), q[10_000:90_000], refs[3], refs[7][5_000:], synth.to_bytes(synth.random_codes(rng, 50_000))]
+    sk = capi.Sketch()
+    for i, r in enumerate(refs):
+        sk.add_genome(i, r)
+    ix = sk.index()
+    want = [ix.query_genome(x)[0] for x in queries]
+    got, errors = {}, []
+
+    def work(t):
+        try:
+            for rep in range(3):
+                for j in np.random.default_rng(t).permutation(len(queries)):
+                    got[(t, rep, int(j))] = ix.query_genome(queries[int(j)])[0]
+        except Exception as e:                                   # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    assert len(got) == 4 * 3 * len(queries)
+    for (t, rep, j), h in got.items():
+        assert np.array_equal(h, want[j]), (t, rep, j)
+
+
+def test_indexes_release_their_memory():
+    """every buffer of an index, its workspace included, is released by fa_index_free -- twenty indexes built,
+    queried and dropped leave the device where it was."""
+    import gc
+    q, refs, _ = synth.one_to_many(5, 8, 150_000, lo=0.85, hi=0.99)
+
+    def cycle():
+        sk = capi.Sketch()
+        for i, r in enumerate(refs):
+            sk.add_genome(i, r)
+        ix = sk.index()
+        assert len(ix.query_genome(q)[0]) == 8
+        del ix, sk
+        gc.collect()
+
+    cycle()
+    free0 = capi.mem_info()[0]
+    for _ in range(20):
+        cycle()
+    assert abs(int(capi.mem_info()[0]) - int(free0)) < (64 << 20), (free0, capi.mem_info())
 
 
 def test_query_batch_equals_single_queries():
