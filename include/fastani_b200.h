@@ -162,6 +162,16 @@ FA_API int fa_index_copy_meta(const fa_index *ix, int32_t *seqs_by_genome, uint6
  * in insertion order (winSketch.hpp:180-185).  *n receives the bucket size (0 = KeyError). */
 FA_API int fa_index_copy_keys(const fa_index *ix, uint64_t first, uint64_t n, uint32_t *keys);
 FA_API int fa_index_lookup(const fa_index *ix, uint32_t hash, int32_t *seq, int32_t *wpos, uint64_t cap, uint64_t *n);
+/* MinimizerIndex.__contains__ (pyx:1468-1471): a hash whose list was set to no positions is still a key. */
+FA_API int fa_index_has_key(const fa_index *ix, uint32_t hash, int32_t *found);
+/* MinimizerIndex.__setitem__ (pyx:1480-1497): the position list of `hash` becomes the n (seq, wpos) pairs given, in that
+ * order; the hash is added when absent.  The reference edits the unordered_map that L1 seeding reads
+ * (Sketch::minimizerPosLookupIndex); here the CSR table in device memory is rebuilt around the entry, so the next query
+ * seeds from the new list.  A position that is not the position of a minimizer of the sketch, or given twice, is
+ * FA_ERR_INVALID (the table stores positions as indices of the minimizer array). */
+FA_API int fa_index_set_lookup(fa_index *ix, uint32_t hash, const int32_t *seq, const int32_t *wpos, uint64_t n);
+/* MinimizerIndex.__delitem__ (pyx:1499-1507): *found = 0 when the hash was not a key (KeyError), nothing changes then. */
+FA_API int fa_index_del_lookup(fa_index *ix, uint32_t hash, int32_t *found);
 FA_API int fa_index_occurrence_threshold(const fa_index *ix, int32_t *out);                  /* getFreqThreshold, pyx:596-600 */
 /* Mapper._query_draft, pyx:1006-1136: fragments the contigs, sketches them, L1 seeding,
  * L2 sliding Jaccard, computeCGI, min-fraction filter, sort.  Writes at most `cap` rows;

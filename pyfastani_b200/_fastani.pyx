@@ -105,6 +105,9 @@ cdef extern from "fastani_b200.h" nogil:
     int fa_index_copy_meta(const fa_index* ix, int32_t* seqs_by_genome, uint64_t* genome_len)
     int fa_index_copy_keys(const fa_index* ix, uint64_t first, uint64_t n, uint32_t* keys)
     int fa_index_lookup(const fa_index* ix, uint32_t hash, int32_t* sq, int32_t* w, uint64_t cap, uint64_t* n)
+    int fa_index_has_key(const fa_index* ix, uint32_t hash, int32_t* found)
+    int fa_index_set_lookup(fa_index* ix, uint32_t hash, const int32_t* sq, const int32_t* w, uint64_t n)
+    int fa_index_del_lookup(fa_index* ix, uint32_t hash, int32_t* found)
     int fa_index_occurrence_threshold(const fa_index* ix, int32_t* out)
     int fa_query(fa_index* ix, const fa_contig* contigs, int32_t n, fa_hit* out, uint64_t cap, uint64_t* n_out,
                  fa_query_info* info)
@@ -1133,15 +1136,24 @@ cdef class Position:
 cdef class MinimizerIndex:
     """The index mapping minimizer hash values to their positions (pyx:1431-1539).
 
-    Read-only view over the CSR lookup table held in GPU memory: ``len``, iteration,
-    ``in``, ``[]`` and ``items()`` work as in the reference; item assignment and deletion
-    (which the reference allows on its host hash table) raise `TypeError`.
+    ``Mapper.lookup_index`` is a view over the CSR lookup table held in GPU memory: ``len``, iteration,
+    ``in``, ``[]`` and ``items()`` read it; ``index[h] = positions`` and ``del index[h]`` rebuild the
+    table around that entry (`fa_index_set_lookup` / `fa_index_del_lookup`), so the next query seeds
+    from the edited table, as it does with the reference's host hash table.  Positions assigned must
+    be positions of minimizers of the sketch (the table stores them as indices of the minimizer
+    array); anything else raises `ValueError`.  A `MinimizerIndex()` created on its own is a plain
+    host-side table, as in the reference.
     """
 
     cdef object owner
+    cdef dict   _local
 
     def __cinit__(self):
         self.owner = None
+        self._local = None
+
+    def __init__(self):
+        self._local = {}
 
     cdef fa_index* _index(self) except NULL:
         cdef Mapper mp
@@ -1152,13 +1164,19 @@ cdef class MinimizerIndex:
 
     def __len__(self):
         cdef uint64_t n_unique = 0
+        if self._local is not None:
+            return len(self._local)
         _check(fa_index_counts(self._index(), NULL, &n_unique, NULL, NULL))
         return n_unique
 
     def _keys(self):
-        cdef uint64_t  n = len(self)
+        cdef uint64_t  n
         cdef uint64_t  i
-        cdef uint32_t* k = <uint32_t*> malloc(max(n, 1) * sizeof(uint32_t))
+        cdef uint32_t* k
+        if self._local is not None:
+            return list(self._local)
+        n = len(self)
+        k = <uint32_t*> malloc(max(n, 1) * sizeof(uint32_t))
         try:
             if n:
                 _check(fa_index_copy_keys(self._index(), 0, n, k))
@@ -1170,18 +1188,24 @@ cdef class MinimizerIndex:
         return iter(self._keys())
 
     def __contains__(self, uint32_t item):
-        cdef uint64_t n = 0
-        _check(fa_index_lookup(self._index(), item, NULL, NULL, 0, &n))
-        return n > 0
+        cdef int32_t found = 0
+        if self._local is not None:
+            return item in self._local
+        _check(fa_index_has_key(self._index(), item, &found))
+        return found != 0
 
     def __getitem__(self, uint32_t item):
         cdef uint64_t n = 0
         cdef uint64_t i
         cdef int32_t* s
         cdef int32_t* w
+        if self._local is not None:
+            return list(self._local[item])
+        if item not in self:
+            raise KeyError(item)
         _check(fa_index_lookup(self._index(), item, NULL, NULL, 0, &n))
         if n == 0:
-            raise KeyError(item)
+            return []
         s = <int32_t*> malloc(n * sizeof(int32_t))
         w = <int32_t*> malloc(n * sizeof(int32_t))
         try:
@@ -1191,10 +1215,39 @@ cdef class MinimizerIndex:
             free(s); free(w)
 
     def __setitem__(self, uint32_t item, object value):
-        raise TypeError("the lookup index lives in GPU memory and is read-only")
+        cdef Position position
+        cdef list     positions = []
+        cdef uint64_t n, i
+        cdef int32_t* s
+        cdef int32_t* w
+        for position in value:                    # (a non-Position raises TypeError here, as in the reference)
+            positions.append(position)
+        if self._local is not None:
+            self._local[item] = positions
+            return
+        n = len(positions)
+        s = <int32_t*> malloc(max(n, 1) * sizeof(int32_t))
+        w = <int32_t*> malloc(max(n, 1) * sizeof(int32_t))
+        try:
+            for i in range(n):
+                position = positions[i]
+                s[i] = position.sequence_id
+                w[i] = position.window_position
+            _check(fa_index_set_lookup(self._index(), item, s, w, n))
+        finally:
+            free(s); free(w)
 
     def __delitem__(self, uint32_t item):
-        raise TypeError("the lookup index lives in GPU memory and is read-only")
+        cdef int32_t found = 0
+        if self._local is not None:
+            del self._local[item]
+            return
+        _check(fa_index_del_lookup(self._index(), item, &found))
+        if not found:
+            raise KeyError(item)
+
+    def __reduce__(self):
+        return (MinimizerIndex, (), None, None, self.items())
 
     def items(self):
         for key in self._keys():

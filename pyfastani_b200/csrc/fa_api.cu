@@ -45,6 +45,13 @@ __global__ void lookup_one_kernel(const uint32_t *ukeys, const uint32_t *uoff, u
     else { out[0] = 0; out[1] = 0; }
 }
 
+__global__ void has_key_kernel(const uint32_t *ukeys, uint32_t n_unique, uint32_t h, uint32_t *out)
+{
+    uint32_t lo = 0, hi = n_unique;
+    while (lo < hi) { uint32_t mid = lo + ((hi - lo) >> 1); if (ukeys[mid] < h) lo = mid + 1; else hi = mid; }
+    out[0] = (lo < n_unique && ukeys[lo] == h) ? 1u : 0u;
+}
+
 __global__ void gather_kernel(const RefMini *ref, const uint32_t *pos_idx, uint32_t start, uint32_t n, int32_t *seq, int32_t *wpos)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -503,6 +510,42 @@ int fa_index_lookup(const fa_index *ix, uint32_t hash, int32_t *seq, int32_t *wp
         FA_CUDA(cudaStreamSynchronize(ix->st));
     }
     return FA_OK;
+}
+
+int fa_index_has_key(const fa_index *ix, uint32_t hash, int32_t *found)
+{
+    if (!ix || !found) { set_error("bad arguments"); return FA_ERR_INVALID; }
+    *found = 0;
+    if (ix->n_unique == 0) return FA_OK;
+    FA_CUDA(cudaSetDevice(ix->device));
+    uint32_t h_out[2] = {0, 0};
+    TmpBuf<uint32_t> d_out;
+    FA_TRY(d_out.reserve(2));
+    // (lookup_one_kernel reports entries; a key with an empty list -- possible after fa_index_set_lookup -- has none)
+    has_key_kernel<<<1, 1, 0, ix->st>>>(ix->ukeys.p, (uint32_t)ix->n_unique, hash, d_out.p);
+    FA_CUDA(cudaMemcpyAsync(h_out, d_out.p, 4, cudaMemcpyDeviceToHost, ix->st));
+    FA_CUDA(cudaStreamSynchronize(ix->st));
+    *found = (int32_t)h_out[0];
+    return FA_OK;
+}
+
+int fa_index_set_lookup(fa_index *ix, uint32_t hash, const int32_t *seq, const int32_t *wpos, uint64_t n)
+{
+    if (!ix || (n && (!seq || !wpos))) { set_error("bad arguments"); return FA_ERR_INVALID; }
+    FA_CUDA(cudaSetDevice(ix->device));
+    std::lock_guard<std::mutex> guard(ix->mtx);
+    return edit_lookup(ix, hash, seq, wpos, n, false, nullptr);
+}
+
+int fa_index_del_lookup(fa_index *ix, uint32_t hash, int32_t *found)
+{
+    if (!ix || !found) { set_error("bad arguments"); return FA_ERR_INVALID; }
+    FA_CUDA(cudaSetDevice(ix->device));
+    std::lock_guard<std::mutex> guard(ix->mtx);
+    int missing = 0;
+    const int rc = edit_lookup(ix, hash, nullptr, nullptr, 0, true, &missing);
+    *found = missing ? 0 : 1;
+    return rc;
 }
 
 int fa_index_occurrence_threshold(const fa_index *ix, int32_t *out)

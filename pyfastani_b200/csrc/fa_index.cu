@@ -10,6 +10,7 @@
 // `pos_idx` grouped by hash with insertion order kept inside each group; run-length encoding
 // gives the CSR (ukeys, uoff); a directory over the top bits of the hash narrows each lookup
 // to a few keys.  The sort is cub::DeviceRadixSort (library code); the other kernels are ours.
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <cub/device/device_radix_sort.cuh>
@@ -382,6 +383,143 @@ int build_index(fa_index *ix, int *launches)
     cudaEventElapsedTime(&ix->ms_build, ev.e[0], ev.e[1]);
     cudaEventElapsedTime(&ix->ms_sort, ev.e[2], ev.e[3]);
     d_nruns.release(); tmp.release();
+    return FA_OK;
+}
+
+// ---- mutation of the hash -> positions table (MinimizerIndex.__setitem__ / __delitem__, pyx:1480-1507) ----------
+// The reference edits one entry of an unordered_map on the host.  Here the table is three device arrays in CSR form,
+// so an edit rebuilds them around the entry -- device-to-device copies of the untouched parts and one pass over the
+// offsets -- and then the directory.  Positions are stored as indices into the position-ordered minimizer array, so a
+// position has to be one a minimizer of the sketch sits at (any hash); anything else is FA_ERR_INVALID.
+namespace {
+
+__global__ void find_positions_kernel(const uint2 *hw, const uint32_t *contig_off, uint32_t n_contigs, const int32_t *seq,
+                                      const int32_t *wpos, uint32_t m, uint32_t *out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    uint32_t r = 0xFFFFFFFFu;
+    const int32_t sq = seq[i], wp = wpos[i];
+    if (sq >= 0 && (uint32_t)sq < n_contigs && wp >= 0) {
+        uint32_t lo = contig_off[sq], hi = contig_off[sq + 1];
+        const uint32_t end = hi;
+        while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if ((int32_t)(hw[mid].y & 0x7FFFFFFFu) < wp) lo = mid + 1; else hi = mid; }
+        if (lo < end && (int32_t)(hw[lo].y & 0x7FFFFFFFu) == wp) r = lo;
+    }
+    out[i] = r;
+}
+
+// out = {slot (lower bound of h among the keys), found, first entry, entries}
+__global__ void key_slot_kernel(const uint32_t *ukeys, const uint32_t *uoff, uint32_t n_unique, uint32_t h, uint32_t *out)
+{
+    uint32_t lo = 0, hi = n_unique;
+    while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (ukeys[mid] < h) lo = mid + 1; else hi = mid; }
+    const bool found = lo < n_unique && ukeys[lo] == h;
+    out[0] = lo; out[1] = found ? 1u : 0u; out[2] = uoff[lo]; out[3] = found ? uoff[lo + 1] - uoff[lo] : 0u;
+}
+
+// offsets after the edit: entries up to `slot` keep theirs; later ones come from old entry i + skew, moved by delta
+__global__ void edit_offsets_kernel(const uint32_t *old_off, uint32_t *new_off, uint32_t new_n, uint32_t slot, int skew, int delta)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > new_n) return;
+    new_off[i] = i <= slot ? old_off[i] : (uint32_t)((int64_t)old_off[(int64_t)i + skew] + delta);
+}
+
+}  // namespace
+
+int edit_lookup(fa_index *ix, uint32_t hash, const int32_t *seq, const int32_t *wpos, uint64_t m, bool erase, int *missing)
+{
+    cudaStream_t st = ix->st;
+    if (missing) *missing = 0;
+    if (m >= 0x7FFFFFFFull) { set_error("too many positions"); return FA_ERR_INVALID; }
+    const uint32_t nu = (uint32_t)ix->n_unique;
+    uint32_t h_slot[4] = {0, 0, 0, 0};
+    TmpBuf<uint32_t> d_slot;
+    FA_TRY(d_slot.reserve(4));
+    if (nu) {
+        key_slot_kernel<<<1, 1, 0, st>>>(ix->ukeys.p, ix->uoff.p, nu, hash, d_slot.p);
+        FA_CUDA(cudaMemcpyAsync(h_slot, d_slot.p, 16, cudaMemcpyDeviceToHost, st));
+        FA_CUDA(cudaStreamSynchronize(st));
+    }
+    const uint32_t slot = h_slot[0], start = h_slot[2], old_cnt = h_slot[3];
+    const bool found = h_slot[1] != 0;
+    if (erase && !found) { if (missing) *missing = 1; return FA_OK; }
+    uint32_t old_total = 0;
+    if (nu) {
+        FA_CUDA(cudaMemcpyAsync(&old_total, ix->uoff.p + nu, 4, cudaMemcpyDeviceToHost, st));
+        FA_CUDA(cudaStreamSynchronize(st));
+    }
+    // the new list as indices of the minimizer array
+    TmpBuf<uint32_t> d_list;
+    const uint32_t new_cnt = erase ? 0u : (uint32_t)m;
+    if (new_cnt) {
+        TmpBuf<int32_t> d_sq, d_wp;
+        FA_TRY(d_sq.reserve(new_cnt)); FA_TRY(d_wp.reserve(new_cnt)); FA_TRY(d_list.reserve(new_cnt));
+        FA_CUDA(cudaMemcpyAsync(d_sq.p, seq, (size_t)new_cnt * 4, cudaMemcpyHostToDevice, st));
+        FA_CUDA(cudaMemcpyAsync(d_wp.p, wpos, (size_t)new_cnt * 4, cudaMemcpyHostToDevice, st));
+        find_positions_kernel<<<(new_cnt + 127) / 128, 128, 0, st>>>(ix->hw.p, ix->contig_off.p, (uint32_t)ix->n_contigs, d_sq.p, d_wp.p,
+                                                                      new_cnt, d_list.p);
+        FA_CUDA(cudaGetLastError());
+        std::vector<uint32_t> idx(new_cnt);
+        FA_CUDA(cudaMemcpyAsync(idx.data(), d_list.p, (size_t)new_cnt * 4, cudaMemcpyDeviceToHost, st));
+        FA_CUDA(cudaStreamSynchronize(st));
+        for (uint32_t i = 0; i < new_cnt; i++)
+            if (idx[i] == 0xFFFFFFFFu) {
+                set_error("Position(%d, %d) is not the position of a minimizer of this sketch: the device lookup table stores "
+                          "positions as indices of the minimizer array", seq[i], wpos[i]);
+                return FA_ERR_INVALID;
+            }
+        std::sort(idx.begin(), idx.end());
+        for (uint32_t i = 1; i < new_cnt; i++)
+            if (idx[i] == idx[i - 1]) { set_error("a position occurs twice in the list"); return FA_ERR_INVALID; }
+    }
+    const uint64_t new_total64 = (uint64_t)old_total - old_cnt + new_cnt;
+    if (new_total64 >= 0xFFFFFFF0ull) { set_error("lookup table too large"); return FA_ERR_UNSUPPORTED; }
+    const uint32_t new_total = (uint32_t)new_total64;
+    const uint32_t new_nu = nu + (found ? 0u : 1u) - (erase ? 1u : 0u);
+    // entries
+    DevBuf<uint32_t> pos2, keys2, off2;
+    int rc = pos2.reserve(new_total ? new_total : 1);
+    if (rc == FA_OK) rc = keys2.reserve(new_nu ? new_nu : 1);
+    if (rc == FA_OK) rc = off2.reserve((size_t)new_nu + 1);
+    auto fail = [&](int code) { pos2.release(); keys2.release(); off2.release(); return code; };
+    if (rc != FA_OK) return fail(rc);
+    cudaError_t e = cudaSuccess;
+    auto copy = [&](uint32_t *dst, const uint32_t *src, uint64_t cnt) {
+        if (cnt && e == cudaSuccess) e = cudaMemcpyAsync(dst, src, cnt * 4, cudaMemcpyDeviceToDevice, st);
+    };
+    copy(pos2.p, ix->pos_idx.p, start);
+    copy(pos2.p + start, d_list.p, new_cnt);
+    copy(pos2.p + start + new_cnt, ix->pos_idx.p + start + old_cnt, (uint64_t)old_total - start - old_cnt);
+    // keys
+    copy(keys2.p, ix->ukeys.p, slot);
+    if (!erase && e == cudaSuccess) e = cudaMemcpyAsync(keys2.p + slot, &hash, 4, cudaMemcpyHostToDevice, st);
+    copy(keys2.p + slot + (erase ? 0u : 1u), ix->ukeys.p + slot + (found ? 1u : 0u), (uint64_t)nu - slot - (found ? 1u : 0u));
+    if (e != cudaSuccess) { set_error("lookup edit: %s", cudaGetErrorString(e)); return fail(FA_ERR_CUDA); }
+    // offsets
+    if (nu == 0) {
+        const uint32_t two[2] = {0u, new_cnt};
+        e = cudaMemcpyAsync(off2.p, two, (size_t)(new_nu + 1) * 4, cudaMemcpyHostToDevice, st);
+    } else {
+        const int skew = erase ? 1 : (found ? 0 : -1);
+        const int delta = erase ? -(int)old_cnt : (found ? (int)new_cnt - (int)old_cnt : (int)new_cnt);
+        edit_offsets_kernel<<<(new_nu + 1 + 255) / 256, 256, 0, st>>>(ix->uoff.p, off2.p, new_nu, slot, skew, delta);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_error("lookup edit: %s", cudaGetErrorString(e)); return fail(FA_ERR_CUDA); }
+    ix->pos_idx.release(); ix->ukeys.release(); ix->uoff.release();
+    ix->pos_idx = pos2; ix->ukeys = keys2; ix->uoff = off2;
+    ix->n_unique = new_nu;
+    // directory
+    int bits = 1;
+    while (bits < 24 && (1ull << bits) < new_nu) bits++;
+    ix->dir_bits = bits;                                     // (an emptied table: one bit, all three slots 0)
+    FA_TRY(ix->dir.reserve((1u << bits) + 1));
+    directory_kernel<<<((1u << bits) + 1 + 255) / 256, 256, 0, st>>>(ix->ukeys.p, new_nu, bits, ix->dir.p);
+    FA_CUDA(cudaGetLastError());
+    FA_CUDA(cudaStreamSynchronize(st));
     return FA_OK;
 }
 

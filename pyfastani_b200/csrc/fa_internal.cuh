@@ -153,6 +153,8 @@ struct fa_index {
 
 namespace fa {
 int build_index(fa_index *ix, int *launches);
+// MinimizerIndex.__setitem__ / __delitem__: replace / insert / erase the position list of one hash (fa_index.cu)
+int edit_lookup(fa_index *ix, uint32_t hash, const int32_t *seq, const int32_t *wpos, uint64_t m, bool erase, int *missing);
 // the uploads of a query (whole fragments of every contig that is long enough, pyx:1059-1105) and their layout
 void plan_uploads(const fa_params &P, const fa_contig *contigs, int32_t n_contigs, std::vector<Upload> &ups, uint64_t *total);
 int prefetch_query(fa_index *ix, Prefetch &pf, const fa_contig *contigs, int32_t n_contigs);

@@ -1317,6 +1317,7 @@ l2_slide_kernel(const SlideJob *jobs, const Prep *prep, uint32_t n_cands, const 
                     }
                 }
             }
+            __syncwarp();
             issue_states(__ballot_sync(wmask, wait), blk, s);
         }
         if (!__any_sync(wmask, alive)) break;
@@ -1365,7 +1366,7 @@ l2_slide_kernel(const SlideJob *jobs, const Prep *prep, uint32_t n_cands, const 
         }
         {
             const unsigned tm = __ballot_sync(wmask, turn);
-            if (tm) { issue_states(tm, blk, s); wait = wait || turn; }
+            if (tm) { __syncwarp(); issue_states(tm, blk, s); wait = wait || turn; }   // (the owner's own stores of this trip come first)
         }
         if (fin) {
             if (overflow) {

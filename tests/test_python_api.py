@@ -156,12 +156,82 @@ def test_query_warnings_and_views(pf):
     assert all(isinstance(p, pf.Position) for p in pos)
     with pytest.raises(KeyError):
         li[0xFFFFFFFF]
-    with pytest.raises(TypeError):
-        li[key] = pos
     k2, p2 = next(li.items())
     assert k2 == key and p2 == pos
     dev = pf.DeviceSequence.from_host(g)
     assert mapper.query_genome(dev) == mapper.query_genome(g)
+
+
+def test_lookup_index_mutation(pf):
+    """MinimizerIndex.__setitem__ / __delitem__ (pyx:1480-1507) on `Mapper.lookup_index`: the reference edits the hash
+    table L1 seeding reads, here the CSR table in device memory is rebuilt around the entry.  Erase, restore, move a
+    list to a new hash, an empty list, bad positions; the seed count of a query follows the table, and with every
+    key erased nothing maps."""
+    import synth
+    q, refs, _ = synth.one_to_many(21, 3, 40_000, lo=0.90, hi=0.99)
+    sketch = pf.Sketch()
+    for i, r in enumerate(refs):
+        sketch.add_genome("ref%d" % i, r)
+    mapper = sketch.index()
+    base = mapper.query_genome(q)
+    seeds0 = mapper.last_query_info["seeds"]
+    assert len(base) == 3 and seeds0 > 0
+    li = mapper.lookup_index
+    keys = list(li)
+    n0 = len(li)
+    assert keys == sorted(keys) and n0 == len(keys)
+    # a hash of the query's own sketch that occurs in the references: its positions are seeds of the query
+    qs = pf.Sketch()
+    qs.add_genome("q", q[:3_000])
+    h = next(m.hash for m in qs.minimizers if m.hash in li)
+    pos = li[h]
+    assert pos and all(isinstance(p, pf.Position) for p in pos)
+    del li[h]
+    assert h not in li and len(li) == n0 - 1
+    with pytest.raises(KeyError):
+        li[h]
+    with pytest.raises(KeyError):
+        del li[h]
+    mapper.query_genome(q)
+    assert mapper.last_query_info["seeds"] < seeds0                    # those seeds are gone
+    li[h] = pos
+    assert h in li and li[h] == pos and len(li) == n0 and list(li) == keys
+    assert mapper.query_genome(q) == base and mapper.last_query_info["seeds"] == seeds0
+    li[h] = pos[:1]                                                    # a shorter list, then the original again
+    assert li[h] == pos[:1]
+    li[h] = list(reversed(pos))
+    assert li[h] == list(reversed(pos))                                # (the order given is kept, as in the reference)
+    assert mapper.query_genome(q) == base and mapper.last_query_info["seeds"] == seeds0
+    # a hash that was not a key: inserted in hash order
+    h2 = next(x for x in range(1, 100_000) if x not in li)
+    li[h2] = pos
+    assert h2 in li and li[h2] == list(pos) and len(li) == n0 + 1 and list(li) == sorted(keys + [h2])
+    assert mapper.query_genome(q) == base                              # (h2 is not in the query's sketch)
+    del li[h2]
+    li[h] = []
+    assert h in li and li[h] == [] and len(li) == n0
+    li[h] = pos
+    with pytest.raises(ValueError):
+        li[h] = [pf.Position(0, 1_000_000_000)]
+    with pytest.raises(ValueError):
+        li[h] = [pos[0], pos[0]]
+    with pytest.raises(TypeError):
+        li[h] = [(0, 1)]
+    assert li[h] == pos and mapper.query_genome(q) == base
+    # a standalone table is a plain host-side mapping, as in the reference (and pickles as one)
+    own = pf.MinimizerIndex()
+    own[7] = pos
+    own[3] = []
+    assert len(own) == 2 and 7 in own and own[7] == pos and dict(own.items()) == {7: pos, 3: []}
+    back = pickle.loads(pickle.dumps(own))
+    assert dict(back.items()) == {7: pos, 3: []}
+    del own[7]
+    assert 7 not in own
+    # every key erased: no seeds, no hits
+    for k in keys:
+        del li[k]
+    assert len(li) == 0 and list(li) == []
+    assert mapper.query_genome(q) == [] and mapper.last_query_info["seeds"] == 0
 
 
 def test_query_many_equals_single_queries(pf):
