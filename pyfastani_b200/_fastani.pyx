@@ -557,6 +557,38 @@ cdef class Sketch(_Parameterized):
         self._names = list(state["names"])
         _restore_sketch(self._sk, state["sketch"], state["lengths"], state["counter"])
 
+    def save(self, path):
+        """save(self, path)\n--
+
+        Write the sketch to `path` (the on-disk form of what `pickle` would carry: parameters, names, genome lengths,
+        sequencesByFileInfo and the minimizer columns), so that a later run can `Sketch.load` it instead of sketching
+        the genomes again."""
+        cdef uint64_t n_min = 0, n_contigs = 0, n_genomes = 0
+        _check(fa_sketch_counts(self._sk, &n_min, &n_contigs, &n_genomes))
+        cdef int32_t*  seqs = <int32_t*> malloc(max(n_genomes, 1) * sizeof(int32_t))
+        cdef uint64_t* lens = <uint64_t*> malloc(max(n_genomes, 1) * sizeof(uint64_t))
+        try:
+            _check(fa_sketch_copy_meta(self._sk, seqs, lens))
+            _save_sketch_file(path, "sketch", _Parameterized.__getstate__(self), list(self._names), n_contigs,
+                              [lens[i] for i in range(n_genomes)], [seqs[i] for i in range(n_genomes)], self.minimizers)
+        finally:
+            free(seqs)
+            free(lens)
+
+    @classmethod
+    def load(cls, path, device=None):
+        """load(cls, path, device=None)\n--
+
+        A `Sketch` with the content of a file written by `Sketch.save` or `Mapper.save`, on `device` (default: 0)."""
+        header, cols = _load_sketch_file(path)
+        cdef Sketch sk = cls.__new__(cls)
+        sk.__setstate__({"parameters": header["parameters"], "device": 0 if device is None else device, "names": [],
+                         "lengths": [], "counter": 0,
+                         "sketch": {"sequencesByFileInfo": [], "minimizers": {"hashes": [], "ids": [], "offsets": [], "length": 0}}})
+        _restore_sketch_columns(sk._sk, cols, header.get("counter", 0))
+        sk._names = list(header["names"])
+        return sk
+
     @property
     def occurences_threshold(self):
         """`int`: The occurence threshold above which minimizers are ignored."""
@@ -716,6 +748,59 @@ cdef int _restore_sketch(fa_sketch* sk, dict sketch_state, object lengths, uint6
     return 0
 
 
+# --- On-disk sketch (SURVEY.md 8f-2) ---------------------------------------------
+# One uncompressed .npz: the minimizer triples as three columns (what `Sketch` / `Mapper` pickle as Python lists,
+# pyx:572-591, 842-865), sequencesByFileInfo, the genome lengths, and a JSON header with the parameters and names.
+# Loading uploads the columns and -- for a Mapper -- rebuilds the lookup index on the GPU, as unpickling does.
+
+_SKETCH_FORMAT = "pyfastani_b200.sketch/1"
+
+
+def _save_sketch_file(path, kind, dict parameters, list names, uint64_t counter, lengths, seqs_by_genome, Minimizers mins):
+    import json
+    import numpy
+    try:
+        header = json.dumps({"format": _SKETCH_FORMAT, "kind": kind, "parameters": parameters, "names": names, "counter": counter})
+    except TypeError:
+        raise TypeError("the on-disk sketch stores genome names as JSON (str / int / float / None); pickle the object for other names") from None
+    h, s, w = mins.arrays()
+    with open(path, "wb") as f:
+        numpy.savez(f, header=numpy.frombuffer(header.encode("utf-8"), dtype=numpy.uint8), hashes=h, ids=s, offsets=w,
+                    lengths=numpy.asarray(lengths, dtype=numpy.uint64), sequences_by_file=numpy.asarray(seqs_by_genome, dtype=numpy.int32))
+
+
+def _load_sketch_file(path):
+    import json
+    import numpy
+    with numpy.load(path, allow_pickle=False) as z:
+        header = json.loads(bytes(z["header"]).decode("utf-8"))
+        if header.get("format") != _SKETCH_FORMAT:
+            raise ValueError("not a pyfastani_b200 sketch file: {!r}".format(header.get("format")))
+        cols = {k: numpy.ascontiguousarray(z[k]) for k in ("hashes", "ids", "offsets", "lengths", "sequences_by_file")}
+    if not (len(cols["hashes"]) == len(cols["ids"]) == len(cols["offsets"])) or len(cols["lengths"]) != len(cols["sequences_by_file"]):
+        raise ValueError("inconsistent column lengths in sketch file")
+    if len(header["names"]) != len(cols["lengths"]):
+        raise ValueError("sketch file holds {} names for {} genomes".format(len(header["names"]), len(cols["lengths"])))
+    return header, cols
+
+
+cdef int _restore_sketch_columns(fa_sketch* sk, dict cols, uint64_t counter) except -1:
+    cdef uint32_t[::1] h = cols["hashes"].astype("uint32", copy=False)
+    cdef int32_t[::1]  s = cols["ids"].astype("int32", copy=False)
+    cdef int32_t[::1]  w = cols["offsets"].astype("int32", copy=False)
+    cdef int32_t[::1]  q = cols["sequences_by_file"].astype("int32", copy=False)
+    cdef uint64_t[::1] l = cols["lengths"].astype("uint64", copy=False)
+    cdef uint64_t n = h.shape[0], g = q.shape[0]
+    cdef uint32_t h0 = 0
+    cdef int32_t  i0 = 0
+    cdef uint64_t l0 = 0
+    if g and counter < <uint64_t> q[g - 1]:
+        counter = q[g - 1]
+    _check(fa_sketch_restore(sk, &h[0] if n else &h0, &s[0] if n else &i0, &w[0] if n else &i0, n,
+                             &q[0] if g else &i0, &l[0] if g else &l0, g, counter))
+    return 0
+
+
 # --- Mapper -------------------------------------------------------------------
 
 @cython.final
@@ -780,6 +865,30 @@ cdef class Mapper(_Parameterized):
             _check(fa_sketch_index(sk, &self._ix))
         finally:
             fa_sketch_free(sk)
+
+    def save(self, path):
+        """save(self, path)\n--
+
+        Write the indexed sketch to `path` (same file format as `Sketch.save`); `Mapper.load` rebuilds the lookup index
+        on the GPU from the minimizer columns, as unpickling does (pyx:853-865), without sketching anything."""
+        cdef uint64_t n_min = 0, n_unique = 0, n_contigs = 0, n_genomes = 0
+        _check(fa_index_counts(self._ix, &n_min, &n_unique, &n_contigs, &n_genomes))
+        cdef int32_t*  seqs = <int32_t*> malloc(max(n_genomes, 1) * sizeof(int32_t))
+        cdef uint64_t* lens = <uint64_t*> malloc(max(n_genomes, 1) * sizeof(uint64_t))
+        try:
+            _check(fa_index_copy_meta(self._ix, seqs, lens))
+            _save_sketch_file(path, "mapper", _Parameterized.__getstate__(self), list(self._names), n_contigs,
+                              [lens[i] for i in range(n_genomes)], [seqs[i] for i in range(n_genomes)], self.minimizers)
+        finally:
+            free(seqs)
+            free(lens)
+
+    @classmethod
+    def load(cls, path, device=None):
+        """load(cls, path, device=None)\n--
+
+        A `Mapper` over the content of a file written by `Mapper.save` or `Sketch.save`, indexed on `device`."""
+        return Sketch.load(path, device).index()
 
     @property
     def lookup_index(self):
@@ -1017,6 +1126,24 @@ cdef class Minimizers:
             raise IndexError(index)
         self._copy(index_, 1, &h, &s, &w)
         return MinimizerInfo(h, s, w)
+
+    def arrays(self):
+        """arrays(self)\n--
+
+        The minimizers as three NumPy arrays ``(hashes: uint32, sequence ids: int32, window positions: int32)`` --
+        one device-to-host copy per column instead of one Python object per minimizer (the SoA form of the on-disk
+        sketch, `Sketch.save`)."""
+        import numpy
+        cdef uint64_t n = self._size()
+        h = numpy.empty(n, dtype=numpy.uint32)
+        s = numpy.empty(n, dtype=numpy.int32)
+        w = numpy.empty(n, dtype=numpy.int32)
+        cdef uint32_t[::1] hv = h
+        cdef int32_t[::1]  sv = s
+        cdef int32_t[::1]  wv = w
+        if n:
+            self._copy(0, n, &hv[0], &sv[0], &wv[0])
+        return h, s, w
 
     cpdef dict __getstate__(self):
         cdef uint64_t  n = self._size()

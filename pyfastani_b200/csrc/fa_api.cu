@@ -167,6 +167,8 @@ int sketch_add_batch(fa_sketch *s, const fa_contig *contigs, int32_t n_contigs, 
         s->ev_ready = true;
     }
     FA_CUDA(cudaEventRecord(s->ev[0], st));
+    NvtxStages nv;
+    nv.next("fa:sketch add (stage + sketch kernels)");
     FA_TRY(stage_sequences(st, s->sc.bytes, s->stage, ups, off, nullptr));
     FA_TRY(s->sc.seqs.reserve(n_seqs)); FA_TRY(s->sc.tile_status.reserve((size_t)tiles));
     FA_TRY(s->sc.counters.reserve(4)); FA_TRY(s->sc.seq_first.reserve(n_seqs)); FA_TRY(s->sc.drops.reserve(n_seqs));

@@ -1,6 +1,7 @@
 // fa_common.cuh -- shared declarations of libfastani_b200 (host + device).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -89,6 +90,15 @@ struct PinBuf {
         return FA_OK;
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// NVTX ranges for the stages of a call (tracing): one range open at a time, closed on scope exit
+// whatever the return path.  Header-only NVTX3: nothing happens unless a profiler is attached.
+struct NvtxStages {
+    bool open = false;
+    void next(const char *name) { if (open) nvtxRangePop(); nvtxRangePushA(name); open = true; }
+    void close() { if (open) nvtxRangePop(); open = false; }
+    ~NvtxStages() { close(); }
 };
 
 // ---- sketching (fa_sketch.cu) ---------------------------------------------------------

@@ -193,6 +193,8 @@ int build_index(fa_index *ix, int *launches)
     // FA_BUILD_TRACE=1: host-clock phase times on stderr (each mark drains the stream first)
     const bool trace = getenv("FA_BUILD_TRACE") != nullptr;
     auto t_last = std::chrono::steady_clock::now();
+    NvtxStages nv;
+    nv.next("fa:index build");
     auto mark = [&](const char *what) {
         if (!trace) return;
         cudaStreamSynchronize(st);

@@ -1868,7 +1868,9 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
 
     std::vector<int32_t> h_count;
     std::vector<float> h_ident;
+    NvtxStages nv;
     FA_CUDA(cudaEventRecord(ws.ev[0], st));
+    nv.next("fa:query stage + h2d");
     if (F > 0 && tiles_per_frag > 0 && ix->n > 0 && G > 0) {
         // ---- upload + sketch the fragments ---------------------------------------------------
         if (pf && pf->valid && pf->contigs == contigs && pf->n_contigs == n_contigs && pf->total == off) {
@@ -1905,6 +1907,7 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
         qi.h2d_bytes += (uint64_t)F * sizeof(SeqDesc);
         FA_CUDA(cudaMemsetAsync(ws.counters.p, 0, CT_N * sizeof(unsigned long long), st));
         FA_CUDA(cudaEventRecord(ws.ev[1], st));
+        nv.next("fa:query sketch");
         FA_TRY(launch_sketch(st, ws.sk, F, n_tiles, k, w, P.alphabet != 4, nullptr, ws.qhash.p, 0, &launches));
         {
             int p2 = 1; while (p2 < cmw) p2 <<= 1;
@@ -1916,6 +1919,7 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
             FA_CUDA(cudaGetLastError()); launches++;
         }
         FA_CUDA(cudaEventRecord(ws.ev[2], st));
+        nv.next("fa:query lookup");
         // ---- lookup + seed counts ------------------------------------------------------------
         lookup_kernel<<<F, 128, 0, st>>>(ws.qhash.p, ws.sk.seq_first.p, ws.qs.p, F, ix->dir.p, ix->dir_bits, ix->ukeys.p,
                                          ix->uoff.p, ws.hit_start.p, ws.hit_cnt.p, ws.frag_seeds.p);
@@ -1935,6 +1939,7 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
         const uint64_t S = h_fs[F];
         qi.seeds = S; qi.sketch_sum = h_ct[CT_SKETCH_SUM];
         FA_CUDA(cudaEventRecord(ws.ev[3], st));
+        nv.next("fa:query seed sort");
         uint64_t C = 0;
         if (S > 0) {
             int dev_sms = 148, smem_optin = 48 * 1024;
@@ -1995,6 +2000,7 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
                 launches += 2 + (shift + fbits + 7) / 8;
             }
             FA_CUDA(cudaEventRecord(ws.ev[4], st));
+            nv.next("fa:query L1");
             // ---- L1 candidates -------------------------------------------------------------------
             if (n_slow < (uint32_t)F) {
                 FA_TRY(ws.cand_tmp.reserve(S));
@@ -2046,6 +2052,7 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
                     FA_CUDA(cudaGetLastError()); launches++;
                 }
                 FA_CUDA(cudaEventRecord(ws.ev[5], st));
+                nv.next("fa:query L2 prep");
                 // ---- L2 -----------------------------------------------------------------------
                 FA_TRY(ws.prep.reserve(C)); FA_TRY(ws.ev_off.reserve(C + 1)); FA_TRY(ws.jobs.reserve(2 * (size_t)C)); FA_TRY(ws.mid.reserve(C));
                 l2_prep_kernel<<<std::min<uint32_t>((uint32_t)((C + 256) / 256), (uint32_t)dev_sms * 8u), 256, 0, st>>>(
@@ -2054,6 +2061,7 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
                 FA_CUDA(cudaGetLastError()); launches++;
                 FA_TRY(excl_scan<uint64_t>(st, ws.cub_tmp, ws.ev_off.p, ws.ev_off.p, (int64_t)C + 1, &launches));
                 FA_CUDA(cudaEventRecord(ws.ev[9], st));
+                nv.next("fa:query L2 events");
                 uint64_t *h_ev = reinterpret_cast<uint64_t *>(h_u + 2);
                 FA_CUDA(cudaMemcpyAsync(h_ev, ws.ev_off.p + C, 8, cudaMemcpyDeviceToHost, st));
                 FA_CUDA(cudaStreamSynchronize(st));                           // sync 3: size of the event lists
@@ -2076,6 +2084,7 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
                         FA_CUDA(cudaGetLastError()); launches++;
                     }
                     FA_CUDA(cudaEventRecord(ws.ev[10], st));
+                    nv.next("fa:query L2 slide");
                     {
                         const int rows = l2_words_for(std::min(std::max(max_s, 1), EV_MAX_S) + 9) + 1;  // slack: one row below, the pivot may stray eight buckets above
                         const size_t smem = (size_t)rows * L2_THREADS * 4;
@@ -2102,6 +2111,7 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
                     FA_CUDA(cudaGetLastError()); launches++;
                 }
                 FA_CUDA(cudaEventRecord(ws.ev[6], st));
+                nv.next("fa:query CGI");
                 // ---- CGI ----------------------------------------------------------------------
                 cgi_best_kernel<<<std::min<uint32_t>((uint32_t)((C + 255) / 256), 148u * 8u), 256, 0, st>>>(
                     ws.cands.p, ws.maps.p, ws.frag_cands.p, F, ix->genome_of_seq.p, ix->bin_base.p, L - 20, ws.cells.p,
@@ -2118,6 +2128,7 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
                                                                  ws.g_count.p, ws.g_identity.p);
         FA_CUDA(cudaGetLastError()); launches++;
         FA_CUDA(cudaEventRecord(ws.ev[7], st));
+        nv.next("fa:query d2h");
         // ---- results back ----------------------------------------------------------------------
         int32_t *h_c = reinterpret_cast<int32_t *>(ws.hres.p + 128);
         float *h_i = reinterpret_cast<float *>(ws.hres.p + 128 + (size_t)B * G * 4);

@@ -45,6 +45,25 @@ def test_fastani_example(pf, genomes, adapter):          # test_ani.py:29-51
     assert round(abs(hits[0].identity - 97.7507), 4) == 0
 
 
+def test_fastani_example_result_files(pf, genomes):
+    """The two result files of the reference CLI (outputCGI / outputPhylip) from `query_many` on the reference's own example:
+    the line FastANI's README shows, and the 2 x 2 lower-triangular matrix."""
+    from pyfastani_b200 import output
+    sketch = pf.Sketch()
+    sketch.add_draft("ecoli.fna", genomes["ecoli"])
+    sketch.add_draft("shigella.fna", genomes["shigella"])
+    mapper = sketch.index()
+    results = mapper.query_many([genomes["shigella"]])
+    lines = list(output.tabular_lines(["shigella.fna"], results))
+    assert lines[0].startswith("shigella.fna\tshigella.fna\t100\t") and lines[0].endswith("\t1608")
+    assert lines[1] == "shigella.fna\tecoli.fna\t97.7507\t1303\t1608"
+    both = mapper.query_many([genomes["ecoli"], genomes["shigella"]])
+    m = list(output.matrix_lines(["ecoli.fna", "shigella.fna"], ["ecoli.fna", "shigella.fna"], both))
+    ab = [h for h in both[0] if h.name == "shigella.fna"][0].identity
+    ba = [h for h in both[1] if h.name == "ecoli.fna"][0].identity
+    assert m == ["2", "ecoli.fna", "shigella.fna\t%f" % float((np.float32(ba) + np.float32(ab)) / np.float32(2))]
+
+
 def test_escherichia_minimizers(pf, genomes):           # test_ani.py:54-71
     sketch = pf.Sketch()
     assert sketch.window_size == 24
@@ -232,6 +251,51 @@ def test_lookup_index_mutation(pf):
         del li[k]
     assert len(li) == 0 and list(li) == []
     assert mapper.query_genome(q) == [] and mapper.last_query_info["seeds"] == 0
+
+
+def test_sketch_files(pf, tmp_path):
+    """The on-disk sketch (`Sketch.save` / `Sketch.load`, `Mapper.save` / `Mapper.load`): parameters, names, lengths and
+    the minimizer columns survive the round trip, the reloaded mapper answers like the original, and nothing is
+    sketched again."""
+    import synth
+    q, refs, _ = synth.one_to_many(31, 4, 70_000, lo=0.86, hi=0.99)
+    sketch = pf.Sketch(fragment_length=2_000, percentage_identity=82.0)
+    for i, r in enumerate(refs[:3]):
+        sketch.add_genome("ref%d" % i, r)
+    sketch.add_draft("draft", [refs[3][:30_000], refs[3][30_000:31_000], refs[3][31_000:]])
+    h, s, w = sketch.minimizers.arrays()
+    st = sketch.minimizers.__getstate__()
+    assert (h.tolist(), s.tolist(), w.tolist()) == (st["hashes"], st["ids"], st["offsets"]) and len(h) == st["length"]
+    path = tmp_path / "refs.sketch.npz"
+    sketch.save(path)
+    back = pf.Sketch.load(path)
+    assert back.names == sketch.names and back.fragment_length == 2_000 and back.percentage_identity == 82.0
+    assert back.window_size == sketch.window_size and back.k == sketch.k
+    for a, b in zip(back.minimizers.arrays(), (h, s, w)):
+        assert np.array_equal(a, b)
+    assert back.__getstate__() == sketch.__getstate__()
+    back.add_genome("late", refs[0][5_000:60_000])                       # the counter of sequence ids goes on where it was
+    sketch.add_genome("late", refs[0][5_000:60_000])
+    assert back.__getstate__() == sketch.__getstate__()
+    mapper = sketch.index()
+    want = mapper.query_genome(q)
+    assert len(want) == 5
+    assert back.index().query_genome(q) == want
+    mpath = tmp_path / "refs.mapper.npz"
+    mapper.save(mpath)
+    again = pf.Mapper.load(mpath)
+    assert again.names == mapper.names and len(again.lookup_index) == len(mapper.lookup_index)
+    assert again.query_genome(q) == want and again.query_draft([q[:40_000], q[40_000:]]) == mapper.query_draft([q[:40_000], q[40_000:]])
+    with pytest.raises(ValueError):
+        np.savez(tmp_path / "other.npz", header=np.frombuffer(b'{"format": "x"}', np.uint8))
+        pf.Sketch.load(tmp_path / "other.npz")
+    odd = pf.Sketch()
+    odd.add_genome(("a", "tuple"), refs[0])                               # names that are not JSON: pickle is the way
+    odd.save(tmp_path / "odd.npz")                                        # (a tuple becomes a list: still JSON)
+    odd2 = pf.Sketch()
+    odd2.add_genome(object(), refs[0])
+    with pytest.raises(TypeError):
+        odd2.save(tmp_path / "odd2.npz")
 
 
 def test_query_many_equals_single_queries(pf):
