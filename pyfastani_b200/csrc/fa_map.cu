@@ -540,8 +540,11 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
                 const uint32_t t = base + (uint32_t)(e0 + lane);
                 jv[u] = 0xFFFFFFFFu;
                 if (e0 < L1_TILE + m - 1 && t < n) {
-                    uint32_t c = blk_chunk[(base + (uint32_t)e0) >> 5];
-                    while (hist[c] <= t) c++;
+                    // the chunk of hit t: the first bucket that ends behind it, between the chunks of the two hits that
+                    // bracket its block of 32 (chance hits of a large index lie thousands of empty chunks apart)
+                    const uint32_t q = (base + (uint32_t)e0) >> 5;
+                    uint32_t c = blk_chunk[q], hi = ((q + 1u) << 5) < n ? (uint32_t)blk_chunk[q + 1u] : n_chunks - 1u;
+                    while (c < hi) { const uint32_t mid = (c + hi) >> 1; if (hist[mid] <= t) c = mid + 1u; else hi = mid; }
                     jv[u] = (c << L1_SHIFT) | (uint32_t)keys[t];
                 }
             }
