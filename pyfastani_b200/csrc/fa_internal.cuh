@@ -50,6 +50,7 @@ struct Workspace {
     DevBuf<uint64_t> ev_off;            // per candidate: padded event count, then exclusive prefix (C + 1)
     DevBuf<uint4>    jobs;              // per candidate: slide descriptor (fa_map.cu SlideJob, two entries each)
     DevBuf<uint32_t> mid;               // per candidate: begin / end index of the window its slide starts from
+    DevBuf<uint32_t> seq_cnt;           // per fragment: minimizers the sketch kernel emitted into its slot of qhash
     DevBuf<uint16_t> events;            // the merged, classified insert/delete events of all candidates
     DevBuf<uint32_t> cells;             // per (ref contig, bin): best identity bits (computeCGI pass 2)
     DevBuf<float>    g_identity;        // per genome
@@ -66,7 +67,7 @@ struct Workspace {
         stage.release(); frag_q.release(); qhash.release(); qs.release(); hit_start.release(); hit_cnt.release();
         frag_seeds.release(); seeds_a.release(); seeds_b.release(); fb_seeds.release(); cand_tmp.release(); hfs.release();
         cub_tmp.release(); frag_cands.release(); work_base.release(); cands.release(); maps.release(); prep.release();
-        ev_off.release(); jobs.release(); mid.release(); events.release(); cells.release(); g_identity.release();
+        ev_off.release(); jobs.release(); mid.release(); seq_cnt.release(); events.release(); cells.release(); g_identity.release();
         g_count.release(); counters.release(); hres.release();
         if (ev_ready) for (auto &e : ev) cudaEventDestroy(e);
         ev_ready = false;

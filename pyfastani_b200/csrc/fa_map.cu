@@ -68,15 +68,14 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_warp
 }
 
 // ---- per-fragment sort + unique of the query minimizer hashes (pyx:929-938) -----------------
-__global__ void sort_unique_kernel(uint32_t *qhash, const uint64_t *seq_first, const unsigned long long *sk_counters,
+__global__ void sort_unique_kernel(uint32_t *qhash, const uint64_t *seq_first, const uint32_t *seq_cnt,
                                    int n_frags, int cap, int s_max, int32_t *qs, unsigned long long *counters)
 {
     extern __shared__ uint32_t s_h[];
     __shared__ uint32_t s_warp[8];
     const int f = blockIdx.x, tid = threadIdx.x;
-    const uint64_t b = seq_first[f];
-    const uint64_t e = (f + 1 < n_frags) ? seq_first[f + 1] : sk_counters[1];
-    const int n = (int)(e - b);
+    const uint64_t b = seq_first[f];                     // the fragment's slot (launch_sketch with slot_cap)
+    const int n = (int)seq_cnt[f];
     if (n > cap) {
         if (tid == 0) { atomicOr(&counters[CT_ERR], (unsigned long long)ERR_SORT_CAP); qs[f] = 0; }
         return;
@@ -1911,13 +1910,14 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
         FA_CUDA(cudaMemsetAsync(ws.counters.p, 0, CT_N * sizeof(unsigned long long), st));
         FA_CUDA(cudaEventRecord(ws.ev[1], st));
         nv.next("fa:query sketch");
-        FA_TRY(launch_sketch(st, ws.sk, F, n_tiles, k, w, P.alphabet != 4, nullptr, ws.qhash.p, 0, &launches));
+        FA_TRY(ws.seq_cnt.reserve(F));
+        FA_TRY(launch_sketch(st, ws.sk, F, n_tiles, k, w, P.alphabet != 4, nullptr, ws.qhash.p, 0, &launches, std::max(cmw, 1), ws.seq_cnt.p));
         {
             int p2 = 1; while (p2 < cmw) p2 <<= 1;
             int sort_cap = std::min(p2, 32768);
             size_t smem = (size_t)sort_cap * 4;
             if (smem > 48 * 1024) FA_CUDA(cudaFuncSetAttribute(sort_unique_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            sort_unique_kernel<<<F, 256, smem, st>>>(ws.qhash.p, ws.sk.seq_first.p, ws.sk.counters.p, F, sort_cap, ix->s_max,
+            sort_unique_kernel<<<F, 256, smem, st>>>(ws.qhash.p, ws.sk.seq_first.p, ws.seq_cnt.p, F, sort_cap, ix->s_max,
                                                      ws.qs.p, ws.counters.p);
             FA_CUDA(cudaGetLastError()); launches++;
         }

@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(SK_THREADS)
 sketch_kernel(const uint8_t *__restrict__ bytes, const SeqDesc *__restrict__ seqs, int n_seqs, int n_tiles,
               int k, int w, int fwd_only, int nb_cap, int nk_cap,
               unsigned long long *status, unsigned long long *counters, uint64_t *seq_first,
-              RefMini *out_ref, uint32_t *out_hash, uint64_t out_base)
+              RefMini *out_ref, uint32_t *out_hash, uint64_t out_base, int slot_cap, uint32_t *seq_cnt)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *sf = smem;                                        // normalised forward bytes
@@ -281,10 +281,15 @@ sketch_kernel(const uint8_t *__restrict__ bytes, const SeqDesc *__restrict__ seq
     for (int q = 0; q < SK_THREADS / 32; q++) { if (q < wid) wbase += s_warp[q]; agg += s_warp[q]; }
     const uint32_t local_off = wbase + incl - (uint32_t)e_cnt;
 
+    // slot_cap > 0 (query fragments): every sequence writes into its own slot of slot_cap entries, so a tile needs the
+    // counts of the earlier tiles of ITS sequence only -- the first tile of a sequence publishes a prefix at once and
+    // the look-back of the others ends there, two tiles back at most.  slot_cap == 0 (reference genomes): one
+    // (sequence, position)-ordered array, look-back over all tiles.
+    const bool local = slot_cap > 0;
     if (wid == 0) {
         unsigned long long excl = 0;
-        if (tile == 0) {
-            if (lane == 0) atomicExch(&status[0], ST_PREFIX | (unsigned long long)agg);
+        if (tile == 0 || (local && t0 == 0)) {
+            if (lane == 0) atomicExch(&status[tile], ST_PREFIX | (unsigned long long)agg);
         } else {
             if (lane == 0) atomicExch(&status[tile], ST_AGG | (unsigned long long)agg);
             int p = tile - 1;
@@ -307,8 +312,10 @@ sketch_kernel(const uint8_t *__restrict__ bytes, const SeqDesc *__restrict__ seq
             if (lane == 0) atomicExch(&status[tile], ST_PREFIX | (excl + agg));
         }
         if (lane == 0) {
-            s_excl = excl;
-            if (t0 == 0) seq_first[lo_s] = excl;
+            const unsigned long long slot = local ? (unsigned long long)lo_s * (unsigned long long)slot_cap : 0ull;
+            s_excl = slot + excl;
+            if (t0 == 0) seq_first[lo_s] = slot + excl;
+            if (local && hi == nk) seq_cnt[lo_s] = (uint32_t)(excl + agg);
             if (tile == n_tiles - 1) counters[1] = excl + agg;
         }
     }
@@ -396,7 +403,7 @@ static int init_tables()
 }
 
 int launch_sketch(cudaStream_t st, const SketchScratch &sc, int n_seqs, int n_tiles, int k, int w, int fwd_only,
-                  RefMini *out_ref, uint32_t *out_hash, uint64_t out_base, int *launches)
+                  RefMini *out_ref, uint32_t *out_hash, uint64_t out_base, int *launches, int slot_cap, uint32_t *seq_cnt)
 {
     FA_TRY(init_tables());
     const int halo = 2 * w - 2;
@@ -410,7 +417,8 @@ int launch_sketch(cudaStream_t st, const SketchScratch &sc, int n_seqs, int n_ti
     auto kern = (k == 16) ? sketch_kernel<true> : sketch_kernel<false>;
     if (smem > 48 * 1024) FA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<n_tiles, SK_THREADS, smem, st>>>(sc.bytes.p, sc.seqs.p, n_seqs, n_tiles, k, w, fwd_only, nb_cap, nk_cap,
-                                            sc.tile_status.p, sc.counters.p, sc.seq_first.p, out_ref, out_hash, out_base);
+                                            sc.tile_status.p, sc.counters.p, sc.seq_first.p, out_ref, out_hash, out_base,
+                                            seq_cnt ? slot_cap : 0, seq_cnt);
     FA_CUDA(cudaGetLastError());
     if (launches) *launches += 1;
     return FA_OK;
