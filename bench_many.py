@@ -286,7 +286,11 @@ def main():
     if world > 1:
         # ---- both multi-GPU layouts: every rank maps its list of queries in chunks through query_many -----------------
         if by_refs:
-            mine = list(range(G))                     # every rank maps every query against its shard (collective calls)
+            # every rank maps every query against its shard (collective calls).  Neighbouring genomes of the collection are
+            # related, so a chunk of consecutive queries would put all of its real mapping work on the one rank that holds
+            # their relatives while the others wait at the chunk's all-gather: the queries go in a fixed shuffled order
+            # (the same on every rank), which spreads every chunk over all shards.
+            mine = [int(x) for x in np.random.default_rng(a.seed + 977).permutation(G)]
         else:
             mine = sharding.partition_queries(frag_counts, world)[rank]
         items = [item(wrap(dev_contigs[i])) for i in mine]
@@ -321,7 +325,9 @@ def main():
         stage_min = {k: -reduce(-float(v)) for k, v in sorted(acc.items()) if k.startswith("ms_")}
         count_sum = {k: int(reduce(int(acc.get(k, 0)), "sum", torch.int64)) for k in COUNTERS}
         if by_refs:
-            rows_all = rows                           # merged rows of every query, identical on every rank
+            rows_all = [None] * G                     # merged rows of every query, identical on every rank
+            for q, r in zip(mine, rows):
+                rows_all[q] = r
             ok = all(len(m) and q in m["ref_genome"][:4] for q, m in enumerate(rows_all))    # every genome finds itself at the top
         else:
             # gather the rows of the partitioned queries on rank 0 for the histogram / sample (outside the timed region)
@@ -341,7 +347,7 @@ def main():
             stages = stage_report(inf, bases, peak * world)
             cfg["workload"] = ("configs[%d] layout: %s; %s" % (
                 4 if by_refs else 3, workload_text(a, G),
-                ("reference genomes sharded over %d GPUs (%s per rank), every rank maps all queries (resident), per %d queries one library call "
+                ("reference genomes sharded over %d GPUs (%s per rank), every rank maps all queries (resident, in one shuffled order), per %d queries one library call "
                  "(fa_query_batch_sharded): mapping + one ncclAllGather of the hit rows + merge" % (world, [offsets[r + 1] - offsets[r] for r in range(world)], a.chunk))
                 if by_refs else "queries dealt to %d GPUs (LPT by fragments), replicated index, query_many per %d queries" % (world, a.chunk)))
             line = {"metric": "genome_pairs_per_s", "unit": "genome-pairs/s", "n_gpus": world, "scaling": "strong",
