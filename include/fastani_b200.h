@@ -53,13 +53,29 @@ typedef struct fa_params {
 /* One sequence as the reference receives it (pyx:633-645, 1071-1095): `unit_bytes` is 1
  * for bytes / UCS1 str, 2 or 4 for UCS2 / UCS4 str.  `on_device` != 0 means `data` is a
  * device pointer on the index's device (unit_bytes must be 1); used to time the path
- * with inputs already resident in HBM. */
+ * with inputs already resident in HBM.  `unit_bytes` == FA_UNIT_PACKED2 means `data` points
+ * to an fa_packed (host memory, see below) holding `len` bases at two bits each. */
 typedef struct fa_contig {
     const void *data;
     int32_t     unit_bytes;
     int32_t     on_device;
     int64_t     len;
 } fa_contig;
+
+/* A sequence packed to two bits per base for staging: a quarter of the bytes cross host memory and
+ * PCIe, the device expands them in front of the sketch kernel (unpack_2bit in csrc/fa_map.cu).  Base i sits in bits
+ * 2 (i & 3) .. 2 (i & 3) + 1 of bits[i >> 2]: A = 0, C = 1, G = 2, T = 3; a, c, g, t pack like their capitals (the
+ * path upper-cases before it hashes, pyx:116-153).  Every other byte value -- N, IUPAC codes, anything -- is kept
+ * exactly, as runs of one value: run r covers positions [run_pos[r], run_pos[r] + run_len[r]) with byte run_byte[r]
+ * (ascending, disjoint; the two bits under a run are zero).  Results are identical to the unpacked bytes. */
+typedef struct fa_packed {
+    const uint8_t  *bits;       /* (len + 3) / 4 bytes */
+    const uint32_t *run_pos;
+    const uint32_t *run_len;
+    const uint8_t  *run_byte;
+    uint64_t        n_runs;
+} fa_packed;
+enum { FA_UNIT_PACKED2 = -2 };
 
 /* cgi::CGI_Results, FA/cgi/include/cgid_types.hpp:68-80, after the min-fraction filter
  * and identity-descending stable sort of pyx:1121-1135. */
@@ -225,6 +241,31 @@ FA_API int fa_debug_set_l1_small_cap(fa_index *ix, int64_t cap);
  * larger ones serve indexes whose chunk histogram leaves no room otherwise, i.e. thousands of genomes); `shape` = 0, 1, 2
  * is the smallest one it may pick, -1 restores the default. */
 FA_API int fa_debug_set_l1_small_shape(fa_index *ix, int32_t shape);
+/* -- ingestion --------------------------------------------------------------------------------------
+ * Host helper: packs `len` bytes into the fa_packed layout.  `bits` has (len + 3) / 4 bytes; the run arrays have
+ * `run_cap` entries; *n_runs receives the number of runs the sequence has -- when it exceeds run_cap only the first
+ * run_cap were stored (call again with larger arrays).  len < 2^32. */
+FA_API int fa_pack_2bit(const uint8_t *data, uint64_t len, uint8_t *bits, uint32_t *run_pos, uint32_t *run_len,
+                 uint8_t *run_byte, uint64_t run_cap, uint64_t *n_runs);
+/* The inverse on the host (pickling, tests). */
+FA_API int fa_unpack_2bit(const fa_packed *p, uint64_t len, uint8_t *out);
+/* FASTA text parsed on the device: what the reference's Parser does line by line on the host
+ * (src/pyfastani/_fasta.pyx:41-103 -- a record starts at a line that begins with '>', its id is the rest of that line,
+ * its sequence the following lines up to the next such line with their '\n' removed and letters upper-cased; a text
+ * that does not start with '>' has no records).  The text is uploaded once; header lines and newlines are dropped by a
+ * stream compaction on the GPU and the records stay in device memory, ready to be passed as on_device contigs to
+ * fa_sketch_add_genome / fa_query without ever existing as host strings.
+ * Differences from the reference parser, both outside what a FASTA file holds: its 2048-byte line buffer treats a '>'
+ * at a multiple of 2047 bytes into a longer line as a header, and its SSE2 upper-casing clears bit 5 of non-letters
+ * (digits, punctuation) in the 16-byte blocks of a line. */
+typedef struct fa_fasta fa_fasta;
+FA_API int fa_fasta_parse(int32_t device, const void *text, uint64_t len, fa_fasta **out);
+FA_API void fa_fasta_free(fa_fasta *f);
+FA_API int fa_fasta_counts(const fa_fasta *f, uint64_t *n_records, uint64_t *n_bases);
+/* contigs[r] = the sequence of record r as a device-resident contig (valid until fa_fasta_free); id_begin[r] / id_len[r]
+ * locate its identifier in the text the caller passed (the bytes between '>' and the end of the line). */
+FA_API int fa_fasta_records(const fa_fasta *f, fa_contig *contigs, uint64_t *id_begin, uint64_t *id_len);
+
 /* Device buffers for callers that want inputs resident in HBM before the timed region
  * (fa_contig.on_device). */
 FA_API int fa_device_alloc(int32_t device, uint64_t bytes, void **dptr);

@@ -8,12 +8,14 @@ from . import _fastani
 from ._fastani import (
     MAX_KMER_SIZE,
     CudaError,
+    DeviceFasta,
     DeviceSequence,
     Hit,
     Mapper,
     MinimizerIndex,
     MinimizerInfo,
     Minimizers,
+    PackedSequence,
     Position,
     Sketch,
     device_count,
@@ -22,5 +24,5 @@ from ._fastani import (
 __version__ = _fastani.__version__
 __all__ = [
     "MAX_KMER_SIZE", "Hit", "Mapper", "MinimizerIndex", "MinimizerInfo", "Minimizers", "Position", "Sketch",
-    "CudaError", "DeviceSequence", "device_count",
+    "CudaError", "DeviceFasta", "DeviceSequence", "PackedSequence", "device_count",
 ]

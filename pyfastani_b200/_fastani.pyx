@@ -19,8 +19,9 @@ from cpython.unicode cimport (
     PyUnicode_GET_LENGTH,
     PyUnicode_1BYTE_KIND,
     PyUnicode_2BYTE_KIND,
+    PyUnicode_FromKindAndData,
 )
-from libc.stdint cimport int32_t, int64_t, uint32_t, uint64_t, uintptr_t
+from libc.stdint cimport int32_t, int64_t, uint8_t, uint32_t, uint64_t, uintptr_t
 from libc.stdlib cimport malloc, free
 from libc.string cimport memset
 from cpython.bytes cimport PyBytes_FromStringAndSize
@@ -78,9 +79,17 @@ cdef extern from "fastani_b200.h" nogil:
         uint32_t l1_small_fragments
         uint64_t events_replayed
         float ms_batch
+    ctypedef struct fa_packed:
+        const uint8_t* bits
+        const uint32_t* run_pos
+        const uint32_t* run_len
+        const uint8_t* run_byte
+        uint64_t n_runs
+    int FA_UNIT_PACKED2
     ctypedef struct fa_sketch
     ctypedef struct fa_index
     ctypedef struct fa_comm
+    ctypedef struct fa_fasta
 
     const char* fa_last_error()
     int fa_device_count(int32_t* n)
@@ -123,6 +132,13 @@ cdef extern from "fastani_b200.h" nogil:
     int fa_query_batch_sharded(fa_index* ix, fa_comm* comm, const fa_contig* contigs, const int32_t* contigs_per_query,
                                int32_t n_queries, const int32_t* genome_offsets, fa_hit* out, uint64_t cap,
                                uint64_t* hit_offsets, fa_query_info* info)
+    int fa_pack_2bit(const uint8_t* data, uint64_t n, uint8_t* bits, uint32_t* run_pos, uint32_t* run_len,
+                     uint8_t* run_byte, uint64_t run_cap, uint64_t* n_runs)
+    int fa_unpack_2bit(const fa_packed* p, uint64_t n, uint8_t* out)
+    int fa_fasta_parse(int32_t device, const void* text, uint64_t n, fa_fasta** out)
+    void fa_fasta_free(fa_fasta* f)
+    int fa_fasta_counts(const fa_fasta* f, uint64_t* n_records, uint64_t* n_bases)
+    int fa_fasta_records(const fa_fasta* f, fa_contig* contigs, uint64_t* id_begin, uint64_t* id_len)
     int fa_device_alloc(int32_t device, uint64_t nbytes, void** dptr)
     int fa_device_upload(int32_t device, void* dptr, const void* src, uint64_t nbytes)
     int fa_device_free(int32_t device, void* dptr)
@@ -311,6 +327,142 @@ cdef class DeviceSequence:
         return d
 
 
+cdef class PackedSequence:
+    """A sequence at two bits per base (`fa_packed`), accepted wherever a contig is.
+
+    Not part of the reference API (SURVEY.md 8(f)-2): a quarter of the bytes cross host memory and PCIe, the GPU
+    expands them in front of the sketch kernel.  ``A C G T`` (either case) take two bits; every other byte -- ``N``,
+    IUPAC codes -- is kept exactly, as runs, so results are identical to those of the plain bytes.
+    """
+    cdef readonly int64_t length
+    cdef readonly object  bits       # numpy uint8, (length + 3) // 4
+    cdef readonly object  run_pos    # numpy uint32
+    cdef readonly object  run_len    # numpy uint32
+    cdef readonly object  run_byte   # numpy uint8
+    cdef fa_packed _pk
+
+    def __init__(self, int64_t length, object bits, object run_pos, object run_len, object run_byte):
+        import numpy
+        self.length = length
+        self.bits = numpy.ascontiguousarray(bits, dtype=numpy.uint8)
+        self.run_pos = numpy.ascontiguousarray(run_pos, dtype=numpy.uint32)
+        self.run_len = numpy.ascontiguousarray(run_len, dtype=numpy.uint32)
+        self.run_byte = numpy.ascontiguousarray(run_byte, dtype=numpy.uint8)
+        if length < 0 or self.bits.shape[0] < (length + 3) // 4:
+            raise ValueError("PackedSequence: `bits` is shorter than the length needs")
+        if not (self.run_pos.shape[0] == self.run_len.shape[0] == self.run_byte.shape[0]):
+            raise ValueError("PackedSequence: run arrays of different lengths")
+        cdef const uint8_t[::1] b = self.bits
+        cdef const uint32_t[::1] rp = self.run_pos
+        cdef const uint32_t[::1] rl = self.run_len
+        cdef const uint8_t[::1] rb = self.run_byte
+        self._pk.bits = &b[0] if b.shape[0] else NULL
+        self._pk.n_runs = rp.shape[0]
+        self._pk.run_pos = &rp[0] if rp.shape[0] else NULL
+        self._pk.run_len = &rl[0] if rp.shape[0] else NULL
+        self._pk.run_byte = &rb[0] if rp.shape[0] else NULL
+
+    def __len__(self):
+        return self.length
+
+    def __reduce__(self):
+        return PackedSequence, (self.length, self.bits, self.run_pos, self.run_len, self.run_byte)
+
+    @property
+    def nbytes(self):
+        return self.bits.nbytes + self.run_pos.nbytes + self.run_len.nbytes + self.run_byte.nbytes
+
+    @staticmethod
+    def pack(object data):
+        """Pack `bytes`-like data (or an ASCII `str`)."""
+        import numpy
+        if isinstance(data, str):
+            data = data.encode("ascii")
+        cdef const unsigned char[::1] view = data
+        cdef uint64_t n = view.shape[0], n_runs = 0, cap = 1024
+        bits = numpy.zeros((n + 3) // 4, dtype=numpy.uint8)
+        cdef uint8_t[::1] b = bits
+        cdef uint32_t[::1] rp, rl
+        cdef uint8_t[::1] rb
+        while True:
+            pos = numpy.empty(cap, dtype=numpy.uint32); ln = numpy.empty(cap, dtype=numpy.uint32)
+            byt = numpy.empty(cap, dtype=numpy.uint8)
+            rp = pos; rl = ln; rb = byt
+            _check(fa_pack_2bit(&view[0] if n else NULL, n, &b[0] if n else NULL, &rp[0], &rl[0], &rb[0], cap, &n_runs))
+            if n_runs <= cap:
+                break
+            cap = n_runs
+        return PackedSequence(n, bits, pos[:n_runs].copy(), ln[:n_runs].copy(), byt[:n_runs].copy())
+
+    def unpack(self):
+        """The bytes this sequence stands for (lower-case ``acgt`` come back as capitals)."""
+        cdef bytearray out = bytearray(self.length)
+        cdef unsigned char[::1] o = out
+        if self.length:
+            _check(fa_unpack_2bit(&self._pk, self.length, &o[0]))
+        return bytes(out)
+
+
+cdef class DeviceFasta:
+    """FASTA text parsed on the GPU: the records of the reference's ``Parser`` (``_fasta.pyx:41-103``) with their
+    sequences resident in device memory.
+
+    ``ids[i]`` / ``sequences[i]`` are the identifier and the `DeviceSequence` of record ``i``; pass ``sequences`` to
+    ``Sketch.add_draft`` / ``Mapper.query_draft``.  The text is uploaded once, header lines and newlines are dropped
+    by a stream compaction on the device, and no per-record host string is ever built.
+    """
+    cdef fa_fasta* _f
+    cdef readonly int   device
+    cdef readonly list  ids
+    cdef readonly list  sequences
+    cdef readonly uint64_t bases
+
+    def __cinit__(self):
+        self._f = NULL
+
+    def __dealloc__(self):
+        if self._f != NULL:
+            fa_fasta_free(self._f)
+
+    def __init__(self, object text, int device=0):
+        """`text`: the content of a FASTA file (bytes-like), or a path to read it from."""
+        import os
+        if isinstance(text, (str, os.PathLike)):
+            with open(text, "rb") as fh:
+                text = fh.read()
+        cdef const unsigned char[::1] view = text
+        cdef uint64_t n = view.shape[0], n_rec = 0, n_bases = 0, i
+        cdef const unsigned char* p = &view[0] if n else NULL
+        cdef int rc
+        with nogil:
+            rc = fa_fasta_parse(device, p, n, &self._f)
+        _check(rc)
+        self.device = device
+        _check(fa_fasta_counts(self._f, &n_rec, &n_bases))
+        self.bases = n_bases
+        cdef fa_contig* c = <fa_contig*> malloc(max(n_rec, 1) * sizeof(fa_contig))
+        cdef uint64_t* ib = <uint64_t*> malloc(max(n_rec, 1) * sizeof(uint64_t))
+        cdef uint64_t* il = <uint64_t*> malloc(max(n_rec, 1) * sizeof(uint64_t))
+        cdef DeviceSequence d
+        try:
+            _check(fa_fasta_records(self._f, c, ib, il))
+            self.ids = []
+            self.sequences = []
+            for i in range(n_rec):
+                self.ids.append(PyUnicode_FromKindAndData(PyUnicode_1BYTE_KIND, p + ib[i], il[i]))
+                d = DeviceSequence.__new__(DeviceSequence)
+                d.device = device; d.length = c[i].len; d._ptr = <void*> c[i].data; d._owner = self
+                self.sequences.append(d)
+        finally:
+            free(c); free(ib); free(il)
+
+    def __len__(self):
+        return len(self.ids)
+
+    def __iter__(self):
+        return iter(zip(self.ids, self.sequences))
+
+
 cdef class _Contigs:
     """A C array of `fa_contig` built from Python sequences, keeping the buffers alive."""
     cdef fa_contig* arr
@@ -332,6 +484,7 @@ cdef class _Contigs:
         cdef int kind
         cdef Py_ssize_t i
         cdef DeviceSequence dev
+        cdef PackedSequence pk
         self.n = <int32_t> len(items)
         self.arr = <fa_contig*> malloc(max(self.n, 1) * sizeof(fa_contig))
         if self.arr == NULL:
@@ -354,6 +507,12 @@ cdef class _Contigs:
                 self.arr[i].len = dev.length
                 self.arr[i].unit_bytes = 1
                 self.arr[i].on_device = 1
+                self.keep.append(contig)
+            elif isinstance(contig, PackedSequence):
+                pk = contig
+                self.arr[i].data = &pk._pk
+                self.arr[i].len = pk.length
+                self.arr[i].unit_bytes = FA_UNIT_PACKED2
                 self.keep.append(contig)
             else:
                 # anything exposing a contiguous byte buffer (pyx:638-645)

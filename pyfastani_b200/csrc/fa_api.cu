@@ -113,9 +113,7 @@ int sketch_add_batch(fa_sketch *s, const fa_contig *contigs, int32_t n_contigs, 
     uint64_t counter = s->counter, cur_len = s->cur_len;
     for (int32_t c = 0; c < n_contigs; c++) {
         const fa_contig &ct = contigs[c];
-        if (ct.len < 0 || (ct.len > 0 && !ct.data)) { set_error("contig %d: bad buffer", c); return FA_ERR_INVALID; }
-        if (ct.unit_bytes != 1 && ct.unit_bytes != 2 && ct.unit_bytes != 4) { set_error("unit_bytes must be 1, 2 or 4"); return FA_ERR_INVALID; }
-        if (ct.on_device && ct.unit_bytes != 1) { set_error("device-resident contigs must be bytes"); return FA_ERR_INVALID; }
+        FA_TRY(check_contig(ct, c));
         if (ct.len > 0x7FFFFF00ll) { set_error("contigs longer than 2^31 bases are not supported"); return FA_ERR_UNSUPPORTED; }
     }
     uint64_t bases = 0;
@@ -137,7 +135,7 @@ int sketch_add_batch(fa_sketch *s, const fa_contig *contigs, int32_t n_contigs, 
         if (ct.len >= P.window && ct.len >= P.k) {                                    // pyx:648
             const int nk = (int)ct.len - P.k + 1;
             SeqDesc d;
-            d.off = off; d.len = (int32_t)ct.len; d.id = id; d.raw = ct.unit_bytes != 1; d.tile0 = (int32_t)tiles;
+            d.off = off; d.len = (int32_t)ct.len; d.id = id; d.raw = contig_prenormalised(ct); d.tile0 = (int32_t)tiles;
             s->h_seqs.push_back(d);
             ups.push_back(Upload{ct.data, ct.unit_bytes, ct.on_device, ct.len, off});
             off += ((uint64_t)ct.len + 15) & ~15ull;

@@ -74,7 +74,7 @@ struct Workspace {
     }
 };
 
-// One host or device buffer to place at `off` in the batch byte buffer.
+// One host or device buffer to place at `off` in the batch byte buffer (unit: fa_contig.unit_bytes).
 struct Upload { const void *ptr; int32_t unit; int32_t on_device; int64_t len; uint64_t off; };
 // The bytes of one query staged ahead of its turn (fa_query_batch): while query q is mapped, a helper thread copies
 // query q + 1 through its own pinned buffer and copy stream into `bytes`; run_query then swaps `bytes` with the
@@ -153,6 +153,21 @@ struct fa_index {
 };
 
 namespace fa {
+// what every entry point accepts as a contig (include/fastani_b200.h fa_contig)
+inline int check_contig(const fa_contig &ct, int c)
+{
+    if (ct.len < 0 || (ct.len > 0 && !ct.data)) { set_error("contig %d: bad buffer", c); return FA_ERR_INVALID; }
+    if (ct.unit_bytes != 1 && ct.unit_bytes != 2 && ct.unit_bytes != 4 && ct.unit_bytes != FA_UNIT_PACKED2) {
+        set_error("unit_bytes must be 1, 2, 4 or FA_UNIT_PACKED2"); return FA_ERR_INVALID;
+    }
+    if (ct.on_device && ct.unit_bytes != 1) { set_error("device-resident contigs must be bytes"); return FA_ERR_INVALID; }
+    if (ct.unit_bytes == FA_UNIT_PACKED2 && ct.len > 0) {
+        const fa_packed *pk = (const fa_packed *)ct.data;
+        if (!pk->bits || (pk->n_runs && (!pk->run_pos || !pk->run_len || !pk->run_byte))) { set_error("contig %d: bad packed buffer", c); return FA_ERR_INVALID; }
+    }
+    return FA_OK;
+}
+inline bool contig_prenormalised(const fa_contig &ct) { return ct.unit_bytes == 2 || ct.unit_bytes == 4; }   // SeqDesc.raw
 int build_index(fa_index *ix, int *launches);
 // MinimizerIndex.__setitem__ / __delitem__: replace / insert / erase the position list of one hash (fa_index.cu)
 int edit_lookup(fa_index *ix, uint32_t hash, const int32_t *seq, const int32_t *wpos, uint64_t m, bool erase, int *missing);

@@ -1628,7 +1628,9 @@ int excl_scan(cudaStream_t st, DevBuf<uint8_t> &tmp, const T *in, T *out, int64_
 
 // Device-resident contigs of a draft (hundreds per query) into the batch buffer with ONE launch instead of one
 // cudaMemcpyAsync each: thread t owns the 16 bytes at 16 t; uploads start at ascending 16-byte aligned offsets.
-struct DevCopy { const uint8_t *src; uint64_t off; int64_t len; };
+// kind 1: the source is a 2-bit packed sequence (fa_packed.bits, already in device memory behind the batch bytes) and
+// the 16 bytes are expanded from one 32-bit word of it.
+struct DevCopy { const uint8_t *src; uint64_t off; int64_t len; int64_t kind; };
 __global__ void gather_contigs_kernel(const DevCopy *tab, int n, uint8_t *dst, uint64_t n_chunks)
 {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1640,12 +1642,40 @@ __global__ void gather_contigs_kernel(const DevCopy *tab, int n, uint8_t *dst, u
     if (c < d.off) return;
     const int64_t rel = (int64_t)(c - d.off);
     if (rel >= d.len) return;                                // padding between two uploads
+    if (d.kind == 1) {
+        // 16 bases = 4 packed bytes (the packed copy is padded to a multiple of 4 bytes); A C G T = 0 1 2 3
+        const uint32_t wd = *reinterpret_cast<const uint32_t *>(d.src + (rel >> 2));
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t v = (wd >> (8 * j + 2 * i)) & 3u;
+                x |= ((0x54474341u >> (8 * v)) & 0xFFu) << (8 * i);   // "ACGT" little-endian
+            }
+            o[j] = x;
+        }
+        *reinterpret_cast<uint4 *>(dst + c) = make_uint4(o[0], o[1], o[2], o[3]);   // (the slack behind an upload is ours: offsets are 16-aligned)
+        return;
+    }
     const uint8_t *sp = d.src + rel;
     if (d.len - rel >= 16 && ((uintptr_t)sp & 15) == 0) *reinterpret_cast<uint4 *>(dst + c) = *reinterpret_cast<const uint4 *>(sp);
     else {
         const int m = (int)min((int64_t)16, d.len - rel);
         for (int i = 0; i < m; i++) dst[c + i] = sp[i];
     }
+}
+
+// The bytes of a packed sequence that are not A, C, G or T (fa_packed runs): one warp per run writes its value over the
+// expanded bases.
+struct RunDesc { uint64_t off; uint32_t len; uint32_t byte; };
+__global__ void packed_runs_kernel(const RunDesc *runs, uint64_t n_runs, uint8_t *dst)
+{
+    const uint64_t r = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_runs) return;
+    const RunDesc d = runs[r];
+    for (uint32_t i = threadIdx.x & 31; i < d.len; i += 32) dst[d.off + i] = (uint8_t)d.byte;
 }
 
 inline int bits_for(uint64_t n) { int b = 1; while (b < 63 && (1ull << b) < n) b++; return b; }
@@ -1657,44 +1687,74 @@ inline int bits_for(uint64_t n) { int b = 1; while (b < 63 && (1ull << b) < n) b
 // while the host fills the next.  `workers` > 0: that many helper threads fill the pieces and this thread only issues
 // the copies, in order, as pieces complete -- used when a whole pass of fa_query_batch (tens of MB) is staged ahead;
 // for a lone 5 MB query spawning the threads costs more than the 0.3 ms they save.
+// 2-bit packed sources (fa_packed): their bits and their run table travel to a region behind the batch bytes -- a
+// quarter of the bytes through host memory and PCIe -- and gather_contigs_kernel / packed_runs_kernel expand them.
 int stage_sequences(cudaStream_t st, DevBuf<uint8_t> &bytes, PinBuf &stage, const std::vector<Upload> &ups, uint64_t total,
                     uint64_t *h2d_bytes, int workers)
 {
     // device-resident sources: more than a few go through one gather launch, its table behind the bytes
     std::vector<DevCopy> dcopy;
-    for (const Upload &u : ups)
-        if (u.on_device && u.len > 0) dcopy.push_back(DevCopy{(const uint8_t *)u.ptr, u.off, u.len});
-    const bool gather = dcopy.size() > 4;
-    const uint64_t tab_off = (total + 64 + 15) & ~15ull, tab_bytes = gather ? dcopy.size() * sizeof(DevCopy) : 0;
-    FA_TRY(bytes.reserve(tab_off + tab_bytes));
-    struct Piece { const Upload *u; int64_t o, n; };
+    struct Packed { const Upload *u; const fa_packed *pk; uint64_t bits_off, bits_bytes; };
+    std::vector<Packed> packed;
+    std::vector<RunDesc> runs;
+    size_t n_dev = 0;
+    for (const Upload &u : ups) {
+        if (u.len <= 0) continue;
+        if (u.unit == FA_UNIT_PACKED2) packed.push_back(Packed{&u, (const fa_packed *)u.ptr, 0, ((uint64_t)u.len + 3) / 4});
+        else if (u.on_device) n_dev++;
+    }
+    const bool gather = n_dev > 4 || !packed.empty();
+    const uint64_t tab_off = (total + 64 + 15) & ~15ull, tab_bytes = gather ? (n_dev + packed.size()) * sizeof(DevCopy) : 0;
+    uint64_t end = tab_off + tab_bytes;
+    for (Packed &pk : packed) {
+        pk.bits_off = (end + 15) & ~15ull;
+        end = pk.bits_off + ((pk.bits_bytes + 3) & ~3ull);
+        for (uint64_t r = 0; r < pk.pk->n_runs; r++) {
+            const uint64_t pos = pk.pk->run_pos[r];
+            if (pos >= (uint64_t)pk.u->len) break;                       // (a query stages whole fragments only)
+            runs.push_back(RunDesc{pk.u->off + pos, (uint32_t)std::min<uint64_t>(pk.pk->run_len[r], (uint64_t)pk.u->len - pos), pk.pk->run_byte[r]});
+        }
+    }
+    const uint64_t run_off = (end + 15) & ~15ull;
+    end = run_off + runs.size() * sizeof(RunDesc);
+    FA_TRY(bytes.reserve(end));
+    // (source, destination offset, bytes, unit): units 2 / 4 are narrowed on the way
+    struct Piece { const void *src; uint64_t dst; int64_t n; int unit; };
     std::vector<Piece> pieces;
     const int64_t piece = 1ll << 20;
     for (const Upload &u : ups) {
-        if (u.on_device || u.len <= 0) continue;
-        for (int64_t o = 0; o < u.len; o += piece) pieces.push_back(Piece{&u, o, std::min<int64_t>(piece, u.len - o)});
+        if (u.on_device || u.len <= 0 || u.unit == FA_UNIT_PACKED2) continue;
+        for (int64_t o = 0; o < u.len; o += piece)
+            pieces.push_back(Piece{(const uint8_t *)u.ptr + o * u.unit, u.off + (uint64_t)o, std::min<int64_t>(piece, u.len - o), u.unit});
     }
-    if (!pieces.empty() || gather) FA_TRY(stage.reserve(tab_off + tab_bytes));
+    for (const Packed &pk : packed)
+        for (uint64_t o = 0; o < pk.bits_bytes; o += (uint64_t)piece)
+            pieces.push_back(Piece{pk.pk->bits + o, pk.bits_off + o, (int64_t)std::min<uint64_t>((uint64_t)piece, pk.bits_bytes - o), 1});
+    if (!pieces.empty() || gather) FA_TRY(stage.reserve(end));
     if (!pieces.empty()) {
         uint8_t *const sp = stage.p;
         auto fill = [sp](const Piece &pc) {
-            const Upload &u = *pc.u;
-            uint8_t *dst = sp + u.off + pc.o;
-            if (u.unit == 1) memcpy(dst, (const uint8_t *)u.ptr + pc.o, (size_t)pc.n);
+            uint8_t *dst = sp + pc.dst;
+            if (pc.unit == 1) memcpy(dst, pc.src, (size_t)pc.n);
             else {
                 // pyx:147-148: (char)toupper(code point); glibc's toupper leaves values outside
                 // [-128, 255] unchanged
                 for (int64_t i = 0; i < pc.n; i++) {
-                    uint32_t cp = u.unit == 2 ? ((const uint16_t *)u.ptr)[pc.o + i] : ((const uint32_t *)u.ptr)[pc.o + i];
+                    uint32_t cp = pc.unit == 2 ? ((const uint16_t *)pc.src)[i] : ((const uint32_t *)pc.src)[i];
                     if (cp >= 'a' && cp <= 'z') cp -= 32;
                     dst[i] = (uint8_t)cp;
                 }
             }
         };
-        uint64_t sent = 0;                                   // stage.p[0 .. sent) is on its way (uploads lie at increasing offsets)
-        auto flush = [&](uint64_t upto) -> int {
-            if (upto > sent) FA_CUDA(cudaMemcpyAsync(bytes.p + sent, sp + sent, upto - sent, cudaMemcpyHostToDevice, st));
-            sent = std::max(sent, upto);
+        // stage.p[lo .. hi) is filled and not yet on its way; pieces come at increasing offsets, a gap (the slots of
+        // device-resident contigs, the table) starts a new copy
+        uint64_t lo = pieces[0].dst, hi = lo;
+        auto flush = [&]() -> int {
+            if (hi > lo) {
+                FA_CUDA(cudaMemcpyAsync(bytes.p + lo, sp + lo, hi - lo, cudaMemcpyHostToDevice, st));
+                if (h2d_bytes) *h2d_bytes += hi - lo;
+            }
+            lo = hi;
             return FA_OK;
         };
         const size_t np = pieces.size();
@@ -1719,24 +1779,40 @@ int stage_sequences(cudaStream_t st, DevBuf<uint8_t> &bytes, PinBuf &stage, cons
         for (size_t i = 0; i < np; i++) {
             if (nw > 0) { while (!ready[i].load(std::memory_order_acquire)) std::this_thread::yield(); }
             else fill(pieces[i]);
-            const uint64_t end = pieces[i].u->off + (uint64_t)(pieces[i].o + pieces[i].n);
-            if (rc == FA_OK && end - sent >= (uint64_t)piece) rc = flush(end);       // (keep draining the workers after an error)
+            if (rc != FA_OK) continue;                                   // (keep draining the workers after an error)
+            if (pieces[i].dst > hi + 64) { rc = flush(); lo = hi = pieces[i].dst; }
+            hi = pieces[i].dst + (uint64_t)pieces[i].n;
+            if (rc == FA_OK && hi - lo >= (uint64_t)piece) rc = flush();
         }
         for (auto &t : pool) t.join();
         FA_TRY(rc);
-        FA_TRY(flush(total));
-        if (h2d_bytes) *h2d_bytes += total;
+        FA_TRY(flush());
     }
     if (gather) {
+        for (const Upload &u : ups)
+            if (u.len > 0 && (u.on_device || u.unit == FA_UNIT_PACKED2)) dcopy.push_back(DevCopy{(const uint8_t *)u.ptr, u.off, u.len, 0});
+        size_t ip = 0;
+        for (DevCopy &d : dcopy)
+            if (ip < packed.size() && d.off == packed[ip].u->off && d.src == (const uint8_t *)packed[ip].pk) {
+                d.src = bytes.p + packed[ip].bits_off; d.kind = 1; ip++;
+            }
         memcpy(stage.p + tab_off, dcopy.data(), (size_t)tab_bytes);
         FA_CUDA(cudaMemcpyAsync(bytes.p + tab_off, stage.p + tab_off, (size_t)tab_bytes, cudaMemcpyHostToDevice, st));
         const uint64_t n_chunks = (total + 15) / 16;
         gather_contigs_kernel<<<(unsigned int)((n_chunks + 255) / 256), 256, 0, st>>>(
             reinterpret_cast<const DevCopy *>(bytes.p + tab_off), (int)dcopy.size(), bytes.p, n_chunks);
         FA_CUDA(cudaGetLastError());
+        if (!runs.empty()) {
+            memcpy(stage.p + run_off, runs.data(), runs.size() * sizeof(RunDesc));
+            FA_CUDA(cudaMemcpyAsync(bytes.p + run_off, stage.p + run_off, runs.size() * sizeof(RunDesc), cudaMemcpyHostToDevice, st));
+            if (h2d_bytes) *h2d_bytes += runs.size() * sizeof(RunDesc);
+            packed_runs_kernel<<<(unsigned int)((runs.size() * 32 + 255) / 256), 256, 0, st>>>(
+                reinterpret_cast<const RunDesc *>(bytes.p + run_off), runs.size(), bytes.p);
+            FA_CUDA(cudaGetLastError());
+        }
     } else {
-        for (const DevCopy &d : dcopy)
-            FA_CUDA(cudaMemcpyAsync(bytes.p + d.off, d.src, (size_t)d.len, cudaMemcpyDeviceToDevice, st));
+        for (const Upload &u : ups)
+            if (u.on_device && u.len > 0) FA_CUDA(cudaMemcpyAsync(bytes.p + u.off, u.ptr, (size_t)u.len, cudaMemcpyDeviceToDevice, st));
     }
     return FA_OK;
 }
@@ -1775,9 +1851,7 @@ int prefetch_query(fa_index *ix, Prefetch &pf, const fa_contig *contigs, int32_t
     pf.valid = false;
     if (ix->prm.frag_len <= 0 || ix->prm.frag_len > 32767) return FA_OK;
     for (int32_t c = 0; c < n_contigs; c++) {
-        if (contigs[c].len < 0 || (contigs[c].len > 0 && !contigs[c].data)) return FA_OK;
-        if (contigs[c].unit_bytes != 1 && contigs[c].unit_bytes != 2 && contigs[c].unit_bytes != 4) return FA_OK;
-        if (contigs[c].on_device && contigs[c].unit_bytes != 1) return FA_OK;
+        if (check_contig(contigs[c], c) != FA_OK) return FA_OK;
     }
     FA_CUDA(cudaSetDevice(ix->device));
     if (!pf.st) FA_CUDA(cudaStreamCreateWithFlags(&pf.st, cudaStreamNonBlocking));
@@ -1841,17 +1915,14 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
         for (int32_t c = n_contigs; c < n_contigs + contigs_per_query[q]; c++) {
             const int64_t slen = contigs[c].len;
             if (slen < lim) { qi.short_contigs++; continue; }                  // pyx:1062-1070
-            if (contigs[c].unit_bytes != 1 && contigs[c].unit_bytes != 2 && contigs[c].unit_bytes != 4) {
-                set_error("unit_bytes must be 1, 2 or 4"); return FA_ERR_INVALID;
-            }
-            if (contigs[c].on_device && contigs[c].unit_bytes != 1) { set_error("device-resident contigs must be bytes"); return FA_ERR_INVALID; }
+            FA_TRY(check_contig(contigs[c], c));
             const int64_t nfrag = slen / L;                                      // pyx:1097
             if (nfrag > 0) {
                 ups.push_back(Upload{contigs[c].data, contigs[c].unit_bytes, contigs[c].on_device, nfrag * L, off});
                 for (int64_t i = 0; i < nfrag; i++) {
                     SeqDesc d;
                     d.off = off + (uint64_t)i * L; d.len = L; d.id = (int32_t)(total_frags + i);
-                    d.raw = contigs[c].unit_bytes != 1; d.tile0 = (int32_t)((total_frags + i) * tiles_per_frag);
+                    d.raw = contig_prenormalised(contigs[c]); d.tile0 = (int32_t)((total_frags + i) * tiles_per_frag);
                     ws.h_seqs.push_back(d);
                 }
                 if (B > 1) ws.h_fragq.insert(ws.h_fragq.end(), (size_t)nfrag, (int32_t)q);

@@ -87,9 +87,90 @@ def as_buf(seq):
     return arr, (arr.ctypes.data if arr.size else 0), 1, arr.size
 
 
+class PackedStruct(C.Structure):
+    _fields_ = [("bits", C.c_void_p), ("run_pos", C.c_void_p), ("run_len", C.c_void_p), ("run_byte", C.c_void_p),
+                ("n_runs", C.c_uint64)]
+
+
+FA_UNIT_PACKED2 = -2
+
+
+class Packed:
+    """A sequence packed by fa_pack_2bit (include/fastani_b200.h fa_packed); pass it wherever a contig goes."""
+
+    def __init__(self, data):
+        src = np.frombuffer(bytes(data), dtype=np.uint8)
+        self.length = src.size
+        self.bits = np.zeros((src.size + 3) // 4, dtype=np.uint8)
+        cap, n = 16, C.c_uint64()
+        while True:
+            self.run_pos, self.run_len = np.zeros(cap, dtype=np.uint32), np.zeros(cap, dtype=np.uint32)
+            self.run_byte = np.zeros(cap, dtype=np.uint8)
+            check(lib().fa_pack_2bit(C.c_void_p(src.ctypes.data if src.size else 0), C.c_uint64(src.size),
+                                     C.c_void_p(self.bits.ctypes.data), C.c_void_p(self.run_pos.ctypes.data),
+                                     C.c_void_p(self.run_len.ctypes.data), C.c_void_p(self.run_byte.ctypes.data),
+                                     C.c_uint64(cap), C.byref(n)))
+            if n.value <= cap:
+                break
+            cap = n.value
+        self.n_runs = n.value
+        self.struct = PackedStruct(self.bits.ctypes.data, self.run_pos.ctypes.data, self.run_len.ctypes.data,
+                                   self.run_byte.ctypes.data, self.n_runs)
+
+    def unpack(self):
+        out = np.zeros(self.length, dtype=np.uint8)
+        check(lib().fa_unpack_2bit(C.byref(self.struct), C.c_uint64(self.length), C.c_void_p(out.ctypes.data)))
+        return out.tobytes()
+
+
+class DeviceContig:
+    """A contig already in device memory (fa_contig.on_device), e.g. a record of fa_fasta_parse."""
+
+    def __init__(self, ptr, length, keep=None):
+        self.ptr, self.length, self.keep = ptr, length, keep
+
+
+class Fasta:
+    """fa_fasta_parse: FASTA text -> device-resident records."""
+
+    def __init__(self, text, device=0):
+        text = bytes(text)
+        self.h = C.c_void_p()
+        check(lib().fa_fasta_parse(C.c_int32(device), text, C.c_uint64(len(text)), C.byref(self.h)))
+        nr, nb = C.c_uint64(), C.c_uint64()
+        check(lib().fa_fasta_counts(self.h, C.byref(nr), C.byref(nb)))
+        self.n_bases = nb.value
+        arr = (Contig * max(nr.value, 1))()
+        ib, il = (C.c_uint64 * max(nr.value, 1))(), (C.c_uint64 * max(nr.value, 1))()
+        check(lib().fa_fasta_records(self.h, arr, ib, il))
+        self.ids = [text[ib[i]:ib[i] + il[i]].decode("latin-1") for i in range(nr.value)]
+        self.contigs = [DeviceContig(arr[i].data, arr[i].len, self) for i in range(nr.value)]
+        self.device = device
+
+    def download(self, i):
+        c = self.contigs[i]
+        out = np.zeros(c.length, dtype=np.uint8)
+        if c.length:
+            check(lib().fa_device_download(C.c_int32(self.device), C.c_void_p(out.ctypes.data), C.c_void_p(c.ptr), C.c_uint64(c.length)))
+        return out.tobytes()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().fa_fasta_free(self.h)
+            self.h = None
+
+
 def contig_array(contigs):
     keeps, arr = [], (Contig * max(len(contigs), 1))()
     for i, c in enumerate(contigs):
+        if isinstance(c, Packed):
+            keeps.append(c)
+            arr[i] = Contig(C.addressof(c.struct), FA_UNIT_PACKED2, 0, c.length)
+            continue
+        if isinstance(c, DeviceContig):
+            keeps.append(c)
+            arr[i] = Contig(c.ptr, 1, 1, c.length)
+            continue
         keep, ptr, unit, n = as_buf(c)
         keeps.append(keep)
         arr[i] = Contig(ptr, unit, 0, n)
