@@ -107,6 +107,7 @@ typedef struct fa_query_info {
     uint32_t l1_small_fragments;                      /* of the on-chip ones: fragments mapped by the small shape of the L1 kernel (256 threads, several CTAs per SM) */
     uint64_t events_replayed;  /* events the slide kernel went through before its early stop (<= events) */
     float    ms_batch;         /* ONE event pair around the whole call on the library's stream (fa_query: == ms_total) */
+    uint32_t l1_parts;         /* parts the fragments of the large L1 class were cut into (0 = mapped whole) */
 } fa_query_info;
 
 typedef struct fa_sketch fa_sketch;   /* skch::Sketch under construction (pyx:465-470) */
@@ -266,6 +267,10 @@ FA_API int fa_fasta_counts(const fa_fasta *f, uint64_t *n_records, uint64_t *n_b
  * locate its identifier in the text the caller passed (the bytes between '>' and the end of the line). */
 FA_API int fa_fasta_records(const fa_fasta *f, fa_contig *contigs, uint64_t *id_begin, uint64_t *id_len);
 
+/* Test hook: how the on-chip L1 kernel maps fragments with tens of thousands of hits.  parts = -1: cut at genome
+ * boundaries into as many parts as the workload asks for (the default), 0: never, n: exactly n parts.  part_cap: most hits
+ * a part may hold before its fragment falls back to the one-CTA-per-fragment shape (-1 = what fits in shared memory). */
+FA_API int fa_debug_set_l1_parts(fa_index *ix, int32_t parts, int64_t part_cap);
 /* Device buffers for callers that want inputs resident in HBM before the timed region
  * (fa_contig.on_device). */
 FA_API int fa_device_alloc(int32_t device, uint64_t bytes, void **dptr);

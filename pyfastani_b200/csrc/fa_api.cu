@@ -566,6 +566,7 @@ static void add_info(fa_query_info &sum, const fa_query_info &qi)
     sum.ms_l1 += qi.ms_l1; sum.ms_l2 += qi.ms_l2; sum.ms_cgi += qi.ms_cgi; sum.ms_d2h += qi.ms_d2h; sum.ms_total += qi.ms_total;
     sum.ms_l2_prep += qi.ms_l2_prep; sum.ms_l2_events += qi.ms_l2_events; sum.ms_l2_slide += qi.ms_l2_slide;
     sum.ms_batch += qi.ms_batch;
+    sum.l1_parts = std::max(sum.l1_parts, qi.l1_parts);
 }
 
 static int query_checked(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *out, uint64_t cap, uint64_t *n_out,
@@ -723,6 +724,15 @@ int fa_debug_set_l1_small_shape(fa_index *ix, int32_t shape)
     if (!ix || shape > 2) { set_error("bad arguments"); return FA_ERR_INVALID; }
     std::lock_guard<std::mutex> guard(ix->mtx);
     ix->l1_small_shape = shape < 0 ? -1 : shape;
+    return FA_OK;
+}
+
+int fa_debug_set_l1_parts(fa_index *ix, int32_t parts, int64_t part_cap)
+{
+    if (!ix) { set_error("bad arguments"); return FA_ERR_INVALID; }
+    std::lock_guard<std::mutex> guard(ix->mtx);
+    ix->l1_parts = parts < 0 ? -1 : parts;
+    ix->l1_part_cap = part_cap < 0 ? -1 : part_cap;
     return FA_OK;
 }
 

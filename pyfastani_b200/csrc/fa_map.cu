@@ -267,6 +267,52 @@ candidates_kernel(const uint64_t *seeds, const uint64_t *seed_base, const int32_
 // Two shapes of the same kernel: 1024 threads and tiles of 4096 hits for fragments with tens of thousands of hits
 // (one CTA per SM, its shared memory holds the hits), 256 threads and tiles of 1024 for fragments with a few
 // thousand (many-to-many workloads: several CTAs per SM hide each other's barriers and gathers).
+// Parts (round 2): a fragment with tens of thousands of hits (every reference genome related to the query) needs the
+// 1024-thread shape with all of its hits in one CTA's shared memory -- one CTA per SM, every barrier exposed.  Candidate
+// regions never span two genomes, so such a fragment is cut at genome boundaries into L1_PARTS_MAX or fewer parts
+// that are mapped by independent CTAs of the small shape (four per SM).  split_lists_kernel cuts every position list of
+// the fragment at the part boundaries (the lists are ascending reference indices) and counts the hits per part.
+constexpr int L1_PARTS_MAX = 8;
+struct PartCfg { uint32_t first[L1_PARTS_MAX + 1]; };       // first reference index of every part (and one past the last)
+__device__ __forceinline__ uint32_t part_first(const PartCfg &c, int p)
+{
+    uint32_t r = 0;
+#pragma unroll
+    for (int q = 0; q <= L1_PARTS_MAX; q++) r = q == p ? c.first[q] : r;    // (constant indices: the table stays in the parameter bank)
+    return r;
+}
+__global__ void __launch_bounds__(256)
+split_lists_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hit_start, const uint32_t *hit_cnt,
+                   const uint64_t *seed_base, const uint32_t *pos_idx, PartCfg cfg, int n_parts,
+                   uint32_t seed_lo, uint32_t seed_cap, int s_stride, uint32_t *split, uint32_t *part_off)
+{
+    __shared__ uint32_t s_cnt[L1_PARTS_MAX + 1];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const uint64_t nf = seed_base[f + 1] - seed_base[f];
+    if (nf > (uint64_t)seed_cap || nf < (uint64_t)seed_lo) return;
+    const int s = qs[f];
+    const uint64_t qb = seq_first[f];
+    if (tid <= L1_PARTS_MAX) s_cnt[tid] = 0u;
+    __syncthreads();
+    // one thread per (list, inner boundary): the first entry at or behind the boundary
+    for (int i = tid; i < s * (n_parts + 1); i += blockDim.x) {
+        const int q = i / (n_parts + 1), p = i - q * (n_parts + 1);
+        const uint32_t st = hit_start[qb + q], c = hit_cnt[qb + q];
+        uint32_t lo = st, hi = st + c;
+        if (p == 0) hi = lo;
+        else if (p == n_parts) lo = hi;
+        else {
+            const uint32_t r = part_first(cfg, p);
+            while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (__ldg(pos_idx + mid) < r) lo = mid + 1; else hi = mid; }
+        }
+        split[((size_t)f * s_stride + q) * (n_parts + 1) + p] = lo;
+        // entries before boundary p, summed over the lists: hits of the parts below p
+        if (p > 0 && lo > st) atomicAdd(&s_cnt[p], lo - st);
+    }
+    __syncthreads();
+    if (tid <= n_parts) part_off[(size_t)f * (n_parts + 1) + tid] = s_cnt[tid];     // (s_cnt[0] = 0, s_cnt[n_parts] = all hits)
+}
+
 constexpr int L1L_THREADS = 1024, L1L_TILE = 4096;     // the large shape
 constexpr int L1S_THREADS = 256, L1S_TILE = 1024;      // the small shape
 // its shared memory per CTA: four CTAs per SM; three or two when the chunk histogram of a large index (4 B per 2^16
@@ -305,6 +351,50 @@ __device__ __forceinline__ void l1_sort_bucket(uint16_t *k, int n, uint32_t *bm,
             __syncwarp();
             if (lane < n) k[bm[L1_BM + (d0 >> 5)] + __popc(bm[d0 >> 5] & ((1u << (d0 & 31u)) - 1u))] = (uint16_t)v0;
             if (lane + 32 < n) k[bm[L1_BM + (d1 >> 5)] + __popc(bm[d1 >> 5] & ((1u << (d1 & 31u)) - 1u))] = (uint16_t)v1;
+            __syncwarp();
+            return;
+        }
+        // a locus and a stray hit far from it (a k-mer that occurs twice in the genome): rank = keys below, counted
+        // against all keys read as broadcasts (keys of a bucket are distinct reference indices)
+        __syncwarp();
+        uint32_t r0 = 0, r1 = 0;
+        for (int i = 0; i < n; i++) { const uint32_t x = k[i]; r0 += x < v0; r1 += x < v1; }
+        __syncwarp();
+        if (lane < n) k[r0] = (uint16_t)v0;
+        if (lane + 32 < n) k[r1] = (uint16_t)v1;
+        __syncwarp();
+        return;
+    } else if (n <= 256) {
+        // up to eight keys per lane in registers, rank = set bits below in a 1024-bit map (as above)
+        uint32_t v[8], lo = 0xFFFFu, hi = 0u;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int i = lane + 32 * u;
+            v[u] = i < n ? (uint32_t)k[i] : 0xFFFFFFFFu;
+            if (i < n) { lo = min(lo, v[u]); hi = max(hi, v[u]); }
+        }
+        lo = __reduce_min_sync(0xFFFFFFFFu, lo);
+        hi = __reduce_max_sync(0xFFFFFFFFu, hi);
+        if (hi - lo < (uint32_t)(32 * L1_BM)) {
+            bm[lane] = 0u;
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (32 * u >= n) break;
+                if (lane + 32 * u < n) { const uint32_t d = v[u] - lo; atomicOr(&bm[d >> 5], 1u << (d & 31u)); }
+            }
+            __syncwarp();
+            const uint32_t cnt = __popc(bm[lane]);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+            bm[L1_BM + lane] = incl - cnt;
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (32 * u >= n) break;
+                if (lane + 32 * u < n) { const uint32_t d = v[u] - lo; k[bm[L1_BM + (d >> 5)] + __popc(bm[d >> 5] & ((1u << (d & 31u)) - 1u))] = (uint16_t)v[u]; }
+            }
             __syncwarp();
             return;
         }
@@ -354,12 +444,23 @@ __device__ __forceinline__ void l1_sort_bucket(uint16_t *k, int n, uint32_t *bm,
     }
 }
 
-template <int L1_THREADS, int L1_TILE>
+// What the parts mode hands to the kernel (PARTS) and what the large shape needs to step in for a fragment one of whose
+// parts did not fit (n_parts > 0 with PARTS == false: only fragments flagged in `overflow` are mapped).
+struct L1Parts {
+    int n_parts, s_stride;
+    const uint32_t *split;        // [fragment][list][n_parts + 1]: the cuts of every position list
+    const uint32_t *part_off;     // [fragment][n_parts + 1]: hits below every part
+    uint32_t *part_cands;         // [fragment][n_parts]: regions found by every part
+    uint32_t *overflow;           // [fragment]: some part held more hits than a CTA of the small shape stages
+    PartCfg cfg;
+};
+
+template <int L1_THREADS, int L1_TILE, bool PARTS>
 __global__ void __launch_bounds__(L1_THREADS, 1024 / L1_THREADS)
 l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hit_start, const uint32_t *hit_cnt,
                 const uint64_t *seed_base, const uint32_t *pos_idx, const uint32_t *gpos, const uint32_t *irr, const uint2 *hw,
                 const int32_t *min_hits, int frag_len, uint32_t d_near, uint32_t n_chunks, uint32_t seed_lo, uint32_t seed_cap,
-                uint32_t key_cap, Cand *tmp, uint32_t *frag_cands)
+                uint32_t key_cap, Cand *tmp, uint32_t *frag_cands, const L1Parts pt)
 {
     constexpr int L1_PER = L1_TILE / L1_THREADS;
     constexpr int L1_STAGE = l1_stage(L1_THREADS, L1_TILE);
@@ -376,18 +477,41 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
     __shared__ uint32_t s_blk, s_nlist, s_cj, s_cf;
     __shared__ int s_cvalid;
 
-    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint64_t sb = seed_base[f];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int f = PARTS ? (int)(blockIdx.x / (unsigned)pt.n_parts) : (int)blockIdx.x;
+    const int part = PARTS ? (int)blockIdx.x - f * pt.n_parts : 0;
+    uint64_t sb = seed_base[f];
     const uint64_t nf64 = seed_base[f + 1] - sb;
     if (nf64 > (uint64_t)seed_cap) return;                                   // the radix-sort path takes this fragment
     if (nf64 < (uint64_t)seed_lo) return;                                    // the other shape of this kernel does
+    if (!PARTS && pt.n_parts > 0 && pt.overflow[f] == 0u) return;            // (large shape behind the parts: flagged fragments only)
     const int s = qs[f];
     if (s <= 0 || nf64 == 0) { if (tid == 0) frag_cands[f] = 0; return; }
-    const uint32_t n = (uint32_t)nf64;
+    uint32_t n = (uint32_t)nf64;
     const uint64_t qb = seq_first[f];
+    uint32_t c_base = 0;                                                     // first chunk of this CTA's share of the index
+    if (PARTS) {
+        const uint32_t *po = pt.part_off + (size_t)f * (pt.n_parts + 1) + part;
+        sb += po[0];
+        n = po[1] - po[0];
+        const uint32_t r0 = part_first(pt.cfg, part), r1 = part_first(pt.cfg, part + 1);
+        c_base = r0 >> L1_SHIFT;
+        // a part that does not fit (its genomes hold more of the hits than their share): the whole fragment goes to the
+        // large shape, launched behind this kernel
+        if (n > key_cap || (r1 > r0 && ((r1 - 1u) >> L1_SHIFT) - c_base + 1u > n_chunks)) {
+            if (tid == 0) { pt.overflow[f] = 1u; pt.part_cands[(size_t)f * pt.n_parts + part] = 0u; }
+            return;
+        }
+        if (n == 0) { if (tid == 0) pt.part_cands[(size_t)f * pt.n_parts + part] = 0u; return; }
+    }
 
     for (uint32_t i = tid; i <= n_chunks; i += L1_THREADS) hist[i] = 0u;
-    for (int q = tid; q < s; q += L1_THREADS) { s_lst[q] = hit_start[qb + q]; s_lcnt[q] = hit_cnt[qb + q]; }
+    if (PARTS) {
+        const uint32_t *sp = pt.split + ((size_t)f * pt.s_stride) * (pt.n_parts + 1) + part;
+        for (int q = tid; q < s; q += L1_THREADS) { const uint32_t a = sp[(size_t)q * (pt.n_parts + 1)]; s_lst[q] = a; s_lcnt[q] = sp[(size_t)q * (pt.n_parts + 1) + 1] - a; }
+    } else {
+        for (int q = tid; q < s; q += L1_THREADS) { s_lst[q] = hit_start[qb + q]; s_lcnt[q] = hit_cnt[qb + q]; }
+    }
     if (tid == 0) { s_blk = 0u; s_nlist = 0u; s_cvalid = 0; s_cj = 0u; s_cf = 0u; }
     __syncthreads();
 
@@ -395,7 +519,8 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
     // related genome): a warp per list would leave most lanes idle and walk ~30 lists one DRAM round trip after the
     // other.  There the hits are numbered through all lists instead -- s_lcnt becomes the exclusive prefix of the
     // list lengths -- and thread t fetches hit t, t + THREADS, ...: every load of a phase is in flight at once.
-    constexpr bool FLAT = L1_THREADS <= 256;
+    constexpr bool FLAT = L1_THREADS <= 256 && !PARTS;      // (the lists of a part hold dozens of entries: a warp per list)
+    constexpr bool LISTC = L1_THREADS <= 256;               // phase C takes the buckets from a list, one by one
     auto flat_hit = [&](uint32_t t) -> uint32_t {             // the reference index of hit t
         int lo = 0, hi = s - 1;
         while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_lcnt[mid] <= t) lo = mid; else hi = mid - 1; }
@@ -427,7 +552,7 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
 #pragma unroll
                 for (int u = 0; u < 4; u++) { const uint32_t t = t0 + u * 32 + lane; v[u] = t < c ? __ldg(pos_idx + st + t) : 0xFFFFFFFFu; }
 #pragma unroll
-                for (int u = 0; u < 4; u++) if (v[u] != 0xFFFFFFFFu) atomicAdd(&hist[v[u] >> L1_SHIFT], 1u);
+                for (int u = 0; u < 4; u++) if (v[u] != 0xFFFFFFFFu) atomicAdd(&hist[(v[u] >> L1_SHIFT) - c_base], 1u);
             }
         }
     }
@@ -461,13 +586,13 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
                 for (int u = 0; u < 4; u++) { const uint32_t t = t0 + u * 32 + lane; v[u] = t < c ? __ldg(pos_idx + st + t) : 0xFFFFFFFFu; }
 #pragma unroll
                 for (int u = 0; u < 4; u++)
-                    if (v[u] != 0xFFFFFFFFu) { const uint32_t slot = atomicAdd(&hist[v[u] >> L1_SHIFT], 1u); keys[slot] = (uint16_t)v[u]; }
+                    if (v[u] != 0xFFFFFFFFu) { const uint32_t slot = atomicAdd(&hist[(v[u] >> L1_SHIFT) - c_base], 1u); keys[slot] = (uint16_t)v[u]; }
             }
         }
     }
     __syncthreads();
     // ---- C: sort the buckets ------------------------------------------------------------------------
-    if (FLAT) {
+    if (LISTC) {
         // The hits of a many-to-many fragment sit in a few dozen chunks next to each other (the genomes of its genus):
         // blocks of 32 chunks would hand all of them to two or three warps.  The buckets that need sorting are listed
         // first (s_g is free since phase B) and the warps take them one by one.
@@ -491,7 +616,7 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
             }
         }
     }
-    if (!FLAT || s_nlist > (uint32_t)L1_STAGE) {            // (the list overflowed: blocks of 32 chunks, as in the large shape)
+    if (!LISTC || s_nlist > (uint32_t)L1_STAGE) {           // (the list overflowed: blocks of 32 chunks, as in the large shape)
         for (;;) {
             uint32_t blk = 0;
             if (lane == 0) blk = atomicAdd(&s_blk, 1u);
@@ -544,7 +669,7 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
                     const uint32_t q = (base + (uint32_t)e0) >> 5;
                     uint32_t c = blk_chunk[q], hi = ((q + 1u) << 5) < n ? (uint32_t)blk_chunk[q + 1u] : n_chunks - 1u;
                     while (c < hi) { const uint32_t mid = (c + hi) >> 1; if (hist[mid] <= t) c = mid + 1u; else hi = mid; }
-                    jv[u] = (c << L1_SHIFT) | (uint32_t)keys[t];
+                    jv[u] = ((c + c_base) << L1_SHIFT) | (uint32_t)keys[t];
                 }
             }
 #pragma unroll
@@ -625,19 +750,40 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
     }
     if (tid == 0) {
         if (heads_before) out[heads_before - 1].tail = s_cj;
-        frag_cands[f] = heads_before;
+        if (PARTS) {
+            pt.part_cands[(size_t)f * pt.n_parts + part] = heads_before;
+            atomicAdd(&frag_cands[f], heads_before);             // (zeroed before the launch)
+        } else {
+            frag_cands[f] = heads_before;
+            if (pt.n_parts > 0) {                                // in place of the parts of this fragment: everything is "part 0"
+                for (int p2 = 0; p2 < pt.n_parts; p2++) pt.part_cands[(size_t)f * pt.n_parts + p2] = p2 ? 0u : heads_before;
+            }
+        }
     }
 }
 
 // scratch ranges of l1_fused_kernel -> the candidate array in fragment order
-__global__ void compact_cands_kernel(const Cand *tmp, const uint64_t *seed_base, const uint32_t *cand_base, uint32_t seed_cap, Cand *cands)
+// (a fragment mapped in parts left one run of regions per part, each at the seed offset of its part)
+__global__ void compact_cands_kernel(const Cand *tmp, const uint64_t *seed_base, const uint32_t *cand_base, uint32_t seed_cap, Cand *cands,
+                                     uint32_t parts_lo, int n_parts, const uint32_t *part_off, const uint32_t *part_cands)
 {
     const int f = blockIdx.x;
-    const uint64_t sb = seed_base[f];
-    if (seed_base[f + 1] - sb > (uint64_t)seed_cap) return;
+    const uint64_t sb = seed_base[f], nf = seed_base[f + 1] - sb;
+    if (nf > (uint64_t)seed_cap) return;
     const uint32_t c0 = cand_base[f], n = cand_base[f + 1] - c0;
-    const uint4 *src = reinterpret_cast<const uint4 *>(tmp + sb);
     uint4 *dst = reinterpret_cast<uint4 *>(cands + c0);
+    if (n_parts > 0 && nf >= (uint64_t)parts_lo) {
+        // (when a part overflowed the large shape mapped the fragment: its regions are "part 0", at the fragment's own offset)
+        uint32_t done = 0;
+        for (int p = 0; p < n_parts && done < n; p++) {
+            const uint32_t np = part_cands[(size_t)f * n_parts + p];
+            const uint4 *src = reinterpret_cast<const uint4 *>(tmp + sb + part_off[(size_t)f * (n_parts + 1) + p]);
+            for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) dst[done + i] = src[i];
+            done += np;
+        }
+        return;
+    }
+    const uint4 *src = reinterpret_cast<const uint4 *>(tmp + sb);
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
@@ -2021,8 +2167,9 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
             cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ix->device);
             // ---- which fragments fit the on-chip L1 (l1_fused_kernel), which take the radix sort ----
             const uint32_t n_chunks = (uint32_t)((ix->n + (1ull << L1_SHIFT) - 1) >> L1_SHIFT);
-            auto *const l1_large = l1_fused_kernel<L1L_THREADS, L1L_TILE>;
-            auto *const l1_small = l1_fused_kernel<L1S_THREADS, L1S_TILE>;
+            auto *const l1_large = l1_fused_kernel<L1L_THREADS, L1L_TILE, false>;
+            auto *const l1_small = l1_fused_kernel<L1S_THREADS, L1S_TILE, false>;
+            auto *const l1_parts = l1_fused_kernel<L1S_THREADS, L1S_TILE, true>;
             cudaFuncAttributes l1_attr;
             FA_CUDA(cudaFuncGetAttributes(&l1_attr, l1_large));
             const size_t l1_fixed = l1_fixed_smem(n_chunks, l1_stage(L1L_THREADS, L1L_TILE)), l1_room = (size_t)smem_optin - l1_attr.sharedSizeBytes;
@@ -2054,6 +2201,42 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
             }
             if (n_small * 8u < (uint32_t)F) { max_fast = std::max(max_fast, max_small); n_small = 0; small_cap = 0; max_small = 0; }
             const uint32_t n_large = (uint32_t)F - n_slow - n_small;
+            // ---- the large class in parts: cut at genome boundaries into shares of about equal size, each mapped by a CTA
+            // of the small shape at four CTAs per SM (see split_lists_kernel).  The fewest parts whose expected share of the
+            // largest fragment (with a quarter of head-room: the hits need not be spread evenly) fits.
+            L1Parts pt;
+            memset(&pt, 0, sizeof pt);
+            uint32_t part_chunks = 0;
+            uint64_t part_cap = 0;
+            if (n_large && ix->l1_parts != 0 && G >= 2 && ix->max_min_hits - 1 <= L1S_THREADS && max_s <= l1_stage(L1S_THREADS, L1S_TILE)) {
+                if (ix->genome_first.empty()) {               // first reference index of every genome (once per index)
+                    std::vector<uint32_t> co((size_t)ix->n_contigs + 1);
+                    FA_CUDA(cudaMemcpyAsync(co.data(), ix->contig_off.p, co.size() * 4, cudaMemcpyDeviceToHost, st));
+                    FA_CUDA(cudaStreamSynchronize(st));
+                    ix->genome_first.resize((size_t)G + 1);
+                    for (uint32_t g = 0; g <= G; g++) ix->genome_first[g] = co[g == 0 ? 0 : std::min<uint64_t>((uint64_t)ix->seqs_by_genome[g - 1], ix->n_contigs)];
+                    ix->genome_first[G] = (uint32_t)ix->n;
+                }
+                const std::vector<uint32_t> &gf = ix->genome_first;
+                for (int np = 2; np <= std::min<int>(L1_PARTS_MAX, (int)G) && !pt.n_parts; np++) {
+                    if (ix->l1_parts > 0 && np != std::min<int>(std::min<int>(ix->l1_parts, L1_PARTS_MAX), (int)G)) continue;
+                    uint32_t gb[L1_PARTS_MAX + 1];
+                    gb[0] = 0; gb[np] = G;
+                    for (int q = 1; q < np; q++)
+                        gb[q] = (uint32_t)(std::lower_bound(gf.begin(), gf.begin() + G, (uint32_t)(ix->n * (uint64_t)q / np)) - gf.begin());
+                    uint32_t span = 1;
+                    for (int q = 0; q < np; q++)
+                        if (gf[gb[q + 1]] > gf[gb[q]]) span = std::max(span, ((gf[gb[q + 1]] - 1u) >> L1_SHIFT) - (gf[gb[q]] >> L1_SHIFT) + 1u);
+                    const size_t fixed = l1_fixed_smem(span, l1_stage(L1S_THREADS, L1S_TILE));
+                    if (fixed + 8 * 1024 > L1S_SMEM[0]) continue;
+                    const uint64_t cap = ((L1S_SMEM[0] - fixed - 128) * 16 / 33) & ~31ull;
+                    if (ix->l1_parts < 0 && (max_fast + np - 1) / np * 5 / 4 > cap) continue;
+                    pt.n_parts = np; part_chunks = span; part_cap = cap;
+                    for (int q = 0; q <= np; q++) pt.cfg.first[q] = gf[gb[q]];
+                }
+                if (pt.n_parts && ix->l1_part_cap >= 0) part_cap = std::min<uint64_t>(part_cap, (uint64_t)ix->l1_part_cap) & ~31ull;
+            }
+            qi.l1_parts = (uint32_t)pt.n_parts;
             qi.l1_small_fragments = n_small;
             qi.l1_sorted_fragments = n_slow;
             const int shift = bits_for(ix->n), fbits = bits_for((uint64_t)F);
@@ -2078,23 +2261,45 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
             // ---- L1 candidates -------------------------------------------------------------------
             if (n_slow < (uint32_t)F) {
                 FA_TRY(ws.cand_tmp.reserve(S));
+                const L1Parts no_parts{};
+                if (pt.n_parts) FA_CUDA(cudaMemsetAsync(ws.frag_cands.p, 0, ((size_t)F + 1) * 4, st));   // (the parts add their counts)
                 if (n_small) {          // fragments with [0, small_cap] hits
                     const uint64_t key_cap = (max_small + 31) & ~31ull;
                     const size_t smem = l1s_fixed + 2 * key_cap + 2 * (key_cap / 32 + 8);
                     FA_CUDA(cudaFuncSetAttribute(l1_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     l1_small<<<F, L1S_THREADS, smem, st>>>(ws.sk.seq_first.p, ws.qs.p, ws.hit_start.p, ws.hit_cnt.p, ws.frag_seeds.p,
                                                            ix->pos_idx.p, ix->gpos.p, ix->irr.p, ix->hw.p, ix->d_min_hits.p, L, d_near, n_chunks,
-                                                           0u, (uint32_t)small_cap, (uint32_t)key_cap, ws.cand_tmp.p, ws.frag_cands.p);
+                                                           0u, (uint32_t)small_cap, (uint32_t)key_cap, ws.cand_tmp.p, ws.frag_cands.p, no_parts);
                     FA_CUDA(cudaGetLastError()); launches++;
                 }
                 if (n_large) {          // fragments with (small_cap, seed_cap] hits (all of them when the small shape is off)
+                    const uint32_t large_lo = n_small ? (uint32_t)small_cap + 1u : 0u;
+                    if (pt.n_parts) {
+                        const int np = pt.n_parts;
+                        pt.s_stride = std::max(max_s, 1);
+                        FA_TRY(ws.l1_split.reserve((size_t)F * pt.s_stride * (np + 1))); FA_TRY(ws.part_off.reserve((size_t)F * (np + 1)));
+                        FA_TRY(ws.part_cands.reserve((size_t)F * np)); FA_TRY(ws.l1_over.reserve(F));
+                        pt.split = ws.l1_split.p; pt.part_off = ws.part_off.p; pt.part_cands = ws.part_cands.p; pt.overflow = ws.l1_over.p;
+                        FA_CUDA(cudaMemsetAsync(ws.l1_over.p, 0, (size_t)F * 4, st));
+                        split_lists_kernel<<<F, 256, 0, st>>>(ws.sk.seq_first.p, ws.qs.p, ws.hit_start.p, ws.hit_cnt.p, ws.frag_seeds.p, ix->pos_idx.p,
+                                                             pt.cfg, np, large_lo, (uint32_t)seed_cap, pt.s_stride, ws.l1_split.p,
+                                                             ws.part_off.p);
+                        FA_CUDA(cudaGetLastError()); launches++;
+                        const size_t psmem = L1S_SMEM[0];
+                        FA_CUDA(cudaFuncSetAttribute(l1_parts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+                        l1_parts<<<(unsigned int)F * (unsigned int)np, L1S_THREADS, psmem, st>>>(
+                            ws.sk.seq_first.p, ws.qs.p, ws.hit_start.p, ws.hit_cnt.p, ws.frag_seeds.p, ix->pos_idx.p, ix->gpos.p, ix->irr.p, ix->hw.p,
+                            ix->d_min_hits.p, L, d_near, part_chunks, large_lo, (uint32_t)seed_cap, (uint32_t)part_cap, ws.cand_tmp.p, ws.frag_cands.p, pt);
+                        FA_CUDA(cudaGetLastError()); launches++;
+                    }
+                    // (behind the parts: only the fragments one of whose parts did not fit)
                     const uint64_t key_cap = (max_fast + 31) & ~31ull;
                     const size_t smem = l1_fixed + 2 * key_cap + 2 * (key_cap / 32 + 8);
                     FA_CUDA(cudaFuncSetAttribute(l1_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     l1_large<<<F, L1L_THREADS, smem, st>>>(ws.sk.seq_first.p, ws.qs.p, ws.hit_start.p, ws.hit_cnt.p, ws.frag_seeds.p,
                                                            ix->pos_idx.p, ix->gpos.p, ix->irr.p, ix->hw.p, ix->d_min_hits.p, L, d_near, n_chunks,
-                                                           n_small ? (uint32_t)small_cap + 1u : 0u, (uint32_t)seed_cap, (uint32_t)key_cap,
-                                                           ws.cand_tmp.p, ws.frag_cands.p);
+                                                           large_lo, (uint32_t)seed_cap, (uint32_t)key_cap,
+                                                           ws.cand_tmp.p, ws.frag_cands.p, pt);
                     FA_CUDA(cudaGetLastError()); launches++;
                 }
             }
@@ -2117,7 +2322,8 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
             if (C > 0) {
                 FA_TRY(ws.cands.reserve(C)); FA_TRY(ws.maps.reserve(C));
                 if (n_slow < (uint32_t)F) {
-                    compact_cands_kernel<<<F, 128, 0, st>>>(ws.cand_tmp.p, ws.frag_seeds.p, ws.frag_cands.p, (uint32_t)seed_cap, ws.cands.p);
+                    compact_cands_kernel<<<F, 128, 0, st>>>(ws.cand_tmp.p, ws.frag_seeds.p, ws.frag_cands.p, (uint32_t)seed_cap, ws.cands.p,
+                                                            n_small ? (uint32_t)small_cap + 1u : 0u, pt.n_parts, ws.part_off.p, ws.part_cands.p);
                     FA_CUDA(cudaGetLastError()); launches++;
                 }
                 if (n_slow) {

@@ -46,7 +46,15 @@ def _check_hits(hits, names, rows):
         assert h["identity"] == golden_io.f32(ident), (float(h["identity"]).hex(), ident)
 
 
-@pytest.mark.parametrize("l1", ["chip", "chip-large", "shapes", "sort", "mixed"])
+def _l1_parts(ix, l1, mean):
+    """The large class of the on-chip L1 kernel whole ("chip-large"), cut into parts at genome boundaries (a fixed number,
+    or what the library picks), or in parts too small for half of the fragments, which fall back to the whole shape."""
+    if l1.startswith("parts"):
+        ix.set_l1_small_cap(0)
+    ix.set_l1_parts(*{"chip-large": (0,), "parts-3": (3,), "parts-8": (8,), "parts-overflow": (4, max(mean // 4, 0))}.get(l1, (-1,)))
+
+
+@pytest.mark.parametrize("l1", ["chip", "chip-large", "shapes", "sort", "mixed", "parts-3", "parts-overflow"])
 @pytest.mark.parametrize("name", [c["name"] for c in cases.query_cases()])
 def test_queries_match_pyfastani_and_oracle(name, l1):
     """`l1` selects the L1 path: all fragments through the on-chip kernel (the default), all through
@@ -72,8 +80,14 @@ def test_queries_match_pyfastani_and_oracle(name, l1):
         mean = st["seeds"] // max(st["fragments"], 1)
         ix.set_l1_seed_cap({"sort": 0, "mixed": mean - 1}.get(l1, -1))
         ix.set_l1_small_cap({"chip-large": 0, "shapes": mean}.get(l1, -1))
+        _l1_parts(ix, l1, mean)
         hits, out = ix.query_draft(q, dump=True)
-        if l1 in ("chip", "chip-large", "shapes"):
+        if l1.startswith("parts") and len(case["refs"]) >= 2 and st["seeds"]:
+            want = min(int(l1[6:]) if l1[6:].isdigit() else 4, len(case["refs"]))
+            # (k = 12 at 90 %: minHits of the largest sketch the index supports exceeds the look-ahead of the 256-thread
+            # shape, so neither the small shape nor the parts are used)
+            assert out["info"]["l1_parts"] == (0 if name == "k12_pid90" else want)
+        if l1 in ("chip", "chip-large", "shapes") or l1.startswith("parts"):
             assert out["info"]["l1_sorted_fragments"] == 0
             if l1 == "chip-large":
                 assert out["info"]["l1_small_fragments"] == 0
@@ -92,7 +106,8 @@ def test_queries_match_pyfastani_and_oracle(name, l1):
         assert info["kernel_launches"] > 0 or st["fragments"] == 0
 
 
-@pytest.mark.parametrize("l1", ["chip", "chip-large", "shapes", "sort", "mixed", "small-72k", "small-110k"])
+@pytest.mark.parametrize("l1", ["chip", "chip-large", "shapes", "sort", "mixed", "small-72k", "small-110k", "parts-3", "parts-8",
+                                "parts-auto", "parts-overflow"])
 def test_l1_many_references(l1):
     """120 related references: every fragment has several thousand seed hits (more than one 4096-hit
     tile of the on-chip L1 kernel) spread over nine 2^16-minimizer chunks of the index, plus a
@@ -116,8 +131,12 @@ def test_l1_many_references(l1):
         # the small shape with three / two CTAs per SM (72 KB / 110 KB each): what an index of a few thousand genomes
         # selects because its chunk histogram leaves no room for the hits in 54 KB
         ix.set_l1_small_shape({"small-72k": 1, "small-110k": 2}.get(l1, -1))
+        _l1_parts(ix, l1, mean)
         hits, out = ix.query_draft(query, dump=True)
         assert (out["info"]["l1_sorted_fragments"] == 0) == (l1 not in ("sort", "mixed"))
+        if l1.startswith("parts"):
+            assert out["info"]["l1_small_fragments"] == 0
+            assert out["info"]["l1_parts"] == {"parts-3": 3, "parts-8": 8, "parts-overflow": 4}.get(l1, out["info"]["l1_parts"]) >= 2
         if l1 in ("chip", "small-72k", "small-110k"):          # several 1024-hit tiles per fragment in the small shape
             assert out["info"]["l1_small_fragments"] == st["fragments"]
         if l1 == "chip-large":
