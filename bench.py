@@ -616,7 +616,7 @@ def run_b200(a):
         "cpu_baseline": cpu,
         "stages": stage_roofline,
         "counters_rank0_per_step": {k: inf[k] for k in ("fragments", "sketch_sum", "seeds", "candidates", "scanned", "events", "mappings",
-                                                        "l2_fallback", "l1_sorted_fragments", "events_replayed", "queries")},
+                                                        "l2_fallback", "l1_sorted_fragments", "events_replayed", "queries", "l1_parts")},
         "hits": n_hits,
         "parity": parity,
         "config1": c1,

@@ -267,9 +267,10 @@ FA_API int fa_fasta_counts(const fa_fasta *f, uint64_t *n_records, uint64_t *n_b
  * locate its identifier in the text the caller passed (the bytes between '>' and the end of the line). */
 FA_API int fa_fasta_records(const fa_fasta *f, fa_contig *contigs, uint64_t *id_begin, uint64_t *id_len);
 
-/* Test hook: how the on-chip L1 kernel maps fragments with tens of thousands of hits.  parts = -1: cut at genome
- * boundaries into as many parts as the workload asks for (the default), 0: never, n: exactly n parts.  part_cap: most hits
- * a part may hold before its fragment falls back to the one-CTA-per-fragment shape (-1 = what fits in shared memory). */
+/* How the on-chip L1 kernel maps fragments with tens of thousands of hits.  parts = 0: whole, one CTA per fragment (the
+ * default -- measured faster on BASELINE configs[1]); -1: cut at genome boundaries into as many parts as the workload
+ * asks for, each mapped by its own small CTA; n: exactly n parts.  part_cap: most hits a part may hold before its
+ * fragment falls back to the whole shape (-1 = what fits in shared memory).  Same results either way. */
 FA_API int fa_debug_set_l1_parts(fa_index *ix, int32_t parts, int64_t part_cap);
 /* Device buffers for callers that want inputs resident in HBM before the timed region
  * (fa_contig.on_device). */

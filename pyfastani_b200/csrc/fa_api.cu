@@ -6,6 +6,7 @@
 #include <thread>
 #include <vector>
 
+#include <cstdlib>
 #include "fa_internal.cuh"
 
 namespace fa {
@@ -406,6 +407,7 @@ int fa_sketch_index(fa_sketch *s, fa_index **out)
     if (s->prm.frag_len > 32767) { set_error("fragment_length > 32767 is not supported on the device path"); return FA_ERR_UNSUPPORTED; }
     if (s->prm.frag_len <= 20) { set_error("fragment_length <= 20 is not supported (the reference divides by fragment_length - 20)"); return FA_ERR_UNSUPPORTED; }
     fa_index *ix = new (std::nothrow) fa_index();
+    if (ix) { const char *e = getenv("FA_L1_PARTS"); if (e && *e) ix->l1_parts = atoi(e); }   // (experiments: see fa_debug_set_l1_parts)
     if (!ix) return FA_ERR_NOMEM;
     ix->prm = s->prm; ix->device = s->device;
     cudaError_t e = cudaStreamCreateWithFlags(&ix->st, cudaStreamNonBlocking);
@@ -731,7 +733,7 @@ int fa_debug_set_l1_parts(fa_index *ix, int32_t parts, int64_t part_cap)
 {
     if (!ix) { set_error("bad arguments"); return FA_ERR_INVALID; }
     std::lock_guard<std::mutex> guard(ix->mtx);
-    ix->l1_parts = parts < 0 ? -1 : parts;
+    ix->l1_parts = parts < 0 ? -1 : parts;      // (0 is the default)
     ix->l1_part_cap = part_cap < 0 ? -1 : part_cap;
     return FA_OK;
 }

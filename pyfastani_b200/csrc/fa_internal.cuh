@@ -41,6 +41,8 @@ struct Workspace {
     DevBuf<uint64_t> fb_seeds;          // seed prefix (F + 1) over the fragments that take the radix-sort path
     DevBuf<Cand>     cand_tmp;          // l1_fused_kernel: regions of fragment f at its seed offset
     DevBuf<uint32_t> l1_split, part_off, part_cands, l1_over;   // L1 in parts (fa_map.cu L1Parts)
+    DevBuf<uint32_t> chunk_hist;        // hits per chunk of a sample of the heavy fragments (where to cut the parts)
+    PinBuf h_chunk_hist;
     PinBuf hfs;                         // host copy of the seed prefixes
     DevBuf<uint8_t>  cub_tmp;
     DevBuf<uint32_t> frag_cands;        // per fragment: candidate count, then exclusive prefix (F + 1)
@@ -67,7 +69,7 @@ struct Workspace {
         sk.bytes.release(); sk.seqs.release(); sk.tile_status.release(); sk.counters.release(); sk.seq_first.release(); sk.drops.release();
         stage.release(); frag_q.release(); qhash.release(); qs.release(); hit_start.release(); hit_cnt.release();
         frag_seeds.release(); seeds_a.release(); seeds_b.release(); fb_seeds.release(); cand_tmp.release(); hfs.release();
-        l1_split.release(); part_off.release(); part_cands.release(); l1_over.release();
+        l1_split.release(); part_off.release(); part_cands.release(); l1_over.release(); chunk_hist.release(); h_chunk_hist.release();
         cub_tmp.release(); frag_cands.release(); work_base.release(); cands.release(); maps.release(); prep.release();
         ev_off.release(); jobs.release(); mid.release(); seq_cnt.release(); events.release(); cells.release(); g_identity.release();
         g_count.release(); counters.release(); hres.release();
@@ -147,7 +149,7 @@ struct fa_index {
     float ms_build = 0, ms_sort = 0;             // build_index on its stream (CUDA events): everything / the radix sort of (hash, index)
     long long l1_small_cap = -1;                 // test hook: most seeds per fragment for the small shape of the on-chip L1 (-1 = default)
     int l1_small_shape = -1;                     // test hook: smallest entry of L1S_SMEM the small shape may use (-1 = 0: the first that fits)
-    int l1_parts = -1;                           // test hook: -1 = parts chosen from the workload, 0 = never, n = exactly n parts for the large class
+    int l1_parts = 0;                            // 0 = the large class is mapped whole (the default: measured faster), -1 = parts chosen from the workload, n = exactly n parts
     long long l1_part_cap = -1;                  // test hook: most hits a part may hold (-1 = what fits)
     std::vector<uint32_t> genome_first;          // first reference index of every genome (+ n), filled by the first query that maps in parts
     long long l1_seed_cap = -1;                  // test hook: most seeds per fragment for the on-chip L1 (-1 = what fits)

@@ -272,6 +272,7 @@ candidates_kernel(const uint64_t *seeds, const uint64_t *seed_base, const int32_
 // regions never span two genomes, so such a fragment is cut at genome boundaries into L1_PARTS_MAX or fewer parts
 // that are mapped by independent CTAs of the small shape (four per SM).  split_lists_kernel cuts every position list of
 // the fragment at the part boundaries (the lists are ascending reference indices) and counts the hits per part.
+constexpr int L1_SHIFT = 16;             // chunks of 2^16 reference minimizers
 constexpr int L1_PARTS_MAX = 8;
 struct PartCfg { uint32_t first[L1_PARTS_MAX + 1]; };       // first reference index of every part (and one past the last)
 __device__ __forceinline__ uint32_t part_first(const PartCfg &c, int p)
@@ -313,13 +314,31 @@ split_lists_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t 
     if (tid <= n_parts) part_off[(size_t)f * (n_parts + 1) + tid] = s_cnt[tid];     // (s_cnt[0] = 0, s_cnt[n_parts] = all hits)
 }
 
+// Where the hits of the heavy fragments lie: hits per chunk of 2^16 reference minimizers, summed over a sample of the
+// fragments that have at least `min_seeds` hits.  The host cuts the index into parts of about equal hit counts with it
+// (related genomes are not spread evenly: the references of BASELINE configs[1] are ordered by identity).
+constexpr int L1_SAMPLE = 32, L1_SAMPLE_SLICES = 16;    // sampled fragments; CTAs that share the lists of one (the walk is latency bound)
+__global__ void __launch_bounds__(256)
+sample_chunks_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hit_start, const uint32_t *hit_cnt,
+                     const uint64_t *frag_seed_counts, int n_frags, uint32_t min_seeds, const uint32_t *pos_idx, uint32_t *chunk_hist)
+{
+    const int n_samp = gridDim.x / L1_SAMPLE_SLICES, slice = blockIdx.x % L1_SAMPLE_SLICES;
+    const int f = (int)(((long long)(blockIdx.x / L1_SAMPLE_SLICES) * n_frags) / n_samp);
+    if (frag_seed_counts[f] < (uint64_t)min_seeds) return;
+    const int s = qs[f], lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t qb = seq_first[f];
+    for (int q = slice * 8 + wid; q < s; q += 8 * L1_SAMPLE_SLICES) {
+        const uint32_t st = hit_start[qb + q], c = hit_cnt[qb + q];
+        for (uint32_t t = lane; t < c; t += 32) atomicAdd(&chunk_hist[__ldg(pos_idx + st + t) >> L1_SHIFT], 1u);
+    }
+}
+
 constexpr int L1L_THREADS = 1024, L1L_TILE = 4096;     // the large shape
 constexpr int L1S_THREADS = 256, L1S_TILE = 1024;      // the small shape
 // its shared memory per CTA: four CTAs per SM; three or two when the chunk histogram of a large index (4 B per 2^16
 // reference minimizers: 46 KB for 2 000 genomes) leaves no room for the hits otherwise
 constexpr size_t L1S_SMEM[3] = {54 * 1024, 72 * 1024, 110 * 1024};
-constexpr int L1_SHIFT = 16;
-constexpr int L1_BM = 32;                     // bitmap words per warp in phase C (+ as many prefix words)
+constexpr int L1_BM = 32;                     // bitmap words per warp in phase C (+ as many prefix words, + as many stray keys)
 // look-ahead of the pair test: minHits - 1 <= THREADS; staged hits per tile = TILE + THREADS (also holds the s position lists)
 __host__ __device__ constexpr int l1_stage(int threads, int tile) { return tile + threads; }
 
@@ -354,24 +373,17 @@ __device__ __forceinline__ void l1_sort_bucket(uint16_t *k, int n, uint32_t *bm,
             __syncwarp();
             return;
         }
-        // a locus and a stray hit far from it (a k-mer that occurs twice in the genome): rank = keys below, counted
-        // against all keys read as broadcasts (keys of a bucket are distinct reference indices)
-        __syncwarp();
-        uint32_t r0 = 0, r1 = 0;
-        for (int i = 0; i < n; i++) { const uint32_t x = k[i]; r0 += x < v0; r1 += x < v1; }
-        __syncwarp();
-        if (lane < n) k[r0] = (uint16_t)v0;
-        if (lane + 32 < n) k[r1] = (uint16_t)v1;
-        __syncwarp();
-        return;
-    } else if (n <= 256) {
+    }
+    if (n <= 256) {
         // up to eight keys per lane in registers, rank = set bits below in a 1024-bit map (as above)
         uint32_t v[8], lo = 0xFFFFu, hi = 0u;
 #pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = 0xFFFFFFFFu;
+#pragma unroll
         for (int u = 0; u < 8; u++) {
+            if (32 * u >= n) break;
             const int i = lane + 32 * u;
-            v[u] = i < n ? (uint32_t)k[i] : 0xFFFFFFFFu;
-            if (i < n) { lo = min(lo, v[u]); hi = max(hi, v[u]); }
+            if (i < n) { v[u] = (uint32_t)k[i]; lo = min(lo, v[u]); hi = max(hi, v[u]); }
         }
         lo = __reduce_min_sync(0xFFFFFFFFu, lo);
         hi = __reduce_max_sync(0xFFFFFFFFu, hi);
@@ -394,6 +406,61 @@ __device__ __forceinline__ void l1_sort_bucket(uint16_t *k, int n, uint32_t *bm,
             for (int u = 0; u < 8; u++) {
                 if (32 * u >= n) break;
                 if (lane + 32 * u < n) { const uint32_t d = v[u] - lo; k[bm[L1_BM + (d >> 5)] + __popc(bm[d >> 5] & ((1u << (d & 31u)) - 1u))] = (uint16_t)v[u]; }
+            }
+            __syncwarp();
+            return;
+        }
+        // A locus and a few stray hits far from it (a k-mer that occurs twice in the genome, a second locus at the other
+        // end of the chunk): the 1024 positions from the smallest key up, or up to the largest, whichever hold more keys,
+        // go through the bitmap; the rest -- all on one side of them -- are ranked among themselves.
+        int c_lo = 0, c_hi = 0;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (32 * u >= n) break;
+            const bool ok = lane + 32 * u < n;
+            c_lo += __popc(__ballot_sync(0xFFFFFFFFu, ok && v[u] - lo < (uint32_t)(32 * L1_BM)));
+            c_hi += __popc(__ballot_sync(0xFFFFFFFFu, ok && hi - v[u] < (uint32_t)(32 * L1_BM)));
+        }
+        const bool at_lo = c_lo >= c_hi;
+        const int n_in = at_lo ? c_lo : c_hi, n_out = n - n_in;
+        if (n_out <= 32) {
+            const uint32_t w0 = at_lo ? lo : hi - (uint32_t)(32 * L1_BM - 1);
+            uint32_t *stray = bm + 2 * L1_BM;
+            bm[lane] = 0u;
+            __syncwarp();
+            int seen = 0;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (32 * u >= n) break;
+                const bool ok = lane + 32 * u < n;
+                const uint32_t d = v[u] - w0;
+                const bool in = ok && d < (uint32_t)(32 * L1_BM);
+                if (in) atomicOr(&bm[d >> 5], 1u << (d & 31u));
+                const unsigned om = __ballot_sync(0xFFFFFFFFu, ok && !in);
+                if (ok && !in) stray[seen + __popc(om & ((1u << lane) - 1u))] = v[u];
+                seen += __popc(om);
+            }
+            __syncwarp();
+            const uint32_t cnt = __popc(bm[lane]);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+            bm[L1_BM + lane] = incl - cnt;
+            __syncwarp();
+            const int base_in = at_lo ? 0 : n_out, base_out = at_lo ? n_in : 0;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (32 * u >= n) break;
+                if (lane + 32 * u < n) {
+                    const uint32_t d = v[u] - w0;
+                    int pos;
+                    if (d < (uint32_t)(32 * L1_BM)) pos = base_in + (int)(bm[L1_BM + (d >> 5)] + __popc(bm[d >> 5] & ((1u << (d & 31u)) - 1u)));
+                    else {
+                        pos = base_out;
+                        for (int j = 0; j < n_out; j++) pos += stray[j] < v[u];
+                    }
+                    k[pos] = (uint16_t)v[u];
+                }
             }
             __syncwarp();
             return;
@@ -520,7 +587,7 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
     // other.  There the hits are numbered through all lists instead -- s_lcnt becomes the exclusive prefix of the
     // list lengths -- and thread t fetches hit t, t + THREADS, ...: every load of a phase is in flight at once.
     constexpr bool FLAT = L1_THREADS <= 256 && !PARTS;      // (the lists of a part hold dozens of entries: a warp per list)
-    constexpr bool LISTC = L1_THREADS <= 256;               // phase C takes the buckets from a list, one by one
+    constexpr bool LISTC = true;                            // phase C takes the buckets from a list, one by one (false: blocks of 32 chunks per warp)
     auto flat_hit = [&](uint32_t t) -> uint32_t {             // the reference index of hit t
         int lo = 0, hi = s - 1;
         while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_lcnt[mid] <= t) lo = mid; else hi = mid - 1; }
@@ -612,7 +679,7 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
                 if (i >= n_list) break;
                 const uint32_t c = list[i];
                 const uint32_t b0 = c ? hist[c - 1] : 0u;
-                l1_sort_bucket(keys + b0, (int)(hist[c] - b0), s_bm + wid * (2 * L1_BM), lane);
+                l1_sort_bucket(keys + b0, (int)(hist[c] - b0), s_bm + wid * (3 * L1_BM), lane);
             }
         }
     }
@@ -630,7 +697,7 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
             while (todo) {
                 const int l = __ffs(todo) - 1;
                 todo &= todo - 1u;
-                l1_sort_bucket(keys + __shfl_sync(0xFFFFFFFFu, b0, l), (int)__shfl_sync(0xFFFFFFFFu, sz, l), s_bm + wid * (2 * L1_BM), lane);
+                l1_sort_bucket(keys + __shfl_sync(0xFFFFFFFFu, b0, l), (int)__shfl_sync(0xFFFFFFFFu, sz, l), s_bm + wid * (3 * L1_BM), lane);
             }
         }
     }
@@ -2144,6 +2211,17 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
         lookup_kernel<<<F, 128, 0, st>>>(ws.qhash.p, ws.sk.seq_first.p, ws.qs.p, F, ix->dir.p, ix->dir_bits, ix->ukeys.p,
                                          ix->uoff.p, ws.hit_start.p, ws.hit_cnt.p, ws.frag_seeds.p);
         FA_CUDA(cudaGetLastError()); launches++;
+        // (for L1 in parts: where the hits of the heavy fragments lie -- returns at once when no sampled fragment is heavy)
+        const uint32_t n_chunks_ix = (uint32_t)((ix->n + (1ull << L1_SHIFT) - 1) >> L1_SHIFT);
+        const bool sample_parts = ix->l1_parts != 0 && G >= 2;
+        if (sample_parts) {
+            FA_TRY(ws.chunk_hist.reserve(n_chunks_ix)); FA_TRY(ws.h_chunk_hist.reserve((size_t)n_chunks_ix * 4));
+            FA_CUDA(cudaMemsetAsync(ws.chunk_hist.p, 0, (size_t)n_chunks_ix * 4, st));
+            sample_chunks_kernel<<<std::min(F, L1_SAMPLE) * L1_SAMPLE_SLICES, 256, 0, st>>>(ws.sk.seq_first.p, ws.qs.p, ws.hit_start.p, ws.hit_cnt.p, ws.frag_seeds.p, F,
+                                                                       4096u, ix->pos_idx.p, ws.chunk_hist.p);
+            FA_CUDA(cudaGetLastError()); launches++;
+            FA_CUDA(cudaMemcpyAsync(ws.h_chunk_hist.p, ws.chunk_hist.p, (size_t)n_chunks_ix * 4, cudaMemcpyDeviceToHost, st));
+        }
         FA_TRY(excl_scan<uint64_t>(st, ws.cub_tmp, ws.frag_seeds.p, ws.frag_seeds.p, (int64_t)F + 1, &launches));
         FA_TRY(ws.hres.reserve(128 + (size_t)B * G * 8));
         FA_TRY(ws.hfs.reserve(((size_t)F + 1) * 16));
@@ -2218,19 +2296,40 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
                     ix->genome_first[G] = (uint32_t)ix->n;
                 }
                 const std::vector<uint32_t> &gf = ix->genome_first;
+                // cumulative hits of the sampled fragments per chunk; with no heavy fragment in the sample: by index size
+                const uint32_t *ch = reinterpret_cast<const uint32_t *>(ws.h_chunk_hist.p);
+                std::vector<uint64_t> cum((size_t)n_chunks + 1, 0);
+                for (uint32_t c = 0; c < n_chunks; c++) cum[c + 1] = cum[c] + (sample_parts ? ch[c] : 0u);
+                const bool sampled = cum[n_chunks] > 0;
+                if (!sampled) for (uint32_t c = 0; c <= n_chunks; c++) cum[c] = c;
+                auto mass_below = [&](uint32_t ref_idx) -> double {     // sampled hits below a reference index (linear inside a chunk)
+                    const uint32_t c = std::min(ref_idx >> L1_SHIFT, n_chunks - 1);
+                    return (double)cum[c] + (double)(cum[c + 1] - cum[c]) * (double)(ref_idx - (c << L1_SHIFT)) / 65536.0;
+                };
+                const double total = (double)cum[n_chunks];
                 for (int np = 2; np <= std::min<int>(L1_PARTS_MAX, (int)G) && !pt.n_parts; np++) {
                     if (ix->l1_parts > 0 && np != std::min<int>(std::min<int>(ix->l1_parts, L1_PARTS_MAX), (int)G)) continue;
+                    // genome boundaries next to the points that cut the sampled hits into np equal shares
                     uint32_t gb[L1_PARTS_MAX + 1];
                     gb[0] = 0; gb[np] = G;
-                    for (int q = 1; q < np; q++)
-                        gb[q] = (uint32_t)(std::lower_bound(gf.begin(), gf.begin() + G, (uint32_t)(ix->n * (uint64_t)q / np)) - gf.begin());
+                    for (int q = 1; q < np; q++) {
+                        const double want = total * q / np;
+                        uint32_t lo = gb[q - 1], hi = G;                 // first genome whose start holds `want` hits below it
+                        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (mass_below(gf[mid]) < want) lo = mid + 1; else hi = mid; }
+                        if (lo > gb[q - 1] + 1 && lo <= G && want - mass_below(gf[lo - 1]) < mass_below(gf[std::min(lo, G)]) - want) lo--;
+                        gb[q] = std::min(std::max(lo, gb[q - 1]), G);
+                    }
                     uint32_t span = 1;
-                    for (int q = 0; q < np; q++)
+                    double share = 0;
+                    for (int q = 0; q < np; q++) {
                         if (gf[gb[q + 1]] > gf[gb[q]]) span = std::max(span, ((gf[gb[q + 1]] - 1u) >> L1_SHIFT) - (gf[gb[q]] >> L1_SHIFT) + 1u);
+                        share = std::max(share, (mass_below(gf[gb[q + 1]]) - mass_below(gf[gb[q]])) / std::max(total, 1.0));
+                    }
                     const size_t fixed = l1_fixed_smem(span, l1_stage(L1S_THREADS, L1S_TILE));
                     if (fixed + 8 * 1024 > L1S_SMEM[0]) continue;
                     const uint64_t cap = ((L1S_SMEM[0] - fixed - 128) * 16 / 33) & ~31ull;
-                    if (ix->l1_parts < 0 && (max_fast + np - 1) / np * 5 / 4 > cap) continue;
+                    // (an eighth of head-room: a fragment need not follow the sample exactly; what does not fit falls back)
+                    if (ix->l1_parts < 0 && (double)max_fast * share * 1.125 > (double)cap) continue;
                     pt.n_parts = np; part_chunks = span; part_cap = cap;
                     for (int q = 0; q <= np; q++) pt.cfg.first[q] = gf[gb[q]];
                 }

@@ -51,7 +51,7 @@ def _l1_parts(ix, l1, mean):
     or what the library picks), or in parts too small for half of the fragments, which fall back to the whole shape."""
     if l1.startswith("parts"):
         ix.set_l1_small_cap(0)
-    ix.set_l1_parts(*{"chip-large": (0,), "parts-3": (3,), "parts-8": (8,), "parts-overflow": (4, max(mean // 4, 0))}.get(l1, (-1,)))
+    ix.set_l1_parts(*{"chip-large": (0,), "parts-3": (3,), "parts-8": (8,), "parts-overflow": (4, max(mean // 4, 0)), "parts-auto": (-1,)}.get(l1, (0,)))
 
 
 @pytest.mark.parametrize("l1", ["chip", "chip-large", "shapes", "sort", "mixed", "parts-3", "parts-overflow"])
