@@ -599,6 +599,18 @@ int fa_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *
 int fa_query_batch(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_per_query, int32_t n_queries,
                    fa_hit *out, uint64_t cap, uint64_t *hit_offsets, fa_query_info *info)
 {
+    return query_batch_impl(ix, nullptr, contigs, contigs_per_query, n_queries, out, cap, hit_offsets, info);
+}
+
+}  // extern "C"
+
+// `comm` (reference-sharded layout, fa_query_batch_sharded): the queries are cut into groups by their sizes alone -- the
+// same groups on every rank -- and the sketches of a group are made once across the ranks (sketch_exchange); the passes,
+// which every rank sizes from what ITS shard made of the queries so far, stay inside a group and read the gathered
+// sketches.  No collective depends on anything a rank measured.
+int fa::query_batch_impl(fa_index *ix, fa_comm *comm, const fa_contig *contigs, const int32_t *contigs_per_query, int32_t n_queries,
+                         fa_hit *out, uint64_t cap, uint64_t *hit_offsets, fa_query_info *info)
+{
     if (!ix || n_queries < 0 || !hit_offsets || (n_queries > 0 && !contigs_per_query)) { set_error("bad arguments"); return FA_ERR_INVALID; }
     fa_query_info sum;
     memset(&sum, 0, sizeof sum);
@@ -627,17 +639,25 @@ int fa_query_batch(fa_index *ix, const fa_contig *contigs, const int32_t *contig
     FA_CUDA(cudaSetDevice(ix->device));
     FA_CUDA(cudaEventCreate(&outer.a)); FA_CUDA(cudaEventCreate(&outer.b));
     FA_CUDA(cudaEventRecord(outer.a, ix->st));
+    const bool exchange = comm && comm_world(comm) > 1 && exchange_stride(ix->prm) > 0 && !getenv("FA_NO_SKETCH_EXCHANGE");
     std::unique_lock<std::mutex> pre_lock(ix->pre_mtx, std::try_to_lock);      // a second concurrent batch maps without staging ahead
-    const bool ahead = pre_lock.owns_lock() && n_queries > 1;
+    const bool ahead = pre_lock.owns_lock() && n_queries > 1 && !exchange;
     if (pre_lock.owns_lock()) ix->pre[0].valid = ix->pre[1].valid = false;       // nothing staged by an earlier call is ours
 
     constexpr uint64_t PASS_QUERIES = 32, PASS_FRAGS = 48 * 1024, PASS_SEEDS = 96ull << 20, PASS_EVENTS = 256ull << 20;
     double seeds_per_frag = -1.0, events_per_frag = -1.0;      // largest seen so far in this call (-1: nothing seen)
+    int32_t g0 = 0, g1 = n_queries;                              // the group of queries whose sketches are at hand (exchange)
+    auto group_end = [&](int32_t q0) {
+        int32_t q1 = q0 + 1;
+        uint64_t f = frags[q0];
+        while (q1 < n_queries && (uint64_t)(q1 - q0) < PASS_QUERIES && f + frags[q1] <= PASS_FRAGS) f += frags[q1++];
+        return q1;
+    };
     auto pass_end = [&](int32_t q0) {
         int32_t q1 = q0 + 1;
         if (seeds_per_frag < 0) return q1;
         uint64_t f = frags[q0];
-        while (q1 < n_queries && (uint64_t)(q1 - q0) < PASS_QUERIES) {
+        while (q1 < g1 && (uint64_t)(q1 - q0) < PASS_QUERIES) {
             const uint64_t nf = f + frags[q1];
             if (nf > PASS_FRAGS || (double)nf * seeds_per_frag * 1.5 > (double)PASS_SEEDS ||
                 (double)nf * events_per_frag * 1.5 > (double)PASS_EVENTS) break;
@@ -649,10 +669,21 @@ int fa_query_batch(fa_index *ix, const fa_contig *contigs, const int32_t *contig
     uint64_t used = 0;
     std::vector<uint64_t> offs(PASS_QUERIES + 1);
     int slot = 0;
-    int32_t q0 = 0, q1 = n_queries ? pass_end(0) : 0;
+    PreSketch group;
+    float ms_exchange = 0;
+    if (exchange) g1 = 0;                                         // (the first group is formed inside the loop)
+    int32_t q0 = 0, q1 = n_queries && !exchange ? pass_end(0) : 0;
     while (q0 < n_queries) {
+        if (exchange && q0 == g1) {
+            // the next group: its sketches, made once across the ranks
+            if (g1 > 0) { float ms = 0; if (cudaEventSynchronize(ix->ws.ev[13]) == cudaSuccess && cudaEventElapsedTime(&ms, ix->ws.ev[12], ix->ws.ev[13]) == cudaSuccess) ms_exchange += ms; }
+            g0 = g1; g1 = group_end(g0);
+            FA_TRY(sketch_exchange(ix, comm, contigs ? contigs + first[g0] : nullptr, (int32_t)(first[g1] - first[g0]), &group, &sum));
+            q1 = pass_end(q0);
+        }
         const int32_t nq = q1 - q0;
         fa_query_info qi;
+        if (exchange) { group.first_frag = 0; for (int32_t q = g0; q < q0; q++) group.first_frag += frags[q]; }
         // plan the pass after this one with what is known now, and stage it while this one runs
         const int32_t q2 = q1 < n_queries ? pass_end(q1) : q1;
         std::thread helper;
@@ -663,8 +694,11 @@ int fa_query_batch(fa_index *ix, const fa_contig *contigs, const int32_t *contig
             helper = std::thread([ix, pfs, nx, nx_n]() { if (prefetch_query(ix, *pfs, nx, nx_n) != FA_OK) pfs->valid = false; });
         }
         int rc = run_queries(ix, contigs ? contigs + first[q0] : nullptr, contigs_per_query + q0, nq, out ? out + used : nullptr,
-                             cap - used, offs.data(), &qi, ahead ? &ix->pre[slot] : nullptr);
+                             cap - used, offs.data(), &qi, ahead ? &ix->pre[slot] : nullptr, exchange ? &group : nullptr);
         if (helper.joinable()) helper.join();
+        if (rc == FA_RETRY_PLAIN)          // a sketch did not fit its slot of the exchange: this pass sketches its own queries
+            rc = run_queries(ix, contigs ? contigs + first[q0] : nullptr, contigs_per_query + q0, nq, out ? out + used : nullptr,
+                             cap - used, offs.data(), &qi, nullptr, nullptr);
         if (rc == FA_ERR_NOMEM && nq > 1) {
             // the pass was sized from lighter queries: map its queries one by one
             cudaGetLastError();
@@ -693,8 +727,10 @@ int fa_query_batch(fa_index *ix, const fa_contig *contigs, const int32_t *contig
         }
         // the staged pass was planned before this one's counters were known: keep it as planned
         q0 = q1; q1 = q2; slot ^= 1;
-        if (q0 < n_queries && q1 == q0) q1 = pass_end(q0);
+        if (q0 < n_queries && q1 == q0 && !(exchange && q0 == g1)) q1 = pass_end(q0);
     }
+    if (exchange && g1 > 0) { float ms = 0; if (cudaEventSynchronize(ix->ws.ev[13]) == cudaSuccess && cudaEventElapsedTime(&ms, ix->ws.ev[12], ix->ws.ev[13]) == cudaSuccess) ms_exchange += ms; }
+    sum.ms_sketch += ms_exchange;
     FA_CUDA(cudaEventRecord(outer.b, ix->st));
     FA_CUDA(cudaEventSynchronize(outer.b));
     sum.ms_batch = 0;
@@ -702,6 +738,8 @@ int fa_query_batch(fa_index *ix, const fa_contig *contigs, const int32_t *contig
     if (info) *info = sum;
     return FA_OK;
 }
+
+extern "C" {
 
 int fa_debug_last_candidates(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n) { return debug_candidates(ix, rows, cap, n); }
 int fa_debug_last_mappings(fa_index *ix, int32_t *rows, uint64_t cap, uint64_t *n) { return debug_mappings(ix, rows, cap, n); }

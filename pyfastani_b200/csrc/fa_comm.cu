@@ -86,6 +86,29 @@ struct fa_comm {
     uint64_t collectives = 0, bytes_gathered = 0;
 };
 
+// The second exchange of the reference-sharded layout: the query sketches.  Every rank maps every query, so every rank
+// would sketch every query -- the largest stage of a 10 000 x 10 000 run (a third of it).  Instead rank r sketches
+// fragments [r * per, (r + 1) * per) of a group of queries and one ncclAllGather on the mapping stream hands every rank
+// all sketches, packed to `stride` hashes per fragment (a tenth of the bases they were made from).
+int fa::sketch_exchange(fa_index *ix, fa_comm *c, const fa_contig *contigs, int32_t n_contigs, PreSketch *ps, fa_query_info *qi)
+{
+    const int stride = exchange_stride(ix->prm);
+    if (stride <= 0) { set_error("sketch exchange is not available for these parameters"); return FA_ERR_UNSUPPORTED; }
+    uint32_t per = 0;
+    uint64_t frags = 0;
+    FA_TRY(sketch_share(ix, contigs, n_contigs, c->world, c->rank, (uint32_t)stride, &per, &frags, qi));
+    std::lock_guard<std::mutex> guard(c->mtx);
+    const size_t block = (size_t)per * ((size_t)stride + 1);
+    FA_TRY(ix->ws.x_recv.reserve(block * (size_t)c->world));
+    FA_NCCL(c->api, c->api->AllGather(ix->ws.x_send.p, ix->ws.x_recv.p, block, ncclUint32, c->comm, ix->st));
+    FA_CUDA(cudaEventRecord(ix->ws.ev[13], ix->st));
+    c->collectives++; c->bytes_gathered += block * 4 * (size_t)c->world;
+    ps->recv = ix->ws.x_recv.p; ps->per = per; ps->stride = (uint32_t)stride; ps->block = block; ps->first_frag = 0;
+    return FA_OK;
+}
+
+int fa::comm_world(const fa_comm *c) { return c ? c->world : 1; }
+
 extern "C" {
 
 int fa_comm_unique_id(uint8_t *id)
@@ -245,7 +268,7 @@ int fa_query_batch_sharded(fa_index *ix, fa_comm *comm, const fa_contig *contigs
     }
     std::vector<fa_hit> local((size_t)std::max<uint64_t>(n_local, 1) * (size_t)std::max(n_queries, 1));
     std::vector<uint64_t> offs((size_t)n_queries + 1, 0);
-    FA_TRY(fa_query_batch(ix, contigs, contigs_per_query, n_queries, local.data(), local.size(), offs.data(), info));
+    FA_TRY(query_batch_impl(ix, comm, contigs, contigs_per_query, n_queries, local.data(), local.size(), offs.data(), info));
     return fa_gather_hits(comm, local.data(), offs.data(), n_queries, genome_offsets, out, cap, hit_offsets);
 }
 

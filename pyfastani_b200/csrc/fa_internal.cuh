@@ -60,8 +60,9 @@ struct Workspace {
     DevBuf<int32_t>  g_count;
     DevBuf<unsigned long long> counters;   // misc device counters (see fa_map.cu)
     PinBuf hres;                        // pinned result staging
-    cudaEvent_t ev[12] = {};
+    cudaEvent_t ev[14] = {};            // (12, 13: around the sketch exchange of a group)
     bool ev_ready = false;
+    DevBuf<uint32_t> x_send, x_recv;    // sketch exchange of the reference-sharded layout: this rank's share / all shares
     uint64_t last_cands = 0, last_frags = 0;
     // every buffer above, in one place: a member added to the struct is released here or nowhere
     void release()
@@ -72,11 +73,23 @@ struct Workspace {
         l1_split.release(); part_off.release(); part_cands.release(); l1_over.release(); chunk_hist.release(); h_chunk_hist.release();
         cub_tmp.release(); frag_cands.release(); work_base.release(); cands.release(); maps.release(); prep.release();
         ev_off.release(); jobs.release(); mid.release(); seq_cnt.release(); events.release(); cells.release(); g_identity.release();
-        g_count.release(); counters.release(); hres.release();
+        g_count.release(); counters.release(); hres.release(); x_send.release(); x_recv.release();
         if (ev_ready) for (auto &e : ev) cudaEventDestroy(e);
         ev_ready = false;
     }
 };
+
+// The sketches of a group of queries as the reference-sharded layout exchanges them (fa_comm.cu sketch_exchange): every
+// rank sketches `per` fragments of the group, all ranks gather all shares.  Fragment g of the group: `size` sorted
+// unique hashes at recv[(g / per) * block + (g % per) * stride], size at recv[(g / per) * block + per * stride + g % per]
+// (negative: the fragment could not travel -- see import_sketch_kernel).
+struct PreSketch {
+    const uint32_t *recv = nullptr;
+    uint32_t per = 0, stride = 0;
+    uint64_t block = 0;                 // 32-bit words per rank: per * (stride + 1)
+    uint64_t first_frag = 0;            // first fragment of the pass inside the group
+};
+enum { FA_RETRY_PLAIN = 100 };          // internal status of run_queries: a pre-sketched fragment did not fit its slot, sketch this pass here
 
 // One host or device buffer to place at `off` in the batch byte buffer (unit: fa_contig.unit_bytes).
 struct Upload { const void *ptr; int32_t unit; int32_t on_device; int64_t len; uint64_t off; };
@@ -184,7 +197,17 @@ int prefetch_query(fa_index *ix, Prefetch &pf, const fa_contig *contigs, int32_t
 int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *out, uint64_t cap, uint64_t *n_out,
               fa_query_info *info, Prefetch *pf = nullptr);
 int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_per_query, int32_t n_queries, fa_hit *out,
-                uint64_t cap, uint64_t *hit_offsets, fa_query_info *info, Prefetch *pf = nullptr);
+                uint64_t cap, uint64_t *hit_offsets, fa_query_info *info, Prefetch *pf = nullptr, const PreSketch *ps = nullptr);
+// reference-sharded layout: sketch this rank's share of the fragments of a group of queries (fragments
+// [rank * per, rank * per + per) of all of them) and leave [per * stride hashes | per sizes] in ws.x_send
+int exchange_stride(const fa_params &P);
+int sketch_share(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, int world, int rank, uint32_t stride, uint32_t *per_out,
+                 uint64_t *frags_out, fa_query_info *qi);
+// fa_query_batch with an optional communicator: with one, the query sketches are made once across the ranks (fa_comm.cu)
+int query_batch_impl(fa_index *ix, fa_comm *comm, const fa_contig *contigs, const int32_t *contigs_per_query, int32_t n_queries,
+                     fa_hit *out, uint64_t cap, uint64_t *hit_offsets, fa_query_info *info);
+int comm_world(const fa_comm *c);
+int sketch_exchange(fa_index *ix, fa_comm *comm, const fa_contig *contigs, int32_t n_contigs, PreSketch *ps, fa_query_info *qi);
 // shared by the sketch and query paths: narrow/copy the uploads into the batch byte buffer
 int stage_sequences(cudaStream_t st, DevBuf<uint8_t> &bytes, PinBuf &stage, const std::vector<Upload> &ups, uint64_t total,
                     uint64_t *h2d_bytes, int workers = 0);

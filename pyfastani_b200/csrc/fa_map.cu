@@ -32,7 +32,7 @@ namespace {
 
 // device counters (Workspace::counters)
 enum { CT_MAXS = 0, CT_ERR = 1, CT_WORK = 2, CT_SCANNED = 3, CT_MAPPINGS = 4, CT_SKETCH_SUM = 5, CT_REDO = 6, CT_WORK2 = 7, CT_WORK3 = 8, CT_REPLAYED = 9, CT_N = 10 };
-enum { ERR_SORT_CAP = 1, ERR_S_MAX = 2 };
+enum { ERR_SORT_CAP = 1, ERR_S_MAX = 2, ERR_EXCH = 4 };
 
 constexpr int L2_THREADS = 64;          // lanes per L2 CTA: each lane slides one candidate at a time
 constexpr int L2_ITEM = 128;            // candidates of one fragment per work item (lanes pull them one by one)
@@ -110,6 +110,48 @@ __global__ void sort_unique_kernel(uint32_t *qhash, const uint64_t *seq_first, c
         atomicMax(&counters[CT_MAXS], (unsigned long long)carry);
         atomicAdd(&counters[CT_SKETCH_SUM], (unsigned long long)carry);
         if ((int)carry > s_max) atomicOr(&counters[CT_ERR], (unsigned long long)ERR_S_MAX);
+    }
+}
+
+// ---- sketch exchange (reference-sharded layout, fa_comm.cu) -------------------------------------
+// This rank's share, packed for the all-gather: fragment lf -> [stride hashes] at send + lf * stride, its size at
+// send[per * stride + lf].  Size -1: more minimizers than the on-chip sort holds; -3: the sketch does not fit `stride`
+// (the pass that meets such a fragment sketches its queries itself).
+__global__ void pack_sketch_kernel(const uint32_t *qhash, const uint64_t *seq_first, const uint32_t *seq_cnt, const int32_t *qs, int n_local,
+                                   int sort_cap, uint32_t per, uint32_t stride, uint32_t *send)
+{
+    const uint32_t lf = blockIdx.x;
+    int s = 0;
+    if ((int)lf < n_local) {
+        s = qs[lf];
+        if ((int)seq_cnt[lf] > sort_cap) s = -1;
+        else if (s > (int)stride) s = -3;
+        const uint64_t b = seq_first[lf];
+        for (int i = threadIdx.x; i < s; i += blockDim.x) send[(size_t)lf * stride + i] = qhash[b + i];
+    }
+    if (threadIdx.x == 0) send[(size_t)per * stride + lf] = (uint32_t)s;
+}
+
+// The fragments of one pass out of the gathered shares, into the layout the rest of the pipeline reads (slot f * stride
+// of qhash), with the counters sort_unique_kernel keeps.
+__global__ void import_sketch_kernel(const uint32_t *recv, uint32_t per, uint32_t stride, uint64_t block, uint64_t first, int s_max,
+                                     uint32_t *qhash, uint64_t *seq_first, int32_t *qs, unsigned long long *counters)
+{
+    const int f = blockIdx.x;
+    const uint64_t g = first + (uint64_t)f, r = g / per, lf = g % per;
+    const uint32_t *src = recv + r * block + lf * stride;
+    int s = (int)recv[r * block + (uint64_t)per * stride + lf];
+    if (s < 0) {
+        if (threadIdx.x == 0) atomicOr(&counters[CT_ERR], (unsigned long long)(s == -1 ? ERR_SORT_CAP : ERR_EXCH));
+        s = 0;
+    }
+    for (int i = threadIdx.x; i < s; i += blockDim.x) qhash[(size_t)f * stride + i] = src[i];
+    if (threadIdx.x == 0) {
+        seq_first[f] = (uint64_t)f * stride;
+        qs[f] = s;
+        atomicMax(&counters[CT_MAXS], (unsigned long long)s);
+        atomicAdd(&counters[CT_SKETCH_SUM], (unsigned long long)s);
+        if (s > s_max) atomicOr(&counters[CT_ERR], (unsigned long long)ERR_S_MAX);
     }
 }
 
@@ -2049,6 +2091,100 @@ void plan_uploads(const fa_params &P, const fa_contig *contigs, int32_t n_contig
     *total = off;
 }
 
+// The slot a sketch travels in: twice the expected size of a fragment's sketch (2 L / (w + 1) minimizers) and some, never
+// more than a fragment can hold.  0 = packing would not make the sketches smaller than their slots already are.
+int exchange_stride(const fa_params &P)
+{
+    const int L = P.frag_len, w = std::max(P.window, 1), k = P.k;
+    const int cmw = L - (w - 1) - (k - 1);
+    if (cmw <= 0) return 0;
+    const int want = ((4 * L / (w + 1) + 64) + 31) & ~31;
+    return want < cmw ? want : 0;
+}
+
+int sketch_share(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, int world, int rank, uint32_t stride, uint32_t *per_out,
+                 uint64_t *frags_out, fa_query_info *qi)
+{
+    std::lock_guard<std::mutex> guard(ix->mtx);
+    FA_CUDA(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->st;
+    Workspace &ws = ix->ws;
+    const fa_params &P = ix->prm;
+    const int L = P.frag_len, k = P.k, w = P.window;
+    const int lim = std::min(std::min(w, k), L);
+    const int nk = L - k + 1;
+    const int tiles_per_frag = nk > 0 ? (nk + SK_TILE - 1) / SK_TILE : 0;
+    const int cmw = L - (w - 1) - (k - 1);
+    if (L <= 0 || L > 32767 || tiles_per_frag <= 0 || cmw <= 0) { set_error("sketch exchange: unsupported fragment length"); return FA_ERR_UNSUPPORTED; }
+    uint64_t F = 0;
+    for (int32_t c = 0; c < n_contigs; c++) {
+        if (contigs[c].len < lim) continue;
+        FA_TRY(check_contig(contigs[c], c));
+        F += (uint64_t)(contigs[c].len / L);
+    }
+    *frags_out = F;
+    const uint64_t per = std::max<uint64_t>((F + (uint64_t)world - 1) / (uint64_t)world, 1);
+    *per_out = (uint32_t)per;
+    if (per > 0x7FFFFFFFull / (uint64_t)std::max(tiles_per_frag, 1)) { set_error("sketch exchange: group too large"); return FA_ERR_UNSUPPORTED; }
+    const uint64_t f0 = std::min<uint64_t>(F, (uint64_t)rank * per), f1 = std::min<uint64_t>(F, f0 + per);
+    const int n_loc = (int)(f1 - f0);
+    // the bytes of fragments [f0, f1): the slice of every contig that holds some of them (a packed contig from its start)
+    std::vector<Upload> ups;
+    ws.h_seqs.clear();
+    uint64_t a = 0, off = 0;
+    for (int32_t c = 0; c < n_contigs && a < f1; c++) {
+        const fa_contig &ct = contigs[c];
+        if (ct.len < lim) continue;
+        const uint64_t nfrag = (uint64_t)(ct.len / L);
+        const uint64_t x = std::max(a, f0), y = std::min(a + nfrag, f1);
+        if (x < y) {
+            const bool packed = ct.unit_bytes == FA_UNIT_PACKED2;
+            const uint64_t skip = packed ? 0 : x - a;                        // fragments of the contig left out in front
+            const uint8_t *src = (const uint8_t *)ct.data + (packed ? 0 : skip * (uint64_t)L * (uint64_t)ct.unit_bytes);
+            ups.push_back(Upload{src, ct.unit_bytes, ct.on_device, (int64_t)((y - a - skip) * (uint64_t)L), off});
+            for (uint64_t i = x; i < y; i++) {
+                SeqDesc d;
+                d.off = off + (i - a - skip) * (uint64_t)L; d.len = L; d.id = (int32_t)(i - f0);
+                d.raw = contig_prenormalised(ct); d.tile0 = (int32_t)((i - f0) * (uint64_t)tiles_per_frag);
+                ws.h_seqs.push_back(d);
+            }
+            off += (((y - a - skip) * (uint64_t)L) + 15) & ~15ull;
+        }
+        a += nfrag;
+    }
+    if (!ws.ev_ready) {
+        for (auto &e : ws.ev) FA_CUDA(cudaEventCreate(&e));
+        ws.ev_ready = true;
+    }
+    FA_CUDA(cudaEventRecord(ws.ev[12], st));
+    FA_TRY(ws.x_send.reserve((size_t)per * (stride + 1)));
+    FA_TRY(ws.qs.reserve(std::max(n_loc, 1))); FA_TRY(ws.seq_cnt.reserve(std::max(n_loc, 1))); FA_TRY(ws.sk.seq_first.reserve(std::max(n_loc, 1)));
+    FA_TRY(ws.counters.reserve(CT_N));
+    int launches = 0, sort_cap = 0;
+    if (n_loc > 0) {
+        uint64_t h2d = 0;
+        FA_TRY(stage_sequences(st, ws.sk.bytes, ws.stage, ups, off, &h2d));
+        const int n_tiles = n_loc * tiles_per_frag;
+        FA_TRY(ws.sk.seqs.reserve(n_loc)); FA_TRY(ws.sk.tile_status.reserve(n_tiles)); FA_TRY(ws.sk.counters.reserve(4));
+        FA_TRY(ws.qhash.reserve((uint64_t)n_loc * (uint64_t)cmw));
+        FA_CUDA(cudaMemcpyAsync(ws.sk.seqs.p, ws.h_seqs.data(), (size_t)n_loc * sizeof(SeqDesc), cudaMemcpyHostToDevice, st));
+        FA_CUDA(cudaMemsetAsync(ws.counters.p, 0, CT_N * sizeof(unsigned long long), st));
+        FA_TRY(launch_sketch(st, ws.sk, n_loc, n_tiles, k, w, P.alphabet != 4, nullptr, ws.qhash.p, 0, &launches, cmw, ws.seq_cnt.p));
+        int p2 = 1; while (p2 < cmw) p2 <<= 1;
+        sort_cap = std::min(p2, 32768);
+        const size_t smem = (size_t)sort_cap * 4;
+        if (smem > 48 * 1024) FA_CUDA(cudaFuncSetAttribute(sort_unique_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sort_unique_kernel<<<n_loc, 256, smem, st>>>(ws.qhash.p, ws.sk.seq_first.p, ws.seq_cnt.p, n_loc, sort_cap, ix->s_max, ws.qs.p, ws.counters.p);
+        FA_CUDA(cudaGetLastError()); launches++;
+        if (qi) qi->h2d_bytes += h2d + (uint64_t)n_loc * sizeof(SeqDesc);
+    }
+    pack_sketch_kernel<<<(unsigned int)per, 128, 0, st>>>(ws.qhash.p, ws.sk.seq_first.p, ws.seq_cnt.p, ws.qs.p, n_loc, sort_cap, (uint32_t)per, stride,
+                                                         ws.x_send.p);
+    FA_CUDA(cudaGetLastError()); launches++;
+    if (qi) qi->kernel_launches += launches;
+    return FA_OK;
+}
+
 void Prefetch::release()
 {
     bytes.release(); stage.release();
@@ -2095,7 +2231,7 @@ int run_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit 
 // every query has its own (contig, bin) cell table and per-genome sums.  hit_offsets[q + 1] - hit_offsets[q] hits of
 // query q are written at out + hit_offsets[q] (all counted, only those below `cap` stored).
 int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_per_query, int32_t n_queries, fa_hit *out,
-                uint64_t cap, uint64_t *hit_offsets, fa_query_info *info, Prefetch *pf)
+                uint64_t cap, uint64_t *hit_offsets, fa_query_info *info, Prefetch *pf, const PreSketch *ps)
 {
     std::lock_guard<std::mutex> guard(ix->mtx);
     FA_CUDA(cudaSetDevice(ix->device));
@@ -2159,7 +2295,9 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
     nv.next("fa:query stage + h2d");
     if (F > 0 && tiles_per_frag > 0 && ix->n > 0 && G > 0) {
         // ---- upload + sketch the fragments ---------------------------------------------------
-        if (pf && pf->valid && pf->contigs == contigs && pf->n_contigs == n_contigs && pf->total == off) {
+        if (ps) {
+            // (sketched across the ranks and gathered: nothing to stage)
+        } else if (pf && pf->valid && pf->contigs == contigs && pf->n_contigs == n_contigs && pf->total == off) {
             // staged ahead by fa_query_batch: take its buffer (it gets ours, idle since the previous query returned)
             std::swap(ws.sk.bytes.p, pf->bytes.p); std::swap(ws.sk.bytes.cap, pf->bytes.cap);
             FA_CUDA(cudaStreamWaitEvent(st, pf->done, 0));
@@ -2170,7 +2308,7 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
         }
         const int n_tiles = F * tiles_per_frag;
         const int cmw = L - (w - 1) - (k - 1);                                // minimizer windows per fragment
-        const uint64_t emit_cap = (uint64_t)F * (uint64_t)std::max(cmw, 1);
+        const uint64_t emit_cap = (uint64_t)F * (uint64_t)(ps ? ps->stride : (uint32_t)std::max(cmw, 1));
         FA_TRY(ws.sk.seqs.reserve(F)); FA_TRY(ws.sk.tile_status.reserve(n_tiles));
         FA_TRY(ws.sk.counters.reserve(4)); FA_TRY(ws.sk.seq_first.reserve(F));
         FA_TRY(ws.qhash.reserve(emit_cap)); FA_TRY(ws.hit_start.reserve(emit_cap)); FA_TRY(ws.hit_cnt.reserve(emit_cap));
@@ -2189,14 +2327,20 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
             FA_CUDA(cudaMemcpyAsync(ws.frag_q.p, ws.h_fragq.data(), (size_t)F * sizeof(int32_t), cudaMemcpyHostToDevice, st));
             qi.h2d_bytes += (uint64_t)F * sizeof(int32_t);
         }
-        FA_CUDA(cudaMemcpyAsync(ws.sk.seqs.p, ws.h_seqs.data(), (size_t)F * sizeof(SeqDesc), cudaMemcpyHostToDevice, st));
-        qi.h2d_bytes += (uint64_t)F * sizeof(SeqDesc);
+        if (!ps) {
+            FA_CUDA(cudaMemcpyAsync(ws.sk.seqs.p, ws.h_seqs.data(), (size_t)F * sizeof(SeqDesc), cudaMemcpyHostToDevice, st));
+            qi.h2d_bytes += (uint64_t)F * sizeof(SeqDesc);
+        }
         FA_CUDA(cudaMemsetAsync(ws.counters.p, 0, CT_N * sizeof(unsigned long long), st));
         FA_CUDA(cudaEventRecord(ws.ev[1], st));
         nv.next("fa:query sketch");
         FA_TRY(ws.seq_cnt.reserve(F));
-        FA_TRY(launch_sketch(st, ws.sk, F, n_tiles, k, w, P.alphabet != 4, nullptr, ws.qhash.p, 0, &launches, std::max(cmw, 1), ws.seq_cnt.p));
-        {
+        if (ps) {
+            import_sketch_kernel<<<F, 128, 0, st>>>(ps->recv, ps->per, ps->stride, ps->block, ps->first_frag, ix->s_max, ws.qhash.p,
+                                                    ws.sk.seq_first.p, ws.qs.p, ws.counters.p);
+            FA_CUDA(cudaGetLastError()); launches++;
+        } else {
+            FA_TRY(launch_sketch(st, ws.sk, F, n_tiles, k, w, P.alphabet != 4, nullptr, ws.qhash.p, 0, &launches, std::max(cmw, 1), ws.seq_cnt.p));
             int p2 = 1; while (p2 < cmw) p2 <<= 1;
             int sort_cap = std::min(p2, 32768);
             size_t smem = (size_t)sort_cap * 4;
@@ -2231,6 +2375,7 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
         FA_CUDA(cudaMemcpyAsync(h_fs, ws.frag_seeds.p, ((size_t)F + 1) * 8, cudaMemcpyDeviceToHost, st));
         FA_CUDA(cudaStreamSynchronize(st));                                   // sync 1: seed counts, max sketch, errors
         qi.d2h_bytes += ((uint64_t)F + 1) * 8;
+        if (h_ct[CT_ERR] & ERR_EXCH) return FA_RETRY_PLAIN;                   // (a gathered sketch did not fit its slot: the caller maps this pass the plain way)
         if (h_ct[CT_ERR] & ERR_SORT_CAP) { set_error("a fragment produced more minimizers than the on-chip sort holds"); return FA_ERR_UNSUPPORTED; }
         if (h_ct[CT_ERR] & ERR_S_MAX) { set_error("sketch size above %d is not supported on the device path", ix->s_max); return FA_ERR_UNSUPPORTED; }
         const int max_s = (int)h_ct[CT_MAXS];

@@ -237,3 +237,72 @@ def test_query_reference_sharded_world1():
         assert np.array_equal(a, b) and np.array_equal(c, b)
     assert len(want[0]) == 7 and len(want[3]) == 0
     assert comm.info["collectives"] == 1
+
+
+def _sharded_worker(rank, world, port, out_dir, exchange):
+    """One rank of the reference-sharded layout end to end: its shard of the genomes, all queries through
+    fa_query_batch_sharded -- sketches made once across the ranks (sketch_exchange) unless switched off."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if not exchange:
+        os.environ["FA_NO_SKETCH_EXCHANGE"] = "1"
+    import pyfastani_b200 as pf
+    import synth
+
+    drafts, queries, lengths = _sharded_inputs(synth)
+    off = sharding.reference_shards(lengths, world)
+    comm = sharding.connect(world, rank, rank)
+    sk = pf.Sketch(device=rank)
+    for i in range(off[rank], off[rank + 1]):
+        sk.add_draft(i - off[rank], drafts[i])
+    mapper = sk.index()
+    got = sharding.query_reference_sharded(mapper, queries, off, comm)
+    info = dict(mapper.last_query_info)
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), *got, collectives=comm.info["collectives"], ms_sketch=info["ms_sketch"])
+
+
+def _sharded_inputs(synth):
+    query, refs, _ = synth.one_to_many(91, 10, 150_000, lo=0.85, hi=0.99)
+    rng = np.random.default_rng(6)
+    drafts = [synth.fragment(rng, r, 3, min_end=500) for r in refs]
+    lengths = [sum(len(c) for c in d) for d in drafts]
+    # whole genomes, a draft in seven contigs (short ones among them), a packed one, a str, one without a fragment
+    import pyfastani_b200 as pf
+    q_draft = synth.fragment(rng, refs[3], 7, min_end=100) + [b"ACGT", b"ACGTTGCA" * 300]
+    queries = [query, q_draft, pf.PackedSequence.pack(refs[7]), synth.revcomp(refs[5]).decode("ascii"), b"ACGT" * 10,
+               refs[1][:40_000], refs[9]]
+    return drafts, queries, lengths
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("exchange", [True, False])
+def test_reference_sharded_queries_world2(tmp_path, exchange):
+    """Two ranks, genomes sharded, every query mapped by both: merged rows equal those of one index over all genomes --
+    with the query sketches made once across the ranks and all-gathered (the default) and with every rank sketching
+    every query."""
+    import multiprocessing as mp
+    import pyfastani_b200 as pf
+    import synth
+
+    if pf.device_count() < 2:
+        pytest.skip("needs two GPUs; run with gpurun --gpus 2")
+    ctx = mp.get_context("spawn")
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, str(tmp_path), exchange)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+        assert p.exitcode == 0
+    drafts, queries, _ = _sharded_inputs(synth)
+    full = pf.Sketch()
+    for i, d in enumerate(drafts):
+        full.add_draft(i, d)
+    want = full.index().query_many([q if isinstance(q, list) else [q] for q in queries], rows=True)
+    a, b = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    for q in range(len(queries)):
+        assert np.array_equal(a["arr_%d" % q], b["arr_%d" % q])
+        assert np.array_equal(a["arr_%d" % q], want[q]), q
+    assert len(want[0]) == 10 and len(want[4]) == 0
+    # one all-gather of hit rows; with the exchange, one more per group of queries (seven light queries: one group)
+    assert int(a["collectives"]) == (2 if exchange else 1)
