@@ -108,6 +108,7 @@ typedef struct fa_query_info {
     uint64_t events_replayed;  /* events the slide kernel went through before its early stop (<= events) */
     float    ms_batch;         /* ONE event pair around the whole call on the library's stream (fa_query: == ms_total) */
     uint32_t l1_parts;         /* parts the fragments of the large L1 class were cut into (0 = mapped whole) */
+    uint32_t l1_tiny_fragments;/* fragments mapped by the warp-per-fragment shape of the L1 kernel (a few hundred hits at most) */
 } fa_query_info;
 
 typedef struct fa_sketch fa_sketch;   /* skch::Sketch under construction (pyx:465-470) */
@@ -267,6 +268,9 @@ FA_API int fa_fasta_counts(const fa_fasta *f, uint64_t *n_records, uint64_t *n_b
  * locate its identifier in the text the caller passed (the bytes between '>' and the end of the line). */
 FA_API int fa_fasta_records(const fa_fasta *f, fa_contig *contigs, uint64_t *id_begin, uint64_t *id_len);
 
+/* Test hook: cap on the hits per fragment the warp-per-fragment shape of the L1 kernel accepts (0 = off, at most 256);
+ * -1 restores the default (256). */
+FA_API int fa_debug_set_l1_tiny_cap(fa_index *ix, int64_t cap);
 /* How the on-chip L1 kernel maps fragments with tens of thousands of hits.  parts = 0: whole, one CTA per fragment (the
  * default -- measured faster on BASELINE configs[1]); -1: cut at genome boundaries into as many parts as the workload
  * asks for, each mapped by its own small CTA; n: exactly n parts.  part_cap: most hits a part may hold before its

@@ -568,7 +568,7 @@ static void add_info(fa_query_info &sum, const fa_query_info &qi)
     sum.ms_l1 += qi.ms_l1; sum.ms_l2 += qi.ms_l2; sum.ms_cgi += qi.ms_cgi; sum.ms_d2h += qi.ms_d2h; sum.ms_total += qi.ms_total;
     sum.ms_l2_prep += qi.ms_l2_prep; sum.ms_l2_events += qi.ms_l2_events; sum.ms_l2_slide += qi.ms_l2_slide;
     sum.ms_batch += qi.ms_batch;
-    sum.l1_parts = std::max(sum.l1_parts, qi.l1_parts);
+    sum.l1_parts = std::max(sum.l1_parts, qi.l1_parts); sum.l1_tiny_fragments += qi.l1_tiny_fragments;
 }
 
 static int query_checked(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *out, uint64_t cap, uint64_t *n_out,
@@ -764,6 +764,14 @@ int fa_debug_set_l1_small_shape(fa_index *ix, int32_t shape)
     if (!ix || shape > 2) { set_error("bad arguments"); return FA_ERR_INVALID; }
     std::lock_guard<std::mutex> guard(ix->mtx);
     ix->l1_small_shape = shape < 0 ? -1 : shape;
+    return FA_OK;
+}
+
+int fa_debug_set_l1_tiny_cap(fa_index *ix, int64_t cap)
+{
+    if (!ix) { set_error("index is NULL"); return FA_ERR_INVALID; }
+    std::lock_guard<std::mutex> guard(ix->mtx);
+    ix->l1_tiny_cap = cap < 0 ? -1 : (long long)cap;
     return FA_OK;
 }
 

@@ -165,6 +165,7 @@ struct fa_index {
     int l1_parts = 0;                            // 0 = the large class is mapped whole (the default: measured faster), -1 = parts chosen from the workload, n = exactly n parts
     long long l1_part_cap = -1;                  // test hook: most hits a part may hold (-1 = what fits)
     std::vector<uint32_t> genome_first;          // first reference index of every genome (+ n), filled by the first query that maps in parts
+    long long l1_tiny_cap = -1;                  // test hook: most hits per fragment for the warp-per-fragment L1 shape (-1 = 256, 0 = off)
     long long l1_seed_cap = -1;                  // test hook: most seeds per fragment for the on-chip L1 (-1 = what fits)
     std::mutex mtx;                              // serialises queries on the single workspace
     fa::Workspace ws;

@@ -24,6 +24,7 @@
 #include <memory>
 #include <thread>
 
+#include <cstdlib>
 #include "fa_internal.cuh"
 
 namespace fa {
@@ -868,6 +869,96 @@ l1_fused_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hi
                 for (int p2 = 0; p2 < pt.n_parts; p2++) pt.part_cands[(size_t)f * pt.n_parts + p2] = p2 ? 0u : heads_before;
             }
         }
+    }
+}
+
+// The third shape: one WARP per fragment, for fragments with at most L1_TINY hits -- what a fragment of a many-to-many run
+// meets in one reference shard (a few related genomes and the chance hits of its 32-bit hashes).  The two CTA shapes
+// pay for a histogram over all chunks of the index and a dozen barriers whatever the hit count; here the hits are
+// expanded into 1 KB of shared memory, sorted by the warp (bitonic network over the full 32-bit reference indices) and
+// the pair tests / region heads of computeMap.hpp:320-347 run on ballots, with dozens of fragments in flight per SM.
+constexpr int L1_TINY = 256, L1_TINY_WARPS = 4;
+__global__ void __launch_bounds__(32 * L1_TINY_WARPS, 8)
+l1_tiny_kernel(const uint64_t *seq_first, const int32_t *qs, const uint32_t *hit_start, const uint32_t *hit_cnt, const uint64_t *seed_base,
+               const uint32_t *pos_idx, const uint32_t *gpos, const uint32_t *irr, const int32_t *min_hits, int n_frags, int frag_len,
+               uint32_t d_near, uint32_t tiny_cap, Cand *tmp, uint32_t *frag_cands)
+{
+    __shared__ uint32_t s_k[L1_TINY_WARPS][L1_TINY];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int f = blockIdx.x * L1_TINY_WARPS + wid;
+    if (f >= n_frags) return;
+    const uint64_t sb = seed_base[f], nf64 = seed_base[f + 1] - sb;
+    if (nf64 > (uint64_t)tiny_cap) return;                                   // another shape takes this fragment
+    const int s = qs[f], n = (int)nf64;
+    if (s <= 0 || n == 0) { if (lane == 0) frag_cands[f] = 0; return; }
+    const uint64_t qb = seq_first[f];
+    uint32_t *K = s_k[wid];
+    // 1. the position lists, one after the other
+    int base = 0;
+    for (int q0 = 0; q0 < s; q0 += 32) {
+        const int q = q0 + lane;
+        const uint32_t c = q < s ? hit_cnt[qb + q] : 0u, st = q < s ? hit_start[qb + q] : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += t; }
+        const int off = base + (int)(incl - c);
+        for (uint32_t j = 0; j < c; j++) K[off + (int)j] = __ldg(pos_idx + st + j);
+        base += (int)__shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    int p2 = 32;
+    while (p2 < n) p2 <<= 1;
+    for (int i = n + lane; i < p2; i += 32) K[i] = 0xFFFFFFFFu;
+    __syncwarp();
+    // 2. bitonic sort of K[0, p2)
+    for (int k = 2; k <= p2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (p2 >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;      // the t-th comparator of this step
+                const uint32_t a = K[i], b = K[l];
+                if ((a > b) == ((i & k) == 0)) { K[i] = b; K[l] = a; }
+            }
+            __syncwarp();
+        }
+    // 3. valid pairs, region heads and ends
+    const int m = min_hits[s];
+    const uint32_t L = (uint32_t)frag_len;
+    auto marked = [&](uint32_t j) -> uint32_t { return (__ldg(irr + (j >> 15)) >> ((j >> 10) & 31u)) & 1u; };
+    auto near = [&](uint32_t a, uint32_t b2) -> bool {                        // l1_near of l1_fused_kernel
+        const uint32_t d = b2 - a;
+        if (d >= L) return false;
+        if (d <= d_near && (marked(a) | marked(b2)) == 0u) return true;
+        return __ldg(gpos + b2) - __ldg(gpos + a) < L;
+    };
+    Cand *out = tmp + sb;
+    uint32_t heads = 0, carry = 0;
+    bool have = false;                                                       // a valid pair seen so far (its first seed: carry)
+    for (int t0 = 0; t0 + m - 1 < n; t0 += 32) {
+        const int t = t0 + lane;
+        const bool in = t + m - 1 < n;
+        const uint32_t ja = in ? K[t] : 0u, jb = in ? K[t + m - 1] : 0u;
+        const bool valid = in && near(ja, jb);
+        const unsigned vm = __ballot_sync(0xFFFFFFFFu, valid);
+        // the valid pair before this one: in this group of 32, or the carry
+        const unsigned below = vm & ((1u << lane) - 1u);
+        const int pl = below ? 31 - __clz(below) : -1;
+        const uint32_t pj_in = __shfl_sync(0xFFFFFFFFu, ja, pl < 0 ? 0 : pl);
+        const bool pv = pl >= 0 || have;
+        const uint32_t pj = pl >= 0 ? pj_in : carry;
+        const bool head = valid && (!pv || !near(pj, jb));
+        const unsigned hm = __ballot_sync(0xFFFFFFFFu, head);
+        if (head) {
+            const uint32_t slot = heads + __popc(hm & ((1u << lane) - 1u));
+            Cand *o = out + slot;
+            o->frag = f; o->hint = jb; o->spare = 0u;
+            if (pv) out[slot - 1].tail = pj;
+        }
+        heads += __popc(hm);
+        if (vm) { carry = __shfl_sync(0xFFFFFFFFu, ja, 31 - __clz(vm)); have = true; }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        if (heads) out[heads - 1].tail = carry;
+        frag_cands[f] = heads;
     }
 }
 
@@ -2098,7 +2189,8 @@ int exchange_stride(const fa_params &P)
     const int L = P.frag_len, w = std::max(P.window, 1), k = P.k;
     const int cmw = L - (w - 1) - (k - 1);
     if (cmw <= 0) return 0;
-    const int want = ((4 * L / (w + 1) + 64) + 31) & ~31;
+    int want = ((4 * L / (w + 1) + 64) + 31) & ~31;
+    if (const char *e = getenv("FA_EXCHANGE_STRIDE")) { if (*e && atoi(e) > 0) want = (atoi(e) + 31) & ~31; }   // (test hook: slots too small for the sketches)
     return want < cmw ? want : 0;
 }
 
@@ -2410,20 +2502,24 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
             if (l1s_smem && ix->max_min_hits - 1 <= L1S_THREADS && max_s <= l1_stage(L1S_THREADS, L1S_TILE))
                 small_cap = std::min<uint64_t>(seed_cap, ((l1s_smem - l1s_fixed - 128) * 16 / 33) & ~31ull);
             if (ix->l1_small_cap >= 0) small_cap = std::min<uint64_t>(small_cap, (uint64_t)ix->l1_small_cap);
+            // the warp-per-fragment shape takes the fragments with a few hundred hits at most
+            const uint64_t tiny_cap = std::min<uint64_t>(ix->l1_tiny_cap < 0 ? (uint64_t)L1_TINY : std::min<uint64_t>((uint64_t)ix->l1_tiny_cap, (uint64_t)L1_TINY), seed_cap);
             uint64_t max_fast = 0, max_small = 0, S_slow = 0;
-            uint32_t n_slow = 0, n_small = 0;
+            uint32_t n_slow = 0, n_small = 0, n_tiny = 0;
             uint64_t *h_fb = h_fs + F + 1;
             h_fb[0] = 0;
             for (int f = 0; f < F; f++) {
                 const uint64_t nf = h_fs[f + 1] - h_fs[f];
                 const bool slow = nf > seed_cap;
                 if (slow) { n_slow++; S_slow += nf; }
+                else if (tiny_cap && nf <= tiny_cap) n_tiny++;
                 else if (small_cap && nf <= small_cap) { n_small++; max_small = std::max(max_small, nf); }
                 else max_fast = std::max(max_fast, nf);
                 h_fb[f + 1] = h_fb[f] + (slow ? nf : 0);
             }
-            if (n_small * 8u < (uint32_t)F) { max_fast = std::max(max_fast, max_small); n_small = 0; small_cap = 0; max_small = 0; }
-            const uint32_t n_large = (uint32_t)F - n_slow - n_small;
+            if (n_small * 8u < (uint32_t)F - n_tiny) { max_fast = std::max(max_fast, max_small); n_small = 0; small_cap = 0; max_small = 0; }
+            const uint32_t n_large = (uint32_t)F - n_slow - n_small - n_tiny;
+            const uint32_t tiny_lo = n_tiny ? (uint32_t)tiny_cap + 1u : 0u;      // the CTA shapes start above the tiny class
             // ---- the large class in parts: cut at genome boundaries into shares of about equal size, each mapped by a CTA
             // of the small shape at four CTAs per SM (see split_lists_kernel).  The fewest parts whose expected share of the
             // largest fragment (with a quarter of head-room: the hits need not be spread evenly) fits.
@@ -2482,6 +2578,7 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
             }
             qi.l1_parts = (uint32_t)pt.n_parts;
             qi.l1_small_fragments = n_small;
+            qi.l1_tiny_fragments = n_tiny;
             qi.l1_sorted_fragments = n_slow;
             const int shift = bits_for(ix->n), fbits = bits_for((uint64_t)F);
             const uint64_t idx_mask = (1ull << shift) - 1;
@@ -2507,17 +2604,23 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
                 FA_TRY(ws.cand_tmp.reserve(S));
                 const L1Parts no_parts{};
                 if (pt.n_parts) FA_CUDA(cudaMemsetAsync(ws.frag_cands.p, 0, ((size_t)F + 1) * 4, st));   // (the parts add their counts)
-                if (n_small) {          // fragments with [0, small_cap] hits
+                if (n_tiny) {           // fragments with [0, tiny_cap] hits: a warp each
+                    l1_tiny_kernel<<<(F + L1_TINY_WARPS - 1) / L1_TINY_WARPS, 32 * L1_TINY_WARPS, 0, st>>>(
+                        ws.sk.seq_first.p, ws.qs.p, ws.hit_start.p, ws.hit_cnt.p, ws.frag_seeds.p, ix->pos_idx.p, ix->gpos.p, ix->irr.p,
+                        ix->d_min_hits.p, F, L, d_near, (uint32_t)tiny_cap, ws.cand_tmp.p, ws.frag_cands.p);
+                    FA_CUDA(cudaGetLastError()); launches++;
+                }
+                if (n_small) {          // fragments with (tiny_cap, small_cap] hits
                     const uint64_t key_cap = (max_small + 31) & ~31ull;
                     const size_t smem = l1s_fixed + 2 * key_cap + 2 * (key_cap / 32 + 8);
                     FA_CUDA(cudaFuncSetAttribute(l1_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     l1_small<<<F, L1S_THREADS, smem, st>>>(ws.sk.seq_first.p, ws.qs.p, ws.hit_start.p, ws.hit_cnt.p, ws.frag_seeds.p,
                                                            ix->pos_idx.p, ix->gpos.p, ix->irr.p, ix->hw.p, ix->d_min_hits.p, L, d_near, n_chunks,
-                                                           0u, (uint32_t)small_cap, (uint32_t)key_cap, ws.cand_tmp.p, ws.frag_cands.p, no_parts);
+                                                           tiny_lo, (uint32_t)small_cap, (uint32_t)key_cap, ws.cand_tmp.p, ws.frag_cands.p, no_parts);
                     FA_CUDA(cudaGetLastError()); launches++;
                 }
                 if (n_large) {          // fragments with (small_cap, seed_cap] hits (all of them when the small shape is off)
-                    const uint32_t large_lo = n_small ? (uint32_t)small_cap + 1u : 0u;
+                    const uint32_t large_lo = n_small ? (uint32_t)small_cap + 1u : tiny_lo;
                     if (pt.n_parts) {
                         const int np = pt.n_parts;
                         pt.s_stride = std::max(max_s, 1);
@@ -2567,7 +2670,7 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
                 FA_TRY(ws.cands.reserve(C)); FA_TRY(ws.maps.reserve(C));
                 if (n_slow < (uint32_t)F) {
                     compact_cands_kernel<<<F, 128, 0, st>>>(ws.cand_tmp.p, ws.frag_seeds.p, ws.frag_cands.p, (uint32_t)seed_cap, ws.cands.p,
-                                                            n_small ? (uint32_t)small_cap + 1u : 0u, pt.n_parts, ws.part_off.p, ws.part_cands.p);
+                                                            n_small ? (uint32_t)small_cap + 1u : tiny_lo, pt.n_parts, ws.part_off.p, ws.part_cands.p);
                     FA_CUDA(cudaGetLastError()); launches++;
                 }
                 if (n_slow) {

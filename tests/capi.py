@@ -32,7 +32,7 @@ class QueryInfo(C.Structure):
                 + [("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("l2_fallback", C.c_uint64), ("events", C.c_uint64)]
                 + [(n, C.c_float) for n in ("ms_l2_prep", "ms_l2_events", "ms_l2_slide")]
                 + [("l1_sorted_fragments", C.c_uint32), ("l1_small_fragments", C.c_uint32), ("events_replayed", C.c_uint64),
-                   ("ms_batch", C.c_float), ("l1_parts", C.c_uint32)])
+                   ("ms_batch", C.c_float), ("l1_parts", C.c_uint32), ("l1_tiny_fragments", C.c_uint32)])
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -321,6 +321,9 @@ class Index:
     def set_l1_small_cap(self, cap):
         """Test hook: on-chip fragments with more seeds than `cap` take the large shape of the L1 kernel (-1 = default)."""
         check(lib().fa_debug_set_l1_small_cap(self.h, C.c_int64(cap)))
+
+    def set_l1_tiny_cap(self, cap):
+        check(lib().fa_debug_set_l1_tiny_cap(self.h, C.c_int64(cap)))
 
     def set_l1_parts(self, parts, part_cap=-1):
         check(lib().fa_debug_set_l1_parts(self.h, C.c_int32(parts), C.c_int64(part_cap)))

@@ -51,6 +51,8 @@ def _l1_parts(ix, l1, mean):
     or what the library picks), or in parts too small for half of the fragments, which fall back to the whole shape."""
     if l1.startswith("parts"):
         ix.set_l1_small_cap(0)
+    # the warp-per-fragment shape (fragments of at most 256 hits) stays on where the mode does not ask for a CTA shape
+    ix.set_l1_tiny_cap(-1 if l1 in ("chip", "sort", "mixed") else 0)
     ix.set_l1_parts(*{"chip-large": (0,), "parts-3": (3,), "parts-8": (8,), "parts-overflow": (4, max(mean // 4, 0)), "parts-auto": (-1,)}.get(l1, (0,)))
 
 
@@ -89,6 +91,7 @@ def test_queries_match_pyfastani_and_oracle(name, l1):
             assert out["info"]["l1_parts"] == (0 if name == "k12_pid90" else want)
         if l1 in ("chip", "chip-large", "shapes") or l1.startswith("parts"):
             assert out["info"]["l1_sorted_fragments"] == 0
+            assert out["info"]["l1_tiny_fragments"] <= (st["fragments"] if l1 == "chip" else 0)
             if l1 == "chip-large":
                 assert out["info"]["l1_small_fragments"] == 0
         elif st["seeds"]:
@@ -146,6 +149,36 @@ def test_l1_many_references(l1):
         assert np.array_equal(out["candidates"], oinfo["candidates"])
         assert np.array_equal(out["mappings"], oinfo["mappings"])
         assert np.array_equal(hits, ohits)
+
+
+def test_l1_warp_per_fragment_shape():
+    """Fragments with a few dozen hits each (two references at 90 % / 88 %, one unrelated, a draft among them) all take
+    the warp-per-fragment shape of the L1 kernel; with it switched off the CTA shapes give the same regions.  Both
+    against the oracle, for a whole query, its reverse complement and a query cut into contigs."""
+    rng = np.random.default_rng(31)
+    base = synth.random_codes(rng, 150_000)
+    q = synth.to_bytes(base)
+    refs = [[synth.to_bytes(synth.mutate_codes(rng, base, 0.90))],
+            synth.fragment(rng, synth.to_bytes(synth.mutate_codes(rng, base, 0.88)), 6, min_end=400),
+            [synth.to_bytes(synth.random_codes(rng, 80_000))]]
+    sk, osk = capi.Sketch(), _port().sketch()
+    for i, r in enumerate(refs):
+        sk.add_draft(i, r)
+        osk.add_draft(i, r)
+    ix = sk.index()
+    osk.index()
+    for query in ([q], [synth.revcomp(q)], synth.fragment(rng, q, 5, min_end=3100)):
+        ohits, oinfo = osk.query_draft(query, dump=True)
+        mean = oinfo["stats"]["seeds"] // oinfo["stats"]["fragments"]
+        for cap in (-1, 0, mean):                                # all fragments, none, about half of them
+            ix.set_l1_tiny_cap(cap)
+            hits, out = ix.query_draft(query, dump=True)
+            tiny, frags = out["info"]["l1_tiny_fragments"], out["info"]["fragments"]
+            assert tiny == frags if cap == -1 else tiny == 0 if cap == 0 else 0 < tiny < frags
+            assert np.array_equal(out["candidates"], oinfo["candidates"])
+            assert np.array_equal(out["mappings"], oinfo["mappings"])
+            assert np.array_equal(hits, ohits)
+    ix.set_l1_tiny_cap(-1)
 
 
 def test_config1_known_answers():

@@ -246,6 +246,8 @@ def _sharded_worker(rank, world, port, out_dir, exchange):
     os.environ["MASTER_PORT"] = str(port)
     if not exchange:
         os.environ["FA_NO_SKETCH_EXCHANGE"] = "1"
+    if exchange == "tight":                        # slots of 96 hashes: most sketches do not fit, their passes sketch at home
+        os.environ["FA_EXCHANGE_STRIDE"] = "96"
     import pyfastani_b200 as pf
     import synth
 
@@ -275,7 +277,7 @@ def _sharded_inputs(synth):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("exchange", [True, False])
+@pytest.mark.parametrize("exchange", [True, False, "tight"])
 def test_reference_sharded_queries_world2(tmp_path, exchange):
     """Two ranks, genomes sharded, every query mapped by both: merged rows equal those of one index over all genomes --
     with the query sketches made once across the ranks and all-gathered (the default) and with every rank sketching
