@@ -109,6 +109,7 @@ typedef struct fa_query_info {
     float    ms_batch;         /* ONE event pair around the whole call on the library's stream (fa_query: == ms_total) */
     uint32_t l1_parts;         /* parts the fragments of the large L1 class were cut into (0 = mapped whole) */
     uint32_t l1_tiny_fragments;/* fragments mapped by the warp-per-fragment shape of the L1 kernel (a few hundred hits at most) */
+    float    ms_exchange;      /* fa_query_batch_sharded: device time of the sketch exchanges (own stream, one group of queries ahead of the mapping) */
 } fa_query_info;
 
 typedef struct fa_sketch fa_sketch;   /* skch::Sketch under construction (pyx:465-470) */

@@ -81,6 +81,7 @@ cdef extern from "fastani_b200.h" nogil:
         float ms_batch
         uint32_t l1_parts
         uint32_t l1_tiny_fragments
+        float ms_exchange
     ctypedef struct fa_packed:
         const uint8_t* bits
         const uint32_t* run_pos
@@ -1112,7 +1113,7 @@ cdef class Mapper(_Parameterized):
                 "h2d_bytes": info.h2d_bytes, "d2h_bytes": info.d2h_bytes, "l2_fallback": info.l2_fallback, "events": info.events,
                 "ms_l2_prep": info.ms_l2_prep, "ms_l2_events": info.ms_l2_events, "ms_l2_slide": info.ms_l2_slide,
                 "l1_sorted_fragments": info.l1_sorted_fragments, "l1_small_fragments": info.l1_small_fragments, "events_replayed": info.events_replayed,
-                "ms_batch": info.ms_batch, "l1_parts": info.l1_parts, "l1_tiny_fragments": info.l1_tiny_fragments, "l1_tiny_fragments": info.l1_tiny_fragments, "queries": 1,
+                "ms_batch": info.ms_batch, "l1_parts": info.l1_parts, "l1_tiny_fragments": info.l1_tiny_fragments, "ms_exchange": info.ms_exchange, "l1_tiny_fragments": info.l1_tiny_fragments, "ms_exchange": info.ms_exchange, "queries": 1,
             }
         finally:
             free(out)
@@ -1213,7 +1214,7 @@ cdef class Mapper(_Parameterized):
                 "ms_seed_sort": info.ms_seed_sort, "ms_l1": info.ms_l1, "ms_l2": info.ms_l2, "ms_cgi": info.ms_cgi,
                 "ms_d2h": info.ms_d2h, "ms_l2_prep": info.ms_l2_prep, "ms_l2_events": info.ms_l2_events,
                 "ms_l2_slide": info.ms_l2_slide, "l1_small_fragments": info.l1_small_fragments,
-                "l1_sorted_fragments": info.l1_sorted_fragments, "l2_fallback": info.l2_fallback, "ms_batch": info.ms_batch, "l1_parts": info.l1_parts, "l1_tiny_fragments": info.l1_tiny_fragments,
+                "l1_sorted_fragments": info.l1_sorted_fragments, "l2_fallback": info.l2_fallback, "ms_batch": info.ms_batch, "l1_parts": info.l1_parts, "l1_tiny_fragments": info.l1_tiny_fragments, "ms_exchange": info.ms_exchange,
             }
         finally:
             free(counts)

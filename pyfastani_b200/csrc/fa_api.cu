@@ -443,7 +443,7 @@ void fa_index_free(fa_index *ix)
     ix->contig_off.release(); ix->genome_of_seq.release(); ix->bin_base.release(); ix->genome_cell.release();
     ix->pre[0].release(); ix->pre[1].release();
     ix->d_min_hits.release(); ix->d_min_shared.release(); ix->d_id_off.release(); ix->d_identity.release();
-    ix->ws.release();
+    ix->ws.release(); ix->xs.release();
     if (ix->st) cudaStreamDestroy(ix->st);
     delete ix;
 }
@@ -568,7 +568,7 @@ static void add_info(fa_query_info &sum, const fa_query_info &qi)
     sum.ms_l1 += qi.ms_l1; sum.ms_l2 += qi.ms_l2; sum.ms_cgi += qi.ms_cgi; sum.ms_d2h += qi.ms_d2h; sum.ms_total += qi.ms_total;
     sum.ms_l2_prep += qi.ms_l2_prep; sum.ms_l2_events += qi.ms_l2_events; sum.ms_l2_slide += qi.ms_l2_slide;
     sum.ms_batch += qi.ms_batch;
-    sum.l1_parts = std::max(sum.l1_parts, qi.l1_parts); sum.l1_tiny_fragments += qi.l1_tiny_fragments;
+    sum.l1_parts = std::max(sum.l1_parts, qi.l1_parts); sum.l1_tiny_fragments += qi.l1_tiny_fragments; sum.ms_exchange += qi.ms_exchange;
 }
 
 static int query_checked(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *out, uint64_t cap, uint64_t *n_out,
@@ -669,16 +669,29 @@ int fa::query_batch_impl(fa_index *ix, fa_comm *comm, const fa_contig *contigs, 
     uint64_t used = 0;
     std::vector<uint64_t> offs(PASS_QUERIES + 1);
     int slot = 0;
-    PreSketch group;
+    // exchange: the groups are fixed up front; the sketches of group g + 1 are made and gathered (on the exchange stream)
+    // while the passes of group g run
+    std::vector<int32_t> g_end;
+    if (exchange) for (int32_t q = 0; q < n_queries;) { q = group_end(q); g_end.push_back(q); }
+    PreSketch shares[2], group;
     float ms_exchange = 0;
-    if (exchange) g1 = 0;                                         // (the first group is formed inside the loop)
+    size_t gi = 0;
+    auto exchange_time = [&]() { float ms = 0; if (cudaEventSynchronize(ix->xs.t1) == cudaSuccess && cudaEventElapsedTime(&ms, ix->xs.t0, ix->xs.t1) == cudaSuccess) ms_exchange += ms; };
+    if (exchange) {
+        g1 = 0;                                                   // (the first group begins inside the loop)
+        if (!g_end.empty()) FA_TRY(sketch_exchange(ix, comm, contigs, (int32_t)first[g_end[0]], 0, &shares[0], &sum));
+    }
     int32_t q0 = 0, q1 = n_queries && !exchange ? pass_end(0) : 0;
     while (q0 < n_queries) {
         if (exchange && q0 == g1) {
-            // the next group: its sketches, made once across the ranks
-            if (g1 > 0) { float ms = 0; if (cudaEventSynchronize(ix->ws.ev[13]) == cudaSuccess && cudaEventElapsedTime(&ms, ix->ws.ev[12], ix->ws.ev[13]) == cudaSuccess) ms_exchange += ms; }
-            g0 = g1; g1 = group_end(g0);
-            FA_TRY(sketch_exchange(ix, comm, contigs ? contigs + first[g0] : nullptr, (int32_t)(first[g1] - first[g0]), &group, &sum));
+            // the next group: its shares have been on their way since the previous group began
+            g0 = g1; g1 = g_end[gi];
+            FA_CUDA(cudaEventSynchronize(ix->xs.done[gi & 1]));
+            exchange_time();
+            group = shares[gi & 1];
+            if (gi + 1 < g_end.size())
+                FA_TRY(sketch_exchange(ix, comm, contigs + first[g1], (int32_t)(first[g_end[gi + 1]] - first[g1]), (int)((gi + 1) & 1), &shares[(gi + 1) & 1], &sum));
+            gi++;
             q1 = pass_end(q0);
         }
         const int32_t nq = q1 - q0;
@@ -729,8 +742,7 @@ int fa::query_batch_impl(fa_index *ix, fa_comm *comm, const fa_contig *contigs, 
         q0 = q1; q1 = q2; slot ^= 1;
         if (q0 < n_queries && q1 == q0 && !(exchange && q0 == g1)) q1 = pass_end(q0);
     }
-    if (exchange && g1 > 0) { float ms = 0; if (cudaEventSynchronize(ix->ws.ev[13]) == cudaSuccess && cudaEventElapsedTime(&ms, ix->ws.ev[12], ix->ws.ev[13]) == cudaSuccess) ms_exchange += ms; }
-    sum.ms_sketch += ms_exchange;
+    sum.ms_exchange = ms_exchange;                                // (off the critical path except for the first group)
     FA_CUDA(cudaEventRecord(outer.b, ix->st));
     FA_CUDA(cudaEventSynchronize(outer.b));
     sum.ms_batch = 0;

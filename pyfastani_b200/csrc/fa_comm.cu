@@ -89,8 +89,10 @@ struct fa_comm {
 // The second exchange of the reference-sharded layout: the query sketches.  Every rank maps every query, so every rank
 // would sketch every query -- the largest stage of a 10 000 x 10 000 run (a third of it).  Instead rank r sketches
 // fragments [r * per, (r + 1) * per) of a group of queries and one ncclAllGather on the mapping stream hands every rank
-// all sketches, packed to `stride` hashes per fragment (a tenth of the bases they were made from).
-int fa::sketch_exchange(fa_index *ix, fa_comm *c, const fa_contig *contigs, int32_t n_contigs, PreSketch *ps, fa_query_info *qi)
+// all sketches, packed to `stride` hashes per fragment.  The exchange has its own stream and scratch and runs one group
+// ahead of the mapping (query_batch_impl): its kernels fill the gaps of the mapping kernels, and a rank that arrives late
+// at the collective (the one that holds the genus of the current queries) delays the NEXT group's sketches, not a pass.
+int fa::sketch_exchange(fa_index *ix, fa_comm *c, const fa_contig *contigs, int32_t n_contigs, int slot, PreSketch *ps, fa_query_info *qi)
 {
     const int stride = exchange_stride(ix->prm);
     if (stride <= 0) { set_error("sketch exchange is not available for these parameters"); return FA_ERR_UNSUPPORTED; }
@@ -98,12 +100,14 @@ int fa::sketch_exchange(fa_index *ix, fa_comm *c, const fa_contig *contigs, int3
     uint64_t frags = 0;
     FA_TRY(sketch_share(ix, contigs, n_contigs, c->world, c->rank, (uint32_t)stride, &per, &frags, qi));
     std::lock_guard<std::mutex> guard(c->mtx);
+    ExchScratch &xs = ix->xs;
     const size_t block = (size_t)per * ((size_t)stride + 1);
-    FA_TRY(ix->ws.x_recv.reserve(block * (size_t)c->world));
-    FA_NCCL(c->api, c->api->AllGather(ix->ws.x_send.p, ix->ws.x_recv.p, block, ncclUint32, c->comm, ix->st));
-    FA_CUDA(cudaEventRecord(ix->ws.ev[13], ix->st));
+    FA_TRY(xs.recv[slot].reserve(block * (size_t)c->world));
+    FA_NCCL(c->api, c->api->AllGather(xs.send.p, xs.recv[slot].p, block, ncclUint32, c->comm, xs.st));
+    FA_CUDA(cudaEventRecord(xs.t1, xs.st));
+    FA_CUDA(cudaEventRecord(xs.done[slot], xs.st));
     c->collectives++; c->bytes_gathered += block * 4 * (size_t)c->world;
-    ps->recv = ix->ws.x_recv.p; ps->per = per; ps->stride = (uint32_t)stride; ps->block = block; ps->first_frag = 0;
+    ps->recv = xs.recv[slot].p; ps->per = per; ps->stride = (uint32_t)stride; ps->block = block; ps->first_frag = 0;
     return FA_OK;
 }
 

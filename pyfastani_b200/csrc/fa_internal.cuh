@@ -60,9 +60,8 @@ struct Workspace {
     DevBuf<int32_t>  g_count;
     DevBuf<unsigned long long> counters;   // misc device counters (see fa_map.cu)
     PinBuf hres;                        // pinned result staging
-    cudaEvent_t ev[14] = {};            // (12, 13: around the sketch exchange of a group)
+    cudaEvent_t ev[12] = {};
     bool ev_ready = false;
-    DevBuf<uint32_t> x_send, x_recv;    // sketch exchange of the reference-sharded layout: this rank's share / all shares
     uint64_t last_cands = 0, last_frags = 0;
     // every buffer above, in one place: a member added to the struct is released here or nowhere
     void release()
@@ -73,7 +72,7 @@ struct Workspace {
         l1_split.release(); part_off.release(); part_cands.release(); l1_over.release(); chunk_hist.release(); h_chunk_hist.release();
         cub_tmp.release(); frag_cands.release(); work_base.release(); cands.release(); maps.release(); prep.release();
         ev_off.release(); jobs.release(); mid.release(); seq_cnt.release(); events.release(); cells.release(); g_identity.release();
-        g_count.release(); counters.release(); hres.release(); x_send.release(); x_recv.release();
+        g_count.release(); counters.release(); hres.release();
         if (ev_ready) for (auto &e : ev) cudaEventDestroy(e);
         ev_ready = false;
     }
@@ -90,6 +89,30 @@ struct PreSketch {
     uint64_t first_frag = 0;            // first fragment of the pass inside the group
 };
 enum { FA_RETRY_PLAIN = 100 };          // internal status of run_queries: a pre-sketched fragment did not fit its slot, sketch this pass here
+
+// Scratch of the sketch exchange (fa_comm.cu): it runs on its own stream, one group of queries ahead of the mapping, so it
+// owns everything it touches -- staging, sketch scratch, this rank's packed share, and two receive buffers (the passes of
+// group g read one while the shares of group g + 1 land in the other).
+struct ExchScratch {
+    SketchScratch sk;
+    PinBuf stage;
+    std::vector<SeqDesc> h_seqs;
+    DevBuf<uint32_t> qhash, seq_cnt, send, recv[2];
+    DevBuf<int32_t> qs;
+    DevBuf<unsigned long long> counters;
+    cudaStream_t st = nullptr;
+    cudaEvent_t done[2] = {}, t0 = nullptr, t1 = nullptr;
+    void release()
+    {
+        sk.bytes.release(); sk.seqs.release(); sk.tile_status.release(); sk.counters.release(); sk.seq_first.release(); sk.drops.release();
+        stage.release(); qhash.release(); seq_cnt.release(); send.release(); recv[0].release(); recv[1].release(); qs.release(); counters.release();
+        for (auto &e : done) if (e) { cudaEventDestroy(e); e = nullptr; }
+        if (t0) cudaEventDestroy(t0);
+        if (t1) cudaEventDestroy(t1);
+        if (st) cudaStreamDestroy(st);
+        t0 = t1 = nullptr; st = nullptr;
+    }
+};
 
 // One host or device buffer to place at `off` in the batch byte buffer (unit: fa_contig.unit_bytes).
 struct Upload { const void *ptr; int32_t unit; int32_t on_device; int64_t len; uint64_t off; };
@@ -169,6 +192,7 @@ struct fa_index {
     long long l1_seed_cap = -1;                  // test hook: most seeds per fragment for the on-chip L1 (-1 = what fits)
     std::mutex mtx;                              // serialises queries on the single workspace
     fa::Workspace ws;
+    fa::ExchScratch xs;                          // sketch exchange of the reference-sharded layout (one sharded batch at a time)
     std::mutex pre_mtx;                          // one fa_query_batch at a time stages ahead (others map without)
     fa::Prefetch pre[2];
 };
@@ -203,12 +227,12 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
 // [rank * per, rank * per + per) of all of them) and leave [per * stride hashes | per sizes] in ws.x_send
 int exchange_stride(const fa_params &P);
 int sketch_share(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, int world, int rank, uint32_t stride, uint32_t *per_out,
-                 uint64_t *frags_out, fa_query_info *qi);
+                 uint64_t *frags_out, fa_query_info *qi);      // (on ix->xs.st, into ix->xs.send)
 // fa_query_batch with an optional communicator: with one, the query sketches are made once across the ranks (fa_comm.cu)
 int query_batch_impl(fa_index *ix, fa_comm *comm, const fa_contig *contigs, const int32_t *contigs_per_query, int32_t n_queries,
                      fa_hit *out, uint64_t cap, uint64_t *hit_offsets, fa_query_info *info);
 int comm_world(const fa_comm *c);
-int sketch_exchange(fa_index *ix, fa_comm *comm, const fa_contig *contigs, int32_t n_contigs, PreSketch *ps, fa_query_info *qi);
+int sketch_exchange(fa_index *ix, fa_comm *comm, const fa_contig *contigs, int32_t n_contigs, int slot, PreSketch *ps, fa_query_info *qi);
 // shared by the sketch and query paths: narrow/copy the uploads into the batch byte buffer
 int stage_sequences(cudaStream_t st, DevBuf<uint8_t> &bytes, PinBuf &stage, const std::vector<Upload> &ups, uint64_t total,
                     uint64_t *h2d_bytes, int workers = 0);

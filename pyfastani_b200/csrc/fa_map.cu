@@ -416,6 +416,15 @@ __device__ __forceinline__ void l1_sort_bucket(uint16_t *k, int n, uint32_t *bm,
             __syncwarp();
             return;
         }
+        if (n <= 16) {
+            // a handful of chance hits spread over the chunk (the usual bucket of a fragment that is unrelated to the
+            // genomes of this chunk): rank = keys below, by shuffles
+            int r = 0;
+            for (int j = 0; j < n; j++) r += __shfl_sync(0xFFFFFFFFu, v0, j) < v0;
+            if (lane < n) k[r] = (uint16_t)v0;
+            __syncwarp();
+            return;
+        }
     }
     if (n <= 256) {
         // up to eight keys per lane in registers, rank = set bits below in a 1024-bit map (as above)
@@ -2197,10 +2206,14 @@ int exchange_stride(const fa_params &P)
 int sketch_share(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, int world, int rank, uint32_t stride, uint32_t *per_out,
                  uint64_t *frags_out, fa_query_info *qi)
 {
-    std::lock_guard<std::mutex> guard(ix->mtx);
     FA_CUDA(cudaSetDevice(ix->device));
-    cudaStream_t st = ix->st;
-    Workspace &ws = ix->ws;
+    ExchScratch &ws = ix->xs;
+    if (!ws.st) {
+        FA_CUDA(cudaStreamCreateWithFlags(&ws.st, cudaStreamNonBlocking));
+        for (auto &e : ws.done) FA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        FA_CUDA(cudaEventCreate(&ws.t0)); FA_CUDA(cudaEventCreate(&ws.t1));
+    }
+    cudaStream_t st = ws.st;
     const fa_params &P = ix->prm;
     const int L = P.frag_len, k = P.k, w = P.window;
     const int lim = std::min(std::min(w, k), L);
@@ -2244,12 +2257,8 @@ int sketch_share(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, int 
         }
         a += nfrag;
     }
-    if (!ws.ev_ready) {
-        for (auto &e : ws.ev) FA_CUDA(cudaEventCreate(&e));
-        ws.ev_ready = true;
-    }
-    FA_CUDA(cudaEventRecord(ws.ev[12], st));
-    FA_TRY(ws.x_send.reserve((size_t)per * (stride + 1)));
+    FA_CUDA(cudaEventRecord(ws.t0, st));
+    FA_TRY(ws.send.reserve((size_t)per * (stride + 1)));
     FA_TRY(ws.qs.reserve(std::max(n_loc, 1))); FA_TRY(ws.seq_cnt.reserve(std::max(n_loc, 1))); FA_TRY(ws.sk.seq_first.reserve(std::max(n_loc, 1)));
     FA_TRY(ws.counters.reserve(CT_N));
     int launches = 0, sort_cap = 0;
@@ -2271,7 +2280,7 @@ int sketch_share(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, int 
         if (qi) qi->h2d_bytes += h2d + (uint64_t)n_loc * sizeof(SeqDesc);
     }
     pack_sketch_kernel<<<(unsigned int)per, 128, 0, st>>>(ws.qhash.p, ws.sk.seq_first.p, ws.seq_cnt.p, ws.qs.p, n_loc, sort_cap, (uint32_t)per, stride,
-                                                         ws.x_send.p);
+                                                         ws.send.p);
     FA_CUDA(cudaGetLastError()); launches++;
     if (qi) qi->kernel_launches += launches;
     return FA_OK;
@@ -2516,6 +2525,15 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
                 else if (small_cap && nf <= small_cap) { n_small++; max_small = std::max(max_small, nf); }
                 else max_fast = std::max(max_fast, nf);
                 h_fb[f + 1] = h_fb[f] + (slow ? nf : 0);
+            }
+            if (n_tiny * 16u < (uint32_t)F) {
+                // hardly any fragment is that light: not worth a launch over all of them
+                for (int f = 0; f < F && n_tiny; f++) {
+                    const uint64_t nf = h_fs[f + 1] - h_fs[f];
+                    if (nf > tiny_cap || nf > seed_cap) continue;
+                    if (small_cap && nf <= small_cap) { n_small++; max_small = std::max(max_small, nf); } else max_fast = std::max(max_fast, nf);
+                }
+                n_tiny = 0;
             }
             if (n_small * 8u < (uint32_t)F - n_tiny) { max_fast = std::max(max_fast, max_small); n_small = 0; small_cap = 0; max_small = 0; }
             const uint32_t n_large = (uint32_t)F - n_slow - n_small - n_tiny;

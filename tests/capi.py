@@ -32,7 +32,7 @@ class QueryInfo(C.Structure):
                 + [("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("l2_fallback", C.c_uint64), ("events", C.c_uint64)]
                 + [(n, C.c_float) for n in ("ms_l2_prep", "ms_l2_events", "ms_l2_slide")]
                 + [("l1_sorted_fragments", C.c_uint32), ("l1_small_fragments", C.c_uint32), ("events_replayed", C.c_uint64),
-                   ("ms_batch", C.c_float), ("l1_parts", C.c_uint32), ("l1_tiny_fragments", C.c_uint32)])
+                   ("ms_batch", C.c_float), ("l1_parts", C.c_uint32), ("l1_tiny_fragments", C.c_uint32), ("ms_exchange", C.c_float)])
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
