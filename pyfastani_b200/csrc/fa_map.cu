@@ -421,6 +421,7 @@ __device__ __forceinline__ void l1_sort_bucket(uint16_t *k, int n, uint32_t *bm,
             // genomes of this chunk): rank = keys below, by shuffles
             int r = 0;
             for (int j = 0; j < n; j++) r += __shfl_sync(0xFFFFFFFFu, v0, j) < v0;
+            __syncwarp();                                        // (every lane has read its key)
             if (lane < n) k[r] = (uint16_t)v0;
             __syncwarp();
             return;
@@ -2368,12 +2369,14 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
             FA_TRY(check_contig(contigs[c], c));
             const int64_t nfrag = slen / L;                                      // pyx:1097
             if (nfrag > 0) {
-                ups.push_back(Upload{contigs[c].data, contigs[c].unit_bytes, contigs[c].on_device, nfrag * L, off});
-                for (int64_t i = 0; i < nfrag; i++) {
-                    SeqDesc d;
-                    d.off = off + (uint64_t)i * L; d.len = L; d.id = (int32_t)(total_frags + i);
-                    d.raw = contig_prenormalised(contigs[c]); d.tile0 = (int32_t)((total_frags + i) * tiles_per_frag);
-                    ws.h_seqs.push_back(d);
+                if (!ps) {                                                       // (pre-sketched fragments: nothing to stage or sketch)
+                    ups.push_back(Upload{contigs[c].data, contigs[c].unit_bytes, contigs[c].on_device, nfrag * L, off});
+                    for (int64_t i = 0; i < nfrag; i++) {
+                        SeqDesc d;
+                        d.off = off + (uint64_t)i * L; d.len = L; d.id = (int32_t)(total_frags + i);
+                        d.raw = contig_prenormalised(contigs[c]); d.tile0 = (int32_t)((total_frags + i) * tiles_per_frag);
+                        ws.h_seqs.push_back(d);
+                    }
                 }
                 if (B > 1) ws.h_fragq.insert(ws.h_fragq.end(), (size_t)nfrag, (int32_t)q);
                 off += ((uint64_t)(nfrag * L) + 15) & ~15ull;
