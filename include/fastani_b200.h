@@ -206,10 +206,14 @@ FA_API int fa_query_batch(fa_index *ix, const fa_contig *contigs, const int32_t 
                    fa_hit *out, uint64_t cap, uint64_t *hit_offsets, fa_query_info *info);
 /* -- multi-GPU: reference-sharded mapping (BASELINE configs[4]) ----------------------------------------
  * One process per GPU.  Whole reference genomes are dealt to the ranks in contiguous blocks (genome_offsets, world + 1
- * entries: rank r indexes genomes [genome_offsets[r], genome_offsets[r + 1])), every rank maps every query against its
- * shard and the final per-genome rows are exchanged with one small ncclAllGather (a second one only when a rank holds
- * more than 2048 rows for the batch) -- what upstream FastANI does per thread (splitReferenceGenomes /
- * correctRefGenomeIds, FA/cgi/include/computeCoreIdentity.hpp:454-484).  NCCL is bound at run time (libnccl.so.2). */
+ * entries: rank r indexes genomes [genome_offsets[r], genome_offsets[r + 1])) and every rank maps every query against
+ * its shard -- what upstream FastANI does per thread (splitReferenceGenomes / correctRefGenomeIds,
+ * FA/cgi/include/computeCoreIdentity.hpp:454-484).  Two exchange steps over NCCL, both inside fa_query_batch_sharded:
+ * the query sketches are made ONCE across the ranks (rank r sketches 1/world of the fragments of a group of queries, one
+ * ncclAllGather of the packed sketches per group, issued a group ahead of the mapping on its own stream), and the final
+ * per-genome rows are gathered at the end of the call (one small ncclAllGather; a second one only when a rank holds
+ * more than 2048 rows for the batch).  NCCL is bound at run time (libnccl.so.2).  Calls on one communicator -- and
+ * sharded calls on one index -- must not overlap: collectives are matched by issue order. */
 typedef struct fa_comm fa_comm;
 enum { FA_COMM_ID_BYTES = 128 };
 /* ncclGetUniqueId on one rank; the 128 bytes reach the other ranks by whatever channel the host has (a socket, a file,
@@ -224,8 +228,10 @@ FA_API int fa_comm_info(const fa_comm *c, int32_t *world, int32_t *rank, int32_t
  * of pyx:1135 (identity descending, stable in ascending genome id): out[out_offsets[q] .. out_offsets[q + 1]). */
 FA_API int fa_gather_hits(fa_comm *c, const fa_hit *rows, const uint64_t *hit_offsets, int32_t n_queries,
                    const int32_t *genome_offsets, fa_hit *out, uint64_t cap, uint64_t *out_offsets);
-/* Collective.  fa_query_batch against this rank's shard followed by fa_gather_hits: the whole reference-sharded step
- * without the host language in between. */
+/* Collective.  fa_query_batch against this rank's shard -- with the query sketches shared between the ranks as described
+ * above (FA_NO_SKETCH_EXCHANGE=1 in the environment of ALL ranks: every rank sketches every query) -- followed by
+ * fa_gather_hits: the whole reference-sharded step without the host language in between.  Every rank passes the same
+ * queries in the same order. */
 FA_API int fa_query_batch_sharded(fa_index *ix, fa_comm *comm, const fa_contig *contigs, const int32_t *contigs_per_query,
                            int32_t n_queries, const int32_t *genome_offsets, fa_hit *out, uint64_t cap,
                            uint64_t *hit_offsets, fa_query_info *info);
