@@ -592,7 +592,7 @@ int fa_query(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, fa_hit *
 //  * Light queries share a pass of the pipeline (run_queries, fa_map.cu): a many-to-many query has a few thousand
 //    candidates, far too few to fill the GPU's lanes in the L2 slide, and its twenty kernel launches and four host
 //    syncs cost as much as its kernels.  The first pass takes one query; afterwards the seeds and events per fragment
-//    seen so far size the next pass (at most 32 queries / 48 k fragments / the budgets below), so a heavy query --
+//    seen so far size the next pass (at most 64 queries / 96 k fragments / the budgets below), so a heavy query --
 //    config 2: 86 M seeds, 1.8 G events -- still runs alone.
 //  * While a pass is mapped, a helper thread stages the bytes of the next one (its own pinned buffer, copy stream and
 //    device buffer, fa_map.cu prefetch_query), so host copy and H2D overlap the kernels.
@@ -644,7 +644,7 @@ int fa::query_batch_impl(fa_index *ix, fa_comm *comm, const fa_contig *contigs, 
     const bool ahead = pre_lock.owns_lock() && n_queries > 1 && !exchange;
     if (pre_lock.owns_lock()) ix->pre[0].valid = ix->pre[1].valid = false;       // nothing staged by an earlier call is ours
 
-    constexpr uint64_t PASS_QUERIES = 32, PASS_FRAGS = 48 * 1024, PASS_SEEDS = 96ull << 20, PASS_EVENTS = 256ull << 20;
+    constexpr uint64_t PASS_QUERIES = 64, PASS_FRAGS = 96 * 1024, PASS_SEEDS = 192ull << 20, PASS_EVENTS = 512ull << 20;
     double seeds_per_frag = -1.0, events_per_frag = -1.0;      // largest seen so far in this call (-1: nothing seen)
     int32_t g0 = 0, g1 = n_queries;                              // the group of queries whose sketches are at hand (exchange)
     auto group_end = [&](int32_t q0) {
