@@ -7,6 +7,7 @@ the compiled extension is missing, importing this package fails.
 from . import _fastani
 from ._fastani import (
     MAX_KMER_SIZE,
+    Communicator,
     CudaError,
     DeviceFasta,
     DeviceSequence,
@@ -24,5 +25,5 @@ from ._fastani import (
 __version__ = _fastani.__version__
 __all__ = [
     "MAX_KMER_SIZE", "Hit", "Mapper", "MinimizerIndex", "MinimizerInfo", "Minimizers", "Position", "Sketch",
-    "CudaError", "DeviceFasta", "DeviceSequence", "PackedSequence", "device_count",
+    "Communicator", "CudaError", "DeviceFasta", "DeviceSequence", "PackedSequence", "device_count",
 ]

@@ -130,7 +130,8 @@ constexpr int SK_TILE = SK_THREADS * SK_PER_THREAD;
 // slot_cap / seq_cnt (query fragments): sequence f writes its hashes at out_hash[f * slot_cap ...] and its count to
 // seq_cnt[f]; without them the output is one array in (sequence, position) order.
 int launch_sketch(cudaStream_t st, const SketchScratch &sc, int n_seqs, int n_tiles, int k, int w, int fwd_only,
-                  RefMini *out_ref, uint32_t *out_hash, uint64_t out_base, int *launches, int slot_cap = 0, uint32_t *seq_cnt = nullptr);
+                  RefMini *out_ref, uint32_t *out_hash, uint64_t out_base, int *launches, int slot_cap = 0, uint32_t *seq_cnt = nullptr,
+                  int uniform_tiles = 0);     // uniform_tiles > 0: every sequence has that many tiles (query fragments)
 
 // The reference's `wpos == 0` comparison quirk (pyx:219-222) suppresses some
 // minimizers right after window 0 of a contig.  launch_quirk_find records the affected runs of

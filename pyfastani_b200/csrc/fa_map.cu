@@ -2271,7 +2271,7 @@ int sketch_share(fa_index *ix, const fa_contig *contigs, int32_t n_contigs, int 
         FA_TRY(ws.qhash.reserve((uint64_t)n_loc * (uint64_t)cmw));
         FA_CUDA(cudaMemcpyAsync(ws.sk.seqs.p, ws.h_seqs.data(), (size_t)n_loc * sizeof(SeqDesc), cudaMemcpyHostToDevice, st));
         FA_CUDA(cudaMemsetAsync(ws.counters.p, 0, CT_N * sizeof(unsigned long long), st));
-        FA_TRY(launch_sketch(st, ws.sk, n_loc, n_tiles, k, w, P.alphabet != 4, nullptr, ws.qhash.p, 0, &launches, cmw, ws.seq_cnt.p));
+        FA_TRY(launch_sketch(st, ws.sk, n_loc, n_tiles, k, w, P.alphabet != 4, nullptr, ws.qhash.p, 0, &launches, cmw, ws.seq_cnt.p, tiles_per_frag));
         int p2 = 1; while (p2 < cmw) p2 <<= 1;
         sort_cap = std::min(p2, 32768);
         const size_t smem = (size_t)sort_cap * 4;
@@ -2444,7 +2444,7 @@ int run_queries(fa_index *ix, const fa_contig *contigs, const int32_t *contigs_p
                                                     ws.sk.seq_first.p, ws.qs.p, ws.counters.p);
             FA_CUDA(cudaGetLastError()); launches++;
         } else {
-            FA_TRY(launch_sketch(st, ws.sk, F, n_tiles, k, w, P.alphabet != 4, nullptr, ws.qhash.p, 0, &launches, std::max(cmw, 1), ws.seq_cnt.p));
+            FA_TRY(launch_sketch(st, ws.sk, F, n_tiles, k, w, P.alphabet != 4, nullptr, ws.qhash.p, 0, &launches, std::max(cmw, 1), ws.seq_cnt.p, tiles_per_frag));
             int p2 = 1; while (p2 < cmw) p2 <<= 1;
             int sort_cap = std::min(p2, 32768);
             size_t smem = (size_t)sort_cap * 4;
