@@ -29,7 +29,15 @@ constexpr unsigned long long KEY_INF = ~0ull;
 
 __constant__ uint8_t c_comp[128];
 
-__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+// 64-bit rotate by a constant 0 < r < 64, r != 32, as two funnel shifts (the shift / or form compiles to six instructions)
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r)
+{
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    uint32_t nlo, nhi;
+    if (r < 32) { nhi = __funnelshift_l(lo, hi, r); nlo = __funnelshift_l(hi, lo, r); }
+    else { nhi = __funnelshift_l(hi, lo, r - 32); nlo = __funnelshift_l(lo, hi, r - 32); }
+    return ((uint64_t)nhi << 32) | nlo;
+}
 
 __device__ __forceinline__ uint64_t fmix64(uint64_t k)
 {
