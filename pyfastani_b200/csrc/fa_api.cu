@@ -644,7 +644,7 @@ int fa::query_batch_impl(fa_index *ix, fa_comm *comm, const fa_contig *contigs, 
     const bool ahead = pre_lock.owns_lock() && n_queries > 1 && !exchange;
     if (pre_lock.owns_lock()) ix->pre[0].valid = ix->pre[1].valid = false;       // nothing staged by an earlier call is ours
 
-    constexpr uint64_t PASS_QUERIES = 64, PASS_FRAGS = 96 * 1024, PASS_SEEDS = 192ull << 20, PASS_EVENTS = 512ull << 20;
+    constexpr uint64_t PASS_QUERIES = 64, PASS_FRAGS = 96 * 1024, PASS_SEEDS = 384ull << 20, PASS_EVENTS = 1024ull << 20;
     double seeds_per_frag = -1.0, events_per_frag = -1.0;      // largest seen so far in this call (-1: nothing seen)
     int32_t g0 = 0, g1 = n_queries;                              // the group of queries whose sketches are at hand (exchange)
     auto group_end = [&](int32_t q0) {
