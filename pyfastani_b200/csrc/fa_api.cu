@@ -712,8 +712,9 @@ int fa::query_batch_impl(fa_index *ix, fa_comm *comm, const fa_contig *contigs, 
         if (rc == FA_RETRY_PLAIN)          // a sketch did not fit its slot of the exchange: this pass sketches its own queries
             rc = run_queries(ix, contigs ? contigs + first[q0] : nullptr, contigs_per_query + q0, nq, out ? out + used : nullptr,
                              cap - used, offs.data(), &qi, nullptr, nullptr);
-        if (rc == FA_ERR_NOMEM && nq > 1) {
-            // the pass was sized from lighter queries: map its queries one by one
+        if ((rc == FA_ERR_NOMEM || rc == FA_ERR_UNSUPPORTED) && nq > 1) {
+            // the pass was sized from lighter queries (or holds more queries than the cell tables of this index allow):
+            // map its queries one by one
             cudaGetLastError();
             memset(&qi, 0, sizeof qi);
             uint64_t u2 = 0;
