@@ -33,6 +33,15 @@ extern "C" int fa_pack_2bit(const uint8_t *data, uint64_t len, uint8_t *bits, ui
     bool open = false;                                    // the previous byte belongs to run nr - 1
     uint8_t open_byte = 0;
     for (uint64_t i = 0; i < len; i += 4) {
+        if (i + 4 <= len) {
+            // four plain bases: the usual case, no branch per byte
+            const uint8_t c0 = PACK.code[data[i]], c1 = PACK.code[data[i + 1]], c2 = PACK.code[data[i + 2]], c3 = PACK.code[data[i + 3]];
+            if (!((c0 | c1 | c2 | c3) & 4)) {
+                bits[i >> 2] = (uint8_t)(c0 | (c1 << 2) | (c2 << 4) | (c3 << 6));
+                open = false;
+                continue;
+            }
+        }
         uint32_t b = 0;
         const int m = (int)std::min<uint64_t>(4, len - i);
         for (int j = 0; j < m; j++) {
