@@ -1,10 +1,14 @@
-// fa_comm.cu -- the one exchange step of the multi-GPU layouts: reference genomes are dealt to the GPUs
-// as whole genomes, every GPU maps every query against its own shard and produces FINAL hit rows for its genomes (the
-// per-thread split of upstream FastANI, FA/cgi/include/computeCoreIdentity.hpp:454-484: splitReferenceGenomes,
-// correctRefGenomeIds), and the rows of a batch of queries are exchanged with a small ncclAllGather over NVLink and merged
-// into the order of pyx:1135 (identity descending, stable in ascending genome id).  No collective runs inside the mapping
-// kernels: the payload is a few KB per query, so there is nothing to overlap tile by tile -- the exchange is bound by
-// launch latency, which is why the counts and the first rows of every rank travel in ONE collective.
+// fa_comm.cu -- the exchange steps of the reference-sharded multi-GPU layout: reference genomes are dealt to
+// the GPUs as whole genomes, every GPU maps every query against its own shard and produces FINAL hit rows for its genomes
+// (the per-thread split of upstream FastANI, FA/cgi/include/computeCoreIdentity.hpp:454-484: splitReferenceGenomes,
+// correctRefGenomeIds).  Two things travel over NCCL / NVLink:
+//   * the query sketches (sketch_exchange): every rank sketches 1/world of the fragments of a group of queries and one
+//     ncclAllGather hands every rank all of them, on a stream of its own, one group ahead of the mapping;
+//   * the hit rows of a batch of queries (fa_gather_hits): a few KB per query, bound by launch latency, which is why the
+//     counts and the first rows of every rank travel in ONE collective; merged into the order of pyx:1135 (identity
+//     descending, stable in ascending genome id).
+// No collective runs inside the mapping kernels, and none depends on anything a rank measured (pass sizes differ between
+// the ranks; the groups of the sketch exchange depend on the query sizes alone).
 //
 // NCCL is bound at run time (dlopen of libnccl.so.2 at the first fa_comm_* call): a process that already carries an NCCL
 // -- torch.distributed in bench.py -- shares that copy instead of loading a second one, and single-GPU users need none.

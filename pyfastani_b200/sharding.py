@@ -1,5 +1,5 @@
 """Multi-GPU decomposition of the mapping path: one process per GPU,
-no collective inside the mapping path.
+no collective inside the mapping kernels.
 
 Two ways to shard, both result-preserving:
 
@@ -13,9 +13,11 @@ Two ways to shard, both result-preserving:
   (pyx:1124-1126), so every rank produces FINAL hit rows for its genomes -- upstream FastANI does
   the same per thread (splitReferenceGenomes / correctRefGenomeIds, computeCoreIdentity.hpp:
   454-484).  The exchange lives in the library (`fa_gather_hits` / `fa_query_batch_sharded`,
-  csrc/fa_comm.cu): the per-query rows (16 bytes each) of all ranks travel in one small
-  ncclAllGather over NVLink and are merged into the reference's ordering, identity descending,
-  stable in ascending global genome id (pyx:1135).  `merge_hits` is the same merge in numpy, kept
+  csrc/fa_comm.cu): the query sketches are made once across the ranks (each sketches 1/world of
+  the fragments of a group of queries; one ncclAllGather per group, a group ahead of the mapping),
+  and the per-query rows (16 bytes each) of all ranks travel in one small ncclAllGather over
+  NVLink and are merged into the reference's ordering, identity descending, stable in ascending
+  global genome id (pyx:1135).  `merge_hits` is the same merge in numpy, kept
   as the specification the tests compare the library against.
 
 No torch here: the NCCL communicator belongs to the library (`Communicator`), and `connect` hands
